@@ -1,0 +1,337 @@
+// alloc.cu — stage 1: cache allocation (≙ Renderer::AllocateCaches,
+// rendering/renderer.cpp:951-992; shader/cacheGather.comp:93-164;
+// shader/cachePrepareLighting.comp:8-14).
+//
+// B200-first redesign: the reference locks atlas texels with CAS and takes
+// entry indices from one global atomic counter (nondeterministic order, two
+// contended atomics per new cell). Here:
+//   mark    one thread per pixel on the reference's own 16x16 tiles evaluates
+//           the identical trigger predicate (including its tile-edge quirk,
+//           SURVEY B.1) and sets a byte flag per corner cell — plain
+//           idempotent stores, no atomics;
+//   count   per 2048-cell block popcount of the flags;
+//   scan    one block: exclusive scan of the block counts, writes the
+//           LightCacheCounter / indirect args (cachePrepareLighting.comp);
+//   compact per cell: index = #flagged cells with smaller linear id; writes
+//           the atlas texel (0 or index+1, which also replaces the reference's
+//           per-frame atlas clear), the entry position and zeroed SH.
+// The index order (ascending linear cell id) is deterministic and identical
+// on every GPU, so multi-GPU runs replicate this stage without communication.
+#include "ctx.h"
+#include "device_math.cuh"
+
+using namespace drvk;
+
+namespace {
+
+struct AllocParams {
+  int W, H, R, C;
+  int transitions;
+  float zone;
+  float ivp[16];
+  drv_cav_cascade casc[DRV_MAX_CASCADES];
+};
+
+constexpr int kCellsPerThread = 8;
+constexpr int kScanThreads = 256;
+constexpr int kCellsPerBlock = kCellsPerThread * kScanThreads; // 2048
+
+// lightcache.glsl:109-122
+__device__ __forceinline__ int compute_cascade(const AllocParams& p, F3 wp) {
+  int c = 0;
+  for (; c < p.C - 1; ++c) {
+    const drv_cav_cascade& k = p.casc[c];
+    if (wp.x <= k.DecisionMax[0] && wp.y <= k.DecisionMax[1] && wp.z <= k.DecisionMax[2] &&
+        wp.x >= k.DecisionMin[0] && wp.y >= k.DecisionMin[1] && wp.z >= k.DecisionMin[2])
+      break;
+  }
+  return c;
+}
+
+// lightcache.glsl:125-134
+__device__ __forceinline__ float cascade_transition(const AllocParams& p, F3 wp, int c) {
+  const drv_cav_cascade& k = p.casc[c];
+  float ax = ex_sub(k.DecisionMax[0], wp.x), ay = ex_sub(k.DecisionMax[1], wp.y), az = ex_sub(k.DecisionMax[2], wp.z);
+  float bx = ex_sub(wp.x, k.DecisionMin[0]), by = ex_sub(wp.y, k.DecisionMin[1]), bz = ex_sub(wp.z, k.DecisionMin[2]);
+  float minDist = fminf(fminf(fminf(ax, ay), az), fminf(fminf(bx, by), bz));
+  return saturatef(ex_sub(1.0f, ex_div(minDist, ex_mul(k.WorldVoxelSize, p.zone))));
+}
+
+// cacheGather.comp:20-30
+__device__ __forceinline__ int cache_1d_coord(const AllocParams& p, F3 wp, int c) {
+  const drv_cav_cascade& k = p.casc[c];
+  int gx = clampi(ex_trunc(ex_div(ex_sub(wp.x, k.Min[0]), k.WorldVoxelSize)), 0, p.R - 1);
+  int gy = clampi(ex_trunc(ex_div(ex_sub(wp.y, k.Min[1]), k.WorldVoxelSize)), 0, p.R - 1);
+  int gz = clampi(ex_trunc(ex_div(ex_sub(wp.z, k.Min[2]), k.WorldVoxelSize)), 0, p.R - 1);
+  return gx + gy * p.R + gz * p.R * p.R + c * p.R * p.R * p.R;
+}
+
+// cacheGather.comp:32-91 with the index assignment deferred to the scan.
+__device__ __forceinline__ void mark_corners(const AllocParams& p, int coord, int c, uint8_t* __restrict__ flags,
+                                             uint32_t* __restrict__ stats) {
+  const int R = p.R, R2 = R * R, R3 = R2 * R;
+  int local = coord - R3 * c;
+  int bz = local / R2;
+  int by = (local - bz * R2) / R;
+  int bx = local - bz * R2 - by * R;
+  uint8_t* base = flags + (size_t)c * R3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    // offsets (0,0,0)(0,1,0)(0,0,1)(0,1,1)(1,0,0)(1,1,0)(1,0,1)(1,1,1), cacheGather.comp:34-44
+    int x = bx + (i >> 2), y = by + (i & 1), z = bz + ((i >> 1) & 1);
+    if (x >= R || y >= R || z >= R) { // out-of-range +1 corners are skipped and counted
+      atomicAdd(stats + 1, 1u);
+      continue;
+    }
+    uint8_t* f = base + x + y * R + z * R2;
+    if (*f == 0) *f = 1; // idempotent; the read only saves redundant write traffic
+  }
+}
+
+__global__ void __launch_bounds__(256) mark_kernel(AllocParams p, const float* __restrict__ depth,
+                                                   uint8_t* __restrict__ flags, uint32_t* __restrict__ stats) {
+  __shared__ int T1[16][16]; // [local x][local y] like cacheList[x][y]
+  __shared__ int T2[16][16];
+  const int lx = threadIdx.x, ly = threadIdx.y;
+  const int x = blockIdx.x * 16 + lx, y = blockIdx.y * 16 + ly;
+  int own = -1, own2 = -1, casc = -1;
+  if (x < p.W && y < p.H) {
+    float d = __ldg(depth + (size_t)y * p.W + x);
+    if (d > 0.0001f) {
+      float px = (float)x + 0.5f, py = (float)y + 0.5f;
+      float sx = ex_sub(ex_mul(ex_div(px, (float)p.W), 2.0f), 1.0f);
+      float sy = ex_sub(ex_mul(ex_div(py, (float)p.H), 2.0f), 1.0f);
+      F3 wp = ex_unproject(p.ivp, sx, sy, d);
+      casc = compute_cascade(p, wp);
+      own = cache_1d_coord(p, wp, casc);
+      if (p.transitions) {
+        float t = cascade_transition(p, wp, casc);
+        if (t > 0.0f && casc < p.C - 1) own2 = cache_1d_coord(p, wp, casc + 1);
+      }
+    }
+  }
+  T1[lx][ly] = own;
+  T2[lx][ly] = own2;
+  __syncthreads();
+  {
+    int ax = max(0, lx - 1), ay = max(0, ly - 1);
+    if (((T1[lx][ay] != own && T1[ax][ly] != own && T1[ax][ay] != own) || (ax == lx && ay == ly)) && own != -1)
+      mark_corners(p, own, casc, flags, stats);
+  }
+  if (p.transitions) {
+    int bx = min(15, lx + 1), by = min(15, ly + 1);
+    if (((T2[lx][by] != own2 && T2[bx][ly] != own2 && T2[bx][by] != own2) || (bx == 15 && by == 15)) && own2 != -1)
+      mark_corners(p, own2, casc + 1, flags, stats);
+  }
+}
+
+__device__ __forceinline__ uint32_t nonzero_bytes(uint2 v) { // number of non-zero bytes among 8 flags
+  uint32_t a = __vcmpne4(v.x, 0u), b = __vcmpne4(v.y, 0u); // 0xff per non-zero byte
+  return (__popc(a) + __popc(b)) >> 3;
+}
+
+__global__ void __launch_bounds__(kScanThreads) count_kernel(const uint8_t* __restrict__ flags, uint32_t num_cells,
+                                                             uint32_t* __restrict__ block_counts) {
+  __shared__ uint32_t warp_sums[kScanThreads / 32];
+  uint32_t cell = (blockIdx.x * kScanThreads + threadIdx.x) * kCellsPerThread;
+  uint32_t n = 0;
+  if (cell < num_cells) n = nonzero_bytes(*reinterpret_cast<const uint2*>(flags + cell));
+  n = __reduce_add_sync(0xffffffffu, n);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanThreads / 32; ++i) s += warp_sums[i];
+    block_counts[blockIdx.x] = s;
+  }
+}
+
+// One block. Exclusive scan of block_counts in place; writes the counter
+// (cachePrepareLighting.comp:8-14) and the overflow statistic.
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t* __restrict__ block_counts, uint32_t num_blocks,
+                                                           uint32_t max_caches, drv_cache_counter* __restrict__ counter,
+                                                           uint32_t* __restrict__ stats) {
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < num_blocks; base += 1024) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < num_blocks ? block_counts[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t w = warp_tot[threadIdx.x];
+      uint32_t wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (threadIdx.x >= o) wi += t;
+      }
+      warp_tot[threadIdx.x] = wi - w; // exclusive
+    }
+    __syncthreads();
+    uint32_t carry = carry_s;
+    uint32_t excl = carry + warp_tot[threadIdx.x >> 5] + incl - v;
+    if (i < num_blocks) block_counts[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    uint32_t total = carry_s;
+    uint32_t n = total > max_caches ? max_caches : total; // clamp, report
+    stats[0] = total - n;
+    counter->NumCacheLightingThreadGroupsX = (n + DRV_LIGHTING_THREADS_PER_GROUP - 1) / DRV_LIGHTING_THREADS_PER_GROUP;
+    counter->NumCacheLightingThreadGroupsY = 1;
+    counter->NumCacheLightingThreadGroupsZ = 1;
+    counter->TotalLightCacheCount = (int)n;
+  }
+}
+
+template <int STRIDE>
+__global__ void __launch_bounds__(kScanThreads) compact_kernel(AllocParams p, const uint8_t* __restrict__ flags,
+                                                               uint32_t num_cells,
+                                                               const uint32_t* __restrict__ block_offsets,
+                                                               uint32_t max_caches, uint32_t* __restrict__ atlas,
+                                                               uint8_t* __restrict__ entries) {
+  __shared__ uint32_t warp_tot[kScanThreads / 32];
+  const uint32_t cell0 = (blockIdx.x * kScanThreads + threadIdx.x) * kCellsPerThread;
+  uint2 f = make_uint2(0u, 0u);
+  if (cell0 < num_cells) f = *reinterpret_cast<const uint2*>(flags + cell0);
+  const uint32_t mine = nonzero_bytes(f);
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += t;
+  }
+  if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  uint32_t warp_base = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; ++w)
+    if (w < (int)(threadIdx.x >> 5)) warp_base += warp_tot[w];
+  uint32_t index = block_offsets[blockIdx.x] + warp_base + incl - mine;
+  if (cell0 >= num_cells) return;
+
+  const int R = p.R, R2 = R * R, R3 = R2 * R;
+  const uint32_t atlasW = (uint32_t)(R * p.C);
+  // R is a multiple of 8 (checked at create), so the 8 cells share (c, z, y)
+  const int c = cell0 / R3;
+  const int local = cell0 - c * R3;
+  const int z = local / R2;
+  const int y = (local - z * R2) / R;
+  const int x0 = local - z * R2 - y * R;
+  const drv_cav_cascade& k = p.casc[c];
+  uint32_t out[kCellsPerThread];
+#pragma unroll
+  for (int i = 0; i < kCellsPerThread; ++i) {
+    uint32_t word = i < 4 ? f.x : f.y;
+    bool set = ((word >> ((i & 3) * 8)) & 0xffu) != 0u;
+    uint32_t v = 0u;
+    if (set) {
+      if (index < max_caches) {
+        v = index + 1u; // +1 since zero means "cleared", cacheGather.comp:88
+        float4* e = reinterpret_cast<float4*>(entries + (size_t)index * STRIDE);
+        // Position = cell * WorldVoxelSize + Min, cacheGather.comp:65 (mul and add rounded separately)
+        e[0] = make_float4(ex_add(ex_mul((float)(x0 + i), k.WorldVoxelSize), k.Min[0]),
+                           ex_add(ex_mul((float)y, k.WorldVoxelSize), k.Min[1]),
+                           ex_add(ex_mul((float)z, k.WorldVoxelSize), k.Min[2]), 0.0f);
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 1; q < STRIDE / 16; ++q) e[q] = zero; // cacheGather.comp:68-83
+      }
+      ++index;
+    }
+    out[i] = v;
+  }
+  uint4* dst = reinterpret_cast<uint4*>(atlas + (size_t)(x0 + c * R) + (size_t)atlasW * ((size_t)y + (size_t)R * z));
+  dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+  dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+}
+
+// drv_set_synthetic_entries: positions -> entries with zeroed SH.
+template <int STRIDE>
+__global__ void synthetic_entries_kernel(const float4* __restrict__ pos, uint32_t n, uint8_t* __restrict__ entries,
+                                         drv_cache_counter* __restrict__ counter) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    counter->NumCacheLightingThreadGroupsX = (n + 63) / 64;
+    counter->NumCacheLightingThreadGroupsY = 1;
+    counter->NumCacheLightingThreadGroupsZ = 1;
+    counter->TotalLightCacheCount = (int)n;
+  }
+  if (i >= n) return;
+  float4 p = pos[i];
+  p.w = 0.0f;
+  float4* e = reinterpret_cast<float4*>(entries + (size_t)i * STRIDE);
+  e[0] = p;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 1; q < STRIDE / 16; ++q) e[q] = zero;
+}
+
+} // namespace
+
+drv_status drv_impl_allocate(drv_ctx* ctx) {
+  if (!ctx->have_constant || !ctx->have_per_frame || !ctx->have_volume)
+    return ctx->fail(DRV_ERR_NOT_BOUND, "drv_allocate_caches: uniform blocks not set");
+  if (!ctx->gb_depth) return ctx->fail(DRV_ERR_NOT_BOUND, "drv_allocate_caches: g-buffer not bound");
+  AllocParams p;
+  p.W = ctx->constant.BackbufferResolution[0];
+  p.H = ctx->constant.BackbufferResolution[1];
+  p.R = ctx->constant.AddressVolumeResolution;
+  p.C = ctx->constant.NumAddressVolumeCascades;
+  if (p.W != (int)ctx->gb_w || p.H != (int)ctx->gb_h || p.R != (int)ctx->cfg.cav_resolution ||
+      p.C != (int)ctx->cfg.cav_cascades)
+    return ctx->fail(DRV_ERR_INVALID, "drv_allocate_caches: Constant block disagrees with the context configuration");
+  p.transitions = ctx->cfg.cascade_transitions ? 1 : 0;
+  p.zone = ctx->volume.CAVTransitionZoneSize;
+  memcpy(p.ivp, ctx->per_frame.InverseViewProjection, sizeof(p.ivp));
+  memcpy(p.casc, ctx->volume.AddressVolumeCascades, sizeof(p.casc));
+
+  ctx->stage_begin(DRV_STAGE_ALLOCATE_CACHES);
+  // ≙ m_lightCacheCounter->ClearToZero(); the atlas clear (renderer.cpp:969-970) is folded into compact
+  DRV_CUDA(cudaMemsetAsync(ctx->cell_flags, 0, ctx->num_cells, ctx->stream));
+  DRV_CUDA(cudaMemsetAsync(ctx->stats, 0, 2 * sizeof(uint32_t), ctx->stream));
+  dim3 grid((p.W + 15) / 16, (p.H + 15) / 16); // renderer.cpp:981-985
+  mark_kernel<<<grid, dim3(16, 16), 0, ctx->stream>>>(p, ctx->gb_depth, ctx->cell_flags, ctx->stats);
+  DRV_LAUNCH_CHECK();
+  count_kernel<<<ctx->num_scan_blocks, kScanThreads, 0, ctx->stream>>>(ctx->cell_flags, ctx->num_cells,
+                                                                      ctx->block_counts);
+  DRV_LAUNCH_CHECK();
+  scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->block_counts, ctx->num_scan_blocks, ctx->cfg.max_cache_count,
+                                                  ctx->counter, ctx->stats);
+  DRV_LAUNCH_CHECK();
+  if (ctx->entry_stride == 64)
+    compact_kernel<64><<<ctx->num_scan_blocks, kScanThreads, 0, ctx->stream>>>(
+        p, ctx->cell_flags, ctx->num_cells, ctx->block_counts, ctx->cfg.max_cache_count, ctx->atlas, ctx->entries);
+  else
+    compact_kernel<128><<<ctx->num_scan_blocks, kScanThreads, 0, ctx->stream>>>(
+        p, ctx->cell_flags, ctx->num_cells, ctx->block_counts, ctx->cfg.max_cache_count, ctx->atlas, ctx->entries);
+  DRV_LAUNCH_CHECK();
+  ctx->stage_end(DRV_STAGE_ALLOCATE_CACHES);
+  return DRV_OK;
+}
+
+drv_status drv_impl_set_synthetic_entries(drv_ctx* ctx, const float* pos, uint32_t n) {
+  if (n > ctx->cfg.max_cache_count) return ctx->fail(DRV_ERR_CAPACITY, "drv_set_synthetic_entries: n > max_cache_count");
+  uint32_t blocks = (n + 255) / 256;
+  if (blocks == 0) blocks = 1;
+  if (ctx->entry_stride == 64)
+    synthetic_entries_kernel<64><<<blocks, 256, 0, ctx->stream>>>((const float4*)pos, n, ctx->entries, ctx->counter);
+  else
+    synthetic_entries_kernel<128><<<blocks, 256, 0, ctx->stream>>>((const float4*)pos, n, ctx->entries, ctx->counter);
+  DRV_LAUNCH_CHECK();
+  return DRV_OK;
+}
+
+int drv_alloc_cells_per_block() { return kCellsPerBlock; }

@@ -1,0 +1,220 @@
+// apply.cu — stage 5: per-pixel SH cache interpolation
+// (≙ Renderer::ApplyCaches, rendering/renderer.cpp:1047-1079;
+// shader/cacheApply.frag:28-195; shader/lightcache.glsl:109-183).
+//
+// One thread per pixel on 32x8 blocks (a warp = 32 consecutive pixels of a
+// row, so depth / normal / diffuse loads and the HDR read-modify-write are
+// fully coalesced). The eight (sixteen in a transition zone) cache entries
+// are fetched with 128-bit loads; neighbouring pixels hit the same entries,
+// which L1 absorbs, and the whole entry list + atlas is L2-resident.
+// Cascade choice and cell selection are DECISION maths (device_math.cuh) so
+// they agree with the allocation stage and with the oracle bit for bit.
+#include "ctx.h"
+#include "device_math.cuh"
+
+using namespace drvk;
+
+namespace {
+
+__constant__ float c_srgb_lut[256]; // exact piecewise sRGB EOTF per 8-bit code (gbuffer.glsl:1, renderer.cpp:468)
+
+struct ApplyParams {
+  int W, H, R, C;
+  int transitions;
+  float zone;
+  float ivp[16];
+  drv_cav_cascade casc[DRV_MAX_CASCADES];
+  float g0, g1, g2, g20, g22; // ShCosLobeFactor*
+  uint32_t max_caches;
+};
+
+__device__ __forceinline__ int compute_cascade(const ApplyParams& p, F3 wp) { // lightcache.glsl:109-122
+  int c = 0;
+  for (; c < p.C - 1; ++c) {
+    const drv_cav_cascade& k = p.casc[c];
+    if (wp.x <= k.DecisionMax[0] && wp.y <= k.DecisionMax[1] && wp.z <= k.DecisionMax[2] &&
+        wp.x >= k.DecisionMin[0] && wp.y >= k.DecisionMin[1] && wp.z >= k.DecisionMin[2])
+      break;
+  }
+  return c;
+}
+
+__device__ __forceinline__ float cascade_transition(const ApplyParams& p, F3 wp, int c) { // lightcache.glsl:125-134
+  const drv_cav_cascade& k = p.casc[c];
+  float ax = ex_sub(k.DecisionMax[0], wp.x), ay = ex_sub(k.DecisionMax[1], wp.y), az = ex_sub(k.DecisionMax[2], wp.z);
+  float bx = ex_sub(wp.x, k.DecisionMin[0]), by = ex_sub(wp.y, k.DecisionMin[1]), bz = ex_sub(wp.z, k.DecisionMin[2]);
+  float minDist = fminf(fminf(fminf(ax, ay), az), fminf(fminf(bx, by), bz));
+  return saturatef(ex_sub(1.0f, ex_div(minDist, ex_mul(k.WorldVoxelSize, p.zone))));
+}
+
+// SampleCacheIrradiance, lightcache.glsl:137-183. nb* = the per-pixel normal
+// factors, hoisted out of the 8-corner loop.
+template <int ORDER>
+struct NormalBasis {
+  float b1y, b1z, b1x;                 // g1 * n.{y,z,x}
+  float b2xy, b2yz, b20, b2xz, b2dd;   // band 2
+};
+
+template <int ORDER>
+__device__ __forceinline__ void accumulate_corner(const ApplyParams& p, const uint8_t* __restrict__ entries,
+                                                  uint32_t address, const NormalBasis<ORDER>& nb, float w, float& r,
+                                                  float& g, float& b) {
+  constexpr int STRIDE = ORDER == 2 ? 128 : 64;
+  if (address >= p.max_caches) return; // atlas 0 -> 0xFFFFFFFF: no cache, contributes zero
+  const float4* e = reinterpret_cast<const float4*>(entries + (size_t)address * STRIDE);
+  float4 q1 = __ldg(e + 1), q2 = __ldg(e + 2), q3 = __ldg(e + 3); // (SH1neg1,SH00_r) (SH10,SH00_g) (SH1pos1,SH00_b)
+  float ir = q1.w * p.g0, ig = q2.w * p.g0, ib = q3.w * p.g0;
+  ir = fmaf(-q1.x, nb.b1y, ir); ig = fmaf(-q1.y, nb.b1y, ig); ib = fmaf(-q1.z, nb.b1y, ib);
+  ir = fmaf(q2.x, nb.b1z, ir);  ig = fmaf(q2.y, nb.b1z, ig);  ib = fmaf(q2.z, nb.b1z, ib);
+  ir = fmaf(-q3.x, nb.b1x, ir); ig = fmaf(-q3.y, nb.b1x, ig); ib = fmaf(-q3.z, nb.b1x, ib);
+  if (ORDER == 2) {
+    float4 q4 = __ldg(e + 4), q5 = __ldg(e + 5), q6 = __ldg(e + 6), q7 = __ldg(e + 7);
+    // (SH2neg2,SH20_r) (SH2neg1,SH20_g) (SH2pos1,SH20_b) (SH2pos2,-)
+    ir = fmaf(-q4.x, nb.b2xy, ir); ig = fmaf(-q4.y, nb.b2xy, ig); ib = fmaf(-q4.z, nb.b2xy, ib);
+    ir = fmaf(q5.x, nb.b2yz, ir);  ig = fmaf(q5.y, nb.b2yz, ig);  ib = fmaf(q5.z, nb.b2yz, ib);
+    ir = fmaf(q4.w, nb.b20, ir);   ig = fmaf(q5.w, nb.b20, ig);   ib = fmaf(q6.w, nb.b20, ib);
+    ir = fmaf(q6.x, nb.b2xz, ir);  ig = fmaf(q6.y, nb.b2xz, ig);  ib = fmaf(q6.z, nb.b2xz, ib);
+    ir = fmaf(q7.x, nb.b2dd, ir);  ig = fmaf(q7.y, nb.b2dd, ig);  ib = fmaf(q7.z, nb.b2dd, ib);
+  }
+  r = fmaf(fmaxf(ir, 0.0f), w, r); // max(irradiance, 0) then * weight, lightcache.glsl:178, cacheApply.frag:110
+  g = fmaf(fmaxf(ig, 0.0f), w, g);
+  b = fmaf(fmaxf(ib, 0.0f), w, b);
+}
+
+// ComputeLightingFromCaches, cacheApply.frag:28-118 (before the * diffuse / PI).
+template <int ORDER>
+__device__ __forceinline__ void lighting_from_caches(const ApplyParams& p, const uint32_t* __restrict__ atlas,
+                                                     const uint8_t* __restrict__ entries, F3 wp,
+                                                     const NormalBasis<ORDER>& nb, int c, float& r, float& g, float& b) {
+  const drv_cav_cascade& k = p.casc[c];
+  float ax = ex_div(ex_sub(wp.x, k.Min[0]), k.WorldVoxelSize);
+  float ay = ex_div(ex_sub(wp.y, k.Min[1]), k.WorldVoxelSize);
+  float az = ex_div(ex_sub(wp.z, k.Min[2]), k.WorldVoxelSize);
+  int bx = ex_trunc(ax), by = ex_trunc(ay), bz = ex_trunc(az);
+  float fx = ax - (float)bx, fy = ay - (float)by, fz = az - (float)bz;
+  float gx = 1.0f - fx, gy = 1.0f - fy, gz = 1.0f - fz;
+  const int atlasW = p.R * p.C;
+  r = g = b = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { // offsets in cacheApply.frag:43-54 order: x fastest, then y, then z
+    const int ox = i & 1, oy = (i >> 1) & 1, oz = i >> 2;
+    float w = (ox ? fx : gx) * (oy ? fy : gy) * (oz ? fz : gz);
+    int x = bx + ox + p.R * c, y = by + oy, z = bz + oz;
+    uint32_t address = 0u; // texelFetch outside the texture returns 0
+    if (x >= 0 && x < atlasW && y >= 0 && y < p.R && z >= 0 && z < p.R)
+      address = __ldg(atlas + (size_t)x + (size_t)atlasW * ((size_t)y + (size_t)p.R * z));
+    accumulate_corner<ORDER>(p, entries, address - 1u, nb, w, r, g, b);
+  }
+}
+
+template <int ORDER>
+__global__ void __launch_bounds__(256) apply_kernel(ApplyParams p, const float* __restrict__ depth,
+                                                    const int* __restrict__ normal, const uchar4* __restrict__ diffuse,
+                                                    const uint32_t* __restrict__ atlas, const uint8_t* __restrict__ entries,
+                                                    void* __restrict__ out, int format) {
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= p.W || y >= p.H) return;
+  const size_t t = (size_t)y * p.W + x;
+  const float d = __ldg(depth + t);
+  if (d < 0.00001f) { // :128 discard
+    if (format == DRV_HDR_RGBA32F_WRITE) reinterpret_cast<float4*>(out)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  float px = (float)x + 0.5f, py = (float)y + 0.5f; // gl_FragCoord.xy, :134
+  float sx = ex_sub(ex_mul(ex_div(px, (float)p.W), 2.0f), 1.0f);
+  float sy = ex_sub(ex_mul(ex_div(py, (float)p.H), 2.0f), 1.0f);
+  F3 wp = ex_unproject(p.ivp, sx, sy, d);
+  const int c = compute_cascade(p, wp); // :138
+  const int pn = __ldg(normal + t);
+  F3 n = unpack_normal16i((int)(short)(pn & 0xffff), (int)(short)((uint32_t)pn >> 16)); // :140
+  const uchar4 dc = __ldg(diffuse + t);
+  const float albr = c_srgb_lut[dc.x], albg = c_srgb_lut[dc.y], albb = c_srgb_lut[dc.z]; // :144
+  NormalBasis<ORDER> nb;
+  nb.b1y = p.g1 * n.y; nb.b1z = p.g1 * n.z; nb.b1x = p.g1 * n.x;
+  if (ORDER == 2) {
+    nb.b2xy = p.g2 * n.x * n.y;
+    nb.b2yz = p.g2 * n.y * n.z;
+    nb.b20 = p.g20 * (n.z * n.z * 3.0f - 1.0f);
+    nb.b2xz = p.g2 * n.x * n.z;
+    nb.b2dd = p.g22 * (n.x * n.x - n.y * n.y);
+  }
+  float r, g, b;
+  lighting_from_caches<ORDER>(p, atlas, entries, wp, nb, c, r, g, b);
+  if (p.transitions) { // :172-184
+    float tr = cascade_transition(p, wp, c);
+    if (tr > 0.0f && c < p.C - 1) {
+      float r2, g2, b2;
+      lighting_from_caches<ORDER>(p, atlas, entries, wp, nb, c + 1, r2, g2, b2);
+      r = fmaf(r2 - r, tr, r); g = fmaf(g2 - g, tr, g); b = fmaf(b2 - b, tr, b);
+    }
+  }
+  const float inv_pi = 1.0f / DRV_GLSL_PI;
+  r = r * albr * inv_pi; g = g * albg * inv_pi; b = b * albb * inv_pi; // :114
+  if (format == DRV_HDR_RGBA32F_WRITE) {
+    reinterpret_cast<float4*>(out)[t] = make_float4(r, g, b, 1.0f);
+  } else { // additive blend GL_ONE, GL_ONE into RGBA16F (renderer.cpp:119, 480, 1053)
+    uint2* o = reinterpret_cast<uint2*>(out) + t;
+    uint2 old = *o;
+    float2 rg = __half22float2(*reinterpret_cast<__half2*>(&old.x));
+    float2 ba = __half22float2(*reinterpret_cast<__half2*>(&old.y));
+    __half2 nrg = __floats2half2_rn(rg.x + r, rg.y + g);
+    __half2 nba = __floats2half2_rn(ba.x + b, ba.y); // the shader outputs a vec3: alpha is left untouched
+    uint2 nw;
+    nw.x = *reinterpret_cast<uint32_t*>(&nrg);
+    nw.y = *reinterpret_cast<uint32_t*>(&nba);
+    *o = nw;
+  }
+}
+
+} // namespace
+
+void drv_impl_upload_srgb_lut() {
+  float lut[256];
+  for (int v = 0; v < 256; ++v) {
+    double c = (double)v / 255.0;
+    double l = (c <= 0.04045) ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4);
+    lut[v] = (float)l;
+  }
+  cudaMemcpyToSymbol(c_srgb_lut, lut, sizeof(lut));
+}
+
+drv_status drv_impl_apply(drv_ctx* ctx, void* out, uint32_t format) {
+  if (!ctx->have_constant || !ctx->have_per_frame || !ctx->have_volume)
+    return ctx->fail(DRV_ERR_NOT_BOUND, "drv_apply_caches: uniform blocks not set");
+  if (!ctx->gb_depth || !ctx->gb_normal || !ctx->gb_diffuse)
+    return ctx->fail(DRV_ERR_NOT_BOUND, "drv_apply_caches: g-buffer not bound");
+  if (!out) return ctx->fail(DRV_ERR_INVALID, "drv_apply_caches: null output");
+  if (format != DRV_HDR_RGBA16F_ADD && format != DRV_HDR_RGBA32F_WRITE)
+    return ctx->fail(DRV_ERR_INVALID, "drv_apply_caches: unknown output format");
+  ApplyParams p;
+  p.W = ctx->constant.BackbufferResolution[0];
+  p.H = ctx->constant.BackbufferResolution[1];
+  p.R = ctx->constant.AddressVolumeResolution;
+  p.C = ctx->constant.NumAddressVolumeCascades;
+  if (p.W != (int)ctx->gb_w || p.H != (int)ctx->gb_h || p.R != (int)ctx->cfg.cav_resolution ||
+      p.C != (int)ctx->cfg.cav_cascades)
+    return ctx->fail(DRV_ERR_INVALID, "drv_apply_caches: Constant block disagrees with the context configuration");
+  p.transitions = ctx->cfg.cascade_transitions ? 1 : 0;
+  p.zone = ctx->volume.CAVTransitionZoneSize;
+  memcpy(p.ivp, ctx->per_frame.InverseViewProjection, sizeof(p.ivp));
+  memcpy(p.casc, ctx->volume.AddressVolumeCascades, sizeof(p.casc));
+  p.g0 = ctx->constant.ShCosLobeFactor0;
+  p.g1 = ctx->constant.ShCosLobeFactor1;
+  p.g2 = ctx->constant.ShCosLobeFactor2n2_p1_n1;
+  p.g20 = ctx->constant.ShCosLobeFactor20;
+  p.g22 = ctx->constant.ShCosLobeFactor2p2;
+  p.max_caches = ctx->cfg.max_cache_count;
+  ctx->stage_begin(DRV_STAGE_APPLY_CACHES);
+  dim3 block(32, 8), grid((p.W + 31) / 32, (p.H + 7) / 8);
+  if (ctx->cfg.sh_order == 2)
+    apply_kernel<2><<<grid, block, 0, ctx->stream>>>(p, ctx->gb_depth, (const int*)ctx->gb_normal,
+                                                     (const uchar4*)ctx->gb_diffuse, ctx->atlas, ctx->entries, out,
+                                                     (int)format);
+  else
+    apply_kernel<1><<<grid, block, 0, ctx->stream>>>(p, ctx->gb_depth, (const int*)ctx->gb_normal,
+                                                     (const uchar4*)ctx->gb_diffuse, ctx->atlas, ctx->entries, out,
+                                                     (int)format);
+  DRV_LAUNCH_CHECK();
+  ctx->stage_end(DRV_STAGE_APPLY_CACHES);
+  return DRV_OK;
+}

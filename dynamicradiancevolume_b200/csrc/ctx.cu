@@ -1,0 +1,418 @@
+// ctx.cu — the C-ABI of libdrv_gi (include/drv_gi.h): context lifetime,
+// resource ownership and the stage order of the DYN_RADIANCE_VOLUME case of
+// Renderer::Draw (rendering/renderer.cpp:539-570). The context plays the role
+// glhelper's buffer/texture objects + Renderer's members play in the
+// reference (renderer.hpp:227-352).
+#include "ctx.h"
+
+#include <cstring>
+#include <mutex>
+
+namespace {
+std::string g_create_error;
+std::once_flag g_lut_once[16];
+
+uint32_t ilog2(uint32_t v) {
+  uint32_t l = 0;
+  while (v > 1) { v >>= 1; ++l; }
+  return l;
+}
+bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
+
+template <typename T>
+cudaError_t dmalloc(T** p, size_t bytes) {
+  return cudaMalloc(reinterpret_cast<void**>(p), bytes ? bytes : 16);
+}
+} // namespace
+
+#define CREATE_CUDA(expr)                                                          \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      g_create_error = std::string(#expr) + ": " + cudaGetErrorString(_e);         \
+      drv_destroy(ctx);                                                            \
+      return DRV_ERR_CUDA;                                                         \
+    }                                                                              \
+  } while (0)
+
+extern "C" const char* drv_version(void) { return "libdrv_gi 0.1 sm_100a"; }
+
+extern "C" const char* drv_last_error(const drv_ctx* ctx) {
+  return ctx ? ctx->last_error.c_str() : g_create_error.c_str();
+}
+
+extern "C" drv_status drv_create(const drv_config* cfg, drv_ctx** out) {
+  if (!cfg || !out) { g_create_error = "drv_create: null argument"; return DRV_ERR_INVALID; }
+  *out = nullptr;
+  const drv_config& c = *cfg;
+  if (c.max_cache_count == 0 || c.cav_cascades < 1 || c.cav_cascades > DRV_MAX_CASCADES || c.cav_resolution < 8 ||
+      (c.cav_resolution % 8) != 0 || (c.sh_order != 1 && c.sh_order != 2) || c.backbuffer_width == 0 ||
+      c.backbuffer_height == 0 || c.max_lights > DRV_MAX_LIGHTS || !is_pow2(c.voxel_resolution) ||
+      c.voxel_resolution < 16 || (c.max_lights > 0 && !is_pow2(c.max_rsm_resolution))) {
+    g_create_error = "drv_create: invalid configuration";
+    return DRV_ERR_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    g_create_error = "drv_create: no CUDA device (libdrv_gi has no CPU fallback)";
+    return DRV_ERR_NO_DEVICE;
+  }
+  if (c.device < 0 || c.device >= ndev) { g_create_error = "drv_create: bad device ordinal"; return DRV_ERR_INVALID; }
+  drv_ctx* ctx = new drv_ctx();
+  ctx->cfg = c;
+  ctx->device = c.device;
+  CREATE_CUDA(cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  CREATE_CUDA(cudaGetDeviceProperties(&prop, c.device));
+  ctx->num_sms = prop.multiProcessorCount;
+  if (c.stream) {
+    ctx->stream = reinterpret_cast<cudaStream_t>(c.stream);
+  } else {
+    CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  std::call_once(g_lut_once[c.device & 15], drv_impl_upload_srgb_lut);
+
+  ctx->entry_stride = c.sh_order == 2 ? 128 : 64;
+  // "Maximum size per cache": the buffer is max * 128 B whatever the mode (renderer.cpp:266-269)
+  CREATE_CUDA(dmalloc(&ctx->entries, (size_t)c.max_cache_count * 128));
+  CREATE_CUDA(cudaMemsetAsync(ctx->entries, 0, (size_t)c.max_cache_count * 128, ctx->stream));
+  CREATE_CUDA(dmalloc(&ctx->counter, sizeof(drv_cache_counter)));
+  CREATE_CUDA(cudaMemsetAsync(ctx->counter, 0, sizeof(drv_cache_counter), ctx->stream));
+  CREATE_CUDA(dmalloc(&ctx->stats, 2 * sizeof(uint32_t)));
+  CREATE_CUDA(cudaMemsetAsync(ctx->stats, 0, 2 * sizeof(uint32_t), ctx->stream));
+  ctx->num_cells = c.cav_cascades * c.cav_resolution * c.cav_resolution * c.cav_resolution;
+  CREATE_CUDA(dmalloc(&ctx->atlas, (size_t)ctx->num_cells * sizeof(uint32_t))); // renderer.cpp:1179
+  CREATE_CUDA(cudaMemsetAsync(ctx->atlas, 0, (size_t)ctx->num_cells * sizeof(uint32_t), ctx->stream));
+  CREATE_CUDA(dmalloc(&ctx->cell_flags, ctx->num_cells));
+  ctx->num_scan_blocks = (ctx->num_cells + 2047) / 2048;
+  CREATE_CUDA(dmalloc(&ctx->block_counts, (size_t)ctx->num_scan_blocks * sizeof(uint32_t)));
+
+  // voxel volumes (voxelization.cpp:56-66): target (1 level) + persistent (full chain)
+  const uint32_t vr = c.voxel_resolution;
+  ctx->voxel_levels = ilog2(vr) + 1; // glhelper/texture.cpp:54-71
+  ctx->voxel_chain_bytes = voxel_level_offset_bytes(vr, ctx->voxel_levels);
+  CREATE_CUDA(dmalloc(&ctx->voxel_chain, ctx->voxel_chain_bytes + 16));
+  CREATE_CUDA(cudaMemsetAsync(ctx->voxel_chain, 0, ctx->voxel_chain_bytes + 16, ctx->stream));
+  CREATE_CUDA(dmalloc(&ctx->voxel_target, (size_t)vr * vr * vr));
+  CREATE_CUDA(cudaMemsetAsync(ctx->voxel_target, 0, (size_t)vr * vr * vr, ctx->stream));
+
+  for (uint32_t l = 0; l < c.max_lights; ++l) {
+    LightState& S = ctx->lights[l];
+    const size_t texels = (size_t)c.max_rsm_resolution * c.max_rsm_resolution;
+    const size_t mip_texels = texels / 3 + 16; // sum of levels >= 1 < texels / 3
+    CREATE_CUDA(dmalloc(&S.flux_mips, mip_texels * 8));
+    CREATE_CUDA(dmalloc(&S.normal_mips, mip_texels * 4));
+    CREATE_CUDA(dmalloc(&S.depth_mips, mip_texels * 4));
+    CREATE_CUDA(dmalloc(&S.vpls, texels * sizeof(drv_vpl)));
+    CREATE_CUDA(dmalloc(&S.blocks, texels * sizeof(drv_shadow_block)));
+  }
+  for (int s = 0; s < DRV_STAGE_COUNT; ++s) {
+    CREATE_CUDA(cudaEventCreate(&ctx->ev_begin[s]));
+    CREATE_CUDA(cudaEventCreate(&ctx->ev_end[s]));
+  }
+  CREATE_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = ctx;
+  return DRV_OK;
+}
+
+extern "C" void drv_destroy(drv_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->peers_open)
+    for (int r = 0; r < 8; ++r)
+      if (ctx->peer_entries[r]) cudaIpcCloseMemHandle(ctx->peer_entries[r]);
+  cudaFree(ctx->entries); cudaFree(ctx->counter); cudaFree(ctx->stats); cudaFree(ctx->atlas);
+  cudaFree(ctx->cell_flags); cudaFree(ctx->block_counts); cudaFree(ctx->voxel_chain); cudaFree(ctx->voxel_target);
+  cudaFree(ctx->partials); cudaFree(ctx->st_depth); cudaFree(ctx->st_normal); cudaFree(ctx->st_diffuse);
+  cudaFree(ctx->hdr16);
+  for (auto& S : ctx->lights) {
+    cudaFree(S.flux_mips); cudaFree(S.normal_mips); cudaFree(S.depth_mips); cudaFree(S.vpls); cudaFree(S.blocks);
+    cudaFree(S.st_flux); cudaFree(S.st_normal); cudaFree(S.st_depth);
+  }
+  for (int s = 0; s < DRV_STAGE_COUNT; ++s) {
+    if (ctx->ev_begin[s]) cudaEventDestroy(ctx->ev_begin[s]);
+    if (ctx->ev_end[s]) cudaEventDestroy(ctx->ev_end[s]);
+  }
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+#define NEED_CTX() do { if (!ctx) return DRV_ERR_INVALID; cudaSetDevice(ctx->device); } while (0)
+
+extern "C" drv_status drv_set_constant(drv_ctx* ctx, const drv_constant* b) {
+  NEED_CTX();
+  if (!b) return ctx->fail(DRV_ERR_INVALID, "drv_set_constant: null block");
+  ctx->constant = *b;
+  ctx->have_constant = true;
+  return DRV_OK;
+}
+extern "C" drv_status drv_set_per_frame(drv_ctx* ctx, const drv_per_frame* b) {
+  NEED_CTX();
+  if (!b) return ctx->fail(DRV_ERR_INVALID, "drv_set_per_frame: null block");
+  ctx->per_frame = *b;
+  ctx->have_per_frame = true;
+  return DRV_OK;
+}
+extern "C" drv_status drv_set_volume_info(drv_ctx* ctx, const drv_volume_info* b) {
+  NEED_CTX();
+  if (!b) return ctx->fail(DRV_ERR_INVALID, "drv_set_volume_info: null block");
+  ctx->volume = *b;
+  ctx->have_volume = true;
+  return DRV_OK;
+}
+extern "C" drv_status drv_set_light_count(drv_ctx* ctx, uint32_t n) {
+  NEED_CTX();
+  if (n > ctx->cfg.max_lights) return ctx->fail(DRV_ERR_INVALID, "drv_set_light_count: more lights than max_lights");
+  ctx->num_lights = n;
+  return DRV_OK;
+}
+extern "C" drv_status drv_set_spot_light(drv_ctx* ctx, uint32_t light, const drv_spot_light* b) {
+  NEED_CTX();
+  if (!b || light >= ctx->cfg.max_lights) return ctx->fail(DRV_ERR_INVALID, "drv_set_spot_light: bad light index");
+  ctx->lights[light].block = *b;
+  ctx->lights[light].block_set = true;
+  return DRV_OK;
+}
+
+extern "C" drv_status drv_bind_gbuffer(drv_ctx* ctx, const float* depth, const int16_t* normal, const uint8_t* diffuse,
+                                       uint32_t w, uint32_t h) {
+  NEED_CTX();
+  if (!depth || w != ctx->cfg.backbuffer_width || h != ctx->cfg.backbuffer_height)
+    return ctx->fail(DRV_ERR_INVALID, "drv_bind_gbuffer: resolution differs from the configured backbuffer");
+  ctx->gb_depth = depth; ctx->gb_normal = normal; ctx->gb_diffuse = diffuse;
+  ctx->gb_w = w; ctx->gb_h = h;
+  return DRV_OK;
+}
+
+extern "C" drv_status drv_bind_rsm(drv_ctx* ctx, uint32_t light, const uint16_t* flux, const int16_t* normal,
+                                   const uint16_t* depth, uint32_t res) {
+  NEED_CTX();
+  if (light >= ctx->cfg.max_lights || !flux || !normal || !depth || !is_pow2(res) || res > ctx->cfg.max_rsm_resolution)
+    return ctx->fail(DRV_ERR_INVALID, "drv_bind_rsm: bad light index or resolution");
+  LightState& S = ctx->lights[light];
+  S.flux0 = flux; S.normal0 = normal; S.depth0 = depth; S.rsm_res = res;
+  S.rsm_bound = true;
+  S.vpls_external = false;
+  return DRV_OK;
+}
+
+extern "C" drv_status drv_prepare_rsm(drv_ctx* ctx, uint32_t light) {
+  NEED_CTX();
+  if (light >= ctx->cfg.max_lights) return ctx->fail(DRV_ERR_INVALID, "drv_prepare_rsm: bad light index");
+  return drv_impl_prepare_rsm(ctx, light);
+}
+
+extern "C" drv_status drv_voxelize(drv_ctx* ctx, const float* tri_pos, uint32_t num_tris, const float world[16],
+                                   float adaption, uint32_t flags) {
+  NEED_CTX();
+  if ((num_tris && !tri_pos) || !world) return ctx->fail(DRV_ERR_INVALID, "drv_voxelize: null argument");
+  return drv_impl_voxelize(ctx, tri_pos, num_tris, world, adaption, flags);
+}
+
+extern "C" drv_status drv_allocate_caches(drv_ctx* ctx) {
+  NEED_CTX();
+  return drv_impl_allocate(ctx);
+}
+
+extern "C" drv_status drv_light_caches(drv_ctx* ctx) {
+  NEED_CTX();
+  ctx->stage_begin(DRV_STAGE_LIGHT_CACHES);
+  for (uint32_t l = 0; l < ctx->num_lights; ++l) {
+    if (ctx->lights[l].vpls_external) continue;
+    drv_status st = drv_impl_generate_vpls(ctx, l);
+    if (st != DRV_OK) return st;
+  }
+  drv_status st = drv_impl_gather(ctx);
+  ctx->stage_end(DRV_STAGE_LIGHT_CACHES);
+  return st;
+}
+
+extern "C" drv_status drv_apply_caches(drv_ctx* ctx, void* hdr_out, uint32_t format) {
+  NEED_CTX();
+  return drv_impl_apply(ctx, hdr_out, format);
+}
+
+extern "C" drv_status drv_draw(drv_ctx* ctx, void* hdr_out, uint32_t format) {
+  NEED_CTX();
+  drv_status st = drv_impl_allocate(ctx); // renderer.cpp:550
+  if (st != DRV_OK) return st;
+  st = drv_light_caches(ctx);             // renderer.cpp:556
+  if (st != DRV_OK) return st;
+  return drv_impl_apply(ctx, hdr_out, format); // renderer.cpp:570
+}
+
+extern "C" drv_status drv_get_buffers(drv_ctx* ctx, drv_buffers* out) {
+  NEED_CTX();
+  if (!out) return ctx->fail(DRV_ERR_INVALID, "drv_get_buffers: null argument");
+  memset(out, 0, sizeof(*out));
+  out->entries = ctx->entries;
+  out->entry_stride = ctx->entry_stride;
+  out->max_cache_count = ctx->cfg.max_cache_count;
+  out->counter = ctx->counter;
+  out->cav_atlas = ctx->atlas;
+  out->cav_width = ctx->cfg.cav_cascades * ctx->cfg.cav_resolution;
+  out->cav_height = out->cav_depth = ctx->cfg.cav_resolution;
+  out->voxel_chain = ctx->voxel_chain;
+  out->voxel_target = ctx->voxel_target;
+  out->voxel_resolution = ctx->cfg.voxel_resolution;
+  out->voxel_levels = ctx->voxel_levels;
+  out->voxel_chain_bytes = ctx->voxel_chain_bytes;
+  for (uint32_t l = 0; l < ctx->cfg.max_lights; ++l) {
+    out->vpls[l] = ctx->lights[l].vpls;
+    out->shadow_blocks[l] = ctx->lights[l].blocks;
+    out->rsm_flux_mips[l] = ctx->lights[l].flux_mips;
+    out->rsm_normal_mips[l] = ctx->lights[l].normal_mips;
+    out->rsm_depth_mips[l] = ctx->lights[l].depth_mips;
+  }
+  return DRV_OK;
+}
+
+extern "C" uint64_t drv_rsm_level_offset(uint32_t res, uint32_t level) { return rsm_level_offset_texels(res, level); }
+extern "C" uint64_t drv_voxel_level_offset(uint32_t res, uint32_t level) { return voxel_level_offset_bytes(res, level); }
+
+extern "C" drv_status drv_active_cache_count(drv_ctx* ctx, uint32_t* count, uint32_t* overflow, uint32_t* oob) {
+  NEED_CTX();
+  drv_cache_counter c;
+  uint32_t stats[2];
+  DRV_CUDA(cudaMemcpyAsync(&c, ctx->counter, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+  DRV_CUDA(cudaMemcpyAsync(stats, ctx->stats, sizeof(stats), cudaMemcpyDeviceToHost, ctx->stream));
+  DRV_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (count) *count = (uint32_t)c.TotalLightCacheCount;
+  if (overflow) *overflow = stats[0];
+  if (oob) *oob = stats[1];
+  return stats[0] ? DRV_ERR_CAPACITY : DRV_OK;
+}
+
+extern "C" drv_status drv_set_synthetic_entries(drv_ctx* ctx, const float* pos, uint32_t n) {
+  NEED_CTX();
+  if (n && !pos) return ctx->fail(DRV_ERR_INVALID, "drv_set_synthetic_entries: null positions");
+  return drv_impl_set_synthetic_entries(ctx, pos, n);
+}
+
+extern "C" drv_status drv_set_vpls(drv_ctx* ctx, uint32_t light, const drv_vpl* vpls, uint32_t n) {
+  NEED_CTX();
+  if (light >= ctx->cfg.max_lights || !vpls) return ctx->fail(DRV_ERR_INVALID, "drv_set_vpls: bad argument");
+  if ((size_t)n > (size_t)ctx->cfg.max_rsm_resolution * ctx->cfg.max_rsm_resolution)
+    return ctx->fail(DRV_ERR_CAPACITY, "drv_set_vpls: more VPLs than max_rsm_resolution^2");
+  LightState& S = ctx->lights[light];
+  DRV_CUDA(cudaMemcpyAsync(S.vpls, vpls, (size_t)n * sizeof(drv_vpl), cudaMemcpyDefault, ctx->stream));
+  S.num_vpls = n;
+  S.vpls_external = true;
+  return DRV_OK;
+}
+
+extern "C" void drv_shard_range(uint32_t count, uint32_t rank, uint32_t world, uint32_t* begin, uint32_t* end) {
+  if (world == 0) world = 1;
+  uint32_t groups = (count + 63u) / 64u;
+  uint32_t g0 = (uint32_t)(((unsigned long long)groups * rank) / world);
+  uint32_t g1 = (uint32_t)(((unsigned long long)groups * (rank + 1)) / world);
+  uint32_t b = g0 * 64u < count ? g0 * 64u : count;
+  uint32_t e = g1 * 64u < count ? g1 * 64u : count;
+  if (begin) *begin = b;
+  if (end) *end = e;
+}
+
+extern "C" drv_status drv_set_shard(drv_ctx* ctx, uint32_t rank, uint32_t world) {
+  NEED_CTX();
+  if (world == 0 || rank >= world || world > 8) return ctx->fail(DRV_ERR_INVALID, "drv_set_shard: need rank < world <= 8");
+  ctx->shard_rank = rank;
+  ctx->shard_world = world;
+  return DRV_OK;
+}
+
+extern "C" drv_status drv_export_entries_ipc(drv_ctx* ctx, uint8_t handle[DRV_IPC_HANDLE_BYTES]) {
+  NEED_CTX();
+  static_assert(sizeof(cudaIpcMemHandle_t) == DRV_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  DRV_CUDA(cudaIpcGetMemHandle(&h, ctx->entries));
+  memcpy(handle, &h, sizeof(h));
+  return DRV_OK;
+}
+
+extern "C" drv_status drv_import_peer_entries(drv_ctx* ctx, uint32_t peer_rank, const uint8_t handle[DRV_IPC_HANDLE_BYTES]) {
+  NEED_CTX();
+  if (peer_rank >= 8 || peer_rank == ctx->shard_rank) return ctx->fail(DRV_ERR_INVALID, "drv_import_peer_entries: bad peer rank");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return ctx->fail(DRV_ERR_PEER, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+  ctx->peer_entries[peer_rank] = p;
+  ctx->peers_open = true;
+  return DRV_OK;
+}
+
+static const char* kStageNames[DRV_STAGE_COUNT] = {"VoxelizeScene", "VoxelBlendMipMap", "AllocateCaches", "LightCaches",
+                                                   "ApplyCaches",   "PrepareRSM",       "GatherKernel"};
+extern "C" const char* drv_stage_name(drv_stage s) { return (s >= 0 && s < DRV_STAGE_COUNT) ? kStageNames[s] : "?"; }
+
+extern "C" drv_status drv_enable_stage_timers(drv_ctx* ctx, int enable) {
+  NEED_CTX();
+  ctx->timers = enable != 0;
+  for (auto& v : ctx->ev_valid) v = false;
+  return DRV_OK;
+}
+
+extern "C" drv_status drv_stage_ms(drv_ctx* ctx, drv_stage s, float* ms) {
+  NEED_CTX();
+  if (s < 0 || s >= DRV_STAGE_COUNT || !ms) return ctx->fail(DRV_ERR_INVALID, "drv_stage_ms: bad argument");
+  if (!ctx->ev_valid[s]) { *ms = 0.0f; return ctx->fail(DRV_ERR_NOT_BOUND, "drv_stage_ms: stage not recorded"); }
+  DRV_CUDA(cudaEventSynchronize(ctx->ev_end[s]));
+  DRV_CUDA(cudaEventElapsedTime(ms, ctx->ev_begin[s], ctx->ev_end[s]));
+  return DRV_OK;
+}
+
+extern "C" uint64_t drv_kernel_launches(const drv_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- host-buffer convenience (end-to-end measurement) --------------------------------
+extern "C" drv_status drv_upload_gbuffer(drv_ctx* ctx, const float* depth, const int16_t* normal, const uint8_t* diffuse,
+                                         uint32_t w, uint32_t h) {
+  NEED_CTX();
+  if (!depth || !normal || !diffuse || w != ctx->cfg.backbuffer_width || h != ctx->cfg.backbuffer_height)
+    return ctx->fail(DRV_ERR_INVALID, "drv_upload_gbuffer: bad argument");
+  const size_t px = (size_t)w * h;
+  if (!ctx->st_depth) {
+    DRV_CUDA(dmalloc(&ctx->st_depth, px * 4));
+    DRV_CUDA(dmalloc(&ctx->st_normal, px * 4));
+    DRV_CUDA(dmalloc(&ctx->st_diffuse, px * 4));
+  }
+  DRV_CUDA(cudaMemcpyAsync(ctx->st_depth, depth, px * 4, cudaMemcpyHostToDevice, ctx->stream));
+  DRV_CUDA(cudaMemcpyAsync(ctx->st_normal, normal, px * 4, cudaMemcpyHostToDevice, ctx->stream));
+  DRV_CUDA(cudaMemcpyAsync(ctx->st_diffuse, diffuse, px * 4, cudaMemcpyHostToDevice, ctx->stream));
+  return drv_bind_gbuffer(ctx, ctx->st_depth, ctx->st_normal, ctx->st_diffuse, w, h);
+}
+
+extern "C" drv_status drv_upload_rsm(drv_ctx* ctx, uint32_t light, const uint16_t* flux, const int16_t* normal,
+                                     const uint16_t* depth, uint32_t res) {
+  NEED_CTX();
+  if (light >= ctx->cfg.max_lights || !flux || !normal || !depth || !is_pow2(res) || res > ctx->cfg.max_rsm_resolution)
+    return ctx->fail(DRV_ERR_INVALID, "drv_upload_rsm: bad argument");
+  LightState& S = ctx->lights[light];
+  const size_t tx = (size_t)ctx->cfg.max_rsm_resolution * ctx->cfg.max_rsm_resolution;
+  if (!S.st_flux) {
+    DRV_CUDA(dmalloc(&S.st_flux, tx * 8));
+    DRV_CUDA(dmalloc(&S.st_normal, tx * 4));
+    DRV_CUDA(dmalloc(&S.st_depth, tx * 4));
+  }
+  const size_t n = (size_t)res * res;
+  DRV_CUDA(cudaMemcpyAsync(S.st_flux, flux, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  DRV_CUDA(cudaMemcpyAsync(S.st_normal, normal, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  DRV_CUDA(cudaMemcpyAsync(S.st_depth, depth, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  return drv_bind_rsm(ctx, light, S.st_flux, S.st_normal, S.st_depth, res);
+}
+
+extern "C" drv_status drv_draw_to_host(drv_ctx* ctx, void* hdr_host) {
+  NEED_CTX();
+  if (!hdr_host) return ctx->fail(DRV_ERR_INVALID, "drv_draw_to_host: null output");
+  const size_t bytes = (size_t)ctx->cfg.backbuffer_width * ctx->cfg.backbuffer_height * 8;
+  if (!ctx->hdr16) DRV_CUDA(cudaMalloc(&ctx->hdr16, bytes));
+  DRV_CUDA(cudaMemsetAsync(ctx->hdr16, 0, bytes, ctx->stream)); // glClear(GL_COLOR_BUFFER_BIT), renderer.cpp:562
+  drv_status st = drv_draw(ctx, ctx->hdr16, DRV_HDR_RGBA16F_ADD);
+  if (st != DRV_OK) return st;
+  DRV_CUDA(cudaMemcpyAsync(hdr_host, ctx->hdr16, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  DRV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DRV_OK;
+}

@@ -1,0 +1,138 @@
+// ctx.h — internal context of libdrv_gi (not part of the C-ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/drv_gi.h"
+
+#define DRV_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      return ctx->fail(DRV_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    }                                                                                    \
+  } while (0)
+
+#define DRV_LAUNCH_CHECK()                                                               \
+  do {                                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      return ctx->fail(DRV_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+    }                                                                                    \
+    ctx->launches++;                                                                     \
+  } while (0)
+
+// Per-light device state.
+struct LightState {
+  bool block_set = false;   // drv_set_spot_light seen
+  bool rsm_bound = false;   // drv_bind_rsm / drv_upload_rsm seen
+  bool vpls_external = false; // drv_set_vpls: skip VPL generation
+  uint32_t num_vpls = 0;
+  drv_spot_light block{};
+  const uint16_t* flux0 = nullptr;   // level 0 (borrowed or staging)
+  const int16_t* normal0 = nullptr;
+  const uint16_t* depth0 = nullptr;
+  uint32_t rsm_res = 0;
+  uint16_t* flux_mips = nullptr;     // levels >= 1, owned
+  int16_t* normal_mips = nullptr;
+  uint16_t* depth_mips = nullptr;
+  drv_vpl* vpls = nullptr;           // owned, max_rsm_resolution^2
+  drv_shadow_block* blocks = nullptr;
+  // staging for drv_upload_rsm
+  uint16_t* st_flux = nullptr;
+  int16_t* st_normal = nullptr;
+  uint16_t* st_depth = nullptr;
+};
+
+struct drv_ctx {
+  drv_config cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 0;
+  std::string last_error;
+  uint64_t launches = 0;
+
+  // uniform blocks (host copies; passed to kernels by value)
+  drv_constant constant{};
+  drv_per_frame per_frame{};
+  drv_volume_info volume{};
+  bool have_constant = false, have_per_frame = false, have_volume = false;
+  uint32_t num_lights = 0;
+  LightState lights[DRV_MAX_LIGHTS];
+
+  // g-buffer (borrowed or staging)
+  const float* gb_depth = nullptr;
+  const int16_t* gb_normal = nullptr;
+  const uint8_t* gb_diffuse = nullptr;
+  uint32_t gb_w = 0, gb_h = 0;
+  float* st_depth = nullptr;
+  int16_t* st_normal = nullptr;
+  uint8_t* st_diffuse = nullptr;
+  void* hdr16 = nullptr; // owned RGBA16F target for drv_draw_to_host
+
+  // allocation
+  uint32_t entry_stride = 64;
+  uint8_t* entries = nullptr;        // max_cache_count * 128 B (renderer.cpp:266-269)
+  drv_cache_counter* counter = nullptr;
+  uint32_t* stats = nullptr;         // [0] overflow, [1] oob corners
+  uint32_t* atlas = nullptr;
+  uint8_t* cell_flags = nullptr;     // one byte per CAV cell, linear-cell-id order
+  uint32_t* block_counts = nullptr;
+  uint32_t num_cells = 0, num_scan_blocks = 0;
+
+  // voxels
+  uint8_t* voxel_chain = nullptr;
+  uint8_t* voxel_target = nullptr;
+  uint32_t voxel_levels = 0;
+  uint64_t voxel_chain_bytes = 0;
+
+  // gather
+  float* partials = nullptr;         // split-VPL partial sums
+  uint64_t partial_slots = 0;        // capacity in cache slots
+  uint32_t shard_rank = 0, shard_world = 1;
+  void* peer_entries[8] = {nullptr};
+  bool peers_open = false;
+
+  // timers
+  bool timers = false;
+  cudaEvent_t ev_begin[DRV_STAGE_COUNT]{}, ev_end[DRV_STAGE_COUNT]{};
+  bool ev_valid[DRV_STAGE_COUNT]{};
+
+  drv_status fail(drv_status code, const std::string& msg) {
+    last_error = msg;
+    return code;
+  }
+  void stage_begin(drv_stage s) {
+    if (timers) cudaEventRecord(ev_begin[s], stream);
+  }
+  void stage_end(drv_stage s) {
+    if (timers) { cudaEventRecord(ev_end[s], stream); ev_valid[s] = true; }
+  }
+};
+
+// stage implementations (one .cu each)
+drv_status drv_impl_allocate(drv_ctx* ctx);
+drv_status drv_impl_prepare_rsm(drv_ctx* ctx, uint32_t light);
+drv_status drv_impl_generate_vpls(drv_ctx* ctx, uint32_t light);
+drv_status drv_impl_gather(drv_ctx* ctx);
+drv_status drv_impl_apply(drv_ctx* ctx, void* out, uint32_t format);
+drv_status drv_impl_voxelize(drv_ctx* ctx, const float* tris, uint32_t n, const float* world, float adaption,
+                             uint32_t flags);
+drv_status drv_impl_set_synthetic_entries(drv_ctx* ctx, const float* pos, uint32_t n);
+void drv_impl_upload_srgb_lut();
+
+inline uint64_t rsm_level_offset_texels(uint32_t res, uint32_t level) {
+  uint64_t off = 0;
+  for (uint32_t l = 1; l < level; ++l) off += (uint64_t)(res >> l) * (res >> l);
+  return off;
+}
+inline uint64_t voxel_level_offset_bytes(uint32_t res, uint32_t level) {
+  uint64_t off = 0;
+  for (uint32_t l = 0; l < level; ++l) { off += (uint64_t)res * res * res; res >>= 1; }
+  return off;
+}

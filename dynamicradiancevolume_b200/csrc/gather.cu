@@ -1,0 +1,770 @@
+// gather.cu — stage 4: the cache-entry x VPL irradiance gather projected into
+// SH1 / SH2 with voxel-cone-traced indirect visibility
+// (≙ Renderer::LightCachesRSM, rendering/renderer.cpp:899-933;
+// shader/cacheLightingRSM.comp:83-374, INDIRECT_SPECULAR undefined).
+//
+// Reference shape: one thread per cache, 64 caches per group, every group
+// re-derives all R^2 VPLs from three textures and walks them serially, once
+// per light — parallelism = N_cache only (≈600 warps for a 40k-cache frame).
+//
+// B200 shape (this file):
+//  * VPLs and shadow-block records are materialised once per light (rsm.cu).
+//  * N-body tiling over BOTH axes. The work is the grid of UNITS
+//    (cache tile of 128*CPT entries) x (VPL tile of >=128 VPLs of one light),
+//    VPL tile fastest. A persistent grid (SM count x resident CTAs) splits the
+//    flattened unit list into equal contiguous ranges ("stream-K"), so every
+//    CTA gets the same number of units +-1 whatever N_cache and N_vpl are, and
+//    the range bounds are computed on the device from the live cache counter —
+//    no host read-back between allocation and lighting.
+//  * each thread keeps CPT caches in registers (positions + 12/27 raw
+//    accumulators) so every 48-byte VPL fetched from shared memory (three
+//    broadcast 128-bit loads) feeds CPT pair evaluations.
+//  * VPL tiles are staged global->shared with a register-prefetch pipeline
+//    (default) or TMA bulk copies completing on an mbarrier (variant 1).
+//  * the packed variants evaluate two caches per instruction with FP32x2
+//    maths (FFMA2/FMUL2/FADD2, new on sm_100) to halve issue-slot pressure.
+//  * SH basis constants are folded out of the loop: the kernel accumulates raw
+//    moments (rad, rad*t, rad*t_i*t_j) and applies ShEvaFactor* once in the
+//    epilogue: 28 FP32 ops + 2 MUFU per SH1 pair instead of 32 + 2.
+//  * a CTA whose range covers a cache tile completely adds straight into the
+//    entries (`entry.SH += acc`, :358-373). Ranges that start or end inside a
+//    tile write their partial sums to a per-CTA scratch slot; the finalize
+//    kernel adds those in ascending VPL order (deterministic — no float
+//    atomics) and, when peers are mapped, stores the finished entry to every
+//    other GPU over NVLink (fused all-gather).
+#include "ctx.h"
+#include "device_math.cuh"
+
+using namespace drvk;
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kVplTile = 128; // VPLs staged per shared-memory tile
+
+struct GatherLight {
+  const float4* vpls;   // 3 x float4 per VPL: (pos, area) (normal, -) (flux, -)
+  const float4* blocks; // (avgPos, distToSphereRad) per shadow block
+  uint32_t num_vpls;
+  uint32_t interval;    // IndirectShadowComputationSampleInterval
+};
+
+struct GatherParams {
+  GatherLight lights[DRV_MAX_LIGHTS];
+  uint32_t num_lights;
+  uint32_t granule;      // VPLs per scheduling unit: a power of two, >= 32 and >= every shadow interval
+  uint8_t* entries;
+  const drv_cache_counter* counter;
+  float* partials;       // [cta][2][coef][tile cache] floats
+  uint32_t shard_rank, shard_world;
+  uint32_t grid;         // CTAs of the gather launch (the finalize kernel needs it too)
+  float f0, f1, f2, f20, f22;
+  // voxel volume (cone tracing)
+  const uint8_t* chain;
+  int vres, vlevels;
+  float vmin[3];
+  float voxel_size;
+  // fused all-gather: peer copies of the entries buffer (NVLink P2P)
+  uint8_t* peers[8];
+  uint32_t num_peers;
+};
+
+struct Schedule {
+  uint32_t first, count;      // entry range of this shard
+  uint32_t tiles;             // cache tiles
+  uint32_t units_per_tile;    // VPL units over all lights
+  unsigned long long units;   // tiles * units_per_tile
+};
+
+// Same result in every thread of the gather and finalize kernels.
+__device__ __forceinline__ Schedule make_schedule(const GatherParams& p, int tile_caches) {
+  Schedule s;
+  uint32_t n = (uint32_t)max(p.counter->TotalLightCacheCount, 0);
+  // contiguous ranges on 64-entry boundaries of the cell-ordered list (drv_shard_range)
+  uint32_t groups = (n + 63u) / 64u;
+  uint32_t g0 = (uint32_t)(((unsigned long long)groups * p.shard_rank) / p.shard_world);
+  uint32_t g1 = (uint32_t)(((unsigned long long)groups * (p.shard_rank + 1)) / p.shard_world);
+  s.first = min(g0 * 64u, n);
+  s.count = min(g1 * 64u, n) - s.first;
+  s.tiles = (s.count + tile_caches - 1) / tile_caches;
+  uint32_t upt = 0;
+  for (uint32_t l = 0; l < p.num_lights; ++l) upt += (p.lights[l].num_vpls + p.granule - 1) / p.granule;
+  s.units_per_tile = upt;
+  s.units = (unsigned long long)s.tiles * upt;
+  return s;
+}
+__device__ __forceinline__ unsigned long long range_begin(const Schedule& s, uint32_t grid, uint32_t cta) {
+  return (s.units * cta) / grid;
+}
+// the CTA whose range contains unit u
+__device__ __forceinline__ uint32_t owner_of(const Schedule& s, uint32_t grid, unsigned long long u) {
+  return (uint32_t)(((u + 1ull) * grid - 1ull) / s.units);
+}
+
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// ---------------------------------------------------------------- cone trace
+struct VoxelVol {
+  const uint8_t* chain;
+  int res, levels;
+  float vmin[3];
+  float voxel_size;
+};
+
+__device__ __forceinline__ float trilinear_level(const uint8_t* __restrict__ lvl, int r, float px, float py, float pz) {
+  float fr = (float)r;
+  float fx = fmaf(px, fr, -0.5f), fy = fmaf(py, fr, -0.5f), fz = fmaf(pz, fr, -0.5f);
+  float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+  float tx = fx - flx, ty = fy - fly, tz = fz - flz;
+  int x0 = __float2int_rz(flx), y0 = __float2int_rz(fly), z0 = __float2int_rz(flz);
+  int x1 = clampi(x0 + 1, 0, r - 1), y1 = clampi(y0 + 1, 0, r - 1), z1 = clampi(z0 + 1, 0, r - 1);
+  x0 = clampi(x0, 0, r - 1); y0 = clampi(y0, 0, r - 1); z0 = clampi(z0, 0, r - 1);
+  const uint8_t* r00 = lvl + (size_t)r * ((size_t)y0 + (size_t)r * z0);
+  const uint8_t* r10 = lvl + (size_t)r * ((size_t)y1 + (size_t)r * z0);
+  const uint8_t* r01 = lvl + (size_t)r * ((size_t)y0 + (size_t)r * z1);
+  const uint8_t* r11 = lvl + (size_t)r * ((size_t)y1 + (size_t)r * z1);
+  float a000 = (float)__ldg(r00 + x0), a100 = (float)__ldg(r00 + x1);
+  float a010 = (float)__ldg(r10 + x0), a110 = (float)__ldg(r10 + x1);
+  float a001 = (float)__ldg(r01 + x0), a101 = (float)__ldg(r01 + x1);
+  float a011 = (float)__ldg(r11 + x0), a111 = (float)__ldg(r11 + x1);
+  float c00 = fmaf(tx, a100 - a000, a000), c10 = fmaf(tx, a110 - a010, a010);
+  float c01 = fmaf(tx, a101 - a001, a001), c11 = fmaf(tx, a111 - a011, a011);
+  float c0 = fmaf(ty, c10 - c00, c00), c1 = fmaf(ty, c11 - c01, c01);
+  return fmaf(tz, c1 - c0, c0) * (1.0f / 255.0f);
+}
+
+// D.0 trilinearClampMip3D: clamp-to-edge trilinear in two adjacent mips, linear between them.
+__device__ __forceinline__ float sample_voxel(const VoxelVol& V, float px, float py, float pz, float lod) {
+  float maxLod = (float)(V.levels - 1);
+  lod = fminf(fmaxf(lod, 0.0f), maxLod); // fmaxf(NaN,0)=0: also covers log2(<=0), SURVEY B.8
+  float fl = floorf(lod);
+  int l0 = (int)fl;
+  float t = lod - fl;
+  const unsigned long long R3 = (unsigned long long)V.res * V.res * V.res;
+  int r0 = V.res >> l0;
+  // level offset in the contiguous chain: (R^3 - r^3) * 8 / 7
+  const uint8_t* p0 = V.chain + ((R3 - (unsigned long long)r0 * r0 * r0) * 8ull) / 7ull;
+  float a = trilinear_level(p0, r0, px, py, pz);
+  if (t == 0.0f) return a;
+  int l1 = min(l0 + 1, V.levels - 1);
+  int r1 = V.res >> l1;
+  const uint8_t* p1 = V.chain + ((R3 - (unsigned long long)r1 * r1 * r1) * 8ull) / 7ull;
+  float b = trilinear_level(p1, r1, px, py, pz);
+  return fmaf(t, b - a, a);
+}
+
+// cacheLightingRSM.comp:195-230. Distances / step sizes / the break test are
+// decision maths (trip count must equal the oracle's); positions and
+// occlusion are continuous maths.
+__device__ __noinline__ float cone_trace(const VoxelVol& V, float wx, float wy, float wz, float4 blk) {
+  const float fres = (float)V.res;
+  const float inv_extent = 1.0f / (V.voxel_size * fres);
+  float vpx = (wx - V.vmin[0]) * inv_extent, vpy = (wy - V.vmin[1]) * inv_extent, vpz = (wz - V.vmin[2]) * inv_extent; // :104
+  const float k = blk.w;
+  float tx = ex_sub(blk.x, wx), ty = ex_sub(blk.y, wy), tz = ex_sub(blk.z, wz); // :195
+  float lightDist = ex_sqrt(ex_dot3(tx, ty, tz, tx, ty, tz));                     // :196
+  float inv = 1.0f / (lightDist * fres);
+  float dx = tx * inv, dy = ty * inv, dz = tz * inv;                              // :197-198 dirInVoxel
+  float cx = fmaf(dx, 2.0f, vpx), cy = fmaf(dy, 2.0f, vpy), cz = fmaf(dz, 2.0f, vpz); // :201
+  float occlusion = 0.0f;
+  float stepSize = 1.0f;
+  float dist = 0.0f;
+  const float goalDist = ex_sub(ex_div(lightDist, V.voxel_size), 2.0f);           // :206
+  const float radToStep = ex_div(2.0f, ex_sub(1.0f, k));                          // :209
+  for (int s = 0; s < 32; ++s) {
+    cx = fmaf(dx, stepSize, cx); cy = fmaf(dy, stepSize, cy); cz = fmaf(dz, stepSize, cz); // :213
+    dist = ex_add(dist, stepSize);                                                // :214
+    float radius = ex_mul(dist, k);                                               // :216
+    float occ = sample_voxel(V, cx, cy, cz, __log2f(radius));                     // :219
+    occlusion = fmaf(1.0f - occlusion, occ, occlusion);                           // :220
+    if (dist >= goalDist) break;                                                  // :222
+    stepSize = fmaxf(1.0f, ex_mul(radius, radToStep));                            // :225
+  }
+  return saturatef(1.0f - occlusion);                                             // :230
+}
+
+// ------------------------------------------------------------ epilogue helpers
+template <int ORDER>
+constexpr int num_coefs() { return ORDER == 2 ? 27 : 12; }
+
+// Raw moments (a0,ax,ay,az,xy,yz,zz,xz,dd; rgb each) -> the values to ADD at
+// float offsets 4.. of the entry, i.e. in lightcache.glsl:33-57 order.
+template <int ORDER>
+__device__ __forceinline__ void coef_values(const GatherParams& p, const float* raw, float* out /*12 or 28*/) {
+  const float* a0 = raw; const float* ax = raw + 3; const float* ay = raw + 6; const float* az = raw + 9;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    out[0 + c] = -p.f1 * ay[c];  // SH1neg1 -= (f1 * t.y) * rad   :268
+    out[4 + c] = p.f1 * az[c];   // SH10    += (f1 * t.z) * rad   :269
+    out[8 + c] = -p.f1 * ax[c];  // SH1pos1 -= (f1 * t.x) * rad   :270
+  }
+  out[3] = p.f0 * a0[0]; out[7] = p.f0 * a0[1]; out[11] = p.f0 * a0[2]; // SH00 :267
+  if (ORDER == 2) {
+    const float* xy = raw + 12; const float* yz = raw + 15; const float* zz = raw + 18;
+    const float* xz = raw + 21; const float* dd = raw + 24;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      out[12 + c] = -p.f2 * xy[c];  // SH2neg2 :273
+      out[16 + c] = p.f2 * yz[c];   // SH2neg1 :274
+      out[20 + c] = p.f2 * xz[c];   // SH2pos1 :276
+      out[24 + c] = p.f22 * dd[c];  // SH2pos2 :277
+    }
+    out[15] = p.f20 * (3.0f * zz[0] - a0[0]); // SH20 :275 = sum (3 z^2 - 1) rad
+    out[19] = p.f20 * (3.0f * zz[1] - a0[1]);
+    out[23] = p.f20 * (3.0f * zz[2] - a0[2]);
+    out[27] = 0.0f;
+  }
+}
+
+template <int ORDER>
+__device__ __forceinline__ void add_to_entry(const GatherParams& p, uint32_t entry, const float* vals) {
+  constexpr int STRIDE = ORDER == 2 ? 128 : 64;
+  constexpr int NQ = ORDER == 2 ? 7 : 3;
+  float4* e = reinterpret_cast<float4*>(p.entries + (size_t)entry * STRIDE);
+  float4 outq[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    float4 o = e[1 + q];
+    o.x += vals[q * 4 + 0]; o.y += vals[q * 4 + 1]; o.z += vals[q * 4 + 2]; o.w += vals[q * 4 + 3];
+    e[1 + q] = o; // entry.SH += acc, :358-373
+    outq[q] = o;
+  }
+  // fused all-gather: the finished entry goes straight to every peer's copy over NVLink
+  for (uint32_t r = 0; r < p.num_peers; ++r) {
+    if (!p.peers[r]) continue;
+    float4* pe = reinterpret_cast<float4*>(p.peers[r] + (size_t)entry * STRIDE);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) pe[1 + q] = outq[q];
+  }
+}
+
+// ------------------------------------------------------------ scalar pair maths
+template <int ORDER>
+struct Acc {
+  float a0[3], ax[3], ay[3], az[3];
+  float xy[3], yz[3], zz[3], xz[3], dd[3]; // used only when ORDER == 2
+};
+
+// One cache x VPL pair, cacheLightingRSM.comp:249-277 with the basis
+// constants factored out: s = sat(dot(N,-t^))*shadow / (d^2 + A);
+// a0 += F s; a{x,y,z} += F s t^; (SH2) second moments of t^.
+template <int ORDER, bool SHADOW>
+__device__ __forceinline__ void pair_eval(Acc<ORDER>& A, float px, float py, float pz, float4 va, float4 vb, float4 vc,
+                                          float shadow) {
+  float tx = va.x - px, ty = va.y - py, tz = va.z - pz;      // :249
+  float d2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));            // :252
+  float inv = rsqrt_approx(d2);                              // :253
+  float cr = fmaf(vb.z, tz, fmaf(vb.y, ty, vb.x * tx));      // dot(N, t)
+  float cosv = __saturatef(-cr * inv);                       // :256
+  float s = cosv * rcp_approx(d2 + va.w);                    // :262
+  if (SHADOW) s *= shadow;                                   // :258
+  float w = s * inv;
+  float ux = tx * w, uy = ty * w, uz = tz * w;               // s * t^
+  const float fl[3] = {vc.x, vc.y, vc.z};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    A.a0[c] = fmaf(fl[c], s, A.a0[c]);
+    A.ax[c] = fmaf(fl[c], ux, A.ax[c]);
+    A.ay[c] = fmaf(fl[c], uy, A.ay[c]);
+    A.az[c] = fmaf(fl[c], uz, A.az[c]);
+  }
+  if (ORDER == 2) {
+    float nx = tx * inv, ny = ty * inv, nz = tz * inv;       // t^
+    float qxy = nx * uy, qyz = ny * uz, qzz = nz * uz, qxz = nx * uz;
+    float qdd = fmaf(nx, ux, -ny * uy);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      A.xy[c] = fmaf(fl[c], qxy, A.xy[c]);
+      A.yz[c] = fmaf(fl[c], qyz, A.yz[c]);
+      A.zz[c] = fmaf(fl[c], qzz, A.zz[c]);
+      A.xz[c] = fmaf(fl[c], qxz, A.xz[c]);
+      A.dd[c] = fmaf(fl[c], qdd, A.dd[c]);
+    }
+  }
+}
+
+// Policy: CPT caches per thread, scalar FP32 maths, 3 float4 per VPL in shared memory.
+template <int ORDER, bool SHADOW, int CPT_>
+struct ScalarMath {
+  static constexpr int CPT = CPT_;
+  static constexpr int kSmemPerVpl = 3;
+  float px[CPT], py[CPT], pz[CPT];
+  float shadow[CPT];
+  bool live[CPT];
+  Acc<ORDER> A[CPT];
+
+  __device__ __forceinline__ void begin(int j, bool alive, float4 pos) {
+    live[j] = alive;
+    px[j] = pos.x; py[j] = pos.y; pz[j] = pos.z;
+    shadow[j] = 1.0f; // :132
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      A[j].a0[c] = A[j].ax[c] = A[j].ay[c] = A[j].az[c] = 0.0f;
+      A[j].xy[c] = A[j].yz[c] = A[j].zz[c] = A[j].xz[c] = A[j].dd[c] = 0.0f;
+    }
+  }
+  static __device__ __forceinline__ void stage(float4* slot, float4 r0, float4 r1, float4 r2) {
+    slot[0] = r0; slot[1] = r1; slot[2] = r2;
+  }
+  __device__ __forceinline__ void trace(const VoxelVol& V, float4 blk) {
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) shadow[j] = live[j] ? cone_trace(V, px[j], py[j], pz[j], blk) : 0.0f;
+  }
+  __device__ __forceinline__ void eval(const float4* v) {
+    float4 va = v[0], vb = v[1], vc = v[2];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) pair_eval<ORDER, SHADOW>(A[j], px[j], py[j], pz[j], va, vb, vc, shadow[j]);
+  }
+  __device__ __forceinline__ void raw(int j, float* r) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      r[c] = A[j].a0[c]; r[3 + c] = A[j].ax[c]; r[6 + c] = A[j].ay[c]; r[9 + c] = A[j].az[c];
+      r[12 + c] = A[j].xy[c]; r[15 + c] = A[j].yz[c]; r[18 + c] = A[j].zz[c];
+      r[21 + c] = A[j].xz[c]; r[24 + c] = A[j].dd[c];
+    }
+  }
+};
+
+// ------------------------------------------------------------ packed (FFMA2) pair maths
+// Policy: PAIRS x 2 caches per thread; the two caches of a pair ride in the
+// .x/.y halves of 64-bit registers. The shared-memory VPL record duplicates
+// every scalar into both halves so it feeds FFMA2 without register shuffles:
+//  q0 = (x,x,y,y) q1 = (z,z,area,area) q2 = (nx,nx,ny,ny) q3 = (nz,nz,fr,fr) q4 = (fg,fg,fb,fb)
+template <int ORDER, bool SHADOW, int PAIRS>
+struct PackedMath {
+  static constexpr int CPT = PAIRS * 2;
+  static constexpr int kSmemPerVpl = 5;
+  float2 npx[PAIRS], npy[PAIRS], npz[PAIRS]; // NEGATED cache positions
+  float2 shadow[PAIRS];
+  bool live[CPT];
+  float2 a0[PAIRS][3], ax[PAIRS][3], ay[PAIRS][3], az[PAIRS][3];
+  float2 xy[PAIRS][3], yz[PAIRS][3], zz[PAIRS][3], xz[PAIRS][3], dd[PAIRS][3];
+
+  __device__ __forceinline__ void begin(int j, bool alive, float4 pos) {
+    live[j] = alive;
+    const int pr = j >> 1;
+    if (j & 1) { npx[pr].y = -pos.x; npy[pr].y = -pos.y; npz[pr].y = -pos.z; shadow[pr].y = 1.0f; }
+    else       { npx[pr].x = -pos.x; npy[pr].x = -pos.y; npz[pr].x = -pos.z; shadow[pr].x = 1.0f; }
+    const float2 z = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      a0[pr][c] = ax[pr][c] = ay[pr][c] = az[pr][c] = z;
+      xy[pr][c] = yz[pr][c] = zz[pr][c] = xz[pr][c] = dd[pr][c] = z;
+    }
+  }
+  static __device__ __forceinline__ void stage(float4* d, float4 r0, float4 r1, float4 r2) {
+    d[0] = make_float4(r0.x, r0.x, r0.y, r0.y);
+    d[1] = make_float4(r0.z, r0.z, r0.w, r0.w);
+    d[2] = make_float4(r1.x, r1.x, r1.y, r1.y);
+    d[3] = make_float4(r1.z, r1.z, r2.x, r2.x);
+    d[4] = make_float4(r2.y, r2.y, r2.z, r2.z);
+  }
+  __device__ __forceinline__ void trace(const VoxelVol& V, float4 blk) {
+#pragma unroll
+    for (int j = 0; j < PAIRS; ++j) {
+      shadow[j].x = live[j * 2] ? cone_trace(V, -npx[j].x, -npy[j].x, -npz[j].x, blk) : 0.0f;
+      shadow[j].y = live[j * 2 + 1] ? cone_trace(V, -npx[j].y, -npy[j].y, -npz[j].y, blk) : 0.0f;
+    }
+  }
+  __device__ __forceinline__ void eval(const float4* q) {
+    float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
+    const float2 vx = make_float2(q0.x, q0.y), vy = make_float2(q0.z, q0.w), vz = make_float2(q1.x, q1.y);
+    const float2 ar = make_float2(q1.z, q1.w);
+    const float2 nx = make_float2(q2.x, q2.y), ny = make_float2(q2.z, q2.w), nz = make_float2(q3.x, q3.y);
+    const float2 fl[3] = {make_float2(q3.z, q3.w), make_float2(q4.x, q4.y), make_float2(q4.z, q4.w)};
+#pragma unroll
+    for (int j = 0; j < PAIRS; ++j) {
+      float2 tx = __fadd2_rn(vx, npx[j]), ty = __fadd2_rn(vy, npy[j]), tz = __fadd2_rn(vz, npz[j]);
+      float2 d2 = __ffma2_rn(tz, tz, __ffma2_rn(ty, ty, __fmul2_rn(tx, tx)));
+      float2 inv = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
+      float2 cr = __ffma2_rn(nz, tz, __ffma2_rn(ny, ty, __fmul2_rn(nx, tx)));
+      float2 cosv = make_float2(__saturatef(-cr.x * inv.x), __saturatef(-cr.y * inv.y));
+      float2 den = __fadd2_rn(d2, ar);
+      float2 s = __fmul2_rn(cosv, make_float2(rcp_approx(den.x), rcp_approx(den.y)));
+      if (SHADOW) s = __fmul2_rn(s, shadow[j]);
+      float2 w = __fmul2_rn(s, inv);
+      float2 ux = __fmul2_rn(tx, w), uy = __fmul2_rn(ty, w), uz = __fmul2_rn(tz, w);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        a0[j][c] = __ffma2_rn(fl[c], s, a0[j][c]);
+        ax[j][c] = __ffma2_rn(fl[c], ux, ax[j][c]);
+        ay[j][c] = __ffma2_rn(fl[c], uy, ay[j][c]);
+        az[j][c] = __ffma2_rn(fl[c], uz, az[j][c]);
+      }
+      if (ORDER == 2) {
+        float2 hx = __fmul2_rn(tx, inv), hy = __fmul2_rn(ty, inv), hz = __fmul2_rn(tz, inv);
+        float2 qxy = __fmul2_rn(hx, uy), qyz = __fmul2_rn(hy, uz), qzz = __fmul2_rn(hz, uz), qxz = __fmul2_rn(hx, uz);
+        float2 nhy = make_float2(-hy.x, -hy.y);
+        float2 qdd = __ffma2_rn(hx, ux, __fmul2_rn(nhy, uy));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          xy[j][c] = __ffma2_rn(fl[c], qxy, xy[j][c]);
+          yz[j][c] = __ffma2_rn(fl[c], qyz, yz[j][c]);
+          zz[j][c] = __ffma2_rn(fl[c], qzz, zz[j][c]);
+          xz[j][c] = __ffma2_rn(fl[c], qxz, xz[j][c]);
+          dd[j][c] = __ffma2_rn(fl[c], qdd, dd[j][c]);
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void raw(int j, float* r) const {
+    const int pr = j >> 1;
+    const bool hi = (j & 1) != 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#define DRV_H(v) (hi ? (v).y : (v).x)
+      r[c] = DRV_H(a0[pr][c]); r[3 + c] = DRV_H(ax[pr][c]); r[6 + c] = DRV_H(ay[pr][c]); r[9 + c] = DRV_H(az[pr][c]);
+      r[12 + c] = DRV_H(xy[pr][c]); r[15 + c] = DRV_H(yz[pr][c]); r[18 + c] = DRV_H(zz[pr][c]);
+      r[21 + c] = DRV_H(xz[pr][c]); r[24 + c] = DRV_H(dd[pr][c]);
+#undef DRV_H
+    }
+  }
+};
+
+// ------------------------------------------------------------ TMA helpers (variant 1)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------ the gather kernel
+// A cursor over the shared-memory tiles of a CTA's unit range: runs of
+// consecutive units that share (cache tile, light) are contiguous VPL ranges.
+struct Cursor {
+  unsigned long long u, u_next; // first unit of the current run / of the next run
+  uint32_t tile, light;
+  uint32_t base, v_end;         // current shared-memory tile starts at VPL `base`; the run ends at v_end
+  bool valid;
+};
+__device__ __forceinline__ void start_run(const GatherParams& p, const Schedule& S, Cursor& c, unsigned long long u,
+                                          unsigned long long u1) {
+  c.u = u;
+  c.valid = u < u1;
+  if (!c.valid) return;
+  c.tile = (uint32_t)(u / S.units_per_tile);
+  uint32_t j = (uint32_t)(u - (unsigned long long)c.tile * S.units_per_tile), l = 0, ul = 0;
+  for (;; ++l) {
+    ul = (p.lights[l].num_vpls + p.granule - 1) / p.granule;
+    if (j < ul || l + 1 >= p.num_lights) break;
+    j -= ul;
+  }
+  c.light = l;
+  const unsigned long long tile_end = (unsigned long long)(c.tile + 1) * S.units_per_tile;
+  const unsigned long long avail = (u1 < tile_end ? u1 : tile_end) - u;
+  const uint32_t take = (uint32_t)min((unsigned long long)(ul - j), avail);
+  c.base = j * p.granule;
+  c.v_end = min((j + take) * p.granule, p.lights[l].num_vpls);
+  c.u_next = u + take;
+}
+__device__ __forceinline__ void advance(const GatherParams& p, const Schedule& S, Cursor& c, unsigned long long u1) {
+  c.base += kVplTile;
+  if (c.base >= c.v_end) start_run(p, S, c, c.u_next, u1);
+}
+
+template <int ORDER, bool SHADOW, typename Math, bool USE_TMA>
+__global__ void __launch_bounds__(kThreads) gather_kernel(GatherParams p) {
+  constexpr int CPT = Math::CPT;
+  constexpr int TILE = kThreads * CPT;
+  constexpr int NC = num_coefs<ORDER>();
+  constexpr int STRIDE = ORDER == 2 ? 128 : 64;
+  constexpr int SPV = Math::kSmemPerVpl;
+  constexpr int STAGES = USE_TMA ? 2 : 1;
+  __shared__ __align__(128) float4 s_vpl[STAGES][kVplTile * SPV];
+  __shared__ float4 s_blk[SHADOW ? kVplTile : 1];
+  __shared__ __align__(8) uint64_t s_bar[2];
+
+  const Schedule S = make_schedule(p, TILE);
+  if (S.units == 0) return;
+  const unsigned long long u0 = range_begin(S, gridDim.x, blockIdx.x), u1 = range_begin(S, gridDim.x, blockIdx.x + 1);
+  if (u0 >= u1) return;
+  VoxelVol V;
+  if (SHADOW) {
+    V.chain = p.chain; V.res = p.vres; V.levels = p.vlevels; V.voxel_size = p.voxel_size;
+    V.vmin[0] = p.vmin[0]; V.vmin[1] = p.vmin[1]; V.vmin[2] = p.vmin[2];
+  }
+  uint32_t phase[2] = {0u, 0u};
+  if (USE_TMA) {
+    if (threadIdx.x == 0) {
+      mbar_init(&s_bar[0], 1);
+      mbar_init(&s_bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+
+  Math M;
+  float4 r0, r1, r2, rb; // register-prefetched VPL (and shadow block) of the NEXT shared-memory tile
+  r0 = r1 = r2 = rb = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto prefetch = [&](const Cursor& c) {
+    const GatherLight& L = p.lights[c.light];
+    uint32_t v = c.base + threadIdx.x;
+    bool ok = v < c.v_end;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    r0 = ok ? __ldg(L.vpls + (size_t)v * 3) : make_float4(0.f, 0.f, 0.f, 1.f);
+    r1 = ok ? __ldg(L.vpls + (size_t)v * 3 + 1) : z;
+    r2 = ok ? __ldg(L.vpls + (size_t)v * 3 + 2) : z;
+    if (SHADOW) {
+      uint32_t b = c.base / L.interval + threadIdx.x;
+      rb = ((unsigned long long)b * L.interval < c.v_end) ? __ldg(L.blocks + b) : z;
+    }
+  };
+  auto tma_issue = [&](const Cursor& c, int st) {
+    const GatherLight& L = p.lights[c.light];
+    uint32_t n = min((uint32_t)kVplTile, c.v_end - c.base);
+    mbar_expect_tx(&s_bar[st], n * 48u);
+    tma_bulk_g2s(&s_vpl[st][0], L.vpls + (size_t)c.base * 3, n * 48u, &s_bar[st]);
+  };
+
+  Cursor cur;
+  start_run(p, S, cur, u0, u1);
+  if (USE_TMA) {
+    if (threadIdx.x == 0) tma_issue(cur, 0);
+  } else {
+    prefetch(cur);
+  }
+  bool seg_open = false;
+  uint32_t seg_first_j = 0;
+  uint32_t step = 0;
+  while (cur.valid) {
+    if (!seg_open) { // (re)load this thread's caches and clear the accumulators
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        uint32_t local = cur.tile * TILE + j * kThreads + threadIdx.x;
+        bool alive = local < S.count;
+        float4 pos = alive ? *reinterpret_cast<const float4*>(p.entries + (size_t)(S.first + local) * STRIDE)
+                           : make_float4(1e30f, 1e30f, 1e30f, 0.f); // :83
+        M.begin(j, alive, pos);
+      }
+      seg_first_j = (uint32_t)(cur.u - (unsigned long long)cur.tile * S.units_per_tile);
+      seg_open = true;
+    }
+    Cursor nxt = cur;
+    advance(p, S, nxt, u1);
+    const int st = USE_TMA ? (int)(step & 1u) : 0;
+    if (USE_TMA) {
+      if (threadIdx.x == 0 && nxt.valid) tma_issue(nxt, st ^ 1); // stage st^1 was released by the last __syncthreads
+      mbar_wait(&s_bar[st], phase[st]);
+      phase[st] ^= 1u;
+    } else {
+      __syncthreads(); // previous tile fully consumed
+      Math::stage(&s_vpl[0][threadIdx.x * SPV], r0, r1, r2);
+      if (SHADOW) s_blk[threadIdx.x] = rb;
+      __syncthreads();
+      if (nxt.valid) prefetch(nxt);
+    }
+    const int n = (int)min((uint32_t)kVplTile, cur.v_end - cur.base);
+    const float4* sv = &s_vpl[st][0];
+    if (SHADOW) {
+      const uint32_t interval = p.lights[cur.light].interval;
+      for (int i = 0; i < n; ++i) {
+        uint32_t k = cur.base + i;
+        if ((k & (interval - 1u)) == 0u) M.trace(V, s_blk[(k - cur.base) / interval]); // :169; SURVEY B.12
+        M.eval(sv + i * SPV);
+      }
+    } else {
+#pragma unroll 4
+      for (int i = 0; i < n; ++i) M.eval(sv + i * SPV);
+    }
+    if (USE_TMA) __syncthreads(); // stage st consumed by every warp
+    ++step;
+    if (!nxt.valid || nxt.tile != cur.tile) { // segment end
+      const uint32_t last_j = (uint32_t)(cur.u_next - 1ull - (unsigned long long)cur.tile * S.units_per_tile);
+      const bool full = seg_first_j == 0 && last_j == S.units_per_tile - 1;
+      // partial slot 0: the segment in the tile that contains u0; slot 1: a later (the last) one
+      const int slot = (cur.tile == (uint32_t)(u0 / S.units_per_tile)) ? 0 : 1;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        uint32_t in_tile = j * kThreads + threadIdx.x;
+        uint32_t local = cur.tile * TILE + in_tile;
+        float raw[27];
+        M.raw(j, raw);
+        if (full) {
+          if (local < S.count) {
+            float vals[28];
+            coef_values<ORDER>(p, raw, vals);
+            add_to_entry<ORDER>(p, S.first + local, vals);
+          }
+        } else {
+          float* dst = p.partials + ((size_t)blockIdx.x * 2 + slot) * NC * TILE + in_tile;
+#pragma unroll
+          for (int q = 0; q < NC; ++q) dst[(size_t)q * TILE] = raw[q];
+        }
+      }
+      seg_open = false;
+    }
+    cur = nxt;
+  }
+}
+
+// ------------------------------------------------------------ finalize: add the partial segments in VPL order
+template <int ORDER>
+__global__ void __launch_bounds__(256) gather_finalize_kernel(GatherParams p, int tile_caches) {
+  constexpr int NC = num_coefs<ORDER>();
+  const Schedule S = make_schedule(p, tile_caches);
+  if (S.units == 0) return;
+  const uint32_t G = p.grid;
+  for (uint32_t local = blockIdx.x * blockDim.x + threadIdx.x; local < S.count; local += gridDim.x * blockDim.x) {
+    const uint32_t tile = local / tile_caches, in_tile = local - tile * tile_caches;
+    const unsigned long long ua = (unsigned long long)tile * S.units_per_tile, ub = ua + S.units_per_tile;
+    const uint32_t c_lo = owner_of(S, G, ua), c_hi = owner_of(S, G, ub - 1);
+    if (c_lo == c_hi) continue; // one CTA covered the whole tile and already wrote it
+    float raw[27];
+#pragma unroll
+    for (int q = 0; q < 27; ++q) raw[q] = 0.0f;
+    for (uint32_t c = c_lo; c <= c_hi; ++c) {
+      const unsigned long long cb = range_begin(S, G, c), ce = range_begin(S, G, c + 1);
+      if (cb >= ce) continue;
+      const int slot = ((uint32_t)(cb / S.units_per_tile) == tile) ? 0 : 1;
+      const float* src = p.partials + ((size_t)c * 2 + slot) * NC * tile_caches + in_tile;
+#pragma unroll
+      for (int q = 0; q < NC; ++q) raw[q] += __ldcs(src + (size_t)q * tile_caches);
+    }
+    float vals[28];
+    coef_values<ORDER>(p, raw, vals);
+    add_to_entry<ORDER>(p, S.first + local, vals);
+  }
+}
+
+} // namespace
+
+// -------------------------------------------------------------------------------- host side
+namespace {
+
+template <typename K>
+drv_status launch_gather(drv_ctx* ctx, K kernel, GatherParams& p, int tile_caches, int order) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  const int grid = ctx->num_sms * per_sm;
+  const size_t need = (size_t)grid * 2 * (order == 2 ? 27 : 12) * tile_caches;
+  if (need > ctx->partial_slots) { // grow the per-CTA partial scratch (first launch of a variant)
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->partials) cudaFree(ctx->partials);
+    ctx->partials = nullptr;
+    ctx->partial_slots = 0;
+    DRV_CUDA(cudaMalloc(&ctx->partials, need * sizeof(float)));
+    ctx->partial_slots = need;
+  }
+  p.partials = ctx->partials;
+  p.grid = (uint32_t)grid;
+  ctx->stage_begin(DRV_STAGE_GATHER_KERNEL);
+  kernel<<<grid, kThreads, 0, ctx->stream>>>(p);
+  DRV_LAUNCH_CHECK();
+  ctx->stage_end(DRV_STAGE_GATHER_KERNEL);
+  const int fin_grid = ctx->num_sms * 4;
+  if (order == 1) gather_finalize_kernel<1><<<fin_grid, 256, 0, ctx->stream>>>(p, tile_caches);
+  else gather_finalize_kernel<2><<<fin_grid, 256, 0, ctx->stream>>>(p, tile_caches);
+  DRV_LAUNCH_CHECK();
+  return DRV_OK;
+}
+
+} // namespace
+
+drv_status drv_impl_gather(drv_ctx* ctx) {
+  if (!ctx->have_constant) return ctx->fail(DRV_ERR_NOT_BOUND, "drv_light_caches: Constant block not set");
+  const bool shadow = ctx->cfg.indirect_shadow != 0;
+  if (shadow && !ctx->have_volume) return ctx->fail(DRV_ERR_NOT_BOUND, "drv_light_caches: VolumeInfo not set");
+  if (ctx->num_lights == 0) return DRV_OK;
+  GatherParams p;
+  memset(&p, 0, sizeof(p));
+  p.num_lights = ctx->num_lights;
+  uint32_t granule = 32; // scheduling quantum in VPLs (a shared-memory tile still holds up to kVplTile)
+  for (uint32_t l = 0; l < ctx->num_lights; ++l) {
+    LightState& S = ctx->lights[l];
+    p.lights[l].vpls = (const float4*)S.vpls;
+    p.lights[l].blocks = (const float4*)S.blocks;
+    p.lights[l].num_vpls = S.num_vpls;
+    uint32_t interval = shadow ? (uint32_t)S.block.IndirectShadowComputationSampleInterval : 1u;
+    if (interval == 0 || (interval & (interval - 1)) != 0)
+      return ctx->fail(DRV_ERR_INVALID, "drv_light_caches: shadow sample interval must be a power of two");
+    if (shadow && S.vpls_external)
+      return ctx->fail(DRV_ERR_INVALID, "drv_light_caches: drv_set_vpls cannot be combined with indirect shadows");
+    p.lights[l].interval = interval;
+    if (interval > granule) granule = interval;
+  }
+  p.granule = granule;
+  p.entries = ctx->entries;
+  p.counter = ctx->counter;
+  p.shard_rank = ctx->shard_rank;
+  p.shard_world = ctx->shard_world;
+  p.f0 = ctx->constant.ShEvaFactor0;
+  p.f1 = ctx->constant.ShEvaFactor1;
+  p.f2 = ctx->constant.ShEvaFactor2n2_p1_n1;
+  p.f20 = ctx->constant.ShEvaFactor20;
+  p.f22 = ctx->constant.ShEvaFactor2p2;
+  p.chain = ctx->voxel_chain;
+  p.vres = (int)ctx->cfg.voxel_resolution;
+  p.vlevels = (int)ctx->voxel_levels;
+  memcpy(p.vmin, ctx->volume.VolumeWorldMin, 12);
+  p.voxel_size = ctx->volume.VoxelSizeInWorld;
+  if (ctx->peers_open) {
+    p.num_peers = ctx->shard_world;
+    for (uint32_t r = 0; r < ctx->shard_world && r < 8; ++r)
+      p.peers[r] = (r == ctx->shard_rank) ? nullptr : (uint8_t*)ctx->peer_entries[r];
+  }
+  const int order = (int)ctx->cfg.sh_order;
+  const uint32_t variant = ctx->cfg.gather_variant;
+#define DRV_GATHER(ORD, SH, MATH, TMA) \
+  return launch_gather(ctx, gather_kernel<ORD, SH, MATH, TMA>, p, kThreads * MATH::CPT, ORD)
+  using S1n2 = ScalarMath<1, false, 2>; using S1n4 = ScalarMath<1, false, 4>; using S1s1 = ScalarMath<1, true, 1>;
+  using S2n2 = ScalarMath<2, false, 2>; using S2n1 = ScalarMath<2, false, 1>; using S2s1 = ScalarMath<2, true, 1>;
+  using P1n1 = PackedMath<1, false, 1>; using P1n2 = PackedMath<1, false, 2>; using P1s1 = PackedMath<1, true, 1>;
+  using P2n1 = PackedMath<2, false, 1>; using P2s1 = PackedMath<2, true, 1>;
+  switch (variant) {
+    case 1: // scalar maths, TMA bulk staging (unshadowed only; shadowed falls through to the default)
+      if (!shadow) { if (order == 1) DRV_GATHER(1, false, S1n2, true); else DRV_GATHER(2, false, S2n2, true); }
+      break;
+    case 2: // packed FP32x2, widest tiling
+      if (order == 1) { if (shadow) DRV_GATHER(1, true, P1s1, false); else DRV_GATHER(1, false, P1n2, false); }
+      else            { if (shadow) DRV_GATHER(2, true, P2s1, false); else DRV_GATHER(2, false, P2n1, false); }
+      break;
+    case 3: // packed FP32x2, one pair per thread
+      if (order == 1) { if (shadow) DRV_GATHER(1, true, P1s1, false); else DRV_GATHER(1, false, P1n1, false); }
+      else            { if (shadow) DRV_GATHER(2, true, P2s1, false); else DRV_GATHER(2, false, P2n1, false); }
+      break;
+    case 4: // scalar, widest tiling
+      if (order == 1) { if (shadow) DRV_GATHER(1, true, S1s1, false); else DRV_GATHER(1, false, S1n4, false); }
+      else            { if (shadow) DRV_GATHER(2, true, S2s1, false); else DRV_GATHER(2, false, S2n2, false); }
+      break;
+    case 5: // scalar, SH2 with one cache per thread
+      if (order == 2 && !shadow) DRV_GATHER(2, false, S2n1, false);
+      break;
+    default:
+      break;
+  }
+  // variant 0 (default): scalar maths, register-prefetch staging
+  if (order == 1) { if (shadow) DRV_GATHER(1, true, S1s1, false); else DRV_GATHER(1, false, S1n2, false); }
+  else            { if (shadow) DRV_GATHER(2, true, S2s1, false); else DRV_GATHER(2, false, S2n2, false); }
+#undef DRV_GATHER
+}

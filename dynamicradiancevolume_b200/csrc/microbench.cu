@@ -1,0 +1,196 @@
+// microbench.cu — measured roofline denominators for the gather / apply
+// kernels ("FP32 peak must be measured on the box with an FFMA
+// micro-kernel"; MEASURED_PEAKS.json only carries HBM copy and bf16 GEMM).
+// Each benchmark runs a resident grid for a fixed iteration count and reports
+// the best of 5 timed launches (CUDA events).
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/drv_gi.h"
+
+namespace {
+
+constexpr int kIters = 4096;
+
+// 16 independent FFMA chains per thread, 3 distinct register sources each.
+__global__ void __launch_bounds__(256) ffma_kernel(float* out, float a, float b) {
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = (float)(threadIdx.x + i);
+  float x = a + threadIdx.x * 1e-9f, y = b;
+  for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], x, y);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// Same with packed FP32x2 FMAs (FFMA2): 16 float2 chains.
+__global__ void __launch_bounds__(256) ffma2_kernel(float* out, float a, float b) {
+  float2 acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = make_float2((float)(threadIdx.x + i), (float)i);
+  float2 x = make_float2(a + threadIdx.x * 1e-9f, a), y = make_float2(b, b + 1e-9f);
+  for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = __ffma2_rn(acc[i], x, y);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i].x + acc[i].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// The accumulate pattern of the gather: acc_k += f * u_k with 12 accumulators
+// and per-iteration varying multipliers (register-bank pressure like the real loop).
+__global__ void __launch_bounds__(256) ffma_outer_kernel(float* out, float a) {
+  float acc[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+  float f0 = a, f1 = a * 1.1f, f2 = a * 1.2f, u0 = 0.3f + threadIdx.x * 1e-7f, u1 = 0.4f, u2 = 0.5f, u3 = 0.6f;
+  for (int it = 0; it < kIters; ++it) {
+    acc[0] = fmaf(f0, u0, acc[0]); acc[1] = fmaf(f1, u0, acc[1]); acc[2] = fmaf(f2, u0, acc[2]);
+    acc[3] = fmaf(f0, u1, acc[3]); acc[4] = fmaf(f1, u1, acc[4]); acc[5] = fmaf(f2, u1, acc[5]);
+    acc[6] = fmaf(f0, u2, acc[6]); acc[7] = fmaf(f1, u2, acc[7]); acc[8] = fmaf(f2, u2, acc[8]);
+    acc[9] = fmaf(f0, u3, acc[9]); acc[10] = fmaf(f1, u3, acc[10]); acc[11] = fmaf(f2, u3, acc[11]);
+    u0 += 1e-6f; u1 += 1e-6f; u2 += 1e-6f; u3 += 1e-6f;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) s += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) mufu_kernel(float* out, float a) {
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = a + (float)(threadIdx.x + i);
+  for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float r;
+      asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(acc[i]));
+      acc[i] = r;
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// Broadcast 128-bit shared loads (every lane reads the same address), as the VPL fetch does.
+__global__ void __launch_bounds__(256) lds_broadcast_kernel(float* out) {
+  __shared__ float4 s[512];
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) s[i] = make_float4((float)i, 1.f, 2.f, 3.f);
+  __syncthreads();
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int it = 0; it < kIters / 8; ++it) {
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      float4 v = s[(it + i * 8) & 511];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc.x + acc.y + acc.z + acc.w;
+}
+
+// L2-resident streaming read (buffer of 48 MB << 126 MB L2), 128-bit loads.
+__global__ void __launch_bounds__(256) l2_read_kernel(const uint4* __restrict__ buf, size_t n16, int reps, uint32_t* out) {
+  uint32_t acc = 0;
+  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (int r = 0; r < reps; ++r)
+    for (size_t i = tid; i < n16; i += stride) {
+      uint4 v = __ldcg(buf + i);
+      acc += v.x ^ v.y ^ v.z ^ v.w;
+    }
+  if (acc == 0xdeadbeefu) out[0] = acc;
+}
+
+struct Timer {
+  cudaEvent_t a, b;
+  Timer() { cudaEventCreate(&a); cudaEventCreate(&b); }
+  ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+};
+
+template <typename F>
+double best_ms(F launch) {
+  Timer t;
+  launch();
+  cudaDeviceSynchronize();
+  double best = 1e30;
+  for (int i = 0; i < 5; ++i) {
+    cudaEventRecord(t.a);
+    launch();
+    cudaEventRecord(t.b);
+    cudaEventSynchronize(t.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t.a, t.b);
+    if (ms < best) best = ms;
+  }
+  return best;
+}
+
+const char* kNames[] = {
+    "ffma_tflops",         // scalar FFMA, 3 register sources: TFLOP/s (FMA = 2 flop)
+    "ffma2_tflops",        // packed FFMA2: TFLOP/s
+    "ffma_outer_tflops",   // the gather's accumulate pattern: TFLOP/s
+    "mufu_rsq_gops",       // MUFU.RSQ: G ops/s
+    "lds128_bcast_tbs",    // broadcast LDS.128: TB/s of register fill (16 B x 32 lanes per instruction)
+    "l2_read_gbs",         // L2-resident 128-bit loads: GB/s
+    "sm_clock_mhz",        // current SM clock reported by the driver
+};
+
+} // namespace
+
+extern "C" uint32_t drv_microbench_count(void) { return (uint32_t)(sizeof(kNames) / sizeof(kNames[0])); }
+extern "C" const char* drv_microbench_name(uint32_t which) { return which < drv_microbench_count() ? kNames[which] : "?"; }
+
+extern "C" drv_status drv_microbench(int32_t device, uint32_t which, double* result) {
+  if (!result || which >= drv_microbench_count()) return DRV_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return DRV_ERR_NO_DEVICE; }
+  if (cudaSetDevice(device) != cudaSuccess) return DRV_ERR_CUDA;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  const int sms = prop.multiProcessorCount;
+  const int blocks = sms * 8, threads = 256;
+  float* out = nullptr;
+  if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) return DRV_ERR_CUDA;
+  const double lanes = (double)blocks * threads;
+  double r = 0.0;
+  switch (which) {
+    case 0: { double ms = best_ms([&] { ffma_kernel<<<blocks, threads>>>(out, 1.0001f, 0.5f); });
+              r = lanes * kIters * 16 * 2.0 / (ms * 1e-3) / 1e12; } break;
+    case 1: { double ms = best_ms([&] { ffma2_kernel<<<blocks, threads>>>(out, 1.0001f, 0.5f); });
+              r = lanes * kIters * 16 * 4.0 / (ms * 1e-3) / 1e12; } break;
+    case 2: { double ms = best_ms([&] { ffma_outer_kernel<<<blocks, threads>>>(out, 1.0001f); });
+              r = lanes * kIters * 12 * 2.0 / (ms * 1e-3) / 1e12; } break; // the 4 FADDs are not counted
+    case 3: { double ms = best_ms([&] { mufu_kernel<<<blocks, threads>>>(out, 1.5f); });
+              r = lanes * kIters * 8 / (ms * 1e-3) / 1e9; } break;
+    case 4: { double ms = best_ms([&] { lds_broadcast_kernel<<<blocks, threads>>>(out); });
+              r = lanes * (kIters / 8) * 64 * 16.0 / (ms * 1e-3) / 1e12; } break;
+    case 5: {
+      const size_t bytes = 48ull << 20;
+      uint4* buf = nullptr;
+      uint32_t* o2 = nullptr;
+      if (cudaMalloc(&buf, bytes) != cudaSuccess) { cudaFree(out); return DRV_ERR_CUDA; }
+      cudaMalloc(&o2, 4);
+      cudaMemset(buf, 1, bytes);
+      const int reps = 8;
+      double ms = best_ms([&] { l2_read_kernel<<<sms * 8, 256>>>(buf, bytes / 16, reps, o2); });
+      r = (double)bytes * reps / (ms * 1e-3) / 1e9;
+      cudaFree(buf); cudaFree(o2);
+    } break;
+    case 6: { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device); r = khz / 1000.0; } break;
+  }
+  cudaFree(out);
+  if (cudaGetLastError() != cudaSuccess) return DRV_ERR_CUDA;
+  *result = r;
+  return DRV_OK;
+}

@@ -1,0 +1,191 @@
+// rsm.cu — stage 2: RSM mip chain and VPL generation.
+//
+//  drv_prepare_rsm      ≙ Renderer::ShadowMap::PrepareRSM (renderer.cpp:1300-1339)
+//                         running shader/downsamplersm.frag:15-33 per level.
+//  drv_impl_generate_vpls  the VPL load phase of shader/cacheLightingRSM.comp:137-163
+//                         and the cache-independent half of its indirect-shadow
+//                         sample (:168-192), hoisted out of the gather: the
+//                         reference redoes both in every 64-cache work group
+//                         (N/64 x R^2 texture fetches); here they run once per
+//                         light per frame and the gather streams a 48-byte VPL
+//                         record + a 16-byte block record instead.
+#include "ctx.h"
+#include "device_math.cuh"
+
+using namespace drvk;
+
+namespace {
+
+// downsamplersm.frag:15-33. One thread per destination texel.
+__global__ void rsm_downsample_kernel(const uint2* __restrict__ flux_src, const int* __restrict__ normal_src,
+                                      const uint32_t* __restrict__ depth_src, int res, uint2* __restrict__ flux_dst,
+                                      int* __restrict__ normal_dst, uint32_t* __restrict__ depth_dst) {
+  const int h = res >> 1;
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= h || y >= h) return;
+  // textureGather order: (i0,j1) (i1,j1) (i1,j0) (i0,j0)
+  size_t t[4] = {(size_t)(2 * y + 1) * res + 2 * x, (size_t)(2 * y + 1) * res + 2 * x + 1,
+                 (size_t)(2 * y) * res + 2 * x + 1, (size_t)(2 * y) * res + 2 * x};
+  float fr[4], fg[4], fb[4], d0[4], d1[4];
+  F3 n = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint2 f = __ldg(flux_src + t[i]);
+    fr[i] = half_bits_to_float((uint16_t)(f.x & 0xffffu));
+    fg[i] = half_bits_to_float((uint16_t)(f.x >> 16));
+    fb[i] = half_bits_to_float((uint16_t)(f.y & 0xffffu));
+    uint32_t d = __ldg(depth_src + t[i]);
+    d0[i] = half_bits_to_float((uint16_t)(d & 0xffffu));
+    d1[i] = half_bits_to_float((uint16_t)(d >> 16));
+    int pn = __ldg(normal_src + t[i]);
+    F3 u = unpack_normal16i((int)(short)(pn & 0xffff), (int)(short)((uint32_t)pn >> 16));
+    n.x += u.x; n.y += u.y; n.z += u.z;
+  }
+  // flux: sum of the four (:17-22); the RGB16F store rounds to nearest even
+  float sr = ex_add(ex_add(ex_add(fr[0], fr[1]), fr[2]), fr[3]);
+  float sg = ex_add(ex_add(ex_add(fg[0], fg[1]), fg[2]), fg[3]);
+  float sb = ex_add(ex_add(ex_add(fb[0], fb[1]), fb[2]), fb[3]);
+  size_t o = (size_t)y * h + x;
+  flux_dst[o] = make_uint2((uint32_t)float_to_half_bits(sr) | ((uint32_t)float_to_half_bits(sg) << 16),
+                           (uint32_t)float_to_half_bits(sb));
+  // normal: mean direction, renormalised, repacked (:24-30)
+  float inv = rsqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
+  int ox, oy;
+  pack_normal16i(n.x * inv, n.y * inv, n.z * inv, ox, oy);
+  normal_dst[o] = (int)(((uint32_t)ox & 0xffffu) | ((uint32_t)oy << 16));
+  // depthLinSq: linear fetch at the footprint centre = mean of the four (:32)
+  float a0 = ex_mix(d0[3], d0[2], 0.5f), b0 = ex_mix(d0[0], d0[1], 0.5f);
+  float a1 = ex_mix(d1[3], d1[2], 0.5f), b1 = ex_mix(d1[0], d1[1], 0.5f);
+  depth_dst[o] = (uint32_t)float_to_half_bits(ex_mix(a0, b0, 0.5f)) |
+                 ((uint32_t)float_to_half_bits(ex_mix(a1, b1, 0.5f)) << 16);
+}
+
+// cacheLightingRSM.comp:154-155 / :175-176 in decision maths (the block record
+// feeds the cone-march trip count).
+__device__ __forceinline__ F3 rsm_world_position(const drv_spot_light& L, float u, float v, float d) {
+  F3 ws = ex_unproject(L.InverseLightViewProjection, ex_sub(ex_mul(u, 2.0f), 1.0f), ex_sub(ex_mul(v, 2.0f), 1.0f), 0.0f);
+  float dx = ex_sub(ws.x, L.LightPosition[0]), dy = ex_sub(ws.y, L.LightPosition[1]), dz = ex_sub(ws.z, L.LightPosition[2]);
+  float inv = ex_rsqrt(ex_dot3(dx, dy, dz, dx, dy, dz));
+  F3 r = {ex_add(L.LightPosition[0], ex_mul(ex_mul(dx, inv), d)), ex_add(L.LightPosition[1], ex_mul(ex_mul(dy, inv), d)),
+          ex_add(L.LightPosition[2], ex_mul(ex_mul(dz, inv), d))};
+  return r;
+}
+
+// Threads [0, R^2) write VPLs; threads [R^2, R^2 + numBlocks) write shadow-block records.
+__global__ void vplgen_kernel(drv_spot_light L, const uint2* __restrict__ flux, const int* __restrict__ normal,
+                              const uint32_t* __restrict__ depth, const uint32_t* __restrict__ depth_lod,
+                              int with_blocks, float4* __restrict__ vpls, float4* __restrict__ blocks) {
+  const uint32_t R = (uint32_t)L.RSMReadResolution;
+  const uint32_t total = R * R;
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < total) {
+    uint32_t x, y;
+    morton_decode(k, x, y);                                             // :142
+    float u = ex_div((float)x + 0.5f, (float)R), v = ex_div((float)y + 0.5f, (float)R); // :144
+    size_t t = (size_t)y * R + x;
+    uint2 f = __ldg(flux + t);                                          // :147
+    float d = half_bits_to_float((uint16_t)(__ldg(depth + t) & 0xffffu)); // :150
+    F3 p = rsm_world_position(L, u, v, d);                              // :154-155
+    int pn = __ldg(normal + t);
+    F3 n = unpack_normal16i((int)(short)(pn & 0xffff), (int)(short)((uint32_t)pn >> 16)); // :158
+    float4* o = vpls + (size_t)k * 3;
+    o[0] = make_float4(p.x, p.y, p.z, ex_mul(ex_mul(d, d), L.ValAreaFactor)); // :151
+    o[1] = make_float4(n.x, n.y, n.z, 0.0f);
+    o[2] = make_float4(half_bits_to_float((uint16_t)(f.x & 0xffffu)), half_bits_to_float((uint16_t)(f.x >> 16)),
+                       half_bits_to_float((uint16_t)(f.y & 0xffffu)), 0.0f);
+    return;
+  }
+  if (!with_blocks) return;
+  const uint32_t interval = (uint32_t)L.IndirectShadowComputationSampleInterval;
+  uint32_t b = k - total;
+  if (b >= total / interval) return;
+  const int lod = (int)L.IndirectShadowComputationLod;
+  const int Rl = (int)(R >> lod);
+  uint32_t x, y;
+  morton_decode(b * interval, x, y);                                                // :171
+  float u = ex_div(ex_add((float)x, L.IndirectShadowSamplingOffset), (float)R);     // :172
+  float v = ex_div(ex_add((float)y, L.IndirectShadowSamplingOffset), (float)R);
+  // :174 — bilinear, clamp to edge, at mip `lod` of the read level
+  float fx = ex_sub(ex_mul(u, (float)Rl), 0.5f), fy = ex_sub(ex_mul(v, (float)Rl), 0.5f);
+  float flx = floorf(fx), fly = floorf(fy);
+  float tx = ex_sub(fx, flx), ty = ex_sub(fy, fly);
+  int x0 = ex_trunc(flx), y0 = ex_trunc(fly);
+  int x1 = clampi(x0 + 1, 0, Rl - 1), y1 = clampi(y0 + 1, 0, Rl - 1);
+  x0 = clampi(x0, 0, Rl - 1); y0 = clampi(y0, 0, Rl - 1);
+  uint32_t t00 = __ldg(depth_lod + (size_t)y0 * Rl + x0), t10 = __ldg(depth_lod + (size_t)y0 * Rl + x1);
+  uint32_t t01 = __ldg(depth_lod + (size_t)y1 * Rl + x0), t11 = __ldg(depth_lod + (size_t)y1 * Rl + x1);
+  float m1 = ex_mix(ex_mix(half_bits_to_float((uint16_t)(t00 & 0xffffu)), half_bits_to_float((uint16_t)(t10 & 0xffffu)), tx),
+                    ex_mix(half_bits_to_float((uint16_t)(t01 & 0xffffu)), half_bits_to_float((uint16_t)(t11 & 0xffffu)), tx), ty);
+  float m2 = ex_mix(ex_mix(half_bits_to_float((uint16_t)(t00 >> 16)), half_bits_to_float((uint16_t)(t10 >> 16)), tx),
+                    ex_mix(half_bits_to_float((uint16_t)(t01 >> 16)), half_bits_to_float((uint16_t)(t11 >> 16)), tx), ty);
+  F3 avg = rsm_world_position(L, u, v, m1);                                          // :175-176
+  float var = ex_sub(m2, ex_mul(m1, m1));                                            // :181
+  if (!(var > 0.0f)) var = 0.0f;
+  float k2 = ex_div(ex_mul(ex_sqrt(var), 2.0f), m1);
+  float kc = fmaxf(L.IndirectShadowComputationSuperValWidth, k2);                    // :192 (fmaxf drops a NaN k2)
+  if (kc != kc) kc = L.IndirectShadowComputationSuperValWidth;
+  blocks[b] = make_float4(avg.x, avg.y, avg.z, kc);
+}
+
+} // namespace
+
+drv_status drv_impl_prepare_rsm(drv_ctx* ctx, uint32_t li) {
+  LightState& S = ctx->lights[li];
+  if (!S.rsm_bound) return ctx->fail(DRV_ERR_NOT_BOUND, "drv_prepare_rsm: RSM not bound");
+  ctx->stage_begin(DRV_STAGE_PREPARE_RSM);
+  uint32_t res = S.rsm_res;
+  const uint2* fs = (const uint2*)S.flux0;
+  const int* ns = (const int*)S.normal0;
+  const uint32_t* ds = (const uint32_t*)S.depth0;
+  // levels 1 .. log2(res)-1: the 1x1 top level is never rendered (renderer.cpp:1293-1297)
+  for (uint32_t level = 1; (res >> level) >= 2; ++level) {
+    uint32_t src_res = res >> (level - 1), h = src_res >> 1;
+    uint64_t off = rsm_level_offset_texels(res, level);
+    uint2* fd = (uint2*)S.flux_mips + off;
+    int* nd = (int*)S.normal_mips + off;
+    uint32_t* dd = (uint32_t*)S.depth_mips + off;
+    dim3 block(16, 16), grid((h + 15) / 16, (h + 15) / 16);
+    rsm_downsample_kernel<<<grid, block, 0, ctx->stream>>>(fs, ns, ds, (int)src_res, fd, nd, dd);
+    DRV_LAUNCH_CHECK();
+    fs = fd; ns = nd; ds = dd;
+  }
+  ctx->stage_end(DRV_STAGE_PREPARE_RSM);
+  return DRV_OK;
+}
+
+drv_status drv_impl_generate_vpls(drv_ctx* ctx, uint32_t li) {
+  LightState& S = ctx->lights[li];
+  if (!S.block_set) return ctx->fail(DRV_ERR_NOT_BOUND, "drv_light_caches: SpotLight block not set");
+  if (!S.rsm_bound) return ctx->fail(DRV_ERR_NOT_BOUND, "drv_light_caches: RSM not bound");
+  const drv_spot_light& L = S.block;
+  const uint32_t R = (uint32_t)L.RSMReadResolution;
+  if ((uint32_t)L.RSMRenderResolution != S.rsm_res || R == 0 || (S.rsm_res % R) != 0 || R > ctx->cfg.max_rsm_resolution)
+    return ctx->fail(DRV_ERR_INVALID, "drv_light_caches: SpotLight block disagrees with the bound RSM");
+  uint32_t readLod = 0;
+  while ((S.rsm_res >> readLod) > R) ++readLod; // TEXTURE_BASE_LEVEL = rsmReadLod, renderer.cpp:807-809
+  auto level_ptr = [&](const void* l0, const void* mips, uint32_t level, size_t texel_bytes) -> const void* {
+    if (level == 0) return l0;
+    return (const uint8_t*)mips + rsm_level_offset_texels(S.rsm_res, level) * texel_bytes;
+  };
+  const uint2* flux = (const uint2*)level_ptr(S.flux0, S.flux_mips, readLod, 8);
+  const int* normal = (const int*)level_ptr(S.normal0, S.normal_mips, readLod, 4);
+  const uint32_t* depth = (const uint32_t*)level_ptr(S.depth0, S.depth_mips, readLod, 4);
+  int with_blocks = ctx->cfg.indirect_shadow ? 1 : 0;
+  const uint32_t* depth_lod = depth;
+  uint32_t nblocks = 0;
+  if (with_blocks) {
+    uint32_t slod = (uint32_t)L.IndirectShadowComputationLod;
+    uint32_t interval = (uint32_t)L.IndirectShadowComputationSampleInterval;
+    // the sampled level must have been rendered (block < read resolution)
+    if (interval == 0 || (R >> slod) < 2 || interval != (1u << (2 * slod)))
+      return ctx->fail(DRV_ERR_INVALID, "drv_light_caches: indirect shadow LOD out of range for this RSM");
+    depth_lod = (const uint32_t*)level_ptr(S.depth0, S.depth_mips, readLod + slod, 4);
+    nblocks = R * R / interval;
+  }
+  uint32_t threads = R * R + nblocks;
+  vplgen_kernel<<<(threads + 255) / 256, 256, 0, ctx->stream>>>(L, flux, normal, depth, depth_lod, with_blocks,
+                                                               (float4*)S.vpls, (float4*)S.blocks);
+  DRV_LAUNCH_CHECK();
+  S.num_vpls = R * R;
+  return DRV_OK;
+}
