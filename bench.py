@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py — the GI-frame benchmark of BASELINE.json.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo: libdrv_gi (sm_100a CUDA) through the C-ABI
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the scalar C++ transcription of the
+                                                             # reference's GLSL (oracle/), all host threads
+
+metric  = BASELINE.json `metric`: GI ms/frame @1080p, 16k VPLs (configs[1]: procedural atrium 1920x1080, one
+          128^2 RSM read, 2 cascades x 64^3, SH1, unshadowed). Lower is better.
+step    = one frame of the hot path: RSM mip chain (ShadowMap::PrepareRSM) -> [voxelise + blend + mips when
+          indirect shadows are on] -> allocate caches -> VPL generation + cache x VPL gather -> clear HDR ->
+          apply (Renderer::Draw, rendering/renderer.cpp:539-594 minus rasterisation / direct light / tonemap).
+value   = ms per frame with all inputs resident in HBM, CUDA events on the context's stream around every
+          step, L2 flushed (512 MiB memset) between steps, max over ranks.
+e2e     = the same frame through the host-buffer C-ABI calls (drv_upload_gbuffer / drv_upload_rsm /
+          drv_draw_to_host): pinned host G-buffer + RSM level 0 copied H2D and the RGBA16F result copied D2H
+          inside the timed region.
+N > 1   = one process per GPU (torchrun). Allocation is replicated (deterministic scan => identical entry
+          indices on every rank, no communication); the cache x VPL gather is sharded over contiguous
+          cell-ordered entry ranges; finished SH entries are stored to every peer over NVLink from inside the
+          gather epilogue (fused all-gather), an NCCL all-reduce of one word is the cross-GPU barrier; apply is
+          replicated. One frame is split over N GPUs => "scaling": "strong".
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "GI ms/frame @1080p,16k VPLs"
+UNIT = "ms/frame"
+FLOP_PER_PAIR = {1: 48.0, 2: 92.0}   # 32 ops = 48 flop (SH1), 59 ops = 92 flop (SH2), FMA = 2
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4: 148 SMs x 128 lanes x FMA at clocks.max.sm
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs index (0..3); the metric is quoted on 1")
+    ap.add_argument("--variant", type=int, default=0, help="gather kernel variant (drv_config.gather_variant)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps (profiling runs)")
+    ap.add_argument("--no-microbench", action="store_true")
+    ap.add_argument("--stages", action="store_true", help="print the per-stage table to stderr")
+    return ap.parse_args()
+
+
+def workload_for(index):
+    import workloads
+    return workloads.config(index)
+
+
+def workload_name(wl):
+    return ("%s %dx%d, %d light(s) x %d^2 RSM read (%d VPLs), %d cascade(s) x %d^3, SH%d, %s"
+            % (wl.name, wl.width, wl.height, len(wl.lights), int(wl.spot_lights[0].RSMReadResolution), wl.num_vpls,
+               wl.cav_cascades, wl.cav_resolution, wl.sh_order,
+               "cone-traced indirect shadow, %d^3 voxels" % wl.voxel_resolution if wl.indirect_shadow else "unshadowed"))
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "no samples"}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's algorithm on the host cores: oracle/ (scalar C++ transcription of the GLSL, std::thread
+    over tiles / cache entries). Rank 0 only; other ranks exit."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from dynamicradiancevolume_b200 import build as b
+    b.build_aux()
+    from oracle import binding as orc
+    from oracle.frame import OracleFrame
+    wl = workload_for(args.config).build()
+    cores = orc.default_threads()
+    times = []
+    for i in range(args.warmup + args.steps):
+        o = OracleFrame(wl, threads=cores)
+        t = time.perf_counter()
+        o.prepare_inputs()
+        o.frame()
+        dt = (time.perf_counter() - t) * 1e3
+        if i >= args.warmup:
+            times.append(dt)
+    ms = sum(times) / len(times)
+    pairs = o.count * wl.num_vpls
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(wl), "caches": o.count, "vpls": wl.num_vpls},
+        "cpu_baseline": {"value": ms, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "whole frame (RSM mips + VPLs + allocate + light + apply), every step, full size",
+                         "stage_ms": {k: v * 1e3 for k, v in o.timings.items()},
+                         "gather_pairs_per_s": pairs / max(o.timings.get("LightCaches", 0.0), 1e-9)},
+        "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------- this repo's arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import dynamicradiancevolume_b200 as drv
+    import workloads
+    from dynamicradiancevolume_b200 import abi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun (one process per GPU); WORLD_SIZE is 1" % args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libdrv_gi has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    wl = workload_for(args.config).build()
+    stream = torch.cuda.Stream(device=local)
+    g = workloads.DeviceFrame(wl, device=local, stream=stream, gather_variant=args.variant)
+    ctx = g.ctx
+    dev = "cuda:%d" % local
+    px = wl.width * wl.height
+    hdr16 = torch.zeros(wl.height, wl.width, 4, dtype=torch.float16, device=dev)
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    barrier_word = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    if world > 1:  # shard the gather and map every peer's entries buffer (NVLink P2P)
+        ctx.set_shard(rank, world)
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.export_entries_ipc())
+        for r, h in enumerate(handles):
+            if r != rank:
+                ctx.import_peer_entries(r, h)
+
+    def frame_device():
+        with torch.cuda.stream(stream):
+            for i in range(len(g.rsms)):
+                ctx.prepare_rsm(i)
+            if wl.indirect_shadow:
+                ctx.voxelize(g.tris, None, 1.0)
+            hdr16.zero_()  # glClear(GL_COLOR_BUFFER_BIT), renderer.cpp:562
+            if world == 1:
+                ctx.draw(hdr16, abi.DRV_HDR_RGBA16F_ADD)
+            else:
+                ctx.allocate_caches()          # replicated; clears this rank's SH
+                dist.all_reduce(barrier_word)  # every rank has finished clearing before any peer stores arrive
+                ctx.light_caches()             # own shard; epilogue stores finished entries to all peers
+                dist.all_reduce(barrier_word)  # all peers' stores have landed
+                ctx.apply_caches(hdr16, abi.DRV_HDR_RGBA16F_ADD)
+
+    # ---- warm-up + timed region: CUDA events on the context's stream around every step ----
+    torch.cuda.synchronize()
+    ctx.enable_stage_timers(True)
+    n_total = args.warmup + args.steps
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_total)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_total)]
+    stage_ms = {name: [] for name in abi.STAGE_NAMES}
+    step_ms = []
+    sampler = ClockSampler(local)
+    launches0 = 0
+    for i in range(n_total):
+        if i == args.warmup:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            sampler.start()
+            launches0 = ctx.kernel_launches()
+            t_wall0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            if not args.no_flush:
+                flush_buf.zero_()
+            ev0[i].record(stream)
+        frame_device()
+        with torch.cuda.stream(stream):
+            ev1[i].record(stream)
+        ev1[i].synchronize()
+        if i >= args.warmup:
+            step_ms.append(ev0[i].elapsed_time(ev1[i]))
+            for s, name in enumerate(abi.STAGE_NAMES):
+                try:
+                    stage_ms[name].append(ctx.stage_ms(s))
+                except drv.DrvError:
+                    pass
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = ctx.kernel_launches() - launches0
+    ctx.enable_stage_timers(False)
+    total_ms = sum(step_ms)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    n_caches = ctx.active_cache_count()[0]
+
+    # ---- end to end: pinned host inputs -> H2D -> frame -> D2H, through the host-buffer C-ABI calls ----
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_gb = [pin(a) for a in (wl.depth, wl.normal, wl.diffuse)]
+    h_rsm = [[pin(a) for a in r] for r in wl.rsms]
+    h_out = torch.zeros(wl.height, wl.width, 4, dtype=torch.float16).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in h_gb) + sum(t.numel() * t.element_size() for r in h_rsm for t in r)
+    d2h = h_out.numel() * h_out.element_size()
+
+    def frame_e2e():
+        ctx.upload_gbuffer(*h_gb)
+        for i, r in enumerate(h_rsm):
+            ctx.upload_rsm(i, *r)
+            ctx.prepare_rsm(i)
+        if wl.indirect_shadow:
+            ctx.voxelize(g.tris, None, 1.0)
+        if world == 1:
+            ctx.draw_to_host(h_out)
+        else:
+            with torch.cuda.stream(stream):
+                hdr16.zero_()
+                ctx.allocate_caches()
+                dist.all_reduce(barrier_word)
+                ctx.light_caches()
+                dist.all_reduce(barrier_word)
+                ctx.apply_caches(hdr16, abi.DRV_HDR_RGBA16F_ADD)
+                if rank == 0:
+                    h_out.copy_(hdr16, non_blocking=True)
+            stream.synchronize()
+
+    e2e_ms = []
+    for i in range(args.warmup + args.steps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        with torch.cuda.stream(stream):
+            if not args.no_flush:
+                flush_buf.zero_()
+        stream.synchronize()
+        t0 = time.perf_counter()
+        frame_e2e()  # ends with a stream synchronise: the result is in host memory
+        dt = (time.perf_counter() - t0) * 1e3
+        if i >= args.warmup:
+            e2e_ms.append(dt)
+    e2e_total = sum(e2e_ms)
+    if world > 1:
+        t = torch.tensor([e2e_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+    e2e_per_step = e2e_total / args.steps
+    # restore the device-resident bindings (upload_* rebinds to staging copies of the same data)
+    ctx.bind_gbuffer(g.depth, g.normal, g.diffuse)
+    for i, r in enumerate(g.rsms):
+        ctx.bind_rsm(i, *r)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (the cache x VPL gather) ----
+    med = lambda v: statistics.median(v) if v else None
+    gather_ms = (sum(stage_ms["GatherKernel"]) / len(stage_ms["GatherKernel"])) if stage_ms["GatherKernel"] else None
+    shard_caches = n_caches
+    if world > 1:
+        b, e = drv.shard_range(n_caches, rank, world)
+        shard_caches = e - b
+    pairs_per_launch = shard_caches * wl.num_vpls
+    flops = pairs_per_launch * FLOP_PER_PAIR[wl.sh_order]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    micro = {}
+    if not args.no_microbench:
+        lib = drv.load()
+        import ctypes as C
+        for w in range(lib.drv_microbench_count()):
+            r = C.c_double()
+            if lib.drv_microbench(local, w, C.byref(r)) == 0:
+                micro[lib.drv_microbench_name(w).decode()] = r.value
+    fp32_peak = micro.get("ffma_tflops") or NOMINAL_FP32_TFLOPS
+    roofline = None
+    if gather_ms:
+        achieved = flops / (gather_ms * 1e-3) / 1e12
+        roofline = {
+            "kernel": "gather_kernel<SH%d,%s>" % (wl.sh_order, "shadow" if wl.indirect_shadow else "unshadowed"),
+            "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+            "peak_source": ("measured on this GPU at bench start: scalar-FFMA micro-kernel (drv_microbench), FMA = 2 flop"
+                            if "ffma_tflops" in micro else "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"),
+            "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS,
+            "traffic": None,
+            "pairs_per_launch": pairs_per_launch, "flop_per_pair": FLOP_PER_PAIR[wl.sh_order],
+            "pairs_per_s": pairs_per_launch / (gather_ms * 1e-3), "avg_launch_ms": gather_ms,
+            "note": ("CUDA-core FP32 roofline (this is not a tensor-core contraction; MEASURED_PEAKS.json has no FP32 "
+                     "figure). HBM traffic of the gather is ~0 per pair: the VPL list and entries are L2-resident."),
+        }
+    # HBM-side summary of the two streaming stages (algorithmic bytes)
+    stride = abi.entry_stride(wl.sh_order)
+    cells = wl.cav_cascades * wl.cav_resolution ** 3
+    alloc_bytes = 4 * px + cells * (1 + 1 + 1 + 4) + n_caches * stride
+    apply_bytes = px * (4 + 4 + 4 + 16)
+    hbm_peak = peaks.get("hbm_gbs")
+    secondary = {}
+    for name, nbytes in (("AllocateCaches", alloc_bytes), ("ApplyCaches", apply_bytes)):
+        m = med(stage_ms[name])
+        if m:
+            gbs = nbytes / (m * 1e-3) / 1e9
+            secondary[name] = {"bound": "hbm", "algorithmic_bytes": nbytes, "ms": m, "achieved": gbs, "unit": "GB/s",
+                               "peak": hbm_peak, "frac": (gbs / hbm_peak) if hbm_peak else None}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import binding as orc
+        from oracle.frame import OracleFrame
+        cores = orc.default_threads()
+        runs = []
+        for _ in range(3):
+            o = OracleFrame(wl, threads=cores)
+            t0 = time.perf_counter()
+            o.prepare_inputs()
+            o.frame()
+            runs.append((time.perf_counter() - t0) * 1e3)
+        cpu_baseline = {"value": statistics.median(runs), "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "the whole frame at full size, median of 3 runs (oracle/: scalar C++ transcription "
+                                  "of the reference GLSL, std::thread over tiles / cache entries)",
+                        "gather_pairs_per_s": o.count * wl.num_vpls / max(o.timings.get("LightCaches", 0.0), 1e-9)}
+
+    line = {
+        "metric": METRIC, "value": ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(wl), "caches": n_caches, "vpls": wl.num_vpls,
+                   "pairs_per_frame": n_caches * wl.num_vpls,
+                   "l2": "flushed between steps (512 MiB memset outside the event pairs)" if not args.no_flush else "not flushed",
+                   "parallelism": "1 GPU" if world == 1 else "gather sharded over %d GPUs by cell-ordered entry range, "
+                                  "allocation + apply replicated, fused P2P all-gather" % world,
+                   "gather_variant": args.variant},
+        "e2e": {"value": e2e_per_step, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "roofline_streaming_stages": secondary,
+        "cpu_baseline": cpu_baseline,
+        "stage_ms": {k: med(v) for k, v in stage_ms.items() if v},
+        "microbench": micro,
+        "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
+        "gpu": torch.cuda.get_device_name(local),
+    }
+    if args.stages:
+        for k, v in line["stage_ms"].items():
+            sys.stderr.write("%-18s %8.4f ms\n" % (k, v))
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

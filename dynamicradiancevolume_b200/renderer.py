@@ -340,6 +340,13 @@ class Renderer:
         self.m_passedTime = 0.0
         self.m_resolution = tuple(resolution)
         self._device = device
+        # All stage kernels run on ONE stream (the reference issues everything on the GL context's queue);
+        # tensor helpers below (HDR clear) are issued on the same stream so no cross-stream ordering is needed.
+        self._tstream = None
+        if stream is None:
+            import torch
+            self._tstream = torch.cuda.Stream(device=device)
+            stream = self._tstream.cuda_stream
         self._stream = stream
         self._variant = gather_variant
         self._ctx: Optional[Context] = None
@@ -492,8 +499,9 @@ class Renderer:
         import torch
         if hdr is None:
             if self._hdr is None:
-                self._hdr = torch.zeros(self.m_resolution[1], self.m_resolution[0], 4, dtype=torch.float16,
-                                        device="cuda:%d" % self._device)
+                with torch.cuda.stream(self._tstream if self._tstream is not None else torch.cuda.current_stream()):
+                    self._hdr = torch.zeros(self.m_resolution[1], self.m_resolution[0], 4, dtype=torch.float16,
+                                            device="cuda:%d" % self._device)
             hdr = self._hdr
         self.context().apply_caches(hdr, fmt)
         return hdr
@@ -511,6 +519,11 @@ class Renderer:
         if not detachViewFromCameraUpdate:
             self.AllocateCaches()
             self.LightCachesRSM()
-        if hdr is None and self._hdr is not None:
-            self._hdr.zero_()  # glClear(GL_COLOR_BUFFER_BIT), renderer.cpp:562
+        if hdr is None and self._hdr is not None:  # glClear(GL_COLOR_BUFFER_BIT), renderer.cpp:562
+            if self._tstream is not None:
+                import torch
+                with torch.cuda.stream(self._tstream):
+                    self._hdr.zero_()
+            else:
+                self._hdr.zero_()
         return self.ApplyCaches(hdr)

@@ -1,0 +1,138 @@
+"""Whole-frame GPU parity on the BASELINE.json configurations: allocate -> light -> apply through the
+C-ABI (``drv_draw``) against the CPU oracle, plus the host-buffer entry point and the Renderer mirror."""
+import numpy as np
+import pytest
+
+import dynamicradiancevolume_b200 as drv
+import workloads
+from dynamicradiancevolume_b200 import abi
+from oracle.frame import OracleFrame, close
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(wl, **kw):
+    import torch
+    wl.build()
+    g = workloads.DeviceFrame(wl, **kw)
+    o = OracleFrame(wl).prepare_inputs()
+    g.prepare_inputs()
+    g.frame()
+    torch.cuda.synchronize()
+    img_o = o.frame()
+    n, overflow, oob = g.ctx.active_cache_count()
+    assert (n, overflow) == (o.count, 0)
+    e = g.ctx.read_entries(n)
+    img = g.out32.cpu().numpy()
+    return g, o, e, img, img_o
+
+
+def _check(g, o, e, img, img_o):
+    n = o.count
+    assert np.array_equal(e[:, :4], o.entries[:n, :4])
+    ok, ratio = close(e[:, 4:], o.entries[:n, 4:])
+    assert ok, "SH: worst |err|/tol = %.3f" % ratio
+    assert np.array_equal(img[..., 3], img_o[..., 3])
+    ok, ratio = close(img[..., :3], img_o[..., :3])
+    assert ok, "radiance: worst |err|/tol = %.3f" % ratio
+    assert img_o[..., :3].max() > 1e-3
+
+
+def test_config0_cornell_sh1_unshadowed(cuda_device):
+    """BASELINE configs[0]: Cornell 512x512, 64x64 RSM (4k VPLs), 1 x 32^3, SH1, no indirect shadow."""
+    g, o, e, img, img_o = _run(workloads.config(0))
+    _check(g, o, e, img, img_o)
+    g.close()
+
+
+def test_config0_from_rsm_mip(cuda_device):
+    """Same, but the RSM is rendered at 1024^2 and read at LOD 4 (the reference's defaults, scene/light.hpp:12):
+    VPL normals now come from the GPU's own mip chain (1-LSB differences in the int16 normal code are allowed)."""
+    g, o, e, img, img_o = _run(workloads.cornell(rsm_res=1024, read_lod=4))
+    _check(g, o, e, img, img_o)
+    g.close()
+
+
+def test_config1_atrium_1080p(cuda_device):
+    """BASELINE configs[1]: 1920x1080, 128^2 RSM read (16k VPLs), 2 x 64^3 with transitions, SH1, unshadowed."""
+    g, o, e, img, img_o = _run(workloads.config(1))
+    _check(g, o, e, img, img_o)
+    g.close()
+
+
+def test_config2_atrium_shadow_sh2(cuda_device):
+    """BASELINE configs[2]: C2 + 128^3 voxels + mip chain, cone-traced visibility, SH2."""
+    g, o, e, img, img_o = _run(workloads.config(2))
+    assert np.array_equal(g.ctx.read_voxel_chain(), o.chain)
+    _check(g, o, e, img, img_o)
+    g.close()
+
+
+def test_config3_reduced_4_lights_4_cascades(cuda_device):
+    """BASELINE configs[3] at reduced resolution (960x540, 4 x 64^3, 4 lights x 64^2 read): SH2 + shadows."""
+    wl = workloads.config(3, width=960, height=540, cav_resolution=64, rsm_res=256, read_lod=2, max_caches=1 << 17,
+                          voxel_resolution=64)
+    g, o, e, img, img_o = _run(wl)
+    _check(g, o, e, img, img_o)
+    g.close()
+
+
+def test_draw_to_host_matches_device_path(cuda_device):
+    """drv_upload_* + drv_draw_to_host (the end-to-end entry point bench.py times) against the device path."""
+    import torch
+    wl = workloads.config(0).build()
+    g = workloads.DeviceFrame(wl)
+    g.prepare_inputs()
+    g.frame()
+    torch.cuda.synchronize()
+    ref = g.out32.cpu().numpy()
+    ctx = drv.Context(**wl.context_kwargs())
+    ctx.set_constant(wl.constant); ctx.set_per_frame(wl.per_frame); ctx.set_volume_info(wl.volume)
+    ctx.set_light_count(1); ctx.set_spot_light(0, wl.spot_lights[0])
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    d, n, c = pin(wl.depth), pin(wl.normal), pin(wl.diffuse)
+    f, rn, rd = (pin(a) for a in wl.rsms[0])
+    ctx.upload_gbuffer(d, n, c)
+    ctx.upload_rsm(0, f, rn, rd)
+    ctx.prepare_rsm(0)
+    hdr = torch.zeros(wl.height, wl.width, 4, dtype=torch.float16).pin_memory()
+    ctx.draw_to_host(hdr)
+    out = hdr.float().numpy()
+    expect = ref[..., :3].astype(np.float16).astype(np.float32)
+    assert np.array_equal(out[..., :3], expect)
+    assert ctx.kernel_launches() > 0
+    ctx.close()
+    g.close()
+
+
+def test_renderer_mirror_draw(cuda_device):
+    """The reference-shaped host interface (Renderer::Draw, renderer.cpp:501-594) drives the same frame."""
+    import torch
+    wl = workloads.config(0, indirect_shadow=True, sh_order=2).build()
+    scene = drv.Scene(lights=wl.lights, bbox_min=wl.bbox[0], bbox_max=wl.bbox[1])
+    tris = torch.from_numpy(wl.triangles.reshape(-1).copy()).cuda()
+    scene.entities = [(tris, None)]
+    r = drv.Renderer(scene, (wl.width, wl.height))
+    r.SetCAVCascades(wl.cav_cascades, wl.cav_resolution)
+    r.SetCAVCascadeWorldSize(0, wl.cascade_sizes[0])
+    r.SetCAVCascadeTransitionSize(wl.transition)
+    r.SetIndirectDiffuseMode(drv.IndirectDiffuseMode.SH2)
+    r.SetIndirectShadow(True)
+    r.SetVoxelVolumeResultion(wl.voxel_resolution)
+    r.SetVoxelVolumeAdaptionRate(1.0)
+    r.SetMaxCacheCount(wl.max_caches)
+    dev = [torch.from_numpy(a).cuda() for a in (wl.depth, wl.normal, wl.diffuse)]
+    rsm = [torch.from_numpy(a).cuda() for a in wl.rsms[0]]
+    torch.cuda.synchronize()
+    r.BindGBuffer(*dev)
+    r.BindShadowMap(0, *rsm)
+    r.SetReadLightCacheCount(True)
+    hdr = r.Draw(wl.camera, False, 1.0)  # dt * rate * 255 = 255 -> adaption 1: converged volume
+    torch.cuda.synchronize()
+    o = OracleFrame(wl).prepare_inputs()
+    img_o = o.frame()
+    out = hdr.float().cpu().numpy()
+    ok, ratio = close(out[..., :3], img_o[..., :3], rtol=2e-3, atol=1e-4)  # RGBA16F target
+    assert ok, ratio
+    r.Draw(wl.camera, False, 0.0)
+    assert r.GetLightCacheActiveCount() == o.count  # one frame late, renderer.cpp:960-966

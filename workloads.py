@@ -142,3 +142,56 @@ def sweep(n_cache: int, n_vpl: int, seed: int = 0xD27A0001):
 
 def rsm_read_level(light: abi.SpotLight) -> int:
     return int(round(math.log2(light.RSMRenderResolution / light.RSMReadResolution)))
+
+
+class DeviceFrame:
+    """A Workload resident on one GPU, driven through the C-ABI (``drv.Context``).
+
+    PyTorch only moves the host arrays into device memory; every stage call goes
+    to libdrv_gi. ``stream`` (a ``torch.cuda.Stream``) becomes the context's
+    stream so CUDA events recorded on it bracket the kernels.
+    """
+
+    def __init__(self, wl: Workload, device: int = 0, stream=None, gather_variant: int = 0, **overrides):
+        import torch
+        self.torch = torch
+        self.wl = wl
+        self.device = device
+        self.stream = stream
+        kw = wl.context_kwargs()
+        kw.update(overrides)
+        kw.update(device=device, gather_variant=gather_variant,
+                  stream=None if stream is None else stream.cuda_stream)
+        self.ctx = drv.Context(**kw)
+        dev = "cuda:%d" % device
+        self.depth = torch.from_numpy(wl.depth).to(dev)
+        self.normal = torch.from_numpy(wl.normal).to(dev)
+        self.diffuse = torch.from_numpy(wl.diffuse).to(dev)
+        self.rsms = [tuple(torch.from_numpy(a).to(dev) for a in r) for r in wl.rsms]
+        self.tris = torch.from_numpy(np.ascontiguousarray(wl.triangles, np.float32).reshape(-1)).to(dev)
+        self.out32 = torch.zeros(wl.height, wl.width, 4, dtype=torch.float32, device=dev)
+        torch.cuda.synchronize(device)
+        c = self.ctx
+        c.set_constant(wl.constant)
+        c.set_per_frame(wl.per_frame)
+        c.set_volume_info(wl.volume)
+        c.set_light_count(len(wl.spot_lights))
+        for i, s in enumerate(wl.spot_lights):
+            c.set_spot_light(i, s)
+        c.bind_gbuffer(self.depth, self.normal, self.diffuse)
+        for i, r in enumerate(self.rsms):
+            c.bind_rsm(i, *r)
+
+    def prepare_inputs(self):
+        """RSM mip chains (ShadowMap::PrepareRSM) and, with indirect shadows, the voxel volume + mips."""
+        for i in range(len(self.rsms)):
+            self.ctx.prepare_rsm(i)
+        if self.wl.indirect_shadow:
+            self.ctx.voxelize(self.tris, None, 1.0)
+
+    def frame(self, out=None, fmt=abi.DRV_HDR_RGBA32F_WRITE):
+        """allocate -> light -> apply (the DYN_RADIANCE_VOLUME case of Renderer::Draw)."""
+        self.ctx.draw(self.out32 if out is None else out, fmt)
+
+    def close(self):
+        self.ctx.close()
