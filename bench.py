@@ -70,57 +70,92 @@ def workload_name(wl):
 
 # ------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons DURING the timed region, sampled in-process through NVML every few
+    milliseconds (the timed region of a sub-millisecond frame is too short for `nvidia-smi -lms`, whose first
+    sample arrives after ~100 ms); falls back to one `nvidia-smi` query when NVML is unavailable."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+               "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
+        self.samples = []
+        self.stop_flag = threading.Event()
         self.thread = None
+        self.nvml = None
+        self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = gpu_index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[gpu_index])
+                except (ValueError, IndexError):
+                    idx = gpu_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            reasons = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        try:
+            power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+        except Exception:
+            power = float("nan")
+        self.samples.append((sm, reasons, power))
+
+    def _pump(self):
+        while not self.stop_flag.is_set():
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+        if self.nvml is None:
             return
         self.thread = threading.Thread(target=self._pump, daemon=True)
         self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            c = [x.strip() for x in r.split(",")]
-            if len(c) < 9:
-                continue
+        if self.nvml is None:
             try:
-                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
-            except ValueError:
-                continue
-            for nme, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "no samples"}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "power_w_max": max(power), "samples": len(sm)}
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+                sm, mx = [float(x) for x in out.strip().split(",")]
+                return {"sm_mhz": sm, "sm_max_mhz": mx, "reasons": [], "note": "single nvidia-smi query after the run"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML and nvidia-smi unavailable"}
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            try:
+                self._sample()
+            except Exception:
+                pass
+        n = self.nvml
+        try:
+            mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": [], "note": "no samples"}
+        bits = 0
+        for _, r, _ in self.samples:
+            bits |= int(r)
+        reasons = sorted(k for k, v in self.REASONS.items() if bits & v)
+        return {"sm_mhz": statistics.median([s[0] for s in self.samples]), "sm_max_mhz": mx, "reasons": reasons,
+                "power_w_max": max(s[2] for s in self.samples), "samples": len(self.samples),
+                "how": "NVML, 2 ms period, over the timed region"}
 
 
 # ------------------------------------------------------------------------------------------- reference arm

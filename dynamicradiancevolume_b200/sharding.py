@@ -1,0 +1,49 @@
+"""Multi-GPU host logic for the sharded gather (not in the reference, which is single-GPU).
+
+Cache entries are independent units: after the replicated, deterministic allocation every rank holds the same
+cell-ordered entry list; rank r lights the contiguous range ``shard_range(count, r, world)`` (64-entry aligned, so
+a shard is a run of (cascade, brick) keys) and the lit SH payload is exchanged so that every rank can apply.
+
+Two exchange paths:
+  * fused (default on NVLink boxes): ``connect_peers`` maps every rank's entries buffer into every other rank
+    (CUDA IPC); ``drv_light_caches`` then stores each finished entry to all peers from inside the gather
+    epilogue. ``barrier`` (a one-word all-reduce) orders allocation / lighting / apply across ranks.
+  * collective: ``exchange_entries`` broadcasts each rank's range with torch.distributed (NCCL on GPUs; gloo on
+    CPU for the tests).
+"""
+from typing import List, Tuple
+
+from . import _lib  # noqa: F401
+from .renderer import shard_range
+
+
+def shard_ranges(count: int, world: int) -> List[Tuple[int, int]]:
+    return [shard_range(count, r, world) for r in range(world)]
+
+
+def exchange_entries(entries, count: int, world: int, group=None):
+    """All-gather of the lit ranges: after the call rows [0, count) of ``entries`` ([max, stride/4] float32,
+    device tensor for NCCL / CPU tensor for gloo) are complete on every rank. Each rank must have filled its own
+    range. Ranges are uneven (64-entry granularity), hence one broadcast per non-empty range."""
+    import torch.distributed as dist
+    for r, (b, e) in enumerate(shard_ranges(count, world)):
+        if e > b:
+            dist.broadcast(entries[b:e], src=r, group=group)
+    return entries
+
+
+def connect_peers(ctx, rank: int, world: int, group=None):
+    """Fused path set-up: shard the context and map all peers' entries buffers (CUDA IPC over NVLink)."""
+    import torch.distributed as dist
+    ctx.set_shard(rank, world)
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.export_entries_ipc(), group=group)
+    for r, h in enumerate(handles):
+        if r != rank:
+            ctx.import_peer_entries(r, h)
+
+
+def barrier(word, group=None):
+    """Stream-ordered cross-GPU barrier: all-reduce of one int32 on the current stream."""
+    import torch.distributed as dist
+    dist.all_reduce(word, group=group)

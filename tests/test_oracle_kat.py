@@ -1,0 +1,373 @@
+"""Known-answer tests that pin the CPU oracle (oracle/) — CPU only.
+
+The reference ships no golden vectors for this path and cannot run here ("parity unpinned"), so the
+oracle is pinned by (a) hand-derived closed-form cases, (b) independent numpy restatements of the cited shader
+lines in float64, and (c) the committed regression fixtures in tests/golden/ (tests/test_golden.py).
+"""
+import math
+
+import numpy as np
+import pytest
+
+import dynamicradiancevolume_b200 as drv
+import workloads
+from dynamicradiancevolume_b200 import abi
+from oracle import binding as orc
+from oracle.frame import OracleFrame
+
+
+# ---------------------------------------------------------------------------------- encodings
+def test_half_conversions_match_ieee_binary16():
+    codes = np.arange(65536, dtype=np.uint16)
+    ref = codes.view(np.float16).astype(np.float32)
+    got = np.array([orc.half_to_float(int(c)) for c in codes[::7]], np.float32)
+    want = ref[::7]
+    assert np.array_equal(got[~np.isnan(want)], want[~np.isnan(want)])
+    rng = np.random.default_rng(1)
+    vals = np.concatenate([rng.standard_normal(2000).astype(np.float32) * s for s in (1e-7, 1e-4, 1.0, 300.0, 7e4)])
+    vals = np.concatenate([vals, np.array([0.0, -0.0, 65504.0, 65519.9, 65520.0, 5.96e-8, 2.98e-8, 2.9802325e-8,
+                                           1.0009765625, 1.00048828125, 1.00146484375], np.float32)])
+    with np.errstate(over="ignore"):
+        want16 = vals.astype(np.float16).view(np.uint16)
+    got16 = np.array([orc.float_to_half(float(v)) for v in vals], np.uint16)
+    assert np.array_equal(got16, want16)  # round-to-nearest-even, overflow to inf, subnormals
+
+
+def test_srgb_and_morton_and_normals():
+    for v in (0, 1, 10, 11, 128, 255):
+        c = v / 255.0
+        want = c / 12.92 if c <= 0.04045 else ((c + 0.055) / 1.055) ** 2.4
+        assert abs(orc.srgb8_to_linear(v) - want) < 1e-7
+    for k in (0, 1, 2, 3, 0b1101, 0xFFFF, 0xAAAA5555, 12345678):
+        x = sum(((k >> (2 * i)) & 1) << i for i in range(16))
+        y = sum(((k >> (2 * i + 1)) & 1) << i for i in range(16))
+        assert orc.morton_decode(k) == (x, y)  # cacheLightingRSM.comp:46-62
+    # PackNormal16I / UnpackNormal16I (utils.glsl:44-89): round trip within the 16-bit quantisation
+    rng = np.random.default_rng(2)
+    for _ in range(200):
+        n = rng.standard_normal(3)
+        n /= np.linalg.norm(n)
+        px, py = orc.pack_normal16i(n)
+        back = orc.unpack_normal16i(px, py)
+        assert np.abs(back - n).max() < 3e-4
+    assert orc.pack_normal16i((0.0, 0.0, 1.0)) == (0, 32767)       # n.z = 1 would be 32768: clamped
+    assert orc.pack_normal16i((0.0, 1.0, 0.0)) == (16384, 0)       # x == 0 special case: sign(y) * pi/2
+    assert orc.pack_normal16i((0.0, -1.0, 0.0)) == (-16384, 0)
+    assert orc.pack_normal16i((-1.0, 0.0, 0.0))[0] in (32767, -32768)
+
+
+# ---------------------------------------------------------------------------------- stage 1
+def _one_pixel_frame(x, y, depth_value=0.5, res=32, transitions=False):
+    wl = workloads.cornell(width=64, height=64, rsm_res=16, cav_resolution=res,
+                           transition=2.0 if transitions else 0.0).build(render=False)
+    depth = np.zeros((64, 64), np.float32)
+    depth[y, x] = depth_value
+    return wl, depth
+
+
+def _world_pos(wl, x, y, d):
+    """cacheGather.comp:113-119 in float32 numpy, the policy's operation order."""
+    f = np.float32
+    ndc = np.array([f(f(f(x + 0.5) / f(wl.width)) * f(2)) - f(1), f(f(f(y + 0.5) / f(wl.height)) * f(2)) - f(1), f(d), f(1)], f)
+    m = np.array(list(wl.per_frame.InverseViewProjection), f).reshape(4, 4)
+    w4 = np.zeros(4, f)
+    for j in range(4):
+        w4[j] = f(f(f(m[j, 0] * ndc[0]) + f(m[j, 1] * ndc[1])) + f(m[j, 2] * ndc[2])) + f(m[j, 3] * ndc[3])
+    return (w4[:3] / w4[3]).astype(f)
+
+
+def test_one_pixel_allocates_its_eight_corner_cells():
+    # local id (3,5) of tile (1,2): all three compared neighbours hold -1 => the pixel fires
+    wl, depth = _one_pixel_frame(16 + 3, 32 + 5)
+    a = orc.allocate_caches(wl.constant, wl.per_frame, wl.volume, False, depth, 1, 64)
+    assert a["count"] == 8 and a["overflow"] == 0 and a["oob"] == 0
+    c0 = wl.volume.AddressVolumeCascades[0]
+    wp = _world_pos(wl, 19, 37, 0.5)
+    cell = np.clip(((wp - np.array(list(c0.Min), np.float32)) / np.float32(c0.WorldVoxelSize)).astype(np.int32), 0, 31)
+    R = 32
+    want = sorted(int((cell[0] + dx) + (cell[1] + dy) * R + (cell[2] + dz) * R * R)
+                  for dx in (0, 1) for dy in (0, 1) for dz in (0, 1))
+    ids = orc.allocated_cell_ids(wl.constant, wl.per_frame, wl.volume, False, depth)
+    assert list(ids) == want
+    # entries in ascending cell order; Position = cell * voxel + Min (cacheGather.comp:65); atlas = index + 1
+    for i, cid in enumerate(want):
+        x, yy, z = cid % R, (cid // R) % R, cid // (R * R)
+        pos = np.array([x, yy, z], np.float32) * np.float32(c0.WorldVoxelSize) + np.array(list(c0.Min), np.float32)
+        assert np.array_equal(a["entries"][i, :3], pos)
+        assert a["atlas"][z, yy, x] == i + 1
+        assert not a["entries"][i, 3:].any()
+    assert np.count_nonzero(a["atlas"]) == 8
+    assert (a["counter"].NumCacheLightingThreadGroupsX, a["counter"].NumCacheLightingThreadGroupsY,
+            a["counter"].NumCacheLightingThreadGroupsZ, a["counter"].TotalLightCacheCount) == (1, 1, 1, 8)
+
+
+def test_tile_edge_quirk_of_the_trigger_predicate():
+    """SURVEY B.1 (cacheGather.comp:142-150): a lone pixel in column 0 / row 0 of a 16x16 tile compares against
+    its own slot and never allocates — except local (0,0), which always does."""
+    for (x, y, want) in [(16, 32 + 5, 0), (16 + 3, 32, 0), (16, 32, 8), (16 + 1, 32 + 1, 8), (31, 47, 8)]:
+        wl, depth = _one_pixel_frame(x, y)
+        n = len(orc.allocated_cell_ids(wl.constant, wl.per_frame, wl.volume, False, depth))
+        assert n == want, (x, y, n)
+
+
+def test_depth_thresholds_and_dedupe():
+    wl, depth = _one_pixel_frame(19, 37, depth_value=0.0001)  # not > 1e-4: no cache (cacheGather.comp:109)
+    assert len(orc.allocated_cell_ids(wl.constant, wl.per_frame, wl.volume, False, depth)) == 0
+    # a 2x2 block of pixels in the same cell still yields 8 caches (idempotent marking replaces the CAS lock)
+    wl, depth = _one_pixel_frame(19, 37)
+    depth[37:39, 19:21] = 0.5
+    ids = orc.allocated_cell_ids(wl.constant, wl.per_frame, wl.volume, False, depth)
+    assert len(ids) in (8, 12, 18, 27) and len(ids) == len(set(ids.tolist()))
+
+
+# ---------------------------------------------------------------------------------- stage 4
+def _constant():
+    return drv.pack_constant(16, 16, 16, 8, 1, 64)
+
+
+def _light(n_vpl):
+    s = abi.SpotLight()
+    s.RSMReadResolution = int(round(math.sqrt(n_vpl)))
+    s.IndirectShadowComputationSampleInterval = 1
+    return s
+
+
+def test_one_cache_one_vpl_closed_form_sh():
+    cb = _constant()
+    vpl = np.zeros(1, abi.VPL_DTYPE)
+    vpl["Position"] = (0.0, 0.0, 2.0)
+    vpl["Normal"] = (0.0, 0.0, -1.0)
+    vpl["Flux"] = (1.0, 2.0, 3.0)
+    vpl["DiscArea"] = 0.5
+    for order in (1, 2):
+        e = np.zeros((1, abi.entry_stride(order) // 4), np.float32)
+        orc.light_caches(cb, abi.VolumeInfo(), [_light(1)], [vpl], None, None, e, 0, 1, order, False)
+        rad = np.array([1.0, 2.0, 3.0]) / (4.0 + 0.5)  # toVal = (0,0,1), d^2 = 4, cos = 1
+        np.testing.assert_allclose([e[0, 7], e[0, 11], e[0, 15]], cb.ShEvaFactor0 * rad, rtol=1e-6)  # SH00
+        np.testing.assert_allclose(e[0, 8:11], cb.ShEvaFactor1 * rad, rtol=1e-6)                     # SH10 += f1 z rad
+        assert not e[0, 4:7].any() and not e[0, 12:15].any()                                         # y = x = 0
+        if order == 2:
+            np.testing.assert_allclose([e[0, 19], e[0, 23], e[0, 27]], cb.ShEvaFactor20 * 2.0 * rad, rtol=1e-6)  # 3z^2-1
+            assert not e[0, 16:19].any() and not e[0, 20:23].any() and not e[0, 24:27].any() and not e[0, 28:31].any()
+    # a VPL facing away contributes nothing (saturate, :256)
+    vpl["Normal"] = (0.0, 0.0, 1.0)
+    e = np.zeros((1, 16), np.float32)
+    orc.light_caches(cb, abi.VolumeInfo(), [_light(1)], [vpl], None, None, e, 0, 1, 1, False)
+    assert not e[0, 4:].any()
+
+
+def _numpy_gather(cb, pos, vpls, order):
+    """cacheLightingRSM.comp:249-277 restated independently in float64 numpy."""
+    P = pos[:, None, :3].astype(np.float64)
+    t = vpls["Position"][None].astype(np.float64) - P
+    d2 = (t * t).sum(-1)
+    t = t / np.sqrt(d2)[..., None]
+    cosv = np.clip(-(vpls["Normal"][None].astype(np.float64) * t).sum(-1), 0.0, 1.0)
+    s = cosv / (d2 + vpls["DiscArea"][None].astype(np.float64))
+    rad = vpls["Flux"][None].astype(np.float64) * s[..., None]
+    x, y, z = t[..., 0:1], t[..., 1:2], t[..., 2:3]
+    out = np.zeros((len(pos), 32 if order == 2 else 16))
+    out[:, 4:7] = -(cb.ShEvaFactor1 * y * rad).sum(1)
+    out[:, 8:11] = (cb.ShEvaFactor1 * z * rad).sum(1)
+    out[:, 12:15] = -(cb.ShEvaFactor1 * x * rad).sum(1)
+    out[:, [7, 11, 15]] = (cb.ShEvaFactor0 * rad).sum(1)
+    if order == 2:
+        f2 = cb.ShEvaFactor2n2_p1_n1
+        out[:, 16:19] = -(f2 * x * y * rad).sum(1)
+        out[:, 20:23] = (f2 * y * z * rad).sum(1)
+        out[:, 24:27] = (f2 * x * z * rad).sum(1)
+        out[:, 28:31] = (cb.ShEvaFactor2p2 * (x * x - y * y) * rad).sum(1)
+        out[:, [19, 23, 27]] = (cb.ShEvaFactor20 * (3 * z * z - 1) * rad).sum(1)
+    return out
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_gather_against_independent_float64_numpy(order):
+    pos, vpls = workloads.sweep(96, 1024)
+    cb = _constant()
+    want = _numpy_gather(cb, pos, vpls, order)
+    for fp64, rtol, atol in ((True, 2e-5, 1e-9), (False, 3e-4, 2e-7)):
+        e = np.zeros((96, abi.entry_stride(order) // 4), np.float32)
+        e[:, :3] = pos[:, :3]
+        orc.light_caches(cb, abi.VolumeInfo(), [_light(1024)], [vpls], None, None, e, 0, 96, order, False, fp64)
+        np.testing.assert_allclose(e[:, 4:], want[:, 4:], rtol=rtol, atol=atol)
+    # the SH1 result equals the first four coefficient groups of the SH2 result bit for bit
+    e1 = np.zeros((96, 16), np.float32); e1[:, :3] = pos[:, :3]
+    e2 = np.zeros((96, 32), np.float32); e2[:, :3] = pos[:, :3]
+    orc.light_caches(cb, abi.VolumeInfo(), [_light(1024)], [vpls], None, None, e1, 0, 96, 1, False)
+    orc.light_caches(cb, abi.VolumeInfo(), [_light(1024)], [vpls], None, None, e2, 0, 96, 2, False)
+    assert np.array_equal(e1[:, 4:16], e2[:, 4:16])
+
+
+def test_gather_entry_range_and_accumulation():
+    """`id < TotalLightCacheCount` guard and `entry.SH += acc` (cacheLightingRSM.comp:341-374)."""
+    pos, vpls = workloads.sweep(40, 256)
+    cb = _constant()
+    e = np.zeros((40, 16), np.float32); e[:, :3] = pos[:, :3]
+    orc.light_caches(cb, abi.VolumeInfo(), [_light(256)], [vpls], None, None, e, 10, 20, 1, False)
+    assert not e[:10, 4:].any() and not e[30:, 4:].any() and e[10:30, 7].all()
+    once = e.copy()
+    orc.light_caches(cb, abi.VolumeInfo(), [_light(256)], [vpls], None, None, e, 10, 20, 1, False)
+    np.testing.assert_allclose(e[10:30, 4:], 2 * once[10:30, 4:], rtol=1e-6)
+    # ragged thread count > entries
+    e3 = np.zeros((3, 16), np.float32); e3[:, :3] = pos[:3, :3]
+    orc.light_caches(cb, abi.VolumeInfo(), [_light(256)], [vpls], None, None, e3, 0, 3, 1, False, False, 16)
+    assert np.array_equal(e3[:, 4:], once[:0, 4:]) or e3[:, 7].all()
+
+
+# ---------------------------------------------------------------------------------- voxels + cones
+def _volume(res=16):
+    vi = abi.VolumeInfo()
+    vi.VolumeWorldMin[:] = (0.0, 0.0, 0.0)
+    vi.VolumeWorldMax[:] = (float(res),) * 3
+    vi.VoxelSizeInWorld = 1.0
+    return vi
+
+
+def test_voxel_sampler_known_answers():
+    res = 8
+    lvl0 = np.zeros((res, res, res), np.uint8)
+    lvl0[2, 3, 4] = 255  # z, y, x
+    chain = orc.voxel_chain(lvl0.reshape(-1), res)
+    assert len(chain) == 512 + 64 + 8 + 1
+    centre = ((4 + 0.5) / res, (3 + 0.5) / res, (2 + 0.5) / res)
+    assert orc.sample_voxel(chain, res, centre, 0.0) == 1.0                  # texel centre: exact texel
+    assert orc.sample_voxel(chain, res, centre, -3.0) == 1.0                 # lod < 0 clamps to 0
+    half = ((4 + 1.0) / res, (3 + 0.5) / res, (2 + 0.5) / res)
+    assert abs(orc.sample_voxel(chain, res, half, 0.0) - 0.5) < 1e-6         # halfway to an empty neighbour
+    # mips: mean of 8 children, rounded to UNORM8 (voxelmipmap.comp:11-12): 255/8 = 31.875 -> 32
+    l1 = chain[512:576].reshape(4, 4, 4)
+    assert l1[1, 1, 2] == 32 and np.count_nonzero(l1) == 1
+    assert chain[576:584].reshape(2, 2, 2)[0, 0, 1] == 4 and chain[584] == 1  # 32/8 = 4, 4/8 = 0.5 -> 1 (ties up)
+    c1 = ((2 + 0.5) / 4, (1 + 0.5) / 4, (1 + 0.5) / 4)
+    a0, a1 = orc.sample_voxel(chain, res, c1, 0.0), orc.sample_voxel(chain, res, c1, 1.0)
+    assert abs(a1 - 32 / 255.0) < 1e-7
+    assert abs(orc.sample_voxel(chain, res, c1, 0.25) - (0.75 * a0 + 0.25 * a1)) < 1e-6  # mip-linear
+    assert abs(orc.sample_voxel(chain, res, c1, 99.0) - 1 / 255.0) < 1e-7                # clamps to the 1^3 level
+    assert orc.sample_voxel(chain, res, (-5.0, 0.5, 0.5), 0.0) == 0.0                    # clamp to edge
+
+
+def test_cone_trace_empty_full_and_wall():
+    res = 16
+    vi = _volume(res)
+    blk = np.zeros(1, abi.SHADOW_BLOCK_DTYPE)
+    blk["AverageValPos"] = (14.5, 8.5, 8.5)
+    blk["DistToSphereRad"] = 0.05
+    pos = (1.5, 8.5, 8.5)
+    empty = orc.voxel_chain(np.zeros(res ** 3, np.uint8), res)
+    assert orc.cone_trace(vi, empty, res, pos, blk) == 1.0           # empty volume => unshadowed
+    full = np.full(len(empty), 255, np.uint8)
+    assert orc.cone_trace(vi, full, res, pos, blk) == 0.0            # full volume => fully shadowed
+    wall = np.zeros((res, res, res), np.uint8)
+    wall[:, :, 8] = 255                                              # a solid x = 8 slab between cache and light
+    assert orc.cone_trace(vi, orc.voxel_chain(wall.reshape(-1), res), res, pos, blk) < 0.05
+    wall[:] = 0
+    wall[:, :, 15] = 255                                             # geometry behind the light: not reached
+    assert orc.cone_trace(vi, orc.voxel_chain(wall.reshape(-1), res), res, pos, blk) > 0.9
+
+
+def test_voxel_blend_integer_form_equals_the_float_shader():
+    """voxelblend.comp:16 evaluated in float then stored to UNORM8 == the oracle's integer form, for every
+    (old, target) pair and a spread of adaption steps."""
+    old = np.repeat(np.arange(256, dtype=np.uint8), 256)
+    tgt = np.tile(np.arange(256, dtype=np.uint8), 256)
+    pad = 4  # 64^3 = 4 x 65536
+    for k in (1, 2, 3, 7, 50, 127, 128, 254, 255):
+        vol = np.tile(old, pad).copy()
+        orc.voxel_blend(vol, np.tile(tgt, pad), 64, k / 255.0)
+        o = old.astype(np.float64) / 255.0
+        t = tgt.astype(np.float64) / 255.0
+        v = o + np.sign(t - o) * (k / 255.0)
+        want = np.floor(np.clip(v, 0.0, 1.0) * 255.0 + 0.5).astype(np.uint8)
+        assert np.array_equal(vol[:65536], want), k
+
+
+def test_voxelizer_axis_aligned_quad_fills_one_slab():
+    """A floor-sized quad at y = 3.5 voxels fills exactly the y = 3 slab (plus nothing else): hand-checkable."""
+    res = 16
+    vi = _volume(res)
+    y = 3.5
+    quad = np.array([[2, y, 2, 14, y, 2, 14, y, 14], [2, y, 2, 14, y, 14, 2, y, 14]], np.float32)
+    vol = orc.voxelize(vi, res, quad).reshape(res, res, res)  # z, y, x
+    assert vol[:, 3, :].any() and not vol[:, :3, :].any() and not vol[:, 4:, :].any()
+    xs = np.nonzero(vol[:, 3, :].any(0))[0]
+    zs = np.nonzero(vol[:, 3, :].any(1))[0]
+    # conservative: the covered range includes every voxel the quad touches and at most one ring more
+    assert xs.min() in (1, 2) and xs.max() in (13, 14) and zs.min() in (1, 2) and zs.max() in (13, 14)
+    assert vol[2:14, 3, 2:14].all()
+
+
+def test_rsm_downsample_against_numpy_half_arithmetic():
+    rng = np.random.default_rng(3)
+    r = 8
+    flux = np.zeros((r, r, 4), np.float16)
+    flux[..., :3] = rng.random((r, r, 3)) * 0.01
+    d = (rng.random((r, r)) * 10 + 1).astype(np.float16)
+    depth = np.stack([d, (d.astype(np.float32) ** 2).astype(np.float16)], -1)
+    normal = np.zeros((r, r, 2), np.int16)
+    for yy in range(r):
+        for xx in range(r):
+            n = rng.standard_normal(3); n /= np.linalg.norm(n)
+            normal[yy, xx] = orc.pack_normal16i(n)
+    f1, n1, d1 = orc.rsm_downsample(flux.view(np.uint16), normal, depth.view(np.uint16))
+    f32 = flux.astype(np.float32)
+    # flux: SUM of the four texels (energy preserving, downsamplersm.frag:17-22), textureGather order
+    s = ((f32[1::2, 0::2] + f32[1::2, 1::2]) + f32[0::2, 1::2]) + f32[0::2, 0::2]
+    assert np.array_equal(f1.view(np.float16)[..., :3], s.astype(np.float16)[..., :3])
+    dd = depth.astype(np.float32)
+    mean = (dd[0::2, 0::2] * 0.5 + dd[0::2, 1::2] * 0.5) * 0.5 + (dd[1::2, 0::2] * 0.5 + dd[1::2, 1::2] * 0.5) * 0.5
+    assert np.array_equal(d1.view(np.float16), mean.astype(np.float16))  # MEAN of depth and depth^2 (:32)
+    un = np.zeros((r, r, 3))
+    for yy in range(r):
+        for xx in range(r):
+            un[yy, xx] = orc.unpack_normal16i(*normal[yy, xx])
+    m = un[0::2, 0::2] + un[0::2, 1::2] + un[1::2, 0::2] + un[1::2, 1::2]
+    m /= np.linalg.norm(m, axis=-1, keepdims=True)
+    for yy in range(r // 2):
+        for xx in range(r // 2):
+            assert np.abs(orc.unpack_normal16i(*n1[yy, xx]) - m[yy, xx]).max() < 5e-4
+
+
+# ---------------------------------------------------------------------------------- stage 5
+def test_apply_constant_ambient_known_answer():
+    """Every cache holds only SH00 = c: irradiance = ShCosLobeFactor0 * c at every corner, the trilinear weights
+    sum to 1, so the pixel is g0 * c * albedo / pi wherever its 8 corner caches exist (cacheApply.frag:59-114)."""
+    wl = workloads.cornell(width=96, height=96, rsm_res=16).build()
+    o = OracleFrame(wl).allocate()
+    c = 0.37
+    o.entries[:o.count, [7, 11, 15]] = c
+    img = o.apply()
+    shaded = img[..., 3] > 0
+    assert shaded.sum() > 1000 and np.array_equal(shaded, wl.depth >= 1e-5)
+    lut = np.array([orc.srgb8_to_linear(v) for v in range(256)], np.float32)
+    albedo = lut[wl.diffuse[..., :3]]
+    want = wl.constant.ShCosLobeFactor0 * c * albedo / math.pi
+    ratio = img[..., :3][shaded] / want[shaded]
+    assert ratio.max() < 1.0 + 1e-5
+    assert np.mean(np.abs(ratio - 1.0) < 1e-5) > 0.97  # the rest touch a never-allocated corner
+    # negative lobes clamp at zero (lightcache.glsl:178)
+    o.entries[:o.count, [7, 11, 15]] = -c
+    assert not o.apply()[..., :3].any()
+
+
+def test_sh_reconstruction_vs_bruteforce_point_sum_sanity():
+    """irradiance reconstructed from the SH2 cache ~ direct per-point VPL sum with the cosine
+    (bruteforcersm.frag:42-82), up to SH truncation — a sanity bound, not a parity gate."""
+    pos, vpls = workloads.sweep(64, 4096)
+    cb = _constant()
+    e = np.zeros((64, 32), np.float32); e[:, :3] = pos[:, :3]
+    orc.light_caches(cb, abi.VolumeInfo(), [_light(4096)], [vpls], None, None, e, 0, 64, 2, False)
+    n = np.array([0.0, 1.0, 0.0])
+    g0, g1 = cb.ShCosLobeFactor0, cb.ShCosLobeFactor1
+    g2, g20, g22 = cb.ShCosLobeFactor2n2_p1_n1, cb.ShCosLobeFactor20, cb.ShCosLobeFactor2p2
+    rec = (g0 * e[:, 7] - g1 * n[1] * e[:, 4] + g1 * n[2] * e[:, 8] - g1 * n[0] * e[:, 12]
+           - g2 * n[0] * n[1] * e[:, 16] + g2 * n[1] * n[2] * e[:, 20] + g20 * (3 * n[2] ** 2 - 1) * e[:, 19]
+           + g2 * n[0] * n[2] * e[:, 24] + g22 * (n[0] ** 2 - n[1] ** 2) * e[:, 28])
+    P = pos[:, None, :3].astype(np.float64)
+    t = vpls["Position"][None] - P
+    d2 = (t * t).sum(-1)
+    t /= np.sqrt(d2)[..., None]
+    s = np.clip(-(vpls["Normal"][None] * t).sum(-1), 0, 1) / (d2 + vpls["DiscArea"][None])
+    direct = (vpls["Flux"][None, :, 0] * s * np.clip(t[..., 1], 0, 1)).sum(1)
+    # the uploaded band-2 lobe factor is negative (renderer.cpp:298): only a loose agreement holds
+    assert np.corrcoef(rec, direct)[0, 1] > 0.9
