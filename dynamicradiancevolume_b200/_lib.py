@@ -32,6 +32,7 @@ SYMBOLS = [
     ("drv_bind_rsm", _st, [_P, _u32, _P, _P, _P, _u32]),
     ("drv_prepare_rsm", _st, [_P, _u32]),
     ("drv_voxelize", _st, [_P, _P, _u32, C.POINTER(_f32 * 16), _f32, _u32]),
+    ("drv_set_voxel_volume", _st, [_P, _P]),
     ("drv_allocate_caches", _st, [_P]),
     ("drv_light_caches", _st, [_P]),
     ("drv_apply_caches", _st, [_P, _P, _u32]),

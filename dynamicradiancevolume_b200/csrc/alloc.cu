@@ -30,11 +30,21 @@ struct AllocParams {
   float zone;
   float ivp[16];
   drv_cav_cascade casc[DRV_MAX_CASCADES];
+  // 1 / WorldVoxelSize when the voxel size is a power of two (then x / size == x * (1 / size) bit for bit),
+  // else 0: take the IEEE division
+  float inv_voxel[DRV_MAX_CASCADES];
 };
 
 constexpr int kCellsPerThread = 8;
 constexpr int kScanThreads = 256;
 constexpr int kCellsPerBlock = kCellsPerThread * kScanThreads; // 2048
+
+// ndc tables: ((i + .5) / N) * 2 - 1, cacheGather.comp:113-116
+__global__ void ndc_table_kernel(float* __restrict__ out, int W, int H) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < W) out[i] = ex_sub(ex_mul(ex_div((float)i + 0.5f, (float)W), 2.0f), 1.0f);
+  else if (i < W + H) out[i] = ex_sub(ex_mul(ex_div((float)(i - W) + 0.5f, (float)H), 2.0f), 1.0f);
+}
 
 // lightcache.glsl:109-122
 __device__ __forceinline__ int compute_cascade(const AllocParams& p, F3 wp) {
@@ -57,28 +67,31 @@ __device__ __forceinline__ float cascade_transition(const AllocParams& p, F3 wp,
   return saturatef(ex_sub(1.0f, ex_div(minDist, ex_mul(k.WorldVoxelSize, p.zone))));
 }
 
-// cacheGather.comp:20-30
-__device__ __forceinline__ int cache_1d_coord(const AllocParams& p, F3 wp, int c) {
+// cacheGather.comp:20-30; the cell is kept as (x,y,z) packed 10:10:10 next to its linear id
+struct Cell { int id; int x, y, z; };
+__device__ __forceinline__ Cell cache_cell(const AllocParams& p, F3 wp, int c) {
   const drv_cav_cascade& k = p.casc[c];
-  int gx = clampi(ex_trunc(ex_div(ex_sub(wp.x, k.Min[0]), k.WorldVoxelSize)), 0, p.R - 1);
-  int gy = clampi(ex_trunc(ex_div(ex_sub(wp.y, k.Min[1]), k.WorldVoxelSize)), 0, p.R - 1);
-  int gz = clampi(ex_trunc(ex_div(ex_sub(wp.z, k.Min[2]), k.WorldVoxelSize)), 0, p.R - 1);
-  return gx + gy * p.R + gz * p.R * p.R + c * p.R * p.R * p.R;
+  const float inv = p.inv_voxel[c];
+  float fx = ex_sub(wp.x, k.Min[0]), fy = ex_sub(wp.y, k.Min[1]), fz = ex_sub(wp.z, k.Min[2]);
+  if (inv != 0.0f) { fx = ex_mul(fx, inv); fy = ex_mul(fy, inv); fz = ex_mul(fz, inv); }
+  else { fx = ex_div(fx, k.WorldVoxelSize); fy = ex_div(fy, k.WorldVoxelSize); fz = ex_div(fz, k.WorldVoxelSize); }
+  Cell o;
+  o.x = clampi(ex_trunc(fx), 0, p.R - 1);
+  o.y = clampi(ex_trunc(fy), 0, p.R - 1);
+  o.z = clampi(ex_trunc(fz), 0, p.R - 1);
+  o.id = o.x + o.y * p.R + o.z * p.R * p.R + c * p.R * p.R * p.R;
+  return o;
 }
 
 // cacheGather.comp:32-91 with the index assignment deferred to the scan.
-__device__ __forceinline__ void mark_corners(const AllocParams& p, int coord, int c, uint8_t* __restrict__ flags,
+__device__ __forceinline__ void mark_corners(const AllocParams& p, const Cell& cell, int c, uint8_t* __restrict__ flags,
                                              uint32_t* __restrict__ stats) {
-  const int R = p.R, R2 = R * R, R3 = R2 * R;
-  int local = coord - R3 * c;
-  int bz = local / R2;
-  int by = (local - bz * R2) / R;
-  int bx = local - bz * R2 - by * R;
-  uint8_t* base = flags + (size_t)c * R3;
+  const int R = p.R, R2 = R * R;
+  uint8_t* base = flags + (size_t)c * R2 * R;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     // offsets (0,0,0)(0,1,0)(0,0,1)(0,1,1)(1,0,0)(1,1,0)(1,0,1)(1,1,1), cacheGather.comp:34-44
-    int x = bx + (i >> 2), y = by + (i & 1), z = bz + ((i >> 1) & 1);
+    int x = cell.x + (i >> 2), y = cell.y + (i & 1), z = cell.z + ((i >> 1) & 1);
     if (x >= R || y >= R || z >= R) { // out-of-range +1 corners are skipped and counted
       atomicAdd(stats + 1, 1u);
       continue;
@@ -89,38 +102,37 @@ __device__ __forceinline__ void mark_corners(const AllocParams& p, int coord, in
 }
 
 __global__ void __launch_bounds__(256) mark_kernel(AllocParams p, const float* __restrict__ depth,
-                                                   uint8_t* __restrict__ flags, uint32_t* __restrict__ stats) {
-  __shared__ int T1[16][16]; // [local x][local y] like cacheList[x][y]
-  __shared__ int T2[16][16];
+                                                   const float* __restrict__ ndc_xy, uint8_t* __restrict__ flags,
+                                                   uint32_t* __restrict__ stats) {
+  __shared__ int T1[16][17]; // [local x][local y] like cacheList[x][y]; padded against bank conflicts
+  __shared__ int T2[16][17];
   const int lx = threadIdx.x, ly = threadIdx.y;
   const int x = blockIdx.x * 16 + lx, y = blockIdx.y * 16 + ly;
-  int own = -1, own2 = -1, casc = -1;
+  Cell own = {-1, 0, 0, 0}, own2 = {-1, 0, 0, 0};
+  int casc = -1;
   if (x < p.W && y < p.H) {
     float d = __ldg(depth + (size_t)y * p.W + x);
     if (d > 0.0001f) {
-      float px = (float)x + 0.5f, py = (float)y + 0.5f;
-      float sx = ex_sub(ex_mul(ex_div(px, (float)p.W), 2.0f), 1.0f);
-      float sy = ex_sub(ex_mul(ex_div(py, (float)p.H), 2.0f), 1.0f);
-      F3 wp = ex_unproject(p.ivp, sx, sy, d);
+      F3 wp = ex_unproject(p.ivp, __ldg(ndc_xy + x), __ldg(ndc_xy + p.W + y), d);
       casc = compute_cascade(p, wp);
-      own = cache_1d_coord(p, wp, casc);
-      if (p.transitions) {
+      own = cache_cell(p, wp, casc);
+      if (p.transitions && casc < p.C - 1) {
         float t = cascade_transition(p, wp, casc);
-        if (t > 0.0f && casc < p.C - 1) own2 = cache_1d_coord(p, wp, casc + 1);
+        if (t > 0.0f) own2 = cache_cell(p, wp, casc + 1);
       }
     }
   }
-  T1[lx][ly] = own;
-  T2[lx][ly] = own2;
+  T1[lx][ly] = own.id;
+  if (p.transitions) T2[lx][ly] = own2.id;
   __syncthreads();
   {
     int ax = max(0, lx - 1), ay = max(0, ly - 1);
-    if (((T1[lx][ay] != own && T1[ax][ly] != own && T1[ax][ay] != own) || (ax == lx && ay == ly)) && own != -1)
+    if (((T1[lx][ay] != own.id && T1[ax][ly] != own.id && T1[ax][ay] != own.id) || (ax == lx && ay == ly)) && own.id != -1)
       mark_corners(p, own, casc, flags, stats);
   }
   if (p.transitions) {
     int bx = min(15, lx + 1), by = min(15, ly + 1);
-    if (((T2[lx][by] != own2 && T2[bx][ly] != own2 && T2[bx][by] != own2) || (bx == 15 && by == 15)) && own2 != -1)
+    if (((T2[lx][by] != own2.id && T2[bx][ly] != own2.id && T2[bx][by] != own2.id) || (bx == 15 && by == 15)) && own2.id != -1)
       mark_corners(p, own2, casc + 1, flags, stats);
   }
 }
@@ -297,13 +309,19 @@ drv_status drv_impl_allocate(drv_ctx* ctx) {
   p.zone = ctx->volume.CAVTransitionZoneSize;
   memcpy(p.ivp, ctx->per_frame.InverseViewProjection, sizeof(p.ivp));
   memcpy(p.casc, ctx->volume.AddressVolumeCascades, sizeof(p.casc));
+  for (int c = 0; c < DRV_MAX_CASCADES; ++c) {
+    int e = 0;
+    const float v = p.casc[c].WorldVoxelSize;
+    // exact power of two well inside the normal range: division == multiplication by the reciprocal
+    p.inv_voxel[c] = (v > 1e-6f && v < 1e6f && frexpf(v, &e) == 0.5f) ? 1.0f / v : 0.0f;
+  }
 
   ctx->stage_begin(DRV_STAGE_ALLOCATE_CACHES);
   // ≙ m_lightCacheCounter->ClearToZero(); the atlas clear (renderer.cpp:969-970) is folded into compact
   DRV_CUDA(cudaMemsetAsync(ctx->cell_flags, 0, ctx->num_cells, ctx->stream));
   DRV_CUDA(cudaMemsetAsync(ctx->stats, 0, 2 * sizeof(uint32_t), ctx->stream));
   dim3 grid((p.W + 15) / 16, (p.H + 15) / 16); // renderer.cpp:981-985
-  mark_kernel<<<grid, dim3(16, 16), 0, ctx->stream>>>(p, ctx->gb_depth, ctx->cell_flags, ctx->stats);
+  mark_kernel<<<grid, dim3(16, 16), 0, ctx->stream>>>(p, ctx->gb_depth, ctx->ndc_xy, ctx->cell_flags, ctx->stats);
   DRV_LAUNCH_CHECK();
   count_kernel<<<ctx->num_scan_blocks, kScanThreads, 0, ctx->stream>>>(ctx->cell_flags, ctx->num_cells,
                                                                       ctx->block_counts);
@@ -334,4 +352,9 @@ drv_status drv_impl_set_synthetic_entries(drv_ctx* ctx, const float* pos, uint32
   return DRV_OK;
 }
 
-int drv_alloc_cells_per_block() { return kCellsPerBlock; }
+drv_status drv_impl_build_ndc_tables(drv_ctx* ctx) {
+  const int W = (int)ctx->cfg.backbuffer_width, H = (int)ctx->cfg.backbuffer_height;
+  ndc_table_kernel<<<(W + H + 255) / 256, 256, 0, ctx->stream>>>(ctx->ndc_xy, W, H);
+  DRV_LAUNCH_CHECK();
+  return DRV_OK;
+}

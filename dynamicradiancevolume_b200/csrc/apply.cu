@@ -26,6 +26,7 @@ struct ApplyParams {
   drv_cav_cascade casc[DRV_MAX_CASCADES];
   float g0, g1, g2, g20, g22; // ShCosLobeFactor*
   uint32_t max_caches;
+  float inv_voxel[DRV_MAX_CASCADES]; // 1 / WorldVoxelSize when that is a power of two (exact), else 0
 };
 
 __device__ __forceinline__ int compute_cascade(const ApplyParams& p, F3 wp) { // lightcache.glsl:109-122
@@ -55,13 +56,13 @@ struct NormalBasis {
   float b2xy, b2yz, b20, b2xz, b2dd;   // band 2
 };
 
+// One corner: entry `address` (already known to exist) weighted by w.
 template <int ORDER>
 __device__ __forceinline__ void accumulate_corner(const ApplyParams& p, const uint8_t* __restrict__ entries,
                                                   uint32_t address, const NormalBasis<ORDER>& nb, float w, float& r,
                                                   float& g, float& b) {
-  constexpr int STRIDE = ORDER == 2 ? 128 : 64;
-  if (address >= p.max_caches) return; // atlas 0 -> 0xFFFFFFFF: no cache, contributes zero
-  const float4* e = reinterpret_cast<const float4*>(entries + (size_t)address * STRIDE);
+  constexpr uint32_t STRIDE = ORDER == 2 ? 128 : 64;
+  const float4* e = reinterpret_cast<const float4*>(entries + address * STRIDE); // < 2^31 bytes: checked at create
   float4 q1 = __ldg(e + 1), q2 = __ldg(e + 2), q3 = __ldg(e + 3); // (SH1neg1,SH00_r) (SH10,SH00_g) (SH1pos1,SH00_b)
   float ir = q1.w * p.g0, ig = q2.w * p.g0, ib = q3.w * p.g0;
   ir = fmaf(-q1.x, nb.b1y, ir); ig = fmaf(-q1.y, nb.b1y, ig); ib = fmaf(-q1.z, nb.b1y, ib);
@@ -87,23 +88,39 @@ __device__ __forceinline__ void lighting_from_caches(const ApplyParams& p, const
                                                      const uint8_t* __restrict__ entries, F3 wp,
                                                      const NormalBasis<ORDER>& nb, int c, float& r, float& g, float& b) {
   const drv_cav_cascade& k = p.casc[c];
-  float ax = ex_div(ex_sub(wp.x, k.Min[0]), k.WorldVoxelSize);
-  float ay = ex_div(ex_sub(wp.y, k.Min[1]), k.WorldVoxelSize);
-  float az = ex_div(ex_sub(wp.z, k.Min[2]), k.WorldVoxelSize);
-  int bx = ex_trunc(ax), by = ex_trunc(ay), bz = ex_trunc(az);
-  float fx = ax - (float)bx, fy = ay - (float)by, fz = az - (float)bz;
-  float gx = 1.0f - fx, gy = 1.0f - fy, gz = 1.0f - fz;
+  const float inv = p.inv_voxel[c];
+  float ax = ex_sub(wp.x, k.Min[0]), ay = ex_sub(wp.y, k.Min[1]), az = ex_sub(wp.z, k.Min[2]);
+  if (inv != 0.0f) { ax = ex_mul(ax, inv); ay = ex_mul(ay, inv); az = ex_mul(az, inv); } // power-of-two voxel: exact
+  else { ax = ex_div(ax, k.WorldVoxelSize); ay = ex_div(ay, k.WorldVoxelSize); az = ex_div(az, k.WorldVoxelSize); }
+  const int bx = ex_trunc(ax), by = ex_trunc(ay), bz = ex_trunc(az);
+  const float fx = ax - (float)bx, fy = ay - (float)by, fz = az - (float)bz;
+  const float gx = 1.0f - fx, gy = 1.0f - fy, gz = 1.0f - fz;
   const int atlasW = p.R * p.C;
+  const int x0 = bx + p.R * c;
   r = g = b = 0.0f;
+  // first all eight address fetches (independent loads in flight together), then the entries
+  uint32_t addr[8];
+  const bool interior = bx >= 0 && bx + 1 < p.R && by >= 0 && by + 1 < p.R && bz >= 0 && bz + 1 < p.R;
+  if (interior) {
+    const uint32_t* a0 = atlas + (uint32_t)(x0 + atlasW * (by + p.R * bz));
+    const uint32_t sy = (uint32_t)atlasW, sz = (uint32_t)(atlasW * p.R);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) addr[i] = __ldg(a0 + (i & 1) + ((i >> 1) & 1) * sy + (i >> 2) * sz);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { // texelFetch outside the texture returns 0
+      const int x = x0 + (i & 1), y = by + ((i >> 1) & 1), z = bz + (i >> 2);
+      addr[i] = 0u;
+      if (x >= 0 && x < atlasW && y >= 0 && y < p.R && z >= 0 && z < p.R)
+        addr[i] = __ldg(atlas + (uint32_t)(x + atlasW * (y + p.R * z)));
+    }
+  }
+  const float wxy[4] = {gx * gy, fx * gy, gx * fy, fx * fy};
 #pragma unroll
   for (int i = 0; i < 8; ++i) { // offsets in cacheApply.frag:43-54 order: x fastest, then y, then z
-    const int ox = i & 1, oy = (i >> 1) & 1, oz = i >> 2;
-    float w = (ox ? fx : gx) * (oy ? fy : gy) * (oz ? fz : gz);
-    int x = bx + ox + p.R * c, y = by + oy, z = bz + oz;
-    uint32_t address = 0u; // texelFetch outside the texture returns 0
-    if (x >= 0 && x < atlasW && y >= 0 && y < p.R && z >= 0 && z < p.R)
-      address = __ldg(atlas + (size_t)x + (size_t)atlasW * ((size_t)y + (size_t)p.R * z));
-    accumulate_corner<ORDER>(p, entries, address - 1u, nb, w, r, g, b);
+    const float w = wxy[i & 3] * ((i >> 2) ? fz : gz);
+    const uint32_t address = addr[i] - 1u; // atlas 0 -> 0xFFFFFFFF: no cache, contributes zero
+    if (address < p.max_caches) accumulate_corner<ORDER>(p, entries, address, nb, w, r, g, b);
   }
 }
 
@@ -111,24 +128,25 @@ template <int ORDER>
 __global__ void __launch_bounds__(256) apply_kernel(ApplyParams p, const float* __restrict__ depth,
                                                     const int* __restrict__ normal, const uchar4* __restrict__ diffuse,
                                                     const uint32_t* __restrict__ atlas, const uint8_t* __restrict__ entries,
-                                                    void* __restrict__ out, int format) {
+                                                    const float* __restrict__ ndc_xy, void* __restrict__ out, int format) {
+  __shared__ float s_srgb[256]; // sRGB8 -> linear; shared memory serves divergent indices, constant memory would serialise
+  s_srgb[threadIdx.y * 32 + threadIdx.x] = c_srgb_lut[threadIdx.y * 32 + threadIdx.x];
+  __syncthreads();
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if (x >= p.W || y >= p.H) return;
-  const size_t t = (size_t)y * p.W + x;
+  const uint32_t t = (uint32_t)y * p.W + x;
   const float d = __ldg(depth + t);
   if (d < 0.00001f) { // :128 discard
     if (format == DRV_HDR_RGBA32F_WRITE) reinterpret_cast<float4*>(out)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
-  float px = (float)x + 0.5f, py = (float)y + 0.5f; // gl_FragCoord.xy, :134
-  float sx = ex_sub(ex_mul(ex_div(px, (float)p.W), 2.0f), 1.0f);
-  float sy = ex_sub(ex_mul(ex_div(py, (float)p.H), 2.0f), 1.0f);
-  F3 wp = ex_unproject(p.ivp, sx, sy, d);
+  // gl_FragCoord.xy -> NDC (:134) through the per-context tables
+  F3 wp = ex_unproject(p.ivp, __ldg(ndc_xy + x), __ldg(ndc_xy + p.W + y), d);
   const int c = compute_cascade(p, wp); // :138
   const int pn = __ldg(normal + t);
-  F3 n = unpack_normal16i((int)(short)(pn & 0xffff), (int)(short)((uint32_t)pn >> 16)); // :140
+  F3 n = unpack_normal16i_fast((int)(short)(pn & 0xffff), (int)(short)((uint32_t)pn >> 16)); // :140
   const uchar4 dc = __ldg(diffuse + t);
-  const float albr = c_srgb_lut[dc.x], albg = c_srgb_lut[dc.y], albb = c_srgb_lut[dc.z]; // :144
+  const float albr = s_srgb[dc.x], albg = s_srgb[dc.y], albb = s_srgb[dc.z]; // :144
   NormalBasis<ORDER> nb;
   nb.b1y = p.g1 * n.y; nb.b1z = p.g1 * n.z; nb.b1x = p.g1 * n.x;
   if (ORDER == 2) {
@@ -140,9 +158,9 @@ __global__ void __launch_bounds__(256) apply_kernel(ApplyParams p, const float* 
   }
   float r, g, b;
   lighting_from_caches<ORDER>(p, atlas, entries, wp, nb, c, r, g, b);
-  if (p.transitions) { // :172-184
+  if (p.transitions && c < p.C - 1) { // :172-184
     float tr = cascade_transition(p, wp, c);
-    if (tr > 0.0f && c < p.C - 1) {
+    if (tr > 0.0f) {
       float r2, g2, b2;
       lighting_from_caches<ORDER>(p, atlas, entries, wp, nb, c + 1, r2, g2, b2);
       r = fmaf(r2 - r, tr, r); g = fmaf(g2 - g, tr, g); b = fmaf(b2 - b, tr, b);
@@ -204,16 +222,21 @@ drv_status drv_impl_apply(drv_ctx* ctx, void* out, uint32_t format) {
   p.g20 = ctx->constant.ShCosLobeFactor20;
   p.g22 = ctx->constant.ShCosLobeFactor2p2;
   p.max_caches = ctx->cfg.max_cache_count;
+  for (int c = 0; c < DRV_MAX_CASCADES; ++c) {
+    int e = 0;
+    const float v = p.casc[c].WorldVoxelSize;
+    p.inv_voxel[c] = (v > 1e-6f && v < 1e6f && frexpf(v, &e) == 0.5f) ? 1.0f / v : 0.0f;
+  }
   ctx->stage_begin(DRV_STAGE_APPLY_CACHES);
   dim3 block(32, 8), grid((p.W + 31) / 32, (p.H + 7) / 8);
   if (ctx->cfg.sh_order == 2)
     apply_kernel<2><<<grid, block, 0, ctx->stream>>>(p, ctx->gb_depth, (const int*)ctx->gb_normal,
-                                                     (const uchar4*)ctx->gb_diffuse, ctx->atlas, ctx->entries, out,
-                                                     (int)format);
+                                                     (const uchar4*)ctx->gb_diffuse, ctx->atlas, ctx->entries,
+                                                     ctx->ndc_xy, out, (int)format);
   else
     apply_kernel<1><<<grid, block, 0, ctx->stream>>>(p, ctx->gb_depth, (const int*)ctx->gb_normal,
-                                                     (const uchar4*)ctx->gb_diffuse, ctx->atlas, ctx->entries, out,
-                                                     (int)format);
+                                                     (const uchar4*)ctx->gb_diffuse, ctx->atlas, ctx->entries,
+                                                     ctx->ndc_xy, out, (int)format);
   DRV_LAUNCH_CHECK();
   ctx->stage_end(DRV_STAGE_APPLY_CACHES);
   return DRV_OK;

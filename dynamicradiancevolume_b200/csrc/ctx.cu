@@ -45,7 +45,7 @@ extern "C" drv_status drv_create(const drv_config* cfg, drv_ctx** out) {
   if (!cfg || !out) { g_create_error = "drv_create: null argument"; return DRV_ERR_INVALID; }
   *out = nullptr;
   const drv_config& c = *cfg;
-  if (c.max_cache_count == 0 || c.cav_cascades < 1 || c.cav_cascades > DRV_MAX_CASCADES || c.cav_resolution < 8 ||
+  if (c.max_cache_count == 0 || c.max_cache_count > (1u << 24) || c.cav_resolution > 256 || c.cav_cascades < 1 || c.cav_cascades > DRV_MAX_CASCADES || c.cav_resolution < 8 ||
       (c.cav_resolution % 8) != 0 || (c.sh_order != 1 && c.sh_order != 2) || c.backbuffer_width == 0 ||
       c.backbuffer_height == 0 || c.max_lights > DRV_MAX_LIGHTS || !is_pow2(c.voxel_resolution) ||
       c.voxel_resolution < 16 || (c.max_lights > 0 && !is_pow2(c.max_rsm_resolution))) {
@@ -97,6 +97,16 @@ extern "C" drv_status drv_create(const drv_config* cfg, drv_ctx** out) {
   CREATE_CUDA(cudaMemsetAsync(ctx->voxel_chain, 0, ctx->voxel_chain_bytes + 16, ctx->stream));
   CREATE_CUDA(dmalloc(&ctx->voxel_target, (size_t)vr * vr * vr));
   CREATE_CUDA(cudaMemsetAsync(ctx->voxel_target, 0, (size_t)vr * vr * vr, ctx->stream));
+  if (ctx->voxel_levels > 15) { g_create_error = "drv_create: voxel_resolution too large"; drv_destroy(ctx); return DRV_ERR_INVALID; }
+  for (uint32_t l = 0, r = vr; l < ctx->voxel_levels; ++l, r >>= 1) {
+    ctx->voxel_record_offset[l] = (uint32_t)ctx->voxel_record_count;
+    ctx->voxel_record_count += (uint64_t)(r + 1) * (r + 1) * (r + 1);
+  }
+  if (ctx->voxel_record_count >= (1ull << 31)) { g_create_error = "drv_create: voxel_resolution too large"; drv_destroy(ctx); return DRV_ERR_INVALID; }
+  if (c.indirect_shadow) {
+    CREATE_CUDA(dmalloc(&ctx->voxel_records, ctx->voxel_record_count * sizeof(uint2)));
+    CREATE_CUDA(cudaMemsetAsync(ctx->voxel_records, 0, ctx->voxel_record_count * sizeof(uint2), ctx->stream));
+  }
 
   for (uint32_t l = 0; l < c.max_lights; ++l) {
     LightState& S = ctx->lights[l];
@@ -108,6 +118,8 @@ extern "C" drv_status drv_create(const drv_config* cfg, drv_ctx** out) {
     CREATE_CUDA(dmalloc(&S.vpls, texels * sizeof(drv_vpl)));
     CREATE_CUDA(dmalloc(&S.blocks, texels * sizeof(drv_shadow_block)));
   }
+  CREATE_CUDA(dmalloc(&ctx->ndc_xy, ((size_t)c.backbuffer_width + c.backbuffer_height) * sizeof(float)));
+  if (drv_impl_build_ndc_tables(ctx) != DRV_OK) { g_create_error = ctx->last_error; drv_destroy(ctx); return DRV_ERR_CUDA; }
   for (int s = 0; s < DRV_STAGE_COUNT; ++s) {
     CREATE_CUDA(cudaEventCreate(&ctx->ev_begin[s]));
     CREATE_CUDA(cudaEventCreate(&ctx->ev_end[s]));
@@ -125,9 +137,9 @@ extern "C" void drv_destroy(drv_ctx* ctx) {
     for (int r = 0; r < 8; ++r)
       if (ctx->peer_entries[r]) cudaIpcCloseMemHandle(ctx->peer_entries[r]);
   cudaFree(ctx->entries); cudaFree(ctx->counter); cudaFree(ctx->stats); cudaFree(ctx->atlas);
-  cudaFree(ctx->cell_flags); cudaFree(ctx->block_counts); cudaFree(ctx->voxel_chain); cudaFree(ctx->voxel_target);
+  cudaFree(ctx->cell_flags); cudaFree(ctx->block_counts); cudaFree(ctx->voxel_chain); cudaFree(ctx->voxel_target); cudaFree(ctx->voxel_records);
   cudaFree(ctx->partials); cudaFree(ctx->st_depth); cudaFree(ctx->st_normal); cudaFree(ctx->st_diffuse);
-  cudaFree(ctx->hdr16);
+  cudaFree(ctx->hdr16); cudaFree(ctx->ndc_xy);
   for (auto& S : ctx->lights) {
     cudaFree(S.flux_mips); cudaFree(S.normal_mips); cudaFree(S.depth_mips); cudaFree(S.vpls); cudaFree(S.blocks);
     cudaFree(S.st_flux); cudaFree(S.st_normal); cudaFree(S.st_depth);
@@ -210,6 +222,12 @@ extern "C" drv_status drv_voxelize(drv_ctx* ctx, const float* tri_pos, uint32_t 
   NEED_CTX();
   if ((num_tris && !tri_pos) || !world) return ctx->fail(DRV_ERR_INVALID, "drv_voxelize: null argument");
   return drv_impl_voxelize(ctx, tri_pos, num_tris, world, adaption, flags);
+}
+
+extern "C" drv_status drv_set_voxel_volume(drv_ctx* ctx, const uint8_t* level0) {
+  NEED_CTX();
+  if (!level0) return ctx->fail(DRV_ERR_INVALID, "drv_set_voxel_volume: null volume");
+  return drv_impl_set_voxel_volume(ctx, level0);
 }
 
 extern "C" drv_status drv_allocate_caches(drv_ctx* ctx) {

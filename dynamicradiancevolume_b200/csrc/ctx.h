@@ -74,6 +74,9 @@ struct drv_ctx {
   int16_t* st_normal = nullptr;
   uint8_t* st_diffuse = nullptr;
   void* hdr16 = nullptr; // owned RGBA16F target for drv_draw_to_host
+  // ndc_x[x] = ((x + .5) / W) * 2 - 1 and ndc_y[y] likewise (cacheGather.comp:113-116), evaluated once per
+  // context with the decision-maths operators instead of two IEEE divisions per pixel per stage
+  float* ndc_xy = nullptr; // W floats then H floats
 
   // allocation
   uint32_t entry_stride = 64;
@@ -90,6 +93,12 @@ struct drv_ctx {
   uint8_t* voxel_target = nullptr;
   uint32_t voxel_levels = 0;
   uint64_t voxel_chain_bytes = 0;
+  // gather-ready copy of the chain for the cone tracer: per level (r+1)^3 records of 8 bytes, record
+  // (x,y,z), x,y,z in [-1, r-1], = the 2x2x2 clamp-to-edge texel neighbourhood whose lower corner is (x,y,z).
+  // One 64-bit load fetches a whole trilinear footprint.
+  uint2* voxel_records = nullptr;
+  uint32_t voxel_record_offset[16] = {0};
+  uint64_t voxel_record_count = 0;
 
   // gather
   float* partials = nullptr;         // split-VPL partial sums
@@ -124,7 +133,9 @@ drv_status drv_impl_apply(drv_ctx* ctx, void* out, uint32_t format);
 drv_status drv_impl_voxelize(drv_ctx* ctx, const float* tris, uint32_t n, const float* world, float adaption,
                              uint32_t flags);
 drv_status drv_impl_set_synthetic_entries(drv_ctx* ctx, const float* pos, uint32_t n);
+drv_status drv_impl_set_voxel_volume(drv_ctx* ctx, const uint8_t* level0);
 void drv_impl_upload_srgb_lut();
+drv_status drv_impl_build_ndc_tables(drv_ctx* ctx);
 
 inline uint64_t rsm_level_offset_texels(uint32_t res, uint32_t level) {
   uint64_t off = 0;

@@ -84,6 +84,19 @@ __device__ __forceinline__ F3 unpack_normal16i(int px, int py) {
   return r;
 }
 
+// The same with MUFU sin/cos (|a| <= pi: absolute error ~1e-6) for the per-pixel apply stage.
+__device__ __forceinline__ F3 unpack_normal16i_fast(int px, int py) {
+  float a = (float)px * (DRV_GLSL_PI / 32768.0f);
+  float z = (float)py * (1.0f / 32768.0f);
+  float sinPhi = sqrtf(fmaxf(1.0f - z * z, 0.0f));
+  float s, c;
+  __sincosf(a, &s, &c);
+  float x = c * sinPhi, y = s * sinPhi;
+  float inv = rsqrtf(x * x + y * y + z * z);
+  F3 r = {x * inv, y * inv, z * inv};
+  return r;
+}
+
 // PackNormal16I, utils.glsl:62-89, int16 clamp.
 __device__ __forceinline__ void pack_normal16i(float nx, float ny, float nz, int& ox, int& oy) {
   float sgn = ny > 0.0f ? 1.0f : (ny < 0.0f ? -1.0f : 0.0f);

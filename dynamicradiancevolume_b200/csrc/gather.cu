@@ -59,8 +59,9 @@ struct GatherParams {
   uint32_t shard_rank, shard_world;
   uint32_t grid;         // CTAs of the gather launch (the finalize kernel needs it too)
   float f0, f1, f2, f20, f22;
-  // voxel volume (cone tracing)
-  const uint8_t* chain;
+  // voxel volume (cone tracing): gather-ready records, see voxel.cu
+  const uint2* rec;
+  uint32_t rec_offset[16];
   int vres, vlevels;
   float vmin[3];
   float voxel_size;
@@ -113,83 +114,139 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 // ---------------------------------------------------------------- cone trace
+// The voxel chain is read through its gather-ready copy (voxel.cu: voxel_records_kernel): one 64-bit load
+// returns the eight clamp-to-edge texels of a trilinear footprint, instead of eight byte loads with per-corner
+// address clamping. Records of level l start at rec_offset[l]; a level holds (r+1)^3 of them, indexed by the
+// footprint's lower corner + 1.
 struct VoxelVol {
-  const uint8_t* chain;
+  const uint2* rec;
+  const uint32_t* rec_offset; // shared-memory copy of GatherParams::rec_offset
   int res, levels;
   float vmin[3];
   float voxel_size;
 };
 
-__device__ __forceinline__ float trilinear_level(const uint8_t* __restrict__ lvl, int r, float px, float py, float pz) {
-  float fr = (float)r;
-  float fx = fmaf(px, fr, -0.5f), fy = fmaf(py, fr, -0.5f), fz = fmaf(pz, fr, -0.5f);
-  float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
-  float tx = fx - flx, ty = fy - fly, tz = fz - flz;
-  int x0 = __float2int_rz(flx), y0 = __float2int_rz(fly), z0 = __float2int_rz(flz);
-  int x1 = clampi(x0 + 1, 0, r - 1), y1 = clampi(y0 + 1, 0, r - 1), z1 = clampi(z0 + 1, 0, r - 1);
-  x0 = clampi(x0, 0, r - 1); y0 = clampi(y0, 0, r - 1); z0 = clampi(z0, 0, r - 1);
-  const uint8_t* r00 = lvl + (size_t)r * ((size_t)y0 + (size_t)r * z0);
-  const uint8_t* r10 = lvl + (size_t)r * ((size_t)y1 + (size_t)r * z0);
-  const uint8_t* r01 = lvl + (size_t)r * ((size_t)y0 + (size_t)r * z1);
-  const uint8_t* r11 = lvl + (size_t)r * ((size_t)y1 + (size_t)r * z1);
-  float a000 = (float)__ldg(r00 + x0), a100 = (float)__ldg(r00 + x1);
-  float a010 = (float)__ldg(r10 + x0), a110 = (float)__ldg(r10 + x1);
-  float a001 = (float)__ldg(r01 + x0), a101 = (float)__ldg(r01 + x1);
-  float a011 = (float)__ldg(r11 + x0), a111 = (float)__ldg(r11 + x1);
-  float c00 = fmaf(tx, a100 - a000, a000), c10 = fmaf(tx, a110 - a010, a010);
-  float c01 = fmaf(tx, a101 - a001, a001), c11 = fmaf(tx, a111 - a011, a011);
+constexpr float kMagic = 12582912.0f; // 1.5 * 2^23: (v + kMagic) - kMagic rounds v to the nearest integer
+
+// floor(v) without the XU pipe (FRND / F2I / I2F are quarter rate): round-to-nearest of v - 0.5 via the magic
+// constant. On exact integers ties-to-even may pick v - 1, in which case frac = 1 and the trilinear result is
+// the same (the filter is continuous across texel boundaries). i = floor as int, f = v - floor.
+__device__ __forceinline__ void floor_frac(float v, int& i, float& f) {
+  float m = (v - 0.5f) + kMagic;
+  i = __float_as_int(m) - 0x4B400000;
+  f = v - (m - kMagic);
+}
+
+// byte `sel` (0..3) of w as a float, exactly: build 2^23 + byte with one PRMT, subtract 2^23.
+template <int SEL>
+__device__ __forceinline__ float byte_as_float_biased(uint32_t w) {
+  return __int_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | SEL)); // 8388608 + byte
+}
+
+struct Footprint {
+  uint32_t index; // record index
+  float tx, ty, tz;
+};
+
+// footprint of the sample at p (volume coordinates in [0,1]^3) in level `l`
+__device__ __forceinline__ Footprint footprint(const VoxelVol& V, int l, float px, float py, float pz) {
+  const int r = V.res >> l;
+  const float fr = __int_as_float(__float_as_int((float)V.res) - (l << 23)); // res * 2^-l, exact (power of two)
+  Footprint F;
+  int x, y, z;
+  floor_frac(fmaf(px, fr, -0.5f), x, F.tx);
+  floor_frac(fmaf(py, fr, -0.5f), y, F.ty);
+  floor_frac(fmaf(pz, fr, -0.5f), z, F.tz);
+  // clamp the lower corner to [-1, r-1]: outside that range both taps of the axis are the same edge texel
+  x = min(max(x, -1), r - 1) + 1;
+  y = min(max(y, -1), r - 1) + 1;
+  z = min(max(z, -1), r - 1) + 1;
+  F.index = V.rec_offset[l] + (uint32_t)(x + (r + 1) * (y + (r + 1) * z));
+  return F;
+}
+
+__device__ __forceinline__ float trilinear(uint2 rec, float tx, float ty, float tz) {
+  const float B = 8388608.0f;
+  float a000 = byte_as_float_biased<0>(rec.x), a100 = byte_as_float_biased<1>(rec.x);
+  float a010 = byte_as_float_biased<2>(rec.x), a110 = byte_as_float_biased<3>(rec.x);
+  float a001 = byte_as_float_biased<0>(rec.y), a101 = byte_as_float_biased<1>(rec.y);
+  float a011 = byte_as_float_biased<2>(rec.y), a111 = byte_as_float_biased<3>(rec.y);
+  // (a1 - a0) is exact on the biased values; only the base needs un-biasing
+  float c00 = fmaf(tx, a100 - a000, a000 - B), c10 = fmaf(tx, a110 - a010, a010 - B);
+  float c01 = fmaf(tx, a101 - a001, a001 - B), c11 = fmaf(tx, a111 - a011, a011 - B);
   float c0 = fmaf(ty, c10 - c00, c00), c1 = fmaf(ty, c11 - c01, c01);
   return fmaf(tz, c1 - c0, c0) * (1.0f / 255.0f);
 }
 
-// D.0 trilinearClampMip3D: clamp-to-edge trilinear in two adjacent mips, linear between them.
-__device__ __forceinline__ float sample_voxel(const VoxelVol& V, float px, float py, float pz, float lod) {
-  float maxLod = (float)(V.levels - 1);
-  lod = fminf(fmaxf(lod, 0.0f), maxLod); // fmaxf(NaN,0)=0: also covers log2(<=0), SURVEY B.8
-  float fl = floorf(lod);
-  int l0 = (int)fl;
-  float t = lod - fl;
-  const unsigned long long R3 = (unsigned long long)V.res * V.res * V.res;
-  int r0 = V.res >> l0;
-  // level offset in the contiguous chain: (R^3 - r^3) * 8 / 7
-  const uint8_t* p0 = V.chain + ((R3 - (unsigned long long)r0 * r0 * r0) * 8ull) / 7ull;
-  float a = trilinear_level(p0, r0, px, py, pz);
-  if (t == 0.0f) return a;
-  int l1 = min(l0 + 1, V.levels - 1);
-  int r1 = V.res >> l1;
-  const uint8_t* p1 = V.chain + ((R3 - (unsigned long long)r1 * r1 * r1) * 8ull) / 7ull;
-  float b = trilinear_level(p1, r1, px, py, pz);
-  return fmaf(t, b - a, a);
-}
-
-// cacheLightingRSM.comp:195-230. Distances / step sizes / the break test are
-// decision maths (trip count must equal the oracle's); positions and
-// occlusion are continuous maths.
-__device__ __noinline__ float cone_trace(const VoxelVol& V, float wx, float wy, float wz, float4 blk) {
+// NC cones of one thread marched in lock step (cacheLightingRSM.comp:195-230 each). Distances, step sizes and
+// the break test are decision maths (the trip count equals the oracle's); positions, filtering and occlusion
+// are continuous maths. Every iteration first issues the loads of all cones, then filters — the loads of
+// different cones overlap, which is what the march (a serial chain of dependent fetches) lacks on its own.
+// A cone also stops once occlusion reached 1: later samples would add (1 - 1) * x = 0.
+template <int NC>
+__device__ __forceinline__ void cone_trace_n(const VoxelVol& V, float wx, float wy, float wz, const float4* blk, int nb,
+                                             float* shadow_out) {
   const float fres = (float)V.res;
   const float inv_extent = 1.0f / (V.voxel_size * fres);
-  float vpx = (wx - V.vmin[0]) * inv_extent, vpy = (wy - V.vmin[1]) * inv_extent, vpz = (wz - V.vmin[2]) * inv_extent; // :104
-  const float k = blk.w;
-  float tx = ex_sub(blk.x, wx), ty = ex_sub(blk.y, wy), tz = ex_sub(blk.z, wz); // :195
-  float lightDist = ex_sqrt(ex_dot3(tx, ty, tz, tx, ty, tz));                     // :196
-  float inv = 1.0f / (lightDist * fres);
-  float dx = tx * inv, dy = ty * inv, dz = tz * inv;                              // :197-198 dirInVoxel
-  float cx = fmaf(dx, 2.0f, vpx), cy = fmaf(dy, 2.0f, vpy), cz = fmaf(dz, 2.0f, vpz); // :201
-  float occlusion = 0.0f;
-  float stepSize = 1.0f;
-  float dist = 0.0f;
-  const float goalDist = ex_sub(ex_div(lightDist, V.voxel_size), 2.0f);           // :206
-  const float radToStep = ex_div(2.0f, ex_sub(1.0f, k));                          // :209
-  for (int s = 0; s < 32; ++s) {
-    cx = fmaf(dx, stepSize, cx); cy = fmaf(dy, stepSize, cy); cz = fmaf(dz, stepSize, cz); // :213
-    dist = ex_add(dist, stepSize);                                                // :214
-    float radius = ex_mul(dist, k);                                               // :216
-    float occ = sample_voxel(V, cx, cy, cz, __log2f(radius));                     // :219
-    occlusion = fmaf(1.0f - occlusion, occ, occlusion);                           // :220
-    if (dist >= goalDist) break;                                                  // :222
-    stepSize = fmaxf(1.0f, ex_mul(radius, radToStep));                            // :225
+  const float vpx = (wx - V.vmin[0]) * inv_extent, vpy = (wy - V.vmin[1]) * inv_extent, vpz = (wz - V.vmin[2]) * inv_extent; // :104
+  const float maxLod = (float)(V.levels - 1);
+  float cx[NC], cy[NC], cz[NC], dx[NC], dy[NC], dz[NC];
+  float dist[NC], stepSize[NC], occ[NC], kk[NC], radToStep[NC], goal[NC];
+  bool live[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const float4 b = blk[c < nb ? c : 0];
+    live[c] = c < nb;
+    kk[c] = b.w;
+    float tx = ex_sub(b.x, wx), ty = ex_sub(b.y, wy), tz = ex_sub(b.z, wz);     // :195
+    float lightDist = ex_sqrt(ex_dot3(tx, ty, tz, tx, ty, tz));                 // :196
+    float inv = 1.0f / (lightDist * fres);
+    dx[c] = tx * inv; dy[c] = ty * inv; dz[c] = tz * inv;                       // :197-198 dirInVoxel
+    cx[c] = fmaf(dx[c], 2.0f, vpx); cy[c] = fmaf(dy[c], 2.0f, vpy); cz[c] = fmaf(dz[c], 2.0f, vpz); // :201
+    occ[c] = 0.0f; stepSize[c] = 1.0f; dist[c] = 0.0f;
+    goal[c] = ex_sub(ex_div(lightDist, V.voxel_size), 2.0f);                    // :206
+    radToStep[c] = ex_div(2.0f, ex_sub(1.0f, b.w));                             // :209
   }
-  return saturatef(1.0f - occlusion);                                             // :230
+  for (int s = 0; s < 32; ++s) {
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) any |= live[c];
+    if (!any) break;
+    Footprint f0[NC], f1[NC];
+    float tl[NC], radius[NC];
+    uint2 r0[NC], r1[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      cx[c] = fmaf(dx[c], stepSize[c], cx[c]); cy[c] = fmaf(dy[c], stepSize[c], cy[c]); cz[c] = fmaf(dz[c], stepSize[c], cz[c]); // :213
+      dist[c] = ex_add(dist[c], stepSize[c]);                                   // :214
+      radius[c] = ex_mul(dist[c], kk[c]);                                       // :216
+      float lod = fminf(fmaxf(__log2f(radius[c]), 0.0f), maxLod);               // :219; fmaxf(NaN,0) = 0
+      int l0; floor_frac(lod, l0, tl[c]);
+      l0 = min(max(l0, 0), V.levels - 1);
+      const int l1 = min(l0 + 1, V.levels - 1);
+      f0[c] = footprint(V, l0, cx[c], cy[c], cz[c]);
+      f1[c] = footprint(V, l1, cx[c], cy[c], cz[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      r0[c] = __ldg(V.rec + f0[c].index);
+      r1[c] = make_uint2(0u, 0u);
+      if (tl[c] != 0.0f) r1[c] = __ldg(V.rec + f1[c].index);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      float a = trilinear(r0[c], f0[c].tx, f0[c].ty, f0[c].tz);
+      float b = trilinear(r1[c], f1[c].tx, f1[c].ty, f1[c].tz);
+      float o = (tl[c] != 0.0f) ? fmaf(tl[c], b - a, a) : a;
+      if (live[c]) {
+        occ[c] = fmaf(1.0f - occ[c], o, occ[c]);                                // :220
+        if (dist[c] >= goal[c] || occ[c] >= 1.0f) live[c] = false;              // :222
+        stepSize[c] = fmaxf(1.0f, ex_mul(radius[c], radToStep[c]));             // :225
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) shadow_out[c] = saturatef(1.0f - occ[c]);        // :230
 }
 
 // ------------------------------------------------------------ epilogue helpers
@@ -315,9 +372,18 @@ struct ScalarMath {
   static __device__ __forceinline__ void stage(float4* slot, float4 r0, float4 r1, float4 r2) {
     slot[0] = r0; slot[1] = r1; slot[2] = r2;
   }
-  __device__ __forceinline__ void trace(const VoxelVol& V, float4 blk) {
+  // CPT cones (one per cache of this thread) x up to NB consecutive shadow blocks, marched in lock step
+  template <int NB>
+  __device__ __forceinline__ void trace(const VoxelVol& V, const float4* blk, int nb, float (&out)[NB][CPT]) {
+    static_assert(CPT == 1, "shadowed gathers keep one cache per thread");
+    float sh[NB];
+    cone_trace_n<NB>(V, px[0], py[0], pz[0], blk, live[0] ? nb : 0, sh);
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) shadow[j] = live[j] ? cone_trace(V, px[j], py[j], pz[j], blk) : 0.0f;
+    for (int b = 0; b < NB; ++b) out[b][0] = live[0] ? sh[b] : 0.0f;
+  }
+  __device__ __forceinline__ void set_shadow(const float (&v)[CPT]) {
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) shadow[j] = v[j];
   }
   __device__ __forceinline__ void eval(const float4* v) {
     float4 va = v[0], vb = v[1], vc = v[2];
@@ -368,12 +434,11 @@ struct PackedMath {
     d[3] = make_float4(r1.z, r1.z, r2.x, r2.x);
     d[4] = make_float4(r2.y, r2.y, r2.z, r2.z);
   }
-  __device__ __forceinline__ void trace(const VoxelVol& V, float4 blk) {
+  template <int NB>
+  __device__ __forceinline__ void trace(const VoxelVol&, const float4*, int, float (&)[NB][CPT]) {} // unshadowed only
+  __device__ __forceinline__ void set_shadow(const float (&v)[CPT]) {
 #pragma unroll
-    for (int j = 0; j < PAIRS; ++j) {
-      shadow[j].x = live[j * 2] ? cone_trace(V, -npx[j].x, -npy[j].x, -npz[j].x, blk) : 0.0f;
-      shadow[j].y = live[j * 2 + 1] ? cone_trace(V, -npx[j].y, -npy[j].y, -npz[j].y, blk) : 0.0f;
-    }
+    for (int j = 0; j < PAIRS; ++j) { shadow[j].x = v[2 * j]; shadow[j].y = v[2 * j + 1]; }
   }
   __device__ __forceinline__ void eval(const float4* q) {
     float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
@@ -492,7 +557,7 @@ __device__ __forceinline__ void advance(const GatherParams& p, const Schedule& S
   if (c.base >= c.v_end) start_run(p, S, c, c.u_next, u1);
 }
 
-template <int ORDER, bool SHADOW, typename Math, bool USE_TMA>
+template <int ORDER, bool SHADOW, typename Math, bool USE_TMA, int CONES = 1>
 __global__ void __launch_bounds__(kThreads) gather_kernel(GatherParams p) {
   constexpr int CPT = Math::CPT;
   constexpr int TILE = kThreads * CPT;
@@ -503,6 +568,7 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(GatherParams p) {
   __shared__ __align__(128) float4 s_vpl[STAGES][kVplTile * SPV];
   __shared__ float4 s_blk[SHADOW ? kVplTile : 1];
   __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ uint32_t s_rec_offset[16];
 
   const Schedule S = make_schedule(p, TILE);
   if (S.units == 0) return;
@@ -510,8 +576,10 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(GatherParams p) {
   if (u0 >= u1) return;
   VoxelVol V;
   if (SHADOW) {
-    V.chain = p.chain; V.res = p.vres; V.levels = p.vlevels; V.voxel_size = p.voxel_size;
+    if (threadIdx.x < 16) s_rec_offset[threadIdx.x] = p.rec_offset[threadIdx.x];
+    V.rec = p.rec; V.rec_offset = s_rec_offset; V.res = p.vres; V.levels = p.vlevels; V.voxel_size = p.voxel_size;
     V.vmin[0] = p.vmin[0]; V.vmin[1] = p.vmin[1]; V.vmin[2] = p.vmin[2];
+    __syncthreads();
   }
   uint32_t phase[2] = {0u, 0u};
   if (USE_TMA) {
@@ -585,12 +653,32 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(GatherParams p) {
     }
     const int n = (int)min((uint32_t)kVplTile, cur.v_end - cur.base);
     const float4* sv = &s_vpl[st][0];
-    if (SHADOW) {
+    if constexpr (SHADOW) {
+      // :169 — a new shadow value every `interval` VPLs. A tile starts on a multiple of the granule, which is
+      // a multiple of every interval <= granule; for longer intervals the value carries over.
       const uint32_t interval = p.lights[cur.light].interval;
-      for (int i = 0; i < n; ++i) {
-        uint32_t k = cur.base + i;
-        if ((k & (interval - 1u)) == 0u) M.trace(V, s_blk[(k - cur.base) / interval]); // :169; SURVEY B.12
-        M.eval(sv + i * SPV);
+      if (interval > (uint32_t)kVplTile) {
+        if ((cur.base & (interval - 1u)) == 0u) {
+          float sh[1][CPT];
+          M.template trace<1>(V, s_blk, 1, sh);
+          M.set_shadow(sh[0]);
+        }
+        for (int i = 0; i < n; ++i) M.eval(sv + i * SPV);
+      } else {
+        const int nblocks = (n + (int)interval - 1) / (int)interval;
+        int i = 0;
+        for (int b0 = 0; b0 < nblocks; b0 += CONES) {
+          float sh[CONES][CPT];
+          M.template trace<CONES>(V, s_blk + b0, min(CONES, nblocks - b0), sh);
+#pragma unroll
+          for (int b = 0; b < CONES; ++b) {
+            if (b0 + b < nblocks) {
+              M.set_shadow(sh[b]);
+              const int end = min(n, i + (int)interval);
+              for (; i < end; ++i) M.eval(sv + i * SPV);
+            }
+          }
+        }
       }
     } else {
 #pragma unroll 4
@@ -628,31 +716,66 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(GatherParams p) {
 }
 
 // ------------------------------------------------------------ finalize: add the partial segments in VPL order
+// One block per 64 consecutive caches of a tile (block-stride loop: the cache count lives on the device).
+// The CTAs that own pieces of the tile are the same for all 64 caches, so their list is derived once per
+// chunk; then every thread sums (coefficient, cache) items over the owners in ascending CTA = ascending VPL
+// order (deterministic, no float atomics) with coalesced loads, and 64 threads apply the SH factors and add
+// the result into the entries with 128-bit accesses (+ the peer stores of the fused all-gather).
+constexpr int kFinChunk = 64;
+constexpr int kFinThreads = 256;
+
 template <int ORDER>
-__global__ void __launch_bounds__(256) gather_finalize_kernel(GatherParams p, int tile_caches) {
+__global__ void __launch_bounds__(kFinThreads) gather_finalize_kernel(GatherParams p, int tile_caches) {
   constexpr int NC = num_coefs<ORDER>();
+  constexpr int ITEMS = (NC * kFinChunk + kFinThreads - 1) / kFinThreads;
+  __shared__ float s_raw[NC][kFinChunk];
   const Schedule S = make_schedule(p, tile_caches);
   if (S.units == 0) return;
   const uint32_t G = p.grid;
-  for (uint32_t local = blockIdx.x * blockDim.x + threadIdx.x; local < S.count; local += gridDim.x * blockDim.x) {
-    const uint32_t tile = local / tile_caches, in_tile = local - tile * tile_caches;
+  const unsigned long long q_u = S.units / G, r_u = S.units % G; // range_begin(c+1) - range_begin(c) = q_u (+1)
+  const uint32_t chunks = (S.count + kFinChunk - 1) / kFinChunk;
+  for (uint32_t chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
+    const uint32_t local0 = chunk * kFinChunk;
+    const uint32_t tile = local0 / tile_caches, in_tile0 = local0 - tile * tile_caches;
     const unsigned long long ua = (unsigned long long)tile * S.units_per_tile, ub = ua + S.units_per_tile;
     const uint32_t c_lo = owner_of(S, G, ua), c_hi = owner_of(S, G, ub - 1);
-    if (c_lo == c_hi) continue; // one CTA covered the whole tile and already wrote it
-    float raw[27];
+    if (c_lo == c_hi) continue; // one CTA covered the whole tile and already wrote it (block-uniform)
+    float acc[ITEMS];
 #pragma unroll
-    for (int q = 0; q < 27; ++q) raw[q] = 0.0f;
+    for (int k = 0; k < ITEMS; ++k) acc[k] = 0.0f;
+    // walk the owners with an incrementally maintained range_begin (no 64-bit division in the loop)
+    unsigned long long cb = range_begin(S, G, c_lo);
+    unsigned long long rem = ((unsigned long long)S.units * c_lo) % G;
     for (uint32_t c = c_lo; c <= c_hi; ++c) {
-      const unsigned long long cb = range_begin(S, G, c), ce = range_begin(S, G, c + 1);
-      if (cb >= ce) continue;
-      const int slot = ((uint32_t)(cb / S.units_per_tile) == tile) ? 0 : 1;
-      const float* src = p.partials + ((size_t)c * 2 + slot) * NC * tile_caches + in_tile;
+      unsigned long long ce = cb + q_u;
+      rem += r_u;
+      if (rem >= G) { rem -= G; ++ce; }
+      if (cb < ce) {
+        const int slot = cb >= ua ? 0 : 1; // slot 0 = the CTA's range starts inside this tile (only c_lo can start before it)
+        const float* src = p.partials + ((size_t)c * 2 + slot) * NC * tile_caches + in_tile0;
 #pragma unroll
-      for (int q = 0; q < NC; ++q) raw[q] += __ldcs(src + (size_t)q * tile_caches);
+        for (int k = 0; k < ITEMS; ++k) {
+          const int item = k * kFinThreads + threadIdx.x;
+          if (item < NC * kFinChunk) acc[k] += __ldcs(src + (size_t)(item / kFinChunk) * tile_caches + (item % kFinChunk));
+        }
+      }
+      cb = ce;
     }
-    float vals[28];
-    coef_values<ORDER>(p, raw, vals);
-    add_to_entry<ORDER>(p, S.first + local, vals);
+    __syncthreads(); // previous chunk's readers are done with s_raw
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      const int item = k * kFinThreads + threadIdx.x;
+      if (item < NC * kFinChunk) s_raw[item / kFinChunk][item % kFinChunk] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < kFinChunk && local0 + threadIdx.x < S.count) {
+      float raw[27];
+#pragma unroll
+      for (int q = 0; q < 27; ++q) raw[q] = q < NC ? s_raw[q < NC ? q : 0][threadIdx.x] : 0.0f;
+      float vals[28];
+      coef_values<ORDER>(p, raw, vals);
+      add_to_entry<ORDER>(p, S.first + local0 + threadIdx.x, vals);
+    }
   }
 }
 
@@ -683,8 +806,8 @@ drv_status launch_gather(drv_ctx* ctx, K kernel, GatherParams& p, int tile_cache
   DRV_LAUNCH_CHECK();
   ctx->stage_end(DRV_STAGE_GATHER_KERNEL);
   const int fin_grid = ctx->num_sms * 4;
-  if (order == 1) gather_finalize_kernel<1><<<fin_grid, 256, 0, ctx->stream>>>(p, tile_caches);
-  else gather_finalize_kernel<2><<<fin_grid, 256, 0, ctx->stream>>>(p, tile_caches);
+  if (order == 1) gather_finalize_kernel<1><<<fin_grid, kFinThreads, 0, ctx->stream>>>(p, tile_caches);
+  else gather_finalize_kernel<2><<<fin_grid, kFinThreads, 0, ctx->stream>>>(p, tile_caches);
   DRV_LAUNCH_CHECK();
   return DRV_OK;
 }
@@ -723,7 +846,8 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   p.f2 = ctx->constant.ShEvaFactor2n2_p1_n1;
   p.f20 = ctx->constant.ShEvaFactor20;
   p.f22 = ctx->constant.ShEvaFactor2p2;
-  p.chain = ctx->voxel_chain;
+  p.rec = ctx->voxel_records;
+  for (int l = 0; l < 16; ++l) p.rec_offset[l] = ctx->voxel_record_offset[l];
   p.vres = (int)ctx->cfg.voxel_resolution;
   p.vlevels = (int)ctx->voxel_levels;
   memcpy(p.vmin, ctx->volume.VolumeWorldMin, 12);
@@ -735,36 +859,33 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   }
   const int order = (int)ctx->cfg.sh_order;
   const uint32_t variant = ctx->cfg.gather_variant;
-#define DRV_GATHER(ORD, SH, MATH, TMA) \
-  return launch_gather(ctx, gather_kernel<ORD, SH, MATH, TMA>, p, kThreads * MATH::CPT, ORD)
+#define DRV_GATHER(ORD, SH, MATH, TMA, CONES) \
+  return launch_gather(ctx, gather_kernel<ORD, SH, MATH, TMA, CONES>, p, kThreads * MATH::CPT, ORD)
   using S1n2 = ScalarMath<1, false, 2>; using S1n4 = ScalarMath<1, false, 4>; using S1s1 = ScalarMath<1, true, 1>;
   using S2n2 = ScalarMath<2, false, 2>; using S2n1 = ScalarMath<2, false, 1>; using S2s1 = ScalarMath<2, true, 1>;
-  using P1n1 = PackedMath<1, false, 1>; using P1n2 = PackedMath<1, false, 2>; using P1s1 = PackedMath<1, true, 1>;
-  using P2n1 = PackedMath<2, false, 1>; using P2s1 = PackedMath<2, true, 1>;
+  using P1n1 = PackedMath<1, false, 1>; using P1n2 = PackedMath<1, false, 2>;
+  using P2n1 = PackedMath<2, false, 1>;
+  if (shadow) { // variants select how many cones a thread marches in lock step
+    const int cones = variant == 6 ? 2 : (variant == 7 ? 4 : 1); // measured on C3: 1 cone/thread is fastest (profiles/)
+    if (order == 1) { if (cones == 1) DRV_GATHER(1, true, S1s1, false, 1); if (cones == 4) DRV_GATHER(1, true, S1s1, false, 4); DRV_GATHER(1, true, S1s1, false, 2); }
+    else            { if (cones == 1) DRV_GATHER(2, true, S2s1, false, 1); if (cones == 4) DRV_GATHER(2, true, S2s1, false, 4); DRV_GATHER(2, true, S2s1, false, 2); }
+  }
   switch (variant) {
-    case 1: // scalar maths, TMA bulk staging (unshadowed only; shadowed falls through to the default)
-      if (!shadow) { if (order == 1) DRV_GATHER(1, false, S1n2, true); else DRV_GATHER(2, false, S2n2, true); }
-      break;
+    case 1: // scalar maths, TMA bulk staging
+      if (order == 1) DRV_GATHER(1, false, S1n2, true, 1); else DRV_GATHER(2, false, S2n2, true, 1);
     case 2: // packed FP32x2, widest tiling
-      if (order == 1) { if (shadow) DRV_GATHER(1, true, P1s1, false); else DRV_GATHER(1, false, P1n2, false); }
-      else            { if (shadow) DRV_GATHER(2, true, P2s1, false); else DRV_GATHER(2, false, P2n1, false); }
-      break;
+      if (order == 1) DRV_GATHER(1, false, P1n2, false, 1); else DRV_GATHER(2, false, P2n1, false, 1);
     case 3: // packed FP32x2, one pair per thread
-      if (order == 1) { if (shadow) DRV_GATHER(1, true, P1s1, false); else DRV_GATHER(1, false, P1n1, false); }
-      else            { if (shadow) DRV_GATHER(2, true, P2s1, false); else DRV_GATHER(2, false, P2n1, false); }
-      break;
+      if (order == 1) DRV_GATHER(1, false, P1n1, false, 1); else DRV_GATHER(2, false, P2n1, false, 1);
     case 4: // scalar, widest tiling
-      if (order == 1) { if (shadow) DRV_GATHER(1, true, S1s1, false); else DRV_GATHER(1, false, S1n4, false); }
-      else            { if (shadow) DRV_GATHER(2, true, S2s1, false); else DRV_GATHER(2, false, S2n2, false); }
-      break;
+      if (order == 1) DRV_GATHER(1, false, S1n4, false, 1); else DRV_GATHER(2, false, S2n2, false, 1);
     case 5: // scalar, SH2 with one cache per thread
-      if (order == 2 && !shadow) DRV_GATHER(2, false, S2n1, false);
+      if (order == 2) DRV_GATHER(2, false, S2n1, false, 1);
       break;
     default:
       break;
   }
   // variant 0 (default): scalar maths, register-prefetch staging
-  if (order == 1) { if (shadow) DRV_GATHER(1, true, S1s1, false); else DRV_GATHER(1, false, S1n2, false); }
-  else            { if (shadow) DRV_GATHER(2, true, S2s1, false); else DRV_GATHER(2, false, S2n2, false); }
+  if (order == 1) DRV_GATHER(1, false, S1n2, false, 1); else DRV_GATHER(2, false, S2n2, false, 1);
 #undef DRV_GATHER
 }

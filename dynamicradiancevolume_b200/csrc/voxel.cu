@@ -177,7 +177,77 @@ __global__ void voxel_mip_kernel(const uint8_t* __restrict__ src, uint8_t* __res
   dst[(size_t)x + (size_t)h * ((size_t)y + (size_t)h * z)] = (uint8_t)((sum + 4) >> 3);
 }
 
+// Gather-ready records for the cone tracer (stage 4): for every level and every lower-corner coordinate
+// (x,y,z) in [-1, r-1]^3 the eight clamp-to-edge texels of the trilinear footprint, packed
+// .x = a000 a100 a010 a110, .y = a001 a101 a011 a111 (low byte first). One thread per record, all levels in
+// one launch; `offsets[l]` = first record of level l.
+struct RecordLevels {
+  uint32_t offset[16];
+  uint32_t chain_offset[16];
+  int levels, res;
+};
+
+__global__ void __launch_bounds__(256) voxel_records_kernel(RecordLevels L, const uint8_t* __restrict__ chain,
+                                                            uint2* __restrict__ records, uint32_t total) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int l = 0;
+#pragma unroll 1
+  while (l + 1 < L.levels && i >= L.offset[l + 1]) ++l;
+  const int r = L.res >> l, rp = r + 1;
+  uint32_t j = i - L.offset[l];
+  int x = (int)(j % rp) - 1;
+  int y = (int)((j / rp) % rp) - 1;
+  int z = (int)(j / (rp * rp)) - 1;
+  const uint8_t* lvl = chain + L.chain_offset[l];
+  int x0 = max(x, 0), x1 = min(x + 1, r - 1), y0 = max(y, 0), y1 = min(y + 1, r - 1), z0 = max(z, 0), z1 = min(z + 1, r - 1);
+  auto T = [&](int xx, int yy, int zz) -> uint32_t { return lvl[(size_t)xx + (size_t)r * ((size_t)yy + (size_t)r * zz)]; };
+  uint2 o;
+  o.x = T(x0, y0, z0) | (T(x1, y0, z0) << 8) | (T(x0, y1, z0) << 16) | (T(x1, y1, z0) << 24);
+  o.y = T(x0, y0, z1) | (T(x1, y0, z1) << 8) | (T(x0, y1, z1) << 16) | (T(x1, y1, z1) << 24);
+  records[i] = o;
+}
+
 } // namespace
+
+// voxelization.cpp:161-171 (mip chain) + the gather-ready records.
+static drv_status drv_impl_voxel_mips_and_records(drv_ctx* ctx) {
+  const int res = (int)ctx->cfg.voxel_resolution;
+  int sres = res;
+  uint8_t* src = ctx->voxel_chain;
+  while (sres > 1) {
+    int h = sres >> 1;
+    uint8_t* dst = src + (size_t)sres * sres * sres;
+    dim3 block(8, 8, 4), grid((h + 7) / 8, (h + 7) / 8, (h + 3) / 4);
+    voxel_mip_kernel<<<grid, block, 0, ctx->stream>>>(src, dst, sres);
+    DRV_LAUNCH_CHECK();
+    src = dst;
+    sres = h;
+  }
+  if (ctx->voxel_records) {
+    RecordLevels L;
+    memset(&L, 0, sizeof(L));
+    L.levels = (int)ctx->voxel_levels;
+    L.res = res;
+    for (uint32_t l = 0; l < ctx->voxel_levels; ++l) {
+      L.offset[l] = ctx->voxel_record_offset[l];
+      L.chain_offset[l] = (uint32_t)voxel_level_offset_bytes((uint32_t)res, l);
+    }
+    const uint32_t total = (uint32_t)ctx->voxel_record_count;
+    voxel_records_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(L, ctx->voxel_chain, ctx->voxel_records, total);
+    DRV_LAUNCH_CHECK();
+  }
+  return DRV_OK;
+}
+
+drv_status drv_impl_set_voxel_volume(drv_ctx* ctx, const uint8_t* level0) {
+  const size_t vox = (size_t)ctx->cfg.voxel_resolution * ctx->cfg.voxel_resolution * ctx->cfg.voxel_resolution;
+  DRV_CUDA(cudaMemcpyAsync(ctx->voxel_chain, level0, vox, cudaMemcpyDefault, ctx->stream));
+  ctx->stage_begin(DRV_STAGE_VOXEL_BLEND_MIPMAP);
+  drv_status st = drv_impl_voxel_mips_and_records(ctx);
+  ctx->stage_end(DRV_STAGE_VOXEL_BLEND_MIPMAP);
+  return st;
+}
 
 drv_status drv_impl_voxelize(drv_ctx* ctx, const float* tris, uint32_t n, const float* world, float adaption,
                              uint32_t flags) {
@@ -207,17 +277,8 @@ drv_status drv_impl_voxelize(drv_ctx* ctx, const float* tris, uint32_t n, const 
   voxel_blend_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, ctx->stream>>>((uint4*)ctx->voxel_chain,
                                                                            (const uint4*)ctx->voxel_target, n16, k);
   DRV_LAUNCH_CHECK();
-  int sres = res;
-  uint8_t* src = ctx->voxel_chain;
-  while (sres > 1) { // voxelization.cpp:161-171
-    int h = sres >> 1;
-    uint8_t* dst = src + (size_t)sres * sres * sres;
-    dim3 block(8, 8, 4), grid((h + 7) / 8, (h + 7) / 8, (h + 3) / 4);
-    voxel_mip_kernel<<<grid, block, 0, ctx->stream>>>(src, dst, sres);
-    DRV_LAUNCH_CHECK();
-    src = dst;
-    sres = h;
-  }
+  drv_status st = drv_impl_voxel_mips_and_records(ctx);
+  if (st != DRV_OK) return st;
   ctx->stage_end(DRV_STAGE_VOXEL_BLEND_MIPMAP);
   return DRV_OK;
 }

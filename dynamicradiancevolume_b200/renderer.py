@@ -207,6 +207,12 @@ class Context:
         ptr = None if tris is None else tris.data_ptr()
         self.check(self.lib.drv_voxelize(self.handle, ptr, n, C.byref(w), adaption, flags))
 
+    def set_voxel_volume(self, level0):
+        """level0: uint8 tensor / array of voxel_resolution^3 bytes (host or device)."""
+        ptr = level0.data_ptr() if hasattr(level0, "data_ptr") else level0.ctypes.data
+        self._keep_vol = level0
+        self.check(self.lib.drv_set_voxel_volume(self.handle, ptr))
+
     def allocate_caches(self): self.check(self.lib.drv_allocate_caches(self.handle))
     def light_caches(self): self.check(self.lib.drv_light_caches(self.handle))
     def apply_caches(self, out, fmt): self.check(self.lib.drv_apply_caches(self.handle, out.data_ptr(), fmt))

@@ -262,6 +262,11 @@ drv_status drv_prepare_rsm(drv_ctx* ctx, uint32_t light);
 drv_status drv_voxelize(drv_ctx* ctx, const float* tri_pos, uint32_t num_tris,
                         const float world[16], float adaption, uint32_t flags);
 
+/* Installs a ready-made level-0 voxel volume (voxel_resolution^3 bytes, x fastest; host or device pointer)
+ * into the persistent volume, bypassing rasterisation and the temporal blend, then rebuilds the mip chain
+ * (voxelmipmap.comp) and the cone tracer's gather-ready records. For volumes produced elsewhere and for tests. */
+drv_status drv_set_voxel_volume(drv_ctx* ctx, const uint8_t* level0);
+
 /* ≙ Renderer::AllocateCaches (renderer.cpp:951-992): cacheGather.comp +
  * cachePrepareLighting.comp. Clears counter + atlas, marks, scans, compacts. */
 drv_status drv_allocate_caches(drv_ctx* ctx);
