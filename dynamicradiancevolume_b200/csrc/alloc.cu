@@ -87,18 +87,22 @@ __device__ __forceinline__ Cell cache_cell(const AllocParams& p, F3 wp, int c) {
 __device__ __forceinline__ void mark_corners(const AllocParams& p, const Cell& cell, int c, uint8_t* __restrict__ flags,
                                              uint32_t* __restrict__ stats) {
   const int R = p.R, R2 = R * R;
-  uint8_t* base = flags + (size_t)c * R2 * R;
+  uint8_t* f = flags + (uint32_t)(c * R2 * R + cell.x + cell.y * R + cell.z * R2);
+  if (cell.x + 1 < R && cell.y + 1 < R && cell.z + 1 < R) {
+    // offsets (0,0,0)(0,1,0)(0,0,1)(0,1,1)(1,0,0)(1,1,0)(1,0,1)(1,1,1), cacheGather.comp:34-44. Plain idempotent
+    // byte stores: no read-before-write, nothing on the critical path waits for memory.
+    f[0] = 1; f[R] = 1; f[R2] = 1; f[R2 + R] = 1;
+    f[1] = 1; f[R + 1] = 1; f[R2 + 1] = 1; f[R2 + R + 1] = 1;
+    return;
+  }
+  uint32_t oob = 0; // out-of-range +1 corners are skipped and counted
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    // offsets (0,0,0)(0,1,0)(0,0,1)(0,1,1)(1,0,0)(1,1,0)(1,0,1)(1,1,1), cacheGather.comp:34-44
-    int x = cell.x + (i >> 2), y = cell.y + (i & 1), z = cell.z + ((i >> 1) & 1);
-    if (x >= R || y >= R || z >= R) { // out-of-range +1 corners are skipped and counted
-      atomicAdd(stats + 1, 1u);
-      continue;
-    }
-    uint8_t* f = base + x + y * R + z * R2;
-    if (*f == 0) *f = 1; // idempotent; the read only saves redundant write traffic
+    const int ox = i >> 2, oy = i & 1, oz = (i >> 1) & 1;
+    if (cell.x + ox >= R || cell.y + oy >= R || cell.z + oz >= R) { ++oob; continue; }
+    f[ox + oy * R + oz * R2] = 1;
   }
+  atomicAdd(stats + 1, oob);
 }
 
 __global__ void __launch_bounds__(256) mark_kernel(AllocParams p, const float* __restrict__ depth,

@@ -212,32 +212,34 @@ __device__ __forceinline__ void cone_trace_n(const VoxelVol& V, float wx, float 
 #pragma unroll
     for (int c = 0; c < NC; ++c) any |= live[c];
     if (!any) break;
-    Footprint f0[NC], f1[NC];
-    float tl[NC], radius[NC];
-    uint2 r0[NC], r1[NC];
+    Footprint f0[NC];
+    float radius[NC], lod[NC];
+    uint2 r0[NC];
+    int l0[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       cx[c] = fmaf(dx[c], stepSize[c], cx[c]); cy[c] = fmaf(dy[c], stepSize[c], cy[c]); cz[c] = fmaf(dz[c], stepSize[c], cz[c]); // :213
       dist[c] = ex_add(dist[c], stepSize[c]);                                   // :214
       radius[c] = ex_mul(dist[c], kk[c]);                                       // :216
-      float lod = fminf(fmaxf(__log2f(radius[c]), 0.0f), maxLod);               // :219; fmaxf(NaN,0) = 0
-      int l0; floor_frac(lod, l0, tl[c]);
-      l0 = min(max(l0, 0), V.levels - 1);
-      const int l1 = min(l0 + 1, V.levels - 1);
-      f0[c] = footprint(V, l0, cx[c], cy[c], cz[c]);
-      f1[c] = footprint(V, l1, cx[c], cy[c], cz[c]);
-    }
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
+      // :219 lod = log2(radius) clamped to the chain; radius <= 1 (the first stretch of every cone: a VAL
+      // block subtends ~1/32 rad) is level 0 exactly, without the log. fmaxf(NaN, 0) = 0.
+      lod[c] = 0.0f;
+      l0[c] = 0;
+      if (radius[c] > 1.0f) {
+        const float l = fminf(__log2f(radius[c]), maxLod); // in (0, maxLod]
+        floor_frac(l, l0[c], lod[c]);                       // lod[c] := fractional part in [0, 1]
+      }
+      f0[c] = footprint(V, l0[c], cx[c], cy[c], cz[c]);
       r0[c] = __ldg(V.rec + f0[c].index);
-      r1[c] = make_uint2(0u, 0u);
-      if (tl[c] != 0.0f) r1[c] = __ldg(V.rec + f1[c].index);
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      float a = trilinear(r0[c], f0[c].tx, f0[c].ty, f0[c].tz);
-      float b = trilinear(r1[c], f1[c].tx, f1[c].ty, f1[c].tz);
-      float o = (tl[c] != 0.0f) ? fmaf(tl[c], b - a, a) : a;
+      float o = trilinear(r0[c], f0[c].tx, f0[c].ty, f0[c].tz);
+      if (lod[c] != 0.0f) { // mip-linear: blend with the next coarser level
+        const Footprint f1 = footprint(V, min(l0[c] + 1, V.levels - 1), cx[c], cy[c], cz[c]);
+        const float b = trilinear(__ldg(V.rec + f1.index), f1.tx, f1.ty, f1.tz);
+        o = fmaf(lod[c], b - o, o);
+      }
       if (live[c]) {
         occ[c] = fmaf(1.0f - occ[c], o, occ[c]);                                // :220
         if (dist[c] >= goal[c] || occ[c] >= 1.0f) live[c] = false;              // :222
@@ -729,10 +731,10 @@ __global__ void __launch_bounds__(kFinThreads) gather_finalize_kernel(GatherPara
   constexpr int NC = num_coefs<ORDER>();
   constexpr int ITEMS = (NC * kFinChunk + kFinThreads - 1) / kFinThreads;
   __shared__ float s_raw[NC][kFinChunk];
+  __shared__ uint32_t s_list[kFinThreads];
   const Schedule S = make_schedule(p, tile_caches);
   if (S.units == 0) return;
   const uint32_t G = p.grid;
-  const unsigned long long q_u = S.units / G, r_u = S.units % G; // range_begin(c+1) - range_begin(c) = q_u (+1)
   const uint32_t chunks = (S.count + kFinChunk - 1) / kFinChunk;
   for (uint32_t chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
     const uint32_t local0 = chunk * kFinChunk;
@@ -743,23 +745,31 @@ __global__ void __launch_bounds__(kFinThreads) gather_finalize_kernel(GatherPara
     float acc[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) acc[k] = 0.0f;
-    // walk the owners with an incrementally maintained range_begin (no 64-bit division in the loop)
-    unsigned long long cb = range_begin(S, G, c_lo);
-    unsigned long long rem = ((unsigned long long)S.units * c_lo) % G;
-    for (uint32_t c = c_lo; c <= c_hi; ++c) {
-      unsigned long long ce = cb + q_u;
-      rem += r_u;
-      if (rem >= G) { rem -= G; ++ce; }
-      if (cb < ce) {
-        const int slot = cb >= ua ? 0 : 1; // slot 0 = the CTA's range starts inside this tile (only c_lo can start before it)
-        const float* src = p.partials + ((size_t)c * 2 + slot) * NC * tile_caches + in_tile0;
+    // owners in batches: every thread derives one owner's partial slot (two 64-bit divisions, in parallel),
+    // then all threads walk the list — the loads of successive owners are independent, so several are in flight
+    for (uint32_t cbase = c_lo; cbase <= c_hi; cbase += kFinThreads) {
+      const uint32_t c = cbase + threadIdx.x;
+      uint32_t entry = 0xFFFFFFFFu;
+      if (c <= c_hi) {
+        const unsigned long long cb = range_begin(S, G, c), ce = range_begin(S, G, c + 1);
+        // slot 0 = the CTA's range starts inside this tile (only c_lo can start before it)
+        if (cb < ce) entry = c * 2u + (cb >= ua ? 0u : 1u);
+      }
+      __syncthreads(); // the previous batch has been consumed
+      s_list[threadIdx.x] = entry;
+      __syncthreads();
+      const int cnt = (int)min((uint32_t)kFinThreads, c_hi - cbase + 1u);
+#pragma unroll 4
+      for (int i = 0; i < cnt; ++i) {
+        const uint32_t e = s_list[i];
+        if (e == 0xFFFFFFFFu) continue;
+        const float* src = p.partials + (size_t)e * NC * tile_caches + in_tile0;
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
           const int item = k * kFinThreads + threadIdx.x;
           if (item < NC * kFinChunk) acc[k] += __ldcs(src + (size_t)(item / kFinChunk) * tile_caches + (item % kFinChunk));
         }
       }
-      cb = ce;
     }
     __syncthreads(); // previous chunk's readers are done with s_raw
 #pragma unroll

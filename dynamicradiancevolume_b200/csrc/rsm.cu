@@ -16,48 +16,100 @@ using namespace drvk;
 
 namespace {
 
-// downsamplersm.frag:15-33. One thread per destination texel.
-__global__ void rsm_downsample_kernel(const uint2* __restrict__ flux_src, const int* __restrict__ normal_src,
-                                      const uint32_t* __restrict__ depth_src, int res, uint2* __restrict__ flux_dst,
-                                      int* __restrict__ normal_dst, uint32_t* __restrict__ depth_dst) {
-  const int h = res >> 1;
-  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= h || y >= h) return;
-  // textureGather order: (i0,j1) (i1,j1) (i1,j0) (i0,j0)
-  size_t t[4] = {(size_t)(2 * y + 1) * res + 2 * x, (size_t)(2 * y + 1) * res + 2 * x + 1,
-                 (size_t)(2 * y) * res + 2 * x + 1, (size_t)(2 * y) * res + 2 * x};
+struct RsmTexel {
+  uint2 flux;     // 4 halfs (r,g,b,x)
+  int normal;     // 2 int16
+  uint32_t depth; // 2 halfs (dist, dist^2)
+};
+
+// downsamplersm.frag:15-33 for one destination texel from its 2x2 footprint, given in textureGather order:
+// t[0] = (x0,y1), t[1] = (x1,y1), t[2] = (x1,y0), t[3] = (x0,y0). Results are rounded to the storage formats
+// (half / int16) exactly as a render to the next mip level does, so chained levels see quantised inputs.
+__device__ __forceinline__ RsmTexel rsm_downsample4(const RsmTexel (&t)[4]) {
   float fr[4], fg[4], fb[4], d0[4], d1[4];
   F3 n = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    uint2 f = __ldg(flux_src + t[i]);
-    fr[i] = half_bits_to_float((uint16_t)(f.x & 0xffffu));
-    fg[i] = half_bits_to_float((uint16_t)(f.x >> 16));
-    fb[i] = half_bits_to_float((uint16_t)(f.y & 0xffffu));
-    uint32_t d = __ldg(depth_src + t[i]);
-    d0[i] = half_bits_to_float((uint16_t)(d & 0xffffu));
-    d1[i] = half_bits_to_float((uint16_t)(d >> 16));
-    int pn = __ldg(normal_src + t[i]);
-    F3 u = unpack_normal16i((int)(short)(pn & 0xffff), (int)(short)((uint32_t)pn >> 16));
+    fr[i] = half_bits_to_float((uint16_t)(t[i].flux.x & 0xffffu));
+    fg[i] = half_bits_to_float((uint16_t)(t[i].flux.x >> 16));
+    fb[i] = half_bits_to_float((uint16_t)(t[i].flux.y & 0xffffu));
+    d0[i] = half_bits_to_float((uint16_t)(t[i].depth & 0xffffu));
+    d1[i] = half_bits_to_float((uint16_t)(t[i].depth >> 16));
+    F3 u = unpack_normal16i((int)(short)(t[i].normal & 0xffff), (int)(short)((uint32_t)t[i].normal >> 16));
     n.x += u.x; n.y += u.y; n.z += u.z;
   }
+  RsmTexel o;
   // flux: sum of the four (:17-22); the RGB16F store rounds to nearest even
   float sr = ex_add(ex_add(ex_add(fr[0], fr[1]), fr[2]), fr[3]);
   float sg = ex_add(ex_add(ex_add(fg[0], fg[1]), fg[2]), fg[3]);
   float sb = ex_add(ex_add(ex_add(fb[0], fb[1]), fb[2]), fb[3]);
-  size_t o = (size_t)y * h + x;
-  flux_dst[o] = make_uint2((uint32_t)float_to_half_bits(sr) | ((uint32_t)float_to_half_bits(sg) << 16),
-                           (uint32_t)float_to_half_bits(sb));
+  o.flux = make_uint2((uint32_t)float_to_half_bits(sr) | ((uint32_t)float_to_half_bits(sg) << 16),
+                      (uint32_t)float_to_half_bits(sb));
   // normal: mean direction, renormalised, repacked (:24-30)
   float inv = rsqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
   int ox, oy;
   pack_normal16i(n.x * inv, n.y * inv, n.z * inv, ox, oy);
-  normal_dst[o] = (int)(((uint32_t)ox & 0xffffu) | ((uint32_t)oy << 16));
+  o.normal = (int)(((uint32_t)ox & 0xffffu) | ((uint32_t)oy << 16));
   // depthLinSq: linear fetch at the footprint centre = mean of the four (:32)
   float a0 = ex_mix(d0[3], d0[2], 0.5f), b0 = ex_mix(d0[0], d0[1], 0.5f);
   float a1 = ex_mix(d1[3], d1[2], 0.5f), b1 = ex_mix(d1[0], d1[1], 0.5f);
-  depth_dst[o] = (uint32_t)float_to_half_bits(ex_mix(a0, b0, 0.5f)) |
-                 ((uint32_t)float_to_half_bits(ex_mix(a1, b1, 0.5f)) << 16);
+  o.depth = (uint32_t)float_to_half_bits(ex_mix(a0, b0, 0.5f)) | ((uint32_t)float_to_half_bits(ex_mix(a1, b1, 0.5f)) << 16);
+  return o;
+}
+
+// Several mip levels per launch (the reference renders one full-screen pass per level, renderer.cpp:1328-1338).
+// A block owns a 32x32 tile of the source level and produces its 16x16, 8x8, ... footprint in up to
+// `levels` (<= 5) successive levels, passing each level to the next through shared memory. With
+// src_res <= 32 a single block walks the rest of the chain. Level l (>= 1) of the chain lives at texel
+// offset `off[l - first_level]`.
+struct RsmMipArgs {
+  const uint2* flux_src; const int* normal_src; const uint32_t* depth_src;
+  uint2* flux_mips; int* normal_mips; uint32_t* depth_mips;
+  uint32_t off[5]; // texel offsets of the destination levels
+  int src_res;     // resolution of the source level
+  int levels;      // destination levels to produce
+};
+
+__global__ void __launch_bounds__(256) rsm_mip_chain_kernel(RsmMipArgs A) {
+  __shared__ RsmTexel s_lvl[2][256];
+  const int tile = min(A.src_res, 32);
+  const int tx0 = blockIdx.x * tile, ty0 = blockIdx.y * tile;
+  int src = A.src_res, span = tile; // span = this block's extent in the current source level
+  for (int l = 0; l < A.levels; ++l) {
+    const int h = src >> 1, hs = span >> 1; // destination resolution / this block's extent in it
+    const int ox0 = (tx0 >> (l + 1)), oy0 = (ty0 >> (l + 1));
+    RsmTexel* cur = s_lvl[l & 1];
+    const RsmTexel* prev = s_lvl[(l & 1) ^ 1];
+    for (int i = threadIdx.x; i < hs * hs; i += blockDim.x) {
+      const int lx = i % hs, ly = i / hs;
+      RsmTexel t[4];
+      if (l == 0) {
+        const int gx = tx0 + 2 * lx, gy = ty0 + 2 * ly;
+        const size_t q[4] = {(size_t)(gy + 1) * src + gx, (size_t)(gy + 1) * src + gx + 1, (size_t)gy * src + gx + 1,
+                             (size_t)gy * src + gx};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          t[k].flux = __ldg(A.flux_src + q[k]);
+          t[k].normal = __ldg(A.normal_src + q[k]);
+          t[k].depth = __ldg(A.depth_src + q[k]);
+        }
+      } else {
+        const int q[4] = {(2 * ly + 1) * span + 2 * lx, (2 * ly + 1) * span + 2 * lx + 1, (2 * ly) * span + 2 * lx + 1,
+                          (2 * ly) * span + 2 * lx};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[k] = prev[q[k]];
+      }
+      const RsmTexel o = rsm_downsample4(t);
+      cur[i] = o;
+      const size_t g = A.off[l] + (size_t)(oy0 + ly) * h + (ox0 + lx);
+      A.flux_mips[g] = o.flux;
+      A.normal_mips[g] = o.normal;
+      A.depth_mips[g] = o.depth;
+    }
+    __syncthreads();
+    src = h;
+    span = hs;
+  }
 }
 
 // cacheLightingRSM.comp:154-155 / :175-176 in decision maths (the block record
@@ -138,16 +190,28 @@ drv_status drv_impl_prepare_rsm(drv_ctx* ctx, uint32_t li) {
   const int* ns = (const int*)S.normal0;
   const uint32_t* ds = (const uint32_t*)S.depth0;
   // levels 1 .. log2(res)-1: the 1x1 top level is never rendered (renderer.cpp:1293-1297)
-  for (uint32_t level = 1; (res >> level) >= 2; ++level) {
-    uint32_t src_res = res >> (level - 1), h = src_res >> 1;
-    uint64_t off = rsm_level_offset_texels(res, level);
-    uint2* fd = (uint2*)S.flux_mips + off;
-    int* nd = (int*)S.normal_mips + off;
-    uint32_t* dd = (uint32_t*)S.depth_mips + off;
-    dim3 block(16, 16), grid((h + 15) / 16, (h + 15) / 16);
-    rsm_downsample_kernel<<<grid, block, 0, ctx->stream>>>(fs, ns, ds, (int)src_res, fd, nd, dd);
+  uint32_t last = 0;
+  while ((res >> (last + 1)) >= 2) ++last; // last level to produce
+  uint32_t level = 1;                      // next level to produce
+  while (level <= last) {
+    RsmMipArgs A;
+    memset(&A, 0, sizeof(A));
+    const uint32_t src_res = res >> (level - 1);
+    A.flux_src = level == 1 ? fs : (const uint2*)S.flux_mips + rsm_level_offset_texels(res, level - 1);
+    A.normal_src = level == 1 ? ns : (const int*)S.normal_mips + rsm_level_offset_texels(res, level - 1);
+    A.depth_src = level == 1 ? ds : (const uint32_t*)S.depth_mips + rsm_level_offset_texels(res, level - 1);
+    A.flux_mips = (uint2*)S.flux_mips; A.normal_mips = (int*)S.normal_mips; A.depth_mips = (uint32_t*)S.depth_mips;
+    A.src_res = (int)src_res;
+    // a 32x32 source tile yields 5 levels (16..1); a single block (src_res <= 32) walks down to the 2x2 level
+    uint32_t n = src_res > 32 ? 5u : 31u;
+    if (n > last - level + 1) n = last - level + 1;
+    if (n > 5) n = 5;
+    A.levels = (int)n;
+    for (uint32_t k = 0; k < n; ++k) A.off[k] = (uint32_t)rsm_level_offset_texels(res, level + k);
+    const uint32_t tiles = src_res > 32 ? src_res / 32 : 1;
+    rsm_mip_chain_kernel<<<dim3(tiles, tiles), 256, 0, ctx->stream>>>(A);
     DRV_LAUNCH_CHECK();
-    fs = fd; ns = nd; ds = dd;
+    level += n;
   }
   ctx->stage_end(DRV_STAGE_PREPARE_RSM);
   return DRV_OK;

@@ -44,14 +44,20 @@ __device__ __forceinline__ void set_voxel(uint8_t* __restrict__ vol, int res, in
   vol[(size_t)x + (size_t)res * ((size_t)y + (size_t)res * z)] = 255;
 }
 
-__global__ void __launch_bounds__(256) voxelize_kernel(VoxParams P, const float* __restrict__ tris, uint32_t num_tris,
-                                                       uint8_t* __restrict__ vol) {
-  const uint32_t tri = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (tri >= num_tris) return;
+// Per-triangle raster set-up (voxelize.vert + voxelize.geom), written to shared memory by one lane.
+struct TriSetup {
+  Plane pl[3];
+  float aabb[4];
+  float vx0, vy0, vz0, gx, gy, maxChange;
+  int side, x0, y0, w, total;
+};
+
+constexpr int kTrisPerBlock = 8;
+
+__device__ __forceinline__ void setup_triangle(const VoxParams& P, const float* __restrict__ tp, TriSetup& T) {
   const int res = P.res;
   const float fres = (float)res;
-  const float* tp = tris + (size_t)tri * 9;
+  T.total = 0;
   float cx[3], cy[3], cz[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) { // voxelize.vert:20-22
@@ -70,6 +76,7 @@ __global__ void __launch_bounds__(256) voxelize_kernel(VoxParams P, const float*
   float an[3] = {fabsf(ex_mul(nr.x, inv)), fabsf(ex_mul(nr.y, inv)), fabsf(ex_mul(nr.z, inv))};
   int side = an[0] > an[1] ? 0 : 1;
   side = (side == 0 ? an[0] : an[1]) > an[2] ? side : 2;
+  T.side = side;
   float rx[3], ry[3], rz[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) { // geom:31-53
@@ -81,7 +88,7 @@ __global__ void __launch_bounds__(256) voxelize_kernel(VoxParams P, const float*
   float aabb[4] = {ex_sub(fminf(fminf(rx[0], rx[1]), rx[2]), h), ex_sub(fminf(fminf(ry[0], ry[1]), ry[2]), h),
                    ex_add(fmaxf(fmaxf(rx[0], rx[1]), rx[2]), h), ex_add(fmaxf(fmaxf(ry[0], ry[1]), ry[2]), h)};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) aabb[i] = ex_mul(ex_add(ex_mul(aabb[i], 0.5f), 0.5f), fres); // geom:61
+  for (int i = 0; i < 4; ++i) T.aabb[i] = aabb[i] = ex_mul(ex_add(ex_mul(aabb[i], 0.5f), 0.5f), fres); // geom:61
   float ax = ex_sub(rx[0], rx[2]), ay = ex_sub(ry[0], ry[2]);
   float bx = ex_sub(rx[1], rx[0]), by = ex_sub(ry[1], ry[0]);
   Plane pl[3];
@@ -95,6 +102,7 @@ __global__ void __launch_bounds__(256) voxelize_kernel(VoxParams P, const float*
   for (int i = 0; i < 3; ++i) {
     pl[i].x = ex_mul(pl[i].x, winding); pl[i].y = ex_mul(pl[i].y, winding); pl[i].z = ex_mul(pl[i].z, winding);
     pl[i].z = ex_sub(pl[i].z, ex_add(ex_mul(h, fabsf(pl[i].x)), ex_mul(h, fabsf(pl[i].y)))); // geom:78-80
+    T.pl[i] = pl[i];
   }
   float vx[3], vy[3], vz[3];
 #pragma unroll
@@ -110,32 +118,62 @@ __global__ void __launch_bounds__(256) voxelize_kernel(VoxParams P, const float*
   float e2x = ex_sub(vx[2], vx[0]), e2y = ex_sub(vy[2], vy[0]), e2z = ex_sub(vz[2], vz[0]);
   float det = ex_sub(ex_mul(e1x, e2y), ex_mul(e2x, e1y));
   if (det == 0.0f || det != det) return;
-  float gx = ex_div(ex_sub(ex_mul(e1z, e2y), ex_mul(e2z, e1y)), det); // dFdx, frag:39
-  float gy = ex_div(ex_sub(ex_mul(e1x, e2z), ex_mul(e2x, e1z)), det); // dFdy, frag:40
-  float maxChange = ex_mul(ex_sqrt(ex_add(ex_mul(gx, gx), ex_mul(gy, gy))), 1.414f); // frag:41
+  T.gx = ex_div(ex_sub(ex_mul(e1z, e2y), ex_mul(e2z, e1y)), det); // dFdx, frag:39
+  T.gy = ex_div(ex_sub(ex_mul(e1x, e2z), ex_mul(e2x, e1z)), det); // dFdy, frag:40
+  T.maxChange = ex_mul(ex_sqrt(ex_add(ex_mul(T.gx, T.gx), ex_mul(T.gy, T.gy))), 1.414f); // frag:41
+  T.vx0 = vx[0]; T.vy0 = vy[0]; T.vz0 = vz[0];
   int x0 = max(0, ex_trunc(floorf(ex_sub(aabb[0], 0.5f))));
   int y0 = max(0, ex_trunc(floorf(ex_sub(aabb[1], 0.5f))));
   int x1 = min(res - 1, ex_trunc(floorf(aabb[2])));
   int y1 = min(res - 1, ex_trunc(floorf(aabb[3])));
   if (x1 < x0 || y1 < y0) return;
-  const int w = x1 - x0 + 1;
-  const int total = w * (y1 - y0 + 1);
-  for (int i = lane; i < total; i += 32) {
-    int py = y0 + i / w, px = x0 + i % w;
+  T.x0 = x0; T.y0 = y0; T.w = x1 - x0 + 1;
+  T.total = T.w * (y1 - y0 + 1);
+}
+
+// A block rasterises kTrisPerBlock triangles: eight lanes set them up, then all 256 threads sweep the
+// concatenated bounding-box pixel lists, so one wall-sized triangle does not serialise on a single warp.
+__global__ void __launch_bounds__(256) voxelize_kernel(VoxParams P, const float* __restrict__ tris, uint32_t num_tris,
+                                                       uint8_t* __restrict__ vol) {
+  __shared__ TriSetup s_tri[kTrisPerBlock];
+  __shared__ int s_start[kTrisPerBlock + 1];
+  const uint32_t tri0 = blockIdx.x * kTrisPerBlock;
+  if (threadIdx.x < kTrisPerBlock) {
+    s_tri[threadIdx.x].total = 0;
+    if (tri0 + threadIdx.x < num_tris) setup_triangle(P, tris + (size_t)(tri0 + threadIdx.x) * 9, s_tri[threadIdx.x]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < kTrisPerBlock; ++i) { s_start[i] = acc; acc += s_tri[i].total; }
+    s_start[kTrisPerBlock] = acc;
+  }
+  __syncthreads();
+  const int res = P.res;
+  const float fres = (float)res;
+  const int total = s_start[kTrisPerBlock];
+  // gridDim.y blocks share one triangle group: block y takes every gridDim.y-th stripe of 256 pixels
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += blockDim.x * gridDim.y) {
+    int t = 0;
+#pragma unroll
+    for (int k = 1; k < kTrisPerBlock; ++k) t += (i >= s_start[k]) ? 1 : 0;
+    const TriSetup& T = s_tri[t];
+    const int j = i - s_start[t];
+    int py = T.y0 + j / T.w, px = T.x0 + j % T.w;
     float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
-    if (fx < aabb[0] || fy < aabb[1] || fx > aabb[2] || fy > aabb[3]) continue; // frag:24-27
+    if (fx < T.aabb[0] || fy < T.aabb[1] || fx > T.aabb[2] || fy > T.aabb[3]) continue; // frag:24-27
     float ccx = ex_sub(ex_mul(ex_div(fx, fres), 2.0f), 1.0f), ccy = ex_sub(ex_mul(ex_div(fy, fres), 2.0f), 1.0f);
     bool inside = true;
 #pragma unroll
     for (int e = 0; e < 3; ++e)
-      if (ex_add(ex_add(ex_mul(pl[e].x, ccx), ex_mul(pl[e].y, ccy)), pl[e].z) > 0.0f) inside = false;
+      if (ex_add(ex_add(ex_mul(T.pl[e].x, ccx), ex_mul(T.pl[e].y, ccy)), T.pl[e].z) > 0.0f) inside = false;
     if (!inside) continue;
-    float zv = ex_add(vz[0], ex_add(ex_mul(gx, ex_sub(fx, vx[0])), ex_mul(gy, ex_sub(fy, vy[0])))); // frag:33
+    float zv = ex_add(T.vz0, ex_add(ex_mul(T.gx, ex_sub(fx, T.vx0)), ex_mul(T.gy, ex_sub(fy, T.vy0)))); // frag:33
     if (zv < 0.0f || zv > fres) continue;
-    int zi = ex_trunc(zv);                                                                        // frag:34
-    set_voxel(vol, res, side, px, py, zi);
-    if (zi != ex_trunc(ex_sub(zv, maxChange))) set_voxel(vol, res, side, px, py, zi - 1);       // frag:46-51
-    if (zi != ex_trunc(ex_add(zv, maxChange))) set_voxel(vol, res, side, px, py, zi + 1);       // frag:52-57
+    int zi = ex_trunc(zv);                                                                          // frag:34
+    set_voxel(vol, res, T.side, px, py, zi);
+    if (zi != ex_trunc(ex_sub(zv, T.maxChange))) set_voxel(vol, res, T.side, px, py, zi - 1);       // frag:46-51
+    if (zi != ex_trunc(ex_add(zv, T.maxChange))) set_voxel(vol, res, T.side, px, py, zi + 1);       // frag:52-57
   }
 }
 
@@ -159,22 +197,49 @@ __global__ void voxel_blend_kernel(uint4* __restrict__ vol, const uint4* __restr
   vol[i] = make_uint4(r[0], r[1], r[2], r[3]);
 }
 
-// voxelmipmap.comp:11-12: one thread per destination voxel quad (4 along x).
-__global__ void voxel_mip_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int sres) {
-  const int h = sres >> 1;
-  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y,
-      z = blockIdx.z * blockDim.z + threadIdx.z;
-  if (x >= h || y >= h || z >= h) return;
-  int sum = 0;
+// voxelmipmap.comp:11-12, several levels per launch (the reference dispatches one pass per level,
+// voxelization.cpp:161-171). A block owns a T^3 tile of the source level (T = min(16, source resolution))
+// and reduces it through shared memory: 16^3 -> 8^3 -> 4^3 -> 2^3 -> 1, storing each level. Every level is
+// rounded to UNORM8 ((sum + 4) >> 3) before it feeds the next one, exactly as separate passes would.
+struct VoxMipArgs {
+  const uint8_t* src;
+  uint8_t* dst[4];
+  int src_res;
+  int levels; // <= 4
+};
+
+__global__ void __launch_bounds__(256) voxel_mip_chain_kernel(VoxMipArgs A) {
+  __shared__ uint8_t s_a[16 * 16 * 16];
+  __shared__ uint8_t s_b[8 * 8 * 8];
+  const int T = min(A.src_res, 16);
+  const int bx = blockIdx.x * T, by = blockIdx.y * T, bz = blockIdx.z * T;
+  // stage the tile (rows of T bytes; T is 16 or a smaller power of two)
+  for (int i = threadIdx.x; i < T * T * T; i += blockDim.x) {
+    const int x = i % T, y = (i / T) % T, z = i / (T * T);
+    s_a[i] = A.src[(size_t)(bx + x) + (size_t)A.src_res * ((size_t)(by + y) + (size_t)A.src_res * (bz + z))];
+  }
+  __syncthreads();
+  uint8_t* cur = s_a;
+  uint8_t* nxt = s_b;
+  int span = T, res = A.src_res;
+  for (int l = 0; l < A.levels; ++l) {
+    const int hs = span >> 1, h = res >> 1;
+    const int ox = bx >> (l + 1), oy = by >> (l + 1), oz = bz >> (l + 1);
+    for (int i = threadIdx.x; i < hs * hs * hs; i += blockDim.x) {
+      const int x = i % hs, y = (i / hs) % hs, z = i / (hs * hs);
+      int sum = 0;
 #pragma unroll
-  for (int dz = 0; dz < 2; ++dz)
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-      const uint8_t* row = src + (size_t)(2 * x) + (size_t)sres * ((size_t)(2 * y + dy) + (size_t)sres * (2 * z + dz));
-      uint16_t two = *reinterpret_cast<const uint16_t*>(row);
-      sum += (two & 0xff) + (two >> 8);
+      for (int k = 0; k < 8; ++k)
+        sum += cur[(2 * x + (k & 1)) + span * ((2 * y + ((k >> 1) & 1)) + span * (2 * z + (k >> 2)))];
+      const uint8_t v = (uint8_t)((sum + 4) >> 3);
+      nxt[i] = v;
+      A.dst[l][(size_t)(ox + x) + (size_t)h * ((size_t)(oy + y) + (size_t)h * (oz + z))] = v;
     }
-  dst[(size_t)x + (size_t)h * ((size_t)y + (size_t)h * z)] = (uint8_t)((sum + 4) >> 3);
+    __syncthreads();
+    uint8_t* t = cur; cur = nxt; nxt = t; // 8^3 fits s_b; 4^3 and below fit either buffer
+    span = hs;
+    res = h;
+  }
 }
 
 // Gather-ready records for the cone tracer (stage 4): for every level and every lower-corner coordinate
@@ -215,14 +280,24 @@ static drv_status drv_impl_voxel_mips_and_records(drv_ctx* ctx) {
   const int res = (int)ctx->cfg.voxel_resolution;
   int sres = res;
   uint8_t* src = ctx->voxel_chain;
-  while (sres > 1) {
-    int h = sres >> 1;
-    uint8_t* dst = src + (size_t)sres * sres * sres;
-    dim3 block(8, 8, 4), grid((h + 7) / 8, (h + 7) / 8, (h + 3) / 4);
-    voxel_mip_kernel<<<grid, block, 0, ctx->stream>>>(src, dst, sres);
+  while (sres > 1) { // up to four levels per launch
+    VoxMipArgs A;
+    memset(&A, 0, sizeof(A));
+    A.src = src;
+    A.src_res = sres;
+    int r = sres, n = 0;
+    uint8_t* level = src;
+    while (n < 4 && r > 1) {
+      level += (size_t)r * r * r;
+      r >>= 1;
+      A.dst[n++] = level;
+    }
+    A.levels = n;
+    const int tiles = sres > 16 ? sres / 16 : 1;
+    voxel_mip_chain_kernel<<<dim3(tiles, tiles, tiles), 256, 0, ctx->stream>>>(A);
     DRV_LAUNCH_CHECK();
-    src = dst;
-    sres = h;
+    src = level;
+    sres = r;
   }
   if (ctx->voxel_records) {
     RecordLevels L;
@@ -265,9 +340,10 @@ drv_status drv_impl_voxelize(drv_ctx* ctx, const float* tris, uint32_t n, const 
     memcpy(P.vmax, ctx->volume.VolumeWorldMax, 12);
     memcpy(P.world, world, 64);
     P.res = res;
-    uint32_t warps_per_block = 8;
-    voxelize_kernel<<<(n + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, ctx->stream>>>(
-        P, tris, n, ctx->voxel_target);
+    const uint32_t groups = (n + kTrisPerBlock - 1) / kTrisPerBlock;
+    // few, large triangles (architectural scenes): spread each group's pixels over several blocks
+    const uint32_t slices = groups >= 4096 ? 1 : (groups >= 512 ? 4 : 16);
+    voxelize_kernel<<<dim3(groups, slices), 256, 0, ctx->stream>>>(P, tris, n, ctx->voxel_target);
     DRV_LAUNCH_CHECK();
   }
   ctx->stage_end(DRV_STAGE_VOXELIZE_SCENE);
