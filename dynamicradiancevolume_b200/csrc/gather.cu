@@ -62,6 +62,8 @@ struct GatherParams {
   // voxel volume (cone tracing): gather-ready records, see voxel.cu
   const uint2* rec;
   uint32_t rec_offset[16];
+  const uint32_t* brick_mask; // 1024 words, see voxel.cu: voxel_brick_mask_kernel
+  int brick_shift;
   int vres, vlevels;
   float vmin[3];
   float voxel_size;
@@ -120,7 +122,9 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // footprint's lower corner + 1.
 struct VoxelVol {
   const uint2* rec;
-  const uint32_t* rec_offset; // shared-memory copy of GatherParams::rec_offset
+  const uint32_t* rec_offset; // GatherParams::rec_offset in the kernel's constant bank (LDC with a register index)
+  const uint32_t* brick_mask; // shared-memory copy of the empty-brick mask
+  int brick_shift;
   int res, levels;
   float vmin[3];
   float voxel_size;
@@ -148,15 +152,21 @@ struct Footprint {
   float tx, ty, tz;
 };
 
-// footprint of the sample at p (volume coordinates in [0,1]^3) in level `l`
-__device__ __forceinline__ Footprint footprint(const VoxelVol& V, int l, float px, float py, float pz) {
+// footprint of the sample at q in level `l`; q is given in level-0 texel units with the half-texel shift
+// already applied (q = p * res - 0.5 for p in [0,1]^3), so level l sees q * 2^-l + (2^-(l+1) - 0.5)
+__device__ __forceinline__ Footprint footprint(const VoxelVol& V, int l, float qx, float qy, float qz) {
   const int r = V.res >> l;
-  const float fr = __int_as_float(__float_as_int((float)V.res) - (l << 23)); // res * 2^-l, exact (power of two)
   Footprint F;
   int x, y, z;
-  floor_frac(fmaf(px, fr, -0.5f), x, F.tx);
-  floor_frac(fmaf(py, fr, -0.5f), y, F.ty);
-  floor_frac(fmaf(pz, fr, -0.5f), z, F.tz);
+  if (l == 0) {
+    floor_frac(qx, x, F.tx); floor_frac(qy, y, F.ty); floor_frac(qz, z, F.tz);
+  } else {
+    const float sc = __int_as_float(0x3f800000 - (l << 23));  // 2^-l
+    const float of = fmaf(sc, 0.5f, -0.5f);
+    floor_frac(fmaf(qx, sc, of), x, F.tx);
+    floor_frac(fmaf(qy, sc, of), y, F.ty);
+    floor_frac(fmaf(qz, sc, of), z, F.tz);
+  }
   // clamp the lower corner to [-1, r-1]: outside that range both taps of the axis are the same edge texel
   x = min(max(x, -1), r - 1) + 1;
   y = min(max(y, -1), r - 1) + 1;
@@ -178,77 +188,94 @@ __device__ __forceinline__ float trilinear(uint2 rec, float tx, float ty, float 
   return fmaf(tz, c1 - c0, c0) * (1.0f / 255.0f);
 }
 
-// NC cones of one thread marched in lock step (cacheLightingRSM.comp:195-230 each). Distances, step sizes and
-// the break test are decision maths (the trip count equals the oracle's); positions, filtering and occlusion
-// are continuous maths. Every iteration first issues the loads of all cones, then filters — the loads of
-// different cones overlap, which is what the march (a serial chain of dependent fetches) lacks on its own.
+// One sample of the march with its loads in flight.
+struct ConeSample {
+  uint2 r0, r1;          // records of level l0 and l0 + 1 (r1 only when t != 0)
+  float tx0, ty0, tz0;   // trilinear fractions in level l0
+  float tx1, ty1, tz1;   // ... in level l0 + 1
+  float t;               // mip fraction: 0 = level l0 only
+  float dist, radius;
+  bool skip;             // sample position lies in an empty brick: the sample is exactly 0, nothing was fetched
+};
+
+// cacheLightingRSM.comp:195-230 for one cache and one shadow block. Distances, step sizes and the break test
+// are decision maths (the trip count equals the oracle's); positions, filtering and occlusion are continuous
+// maths. The march is software-pipelined: where a cone goes next depends only on the distance travelled, not
+// on what it sampled, so the fetch of step s+1 is issued before step s is filtered and the L1/L2 latency of
+// the dependent chain position -> index -> load -> filter -> occlusion overlaps with useful work.
 // A cone also stops once occlusion reached 1: later samples would add (1 - 1) * x = 0.
-template <int NC>
-__device__ __forceinline__ void cone_trace_n(const VoxelVol& V, float wx, float wy, float wz, const float4* blk, int nb,
-                                             float* shadow_out) {
-  const float fres = (float)V.res;
-  const float inv_extent = 1.0f / (V.voxel_size * fres);
-  const float vpx = (wx - V.vmin[0]) * inv_extent, vpy = (wy - V.vmin[1]) * inv_extent, vpz = (wz - V.vmin[2]) * inv_extent; // :104
+template <bool ZSKIP>
+__device__ __forceinline__ float cone_trace(const VoxelVol& V, float wx, float wy, float wz, float4 blk) {
+  // :104 voxelPos, kept in level-0 texel units minus the half-texel shift (q = voxelPos * res - 0.5), so that a
+  // step of `stepSize` voxels along the unit direction is q += dir * stepSize (:197-198, 213)
+  const float inv_voxel = 1.0f / V.voxel_size;
   const float maxLod = (float)(V.levels - 1);
-  float cx[NC], cy[NC], cz[NC], dx[NC], dy[NC], dz[NC];
-  float dist[NC], stepSize[NC], occ[NC], kk[NC], radToStep[NC], goal[NC];
-  bool live[NC];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const float4 b = blk[c < nb ? c : 0];
-    live[c] = c < nb;
-    kk[c] = b.w;
-    float tx = ex_sub(b.x, wx), ty = ex_sub(b.y, wy), tz = ex_sub(b.z, wz);     // :195
-    float lightDist = ex_sqrt(ex_dot3(tx, ty, tz, tx, ty, tz));                 // :196
-    float inv = 1.0f / (lightDist * fres);
-    dx[c] = tx * inv; dy[c] = ty * inv; dz[c] = tz * inv;                       // :197-198 dirInVoxel
-    cx[c] = fmaf(dx[c], 2.0f, vpx); cy[c] = fmaf(dy[c], 2.0f, vpy); cz[c] = fmaf(dz[c], 2.0f, vpz); // :201
-    occ[c] = 0.0f; stepSize[c] = 1.0f; dist[c] = 0.0f;
-    goal[c] = ex_sub(ex_div(lightDist, V.voxel_size), 2.0f);                    // :206
-    radToStep[c] = ex_div(2.0f, ex_sub(1.0f, b.w));                             // :209
-  }
+  const float kk = blk.w;
+  float tx = ex_sub(blk.x, wx), ty = ex_sub(blk.y, wy), tz = ex_sub(blk.z, wz);     // :195
+  const float lightDist = ex_sqrt(ex_dot3(tx, ty, tz, tx, ty, tz));                 // :196
+  const float inv = 1.0f / lightDist;
+  const float dx = tx * inv, dy = ty * inv, dz = tz * inv;                          // :197-198 (dirInVoxel * res)
+  float cx = fmaf(dx, 2.0f, fmaf(wx - V.vmin[0], inv_voxel, -0.5f));                // :201
+  float cy = fmaf(dy, 2.0f, fmaf(wy - V.vmin[1], inv_voxel, -0.5f));
+  float cz = fmaf(dz, 2.0f, fmaf(wz - V.vmin[2], inv_voxel, -0.5f));
+  const float goal = ex_sub(ex_div(lightDist, V.voxel_size), 2.0f);                 // :206
+  const float radToStep = ex_div(2.0f, ex_sub(1.0f, kk));                           // :209
+  float dist = 0.0f;
+
+  // advance by `stepSize` (:213-216) and issue the fetches of that sample (:219)
+  auto fetch = [&](float stepSize) -> ConeSample {
+    ConeSample S;
+    cx = fmaf(dx, stepSize, cx); cy = fmaf(dy, stepSize, cy); cz = fmaf(dz, stepSize, cz); // :213
+    dist = ex_add(dist, stepSize);                                                  // :214
+    S.dist = dist;
+    S.radius = ex_mul(dist, kk);                                                    // :216
+    S.t = 0.0f;
+    S.skip = false;
+    int l0 = 0;
+    if (S.radius > 1.0f) {
+      // lod = log2(radius) clamped to the chain. radius <= 1 — the first stretch of every cone, a VAL block
+      // subtends ~1/32 rad — is level 0 exactly, without the log. fmaxf(NaN, 0) = 0.
+      const float l = fminf(__log2f(S.radius), maxLod);
+      floor_frac(l, l0, S.t);
+    } else if (ZSKIP) {
+      // lod 0: inside a brick whose one-voxel neighbourhood is empty the footprint is all zeros
+      const int vx = __float_as_int(cx + kMagic) - 0x4B400000; // round(q) = floor(q + .5) = voxel of the position
+      const int vy = __float_as_int(cy + kMagic) - 0x4B400000;
+      const int vz = __float_as_int(cz + kMagic) - 0x4B400000;
+      if ((uint32_t)(vx | vy | vz) < (uint32_t)V.res) {
+        const int sh = V.brick_shift;
+        S.skip = (V.brick_mask[(vy >> sh) + 32 * (vz >> sh)] >> (vx >> sh)) & 1u;
+      }
+    }
+    if (!S.skip) {
+      const Footprint f0 = footprint(V, l0, cx, cy, cz);
+      S.r0 = __ldg(V.rec + f0.index);
+      S.tx0 = f0.tx; S.ty0 = f0.ty; S.tz0 = f0.tz;
+      if (S.t != 0.0f) { // mip-linear: also the next coarser level
+        const Footprint f1 = footprint(V, min(l0 + 1, V.levels - 1), cx, cy, cz);
+        S.r1 = __ldg(V.rec + f1.index);
+        S.tx1 = f1.tx; S.ty1 = f1.ty; S.tz1 = f1.tz;
+      }
+    }
+    return S;
+  };
+
+  float occ = 0.0f;
+  ConeSample cur = fetch(1.0f);
   for (int s = 0; s < 32; ++s) {
-    bool any = false;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) any |= live[c];
-    if (!any) break;
-    Footprint f0[NC];
-    float radius[NC], lod[NC];
-    uint2 r0[NC];
-    int l0[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      cx[c] = fmaf(dx[c], stepSize[c], cx[c]); cy[c] = fmaf(dy[c], stepSize[c], cy[c]); cz[c] = fmaf(dz[c], stepSize[c], cz[c]); // :213
-      dist[c] = ex_add(dist[c], stepSize[c]);                                   // :214
-      radius[c] = ex_mul(dist[c], kk[c]);                                       // :216
-      // :219 lod = log2(radius) clamped to the chain; radius <= 1 (the first stretch of every cone: a VAL
-      // block subtends ~1/32 rad) is level 0 exactly, without the log. fmaxf(NaN, 0) = 0.
-      lod[c] = 0.0f;
-      l0[c] = 0;
-      if (radius[c] > 1.0f) {
-        const float l = fminf(__log2f(radius[c]), maxLod); // in (0, maxLod]
-        floor_frac(l, l0[c], lod[c]);                       // lod[c] := fractional part in [0, 1]
-      }
-      f0[c] = footprint(V, l0[c], cx[c], cy[c], cz[c]);
-      r0[c] = __ldg(V.rec + f0[c].index);
+    const bool last = (cur.dist >= goal) || (s == 31);                              // :211, :222
+    ConeSample nxt = cur;
+    if (!last) nxt = fetch(fmaxf(1.0f, ex_mul(cur.radius, radToStep)));             // :225, one step ahead
+    float o = 0.0f;
+    if (!cur.skip) {
+      o = trilinear(cur.r0, cur.tx0, cur.ty0, cur.tz0);
+      if (cur.t != 0.0f) o = fmaf(cur.t, trilinear(cur.r1, cur.tx1, cur.ty1, cur.tz1) - o, o);
     }
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      float o = trilinear(r0[c], f0[c].tx, f0[c].ty, f0[c].tz);
-      if (lod[c] != 0.0f) { // mip-linear: blend with the next coarser level
-        const Footprint f1 = footprint(V, min(l0[c] + 1, V.levels - 1), cx[c], cy[c], cz[c]);
-        const float b = trilinear(__ldg(V.rec + f1.index), f1.tx, f1.ty, f1.tz);
-        o = fmaf(lod[c], b - o, o);
-      }
-      if (live[c]) {
-        occ[c] = fmaf(1.0f - occ[c], o, occ[c]);                                // :220
-        if (dist[c] >= goal[c] || occ[c] >= 1.0f) live[c] = false;              // :222
-        stepSize[c] = fmaxf(1.0f, ex_mul(radius[c], radToStep[c]));             // :225
-      }
-    }
+    occ = fmaf(1.0f - occ, o, occ);                                                 // :220
+    if (last || occ >= 1.0f) break;
+    cur = nxt;
   }
-#pragma unroll
-  for (int c = 0; c < NC; ++c) shadow_out[c] = saturatef(1.0f - occ[c]);        // :230
+  return saturatef(1.0f - occ);                                                     // :230
 }
 
 // ------------------------------------------------------------ epilogue helpers
@@ -375,13 +402,11 @@ struct ScalarMath {
     slot[0] = r0; slot[1] = r1; slot[2] = r2;
   }
   // CPT cones (one per cache of this thread) x up to NB consecutive shadow blocks, marched in lock step
-  template <int NB>
-  __device__ __forceinline__ void trace(const VoxelVol& V, const float4* blk, int nb, float (&out)[NB][CPT]) {
+  // one cone per cache of this thread towards shadow block `blk` (cacheLightingRSM.comp:169-232)
+  template <bool ZSKIP>
+  __device__ __forceinline__ void trace(const VoxelVol& V, const float4* blk) {
     static_assert(CPT == 1, "shadowed gathers keep one cache per thread");
-    float sh[NB];
-    cone_trace_n<NB>(V, px[0], py[0], pz[0], blk, live[0] ? nb : 0, sh);
-#pragma unroll
-    for (int b = 0; b < NB; ++b) out[b][0] = live[0] ? sh[b] : 0.0f;
+    shadow[0] = live[0] ? cone_trace<ZSKIP>(V, px[0], py[0], pz[0], *blk) : 0.0f;
   }
   __device__ __forceinline__ void set_shadow(const float (&v)[CPT]) {
 #pragma unroll
@@ -436,8 +461,8 @@ struct PackedMath {
     d[3] = make_float4(r1.z, r1.z, r2.x, r2.x);
     d[4] = make_float4(r2.y, r2.y, r2.z, r2.z);
   }
-  template <int NB>
-  __device__ __forceinline__ void trace(const VoxelVol&, const float4*, int, float (&)[NB][CPT]) {} // unshadowed only
+  template <bool ZSKIP>
+  __device__ __forceinline__ void trace(const VoxelVol&, const float4*) {} // unshadowed only
   __device__ __forceinline__ void set_shadow(const float (&v)[CPT]) {
 #pragma unroll
     for (int j = 0; j < PAIRS; ++j) { shadow[j].x = v[2 * j]; shadow[j].y = v[2 * j + 1]; }
@@ -559,8 +584,9 @@ __device__ __forceinline__ void advance(const GatherParams& p, const Schedule& S
   if (c.base >= c.v_end) start_run(p, S, c, c.u_next, u1);
 }
 
-template <int ORDER, bool SHADOW, typename Math, bool USE_TMA, int CONES = 1>
-__global__ void __launch_bounds__(kThreads) gather_kernel(GatherParams p) {
+// CONES: 1 = plain cone march, 2 = skipping samples inside empty bricks (shadowed kernels only)
+template <int ORDER, bool SHADOW, typename Math, bool USE_TMA, int CONES = 1, int MINB = 1>
+__global__ void __launch_bounds__(kThreads, MINB) gather_kernel(const __grid_constant__ GatherParams p) {
   constexpr int CPT = Math::CPT;
   constexpr int TILE = kThreads * CPT;
   constexpr int NC = num_coefs<ORDER>();
@@ -570,7 +596,7 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(GatherParams p) {
   __shared__ __align__(128) float4 s_vpl[STAGES][kVplTile * SPV];
   __shared__ float4 s_blk[SHADOW ? kVplTile : 1];
   __shared__ __align__(8) uint64_t s_bar[2];
-  __shared__ uint32_t s_rec_offset[16];
+  __shared__ uint32_t s_brick_mask[(SHADOW && CONES == 2) ? 1024 : 1];
 
   const Schedule S = make_schedule(p, TILE);
   if (S.units == 0) return;
@@ -578,10 +604,13 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(GatherParams p) {
   if (u0 >= u1) return;
   VoxelVol V;
   if (SHADOW) {
-    if (threadIdx.x < 16) s_rec_offset[threadIdx.x] = p.rec_offset[threadIdx.x];
-    V.rec = p.rec; V.rec_offset = s_rec_offset; V.res = p.vres; V.levels = p.vlevels; V.voxel_size = p.voxel_size;
+    V.rec = p.rec; V.rec_offset = p.rec_offset; V.res = p.vres; V.levels = p.vlevels; V.voxel_size = p.voxel_size;
     V.vmin[0] = p.vmin[0]; V.vmin[1] = p.vmin[1]; V.vmin[2] = p.vmin[2];
-    __syncthreads();
+    V.brick_mask = s_brick_mask; V.brick_shift = p.brick_shift;
+    if (CONES == 2) {
+      for (int i = threadIdx.x; i < 1024; i += kThreads) s_brick_mask[i] = __ldg(p.brick_mask + i);
+      __syncthreads();
+    }
   }
   uint32_t phase[2] = {0u, 0u};
   if (USE_TMA) {
@@ -659,27 +688,15 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(GatherParams p) {
       // :169 — a new shadow value every `interval` VPLs. A tile starts on a multiple of the granule, which is
       // a multiple of every interval <= granule; for longer intervals the value carries over.
       const uint32_t interval = p.lights[cur.light].interval;
+      constexpr bool ZSKIP = CONES == 2;
       if (interval > (uint32_t)kVplTile) {
-        if ((cur.base & (interval - 1u)) == 0u) {
-          float sh[1][CPT];
-          M.template trace<1>(V, s_blk, 1, sh);
-          M.set_shadow(sh[0]);
-        }
+        if ((cur.base & (interval - 1u)) == 0u) M.template trace<ZSKIP>(V, s_blk);
         for (int i = 0; i < n; ++i) M.eval(sv + i * SPV);
       } else {
-        const int nblocks = (n + (int)interval - 1) / (int)interval;
-        int i = 0;
-        for (int b0 = 0; b0 < nblocks; b0 += CONES) {
-          float sh[CONES][CPT];
-          M.template trace<CONES>(V, s_blk + b0, min(CONES, nblocks - b0), sh);
-#pragma unroll
-          for (int b = 0; b < CONES; ++b) {
-            if (b0 + b < nblocks) {
-              M.set_shadow(sh[b]);
-              const int end = min(n, i + (int)interval);
-              for (; i < end; ++i) M.eval(sv + i * SPV);
-            }
-          }
+        for (int i = 0, b = 0; i < n; ++b) {
+          M.template trace<ZSKIP>(V, s_blk + b);
+          const int end = min(n, i + (int)interval);
+          for (; i < end; ++i) M.eval(sv + i * SPV);
         }
       }
     } else {
@@ -857,6 +874,8 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   p.f20 = ctx->constant.ShEvaFactor20;
   p.f22 = ctx->constant.ShEvaFactor2p2;
   p.rec = ctx->voxel_records;
+  p.brick_mask = ctx->voxel_brick_mask;
+  p.brick_shift = (int)ctx->voxel_brick_shift;
   for (int l = 0; l < 16; ++l) p.rec_offset[l] = ctx->voxel_record_offset[l];
   p.vres = (int)ctx->cfg.voxel_resolution;
   p.vlevels = (int)ctx->voxel_levels;
@@ -875,10 +894,12 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   using S2n2 = ScalarMath<2, false, 2>; using S2n1 = ScalarMath<2, false, 1>; using S2s1 = ScalarMath<2, true, 1>;
   using P1n1 = PackedMath<1, false, 1>; using P1n2 = PackedMath<1, false, 2>;
   using P2n1 = PackedMath<2, false, 1>;
-  if (shadow) { // variants select how many cones a thread marches in lock step
-    const int cones = variant == 6 ? 2 : (variant == 7 ? 4 : 1); // measured on C3: 1 cone/thread is fastest (profiles/)
-    if (order == 1) { if (cones == 1) DRV_GATHER(1, true, S1s1, false, 1); if (cones == 4) DRV_GATHER(1, true, S1s1, false, 4); DRV_GATHER(1, true, S1s1, false, 2); }
-    else            { if (cones == 1) DRV_GATHER(2, true, S2s1, false, 1); if (cones == 4) DRV_GATHER(2, true, S2s1, false, 4); DRV_GATHER(2, true, S2s1, false, 2); }
+  if (shadow) { // variant 6: skip samples whose position lies in an empty brick (exact: such samples add 0)
+    if (variant == 6) { if (order == 1) DRV_GATHER(1, true, S1s1, false, 2); else DRV_GATHER(2, true, S2s1, false, 2); }
+    if (variant == 7) { if (order == 1) DRV_GATHER(1, true, S1s1, false, 1); else DRV_GATHER(2, true, S2s1, false, 1); }
+    // default: register budget for 4 CTAs / SM (128 registers): +14 % over the unconstrained build (profiles/)
+    if (order == 1) return launch_gather(ctx, gather_kernel<1, true, S1s1, false, 1, 4>, p, kThreads, 1);
+    return launch_gather(ctx, gather_kernel<2, true, S2s1, false, 1, 4>, p, kThreads, 2);
   }
   switch (variant) {
     case 1: // scalar maths, TMA bulk staging
@@ -892,10 +913,24 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
     case 5: // scalar, SH2 with one cache per thread
       if (order == 2) DRV_GATHER(2, false, S2n1, false, 1);
       break;
+    case 8: // scalar, register budget for 8 CTAs / SM
+      if (order == 1) return launch_gather(ctx, gather_kernel<1, false, S1n2, false, 1, 8>, p, kThreads * 2, 1);
+      return launch_gather(ctx, gather_kernel<2, false, S2n2, false, 1, 5>, p, kThreads * 2, 2);
+    case 9: // TMA staging, register budget for 8 CTAs / SM
+      if (order == 1) return launch_gather(ctx, gather_kernel<1, false, S1n2, true, 1, 8>, p, kThreads * 2, 1);
+      return launch_gather(ctx, gather_kernel<2, false, S2n2, true, 1, 5>, p, kThreads * 2, 2);
+    case 10: // packed, one pair per thread, 8 CTAs / SM
+      if (order == 1) return launch_gather(ctx, gather_kernel<1, false, P1n1, false, 1, 7>, p, kThreads * 2, 1);
+      return launch_gather(ctx, gather_kernel<2, false, P2n1, false, 1, 5>, p, kThreads * 2, 2);
+    case 11: // scalar, one cache per thread (most CTAs / SM)
+      if (order == 1) return launch_gather(ctx, gather_kernel<1, false, ScalarMath<1, false, 1>, false, 1, 10>, p, kThreads, 1);
+      break;
     default:
       break;
   }
-  // variant 0 (default): scalar maths, register-prefetch staging
-  if (order == 1) DRV_GATHER(1, false, S1n2, false, 1); else DRV_GATHER(2, false, S2n2, false, 1);
+  // variant 0 (default): packed FP32x2 maths (4 caches / thread for SH1, 2 for SH2) — the fastest in the sweep
+  // (profiles/); variant 12 = scalar maths, register-prefetch staging
+  if (variant == 12) { if (order == 1) DRV_GATHER(1, false, S1n2, false, 1); else DRV_GATHER(2, false, S2n2, false, 1); }
+  if (order == 1) DRV_GATHER(1, false, P1n2, false, 1); else DRV_GATHER(2, false, P2n1, false, 1);
 #undef DRV_GATHER
 }
