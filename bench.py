@@ -12,9 +12,9 @@ step    = one frame of the hot path: RSM mip chain (ShadowMap::PrepareRSM) -> [v
           apply (Renderer::Draw, rendering/renderer.cpp:539-594 minus rasterisation / direct light / tonemap).
 value   = ms per frame with all inputs resident in HBM, CUDA events on the context's stream around every
           step, L2 flushed (512 MiB memset) between steps, max over ranks.
-e2e     = the same frame through the host-buffer C-ABI calls (drv_upload_gbuffer / drv_upload_rsm /
-          drv_draw_to_host): pinned host G-buffer + RSM level 0 copied H2D and the RGBA16F result copied D2H
-          inside the timed region.
+e2e     = the same frame through the host-buffer C-ABI call (drv_draw_host_frame): pinned host G-buffer + RSM
+          level 0 copied H2D and the RGBA16F result copied D2H inside the timed region, copies and stages
+          overlapped within the frame (never across frames).
 N > 1   = one process per GPU (torchrun). Allocation is replicated (deterministic scan => identical entry
           indices on every rank, no communication); the cache x VPL gather is sharded over contiguous
           cell-ordered entry ranges; finished SH entries are stored to every peer over NVLink from inside the
@@ -311,15 +311,17 @@ def run_b200(args):
     d2h = h_out.numel() * h_out.element_size()
 
     def frame_e2e():
-        ctx.upload_gbuffer(*h_gb)
-        for i, r in enumerate(h_rsm):
-            ctx.upload_rsm(i, *r)
-            ctx.prepare_rsm(i)
         if wl.indirect_shadow:
             ctx.voxelize(g.tris, None, 1.0)
         if world == 1:
-            ctx.draw_to_host(h_out)
+            # one call: H2D (RSMs, depth, then normal/albedo bands) -> mips -> allocate -> light -> apply per band
+            # -> D2H per band, overlapped inside the frame; returns when the RGBA16F image is in host memory
+            ctx.draw_host_frame(h_gb[0], h_gb[1], h_gb[2], h_rsm, h_out)
         else:
+            ctx.upload_gbuffer(*h_gb)
+            for i, r in enumerate(h_rsm):
+                ctx.upload_rsm(i, *r)
+                ctx.prepare_rsm(i)
             with torch.cuda.stream(stream):
                 hdr16.zero_()
                 ctx.allocate_caches()

@@ -54,6 +54,7 @@ SYMBOLS = [
     ("drv_upload_gbuffer", _st, [_P, _P, _P, _P, _u32, _u32]),
     ("drv_upload_rsm", _st, [_P, _u32, _P, _P, _P, _u32]),
     ("drv_draw_to_host", _st, [_P, _P]),
+    ("drv_draw_host_frame", _st, [_P, C.POINTER(abi.HostFrame)]),
     ("drv_pack_constant", None, [C.POINTER(abi.Constant), _i32, _i32, _i32, _i32, _i32, _u32]),
     ("drv_pack_per_frame", None, [C.POINTER(abi.PerFrame), _P, _f32]),
     ("drv_pack_volume_info", None, [C.POINTER(abi.VolumeInfo), _P, C.POINTER(_f32 * 3), C.POINTER(_f32 * 3), _i32, _i32,

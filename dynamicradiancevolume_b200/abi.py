@@ -122,6 +122,17 @@ class Buffers(C.Structure):
     ]
 
 
+class HostFrame(C.Structure):
+    """``drv_host_frame`` (drv_gi.h)."""
+    _fields_ = [
+        ("depth", C.c_void_p), ("normal_rg16i", C.c_void_p), ("diffuse_srgb8x", C.c_void_p),
+        ("num_lights", u32),
+        ("rsm_flux_rgbx16f", C.c_void_p * DRV_MAX_LIGHTS), ("rsm_normal_rg16i", C.c_void_p * DRV_MAX_LIGHTS),
+        ("rsm_depthlinsq_rg16f", C.c_void_p * DRV_MAX_LIGHTS), ("rsm_resolution", u32 * DRV_MAX_LIGHTS),
+        ("hdr_out", C.c_void_p), ("bands", u32),
+    ]
+
+
 assert C.sizeof(Constant) == 80
 assert C.sizeof(PerFrame) == 288
 assert C.sizeof(CAVCascade) == 64

@@ -128,12 +128,13 @@ template <int ORDER>
 __global__ void __launch_bounds__(256) apply_kernel(ApplyParams p, const float* __restrict__ depth,
                                                     const int* __restrict__ normal, const uchar4* __restrict__ diffuse,
                                                     const uint32_t* __restrict__ atlas, const uint8_t* __restrict__ entries,
-                                                    const float* __restrict__ ndc_xy, void* __restrict__ out, int format) {
+                                                    const float* __restrict__ ndc_xy, void* __restrict__ out, int format,
+                                                    int y_begin, int y_end) {
   __shared__ float s_srgb[256]; // sRGB8 -> linear; shared memory serves divergent indices, constant memory would serialise
   s_srgb[threadIdx.y * 32 + threadIdx.x] = c_srgb_lut[threadIdx.y * 32 + threadIdx.x];
   __syncthreads();
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if (x >= p.W || y >= p.H) return;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = y_begin + blockIdx.y * 8 + threadIdx.y;
+  if (x >= p.W || y >= y_end) return;
   const uint32_t t = (uint32_t)y * p.W + x;
   const float d = __ldg(depth + t);
   if (d < 0.00001f) { // :128 discard
@@ -197,6 +198,11 @@ void drv_impl_upload_srgb_lut() {
 }
 
 drv_status drv_impl_apply(drv_ctx* ctx, void* out, uint32_t format) {
+  return drv_impl_apply_rows(ctx, out, format, 0, ctx->cfg.backbuffer_height, true);
+}
+
+// Rows [y_begin, y_end) only: the host-frame pipeline applies a band as soon as its normals / albedo have arrived.
+drv_status drv_impl_apply_rows(drv_ctx* ctx, void* out, uint32_t format, uint32_t y_begin, uint32_t y_end, bool timed) {
   if (!ctx->have_constant || !ctx->have_per_frame || !ctx->have_volume)
     return ctx->fail(DRV_ERR_NOT_BOUND, "drv_apply_caches: uniform blocks not set");
   if (!ctx->gb_depth || !ctx->gb_normal || !ctx->gb_diffuse)
@@ -227,17 +233,19 @@ drv_status drv_impl_apply(drv_ctx* ctx, void* out, uint32_t format) {
     const float v = p.casc[c].WorldVoxelSize;
     p.inv_voxel[c] = (v > 1e-6f && v < 1e6f && frexpf(v, &e) == 0.5f) ? 1.0f / v : 0.0f;
   }
-  ctx->stage_begin(DRV_STAGE_APPLY_CACHES);
-  dim3 block(32, 8), grid((p.W + 31) / 32, (p.H + 7) / 8);
+  if (y_end > (uint32_t)p.H) y_end = (uint32_t)p.H;
+  if (y_begin >= y_end) return DRV_OK;
+  if (timed) ctx->stage_begin(DRV_STAGE_APPLY_CACHES);
+  dim3 block(32, 8), grid((p.W + 31) / 32, (y_end - y_begin + 7) / 8);
   if (ctx->cfg.sh_order == 2)
     apply_kernel<2><<<grid, block, 0, ctx->stream>>>(p, ctx->gb_depth, (const int*)ctx->gb_normal,
                                                      (const uchar4*)ctx->gb_diffuse, ctx->atlas, ctx->entries,
-                                                     ctx->ndc_xy, out, (int)format);
+                                                     ctx->ndc_xy, out, (int)format, (int)y_begin, (int)y_end);
   else
     apply_kernel<1><<<grid, block, 0, ctx->stream>>>(p, ctx->gb_depth, (const int*)ctx->gb_normal,
                                                      (const uchar4*)ctx->gb_diffuse, ctx->atlas, ctx->entries,
-                                                     ctx->ndc_xy, out, (int)format);
+                                                     ctx->ndc_xy, out, (int)format, (int)y_begin, (int)y_end);
   DRV_LAUNCH_CHECK();
-  ctx->stage_end(DRV_STAGE_APPLY_CACHES);
+  if (timed) ctx->stage_end(DRV_STAGE_APPLY_CACHES);
   return DRV_OK;
 }

@@ -5,6 +5,7 @@
 // reference (renderer.hpp:227-352).
 #include "ctx.h"
 
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 
@@ -151,6 +152,13 @@ extern "C" void drv_destroy(drv_ctx* ctx) {
     if (ctx->ev_begin[s]) cudaEventDestroy(ctx->ev_begin[s]);
     if (ctx->ev_end[s]) cudaEventDestroy(ctx->ev_end[s]);
   }
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+  for (auto& e : ctx->ev_rsm) if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->ev_band_in) if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->ev_band_done) if (e) cudaEventDestroy(e);
+  if (ctx->ev_depth) cudaEventDestroy(ctx->ev_depth);
+  if (ctx->ev_frame_start) cudaEventDestroy(ctx->ev_frame_start);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -434,6 +442,102 @@ extern "C" drv_status drv_draw_to_host(drv_ctx* ctx, void* hdr_host) {
   drv_status st = drv_draw(ctx, ctx->hdr16, DRV_HDR_RGBA16F_ADD);
   if (st != DRV_OK) return st;
   DRV_CUDA(cudaMemcpyAsync(hdr_host, ctx->hdr16, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  DRV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DRV_OK;
+}
+
+// ---- pipelined end-to-end frame -------------------------------------------------------
+extern "C" drv_status drv_draw_host_frame(drv_ctx* ctx, const drv_host_frame* f) {
+  NEED_CTX();
+  if (!f || !f->depth || !f->normal_rg16i || !f->diffuse_srgb8x || !f->hdr_out || f->num_lights > ctx->cfg.max_lights)
+    return ctx->fail(DRV_ERR_INVALID, "drv_draw_host_frame: bad argument");
+  const uint32_t W = ctx->cfg.backbuffer_width, H = ctx->cfg.backbuffer_height;
+  const size_t px = (size_t)W * H;
+  if (!ctx->copy_in) {
+    DRV_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    DRV_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    for (auto& e : ctx->ev_rsm) DRV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ctx->ev_band_in) DRV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ctx->ev_band_done) DRV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    DRV_CUDA(cudaEventCreateWithFlags(&ctx->ev_depth, cudaEventDisableTiming));
+    DRV_CUDA(cudaEventCreateWithFlags(&ctx->ev_frame_start, cudaEventDisableTiming));
+  }
+  if (!ctx->st_depth) {
+    DRV_CUDA(dmalloc(&ctx->st_depth, px * 4));
+    DRV_CUDA(dmalloc(&ctx->st_normal, px * 4));
+    DRV_CUDA(dmalloc(&ctx->st_diffuse, px * 4));
+  }
+  if (!ctx->hdr16) DRV_CUDA(cudaMalloc(&ctx->hdr16, px * 8));
+  const size_t rsm_cap = (size_t)ctx->cfg.max_rsm_resolution * ctx->cfg.max_rsm_resolution;
+  for (uint32_t l = 0; l < f->num_lights; ++l) {
+    LightState& S = ctx->lights[l];
+    const uint32_t res = f->rsm_resolution[l];
+    if (!f->rsm_flux_rgbx16f[l] || !f->rsm_normal_rg16i[l] || !f->rsm_depthlinsq_rg16f[l] || !is_pow2(res) ||
+        res > ctx->cfg.max_rsm_resolution)
+      return ctx->fail(DRV_ERR_INVALID, "drv_draw_host_frame: bad RSM");
+    if (!S.st_flux) {
+      DRV_CUDA(dmalloc(&S.st_flux, rsm_cap * 8));
+      DRV_CUDA(dmalloc(&S.st_normal, rsm_cap * 4));
+      DRV_CUDA(dmalloc(&S.st_depth, rsm_cap * 4));
+    }
+  }
+  uint32_t bands = f->bands ? f->bands : 8;
+  if (bands > 32) bands = 32;
+  const uint32_t rows_per_band = (((H + bands - 1) / bands) + 7) & ~7u; // whole 8-row apply blocks
+  bands = (H + rows_per_band - 1) / rows_per_band;
+
+  // the copy stream starts after everything already queued on the context's stream (previous users of the staging images)
+  DRV_CUDA(cudaEventRecord(ctx->ev_frame_start, ctx->stream));
+  DRV_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_frame_start, 0));
+  // H2D order = the order in which the stages need their inputs: RSMs, depth, then normal + albedo bands
+  for (uint32_t l = 0; l < f->num_lights; ++l) {
+    LightState& S = ctx->lights[l];
+    const size_t n = (size_t)f->rsm_resolution[l] * f->rsm_resolution[l];
+    DRV_CUDA(cudaMemcpyAsync(S.st_flux, f->rsm_flux_rgbx16f[l], n * 8, cudaMemcpyHostToDevice, ctx->copy_in));
+    DRV_CUDA(cudaMemcpyAsync(S.st_normal, f->rsm_normal_rg16i[l], n * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+    DRV_CUDA(cudaMemcpyAsync(S.st_depth, f->rsm_depthlinsq_rg16f[l], n * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+    DRV_CUDA(cudaEventRecord(ctx->ev_rsm[l], ctx->copy_in));
+  }
+  DRV_CUDA(cudaMemcpyAsync(ctx->st_depth, f->depth, px * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+  DRV_CUDA(cudaEventRecord(ctx->ev_depth, ctx->copy_in));
+  for (uint32_t b = 0; b < bands; ++b) {
+    const size_t y0 = (size_t)b * rows_per_band, y1 = std::min<size_t>(H, y0 + rows_per_band);
+    const size_t off = y0 * W * 4, bytes = (y1 - y0) * W * 4;
+    DRV_CUDA(cudaMemcpyAsync((uint8_t*)ctx->st_normal + off, (const uint8_t*)f->normal_rg16i + off, bytes,
+                             cudaMemcpyHostToDevice, ctx->copy_in));
+    DRV_CUDA(cudaMemcpyAsync(ctx->st_diffuse + off, f->diffuse_srgb8x + off, bytes, cudaMemcpyHostToDevice, ctx->copy_in));
+    DRV_CUDA(cudaEventRecord(ctx->ev_band_in[b], ctx->copy_in));
+  }
+  // compute, on the context's stream
+  DRV_CUDA(cudaMemsetAsync(ctx->hdr16, 0, px * 8, ctx->stream)); // glClear(GL_COLOR_BUFFER_BIT), renderer.cpp:562
+  drv_status st = drv_set_light_count(ctx, f->num_lights);
+  if (st != DRV_OK) return st;
+  for (uint32_t l = 0; l < f->num_lights; ++l) {
+    LightState& S = ctx->lights[l];
+    DRV_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_rsm[l], 0));
+    st = drv_bind_rsm(ctx, l, S.st_flux, S.st_normal, S.st_depth, f->rsm_resolution[l]);
+    if (st == DRV_OK) st = drv_impl_prepare_rsm(ctx, l);
+    if (st != DRV_OK) return st;
+  }
+  DRV_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_depth, 0));
+  st = drv_bind_gbuffer(ctx, ctx->st_depth, ctx->st_normal, ctx->st_diffuse, W, H);
+  if (st == DRV_OK) st = drv_impl_allocate(ctx);
+  if (st == DRV_OK) st = drv_light_caches(ctx);
+  if (st != DRV_OK) return st;
+  ctx->stage_begin(DRV_STAGE_APPLY_CACHES);
+  for (uint32_t b = 0; b < bands; ++b) {
+    const uint32_t y0 = b * rows_per_band, y1 = std::min(H, y0 + rows_per_band);
+    DRV_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_band_in[b], 0));
+    st = drv_impl_apply_rows(ctx, ctx->hdr16, DRV_HDR_RGBA16F_ADD, y0, y1, false);
+    if (st != DRV_OK) return st;
+    DRV_CUDA(cudaEventRecord(ctx->ev_band_done[b], ctx->stream));
+    DRV_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_band_done[b], 0));
+    const size_t off = (size_t)y0 * W * 8, bytes = (size_t)(y1 - y0) * W * 8;
+    DRV_CUDA(cudaMemcpyAsync((uint8_t*)f->hdr_out + off, (const uint8_t*)ctx->hdr16 + off, bytes, cudaMemcpyDeviceToHost,
+                             ctx->copy_out));
+  }
+  ctx->stage_end(DRV_STAGE_APPLY_CACHES);
+  DRV_CUDA(cudaStreamSynchronize(ctx->copy_out));
   DRV_CUDA(cudaStreamSynchronize(ctx->stream));
   return DRV_OK;
 }

@@ -111,6 +111,10 @@ struct drv_ctx {
   void* peer_entries[8] = {nullptr};
   bool peers_open = false;
 
+  // host-frame pipeline (drv_draw_host_frame): copy streams + events
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_rsm[DRV_MAX_LIGHTS]{}, ev_depth = nullptr, ev_band_in[32]{}, ev_band_done[32]{}, ev_frame_start = nullptr;
+
   // timers
   bool timers = false;
   cudaEvent_t ev_begin[DRV_STAGE_COUNT]{}, ev_end[DRV_STAGE_COUNT]{};
@@ -134,6 +138,7 @@ drv_status drv_impl_prepare_rsm(drv_ctx* ctx, uint32_t light);
 drv_status drv_impl_generate_vpls(drv_ctx* ctx, uint32_t light);
 drv_status drv_impl_gather(drv_ctx* ctx);
 drv_status drv_impl_apply(drv_ctx* ctx, void* out, uint32_t format);
+drv_status drv_impl_apply_rows(drv_ctx* ctx, void* out, uint32_t format, uint32_t y_begin, uint32_t y_end, bool timed);
 drv_status drv_impl_voxelize(drv_ctx* ctx, const float* tris, uint32_t n, const float* world, float adaption,
                              uint32_t flags);
 drv_status drv_impl_set_synthetic_entries(drv_ctx* ctx, const float* pos, uint32_t n);

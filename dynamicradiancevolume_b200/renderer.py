@@ -254,6 +254,18 @@ class Context:
 
     def draw_to_host(self, hdr_host): self.check(self.lib.drv_draw_to_host(self.handle, hdr_host.data_ptr()))
 
+    def draw_host_frame(self, depth, normal, diffuse, rsms, hdr_host, bands=0):
+        """Pipelined end-to-end frame from pinned host tensors (``drv_draw_host_frame``). rsms: [(flux, normal, depthLinSq)]."""
+        f = abi.HostFrame()
+        f.depth, f.normal_rg16i, f.diffuse_srgb8x = depth.data_ptr(), normal.data_ptr(), diffuse.data_ptr()
+        f.num_lights = len(rsms)
+        for i, (fl, n, d) in enumerate(rsms):
+            f.rsm_flux_rgbx16f[i], f.rsm_normal_rg16i[i], f.rsm_depthlinsq_rg16f[i] = fl.data_ptr(), n.data_ptr(), d.data_ptr()
+            f.rsm_resolution[i] = fl.shape[0]
+        f.hdr_out = hdr_host.data_ptr()
+        f.bands = bands
+        self.check(self.lib.drv_draw_host_frame(self.handle, C.byref(f)))
+
     def export_entries_ipc(self) -> bytes:
         h = (C.c_uint8 * abi.DRV_IPC_HANDLE_BYTES)()
         self.check(self.lib.drv_export_entries_ipc(self.handle, C.byref(h)))

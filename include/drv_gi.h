@@ -370,6 +370,26 @@ drv_status drv_upload_rsm(drv_ctx* ctx, uint32_t light, const uint16_t* flux_rgb
  * copies it to `hdr_host` (width*height*8 bytes). Synchronises. */
 drv_status drv_draw_to_host(drv_ctx* ctx, void* hdr_host);
 
+/* The same end-to-end frame, pipelined: RSM level 0 and depth are copied first, the mip chain / allocation /
+ * lighting run while the normal + albedo images stream in band by band, every band is applied as soon as it has
+ * arrived and its RGBA16F rows start their way back while the next band is still being applied — H2D, compute
+ * and D2H overlap inside ONE frame (no cross-frame pipelining). Host pointers must be pinned for the overlap to
+ * happen. Uniform blocks must have been set; RSM mips are rebuilt; with indirect shadows the voxel volume is
+ * used as it stands (call drv_voxelize before). Synchronises. */
+typedef struct drv_host_frame {
+  const float* depth;            /* W*H float32 */
+  const int16_t* normal_rg16i;   /* W*H*2 int16 */
+  const uint8_t* diffuse_srgb8x; /* W*H*4 bytes */
+  uint32_t num_lights;
+  const uint16_t* rsm_flux_rgbx16f[DRV_MAX_LIGHTS];
+  const int16_t* rsm_normal_rg16i[DRV_MAX_LIGHTS];
+  const uint16_t* rsm_depthlinsq_rg16f[DRV_MAX_LIGHTS];
+  uint32_t rsm_resolution[DRV_MAX_LIGHTS];
+  void* hdr_out;                 /* W*H*8 bytes RGBA16F (cleared, then the indirect light is added) */
+  uint32_t bands;                /* 0 = default (8); at most 32 */
+} drv_host_frame;
+drv_status drv_draw_host_frame(drv_ctx* ctx, const drv_host_frame* frame);
+
 /* ------------------------------------------------------------------------
  * Host-side packers (pure CPU, usable without a device): C entry points of
  * the C++ packers in include/drv_math.h, which restate

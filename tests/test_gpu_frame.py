@@ -105,6 +105,29 @@ def test_draw_to_host_matches_device_path(cuda_device):
     g.close()
 
 
+@pytest.mark.parametrize("cfg", [0, 2])
+def test_draw_host_frame_pipelined(cuda_device, cfg):
+    """drv_draw_host_frame (banded H2D / apply / D2H overlap) gives the same image as the unpipelined host path."""
+    import torch
+    wl = workloads.config(cfg).build()
+    g = workloads.DeviceFrame(wl)
+    g.prepare_inputs()
+    hdr = torch.zeros(wl.height, wl.width, 4, dtype=torch.float16, device="cuda")
+    torch.cuda.synchronize()
+    g.frame(hdr, abi.DRV_HDR_RGBA16F_ADD)
+    torch.cuda.synchronize()
+    ref = hdr.cpu()
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    gb = [pin(a) for a in (wl.depth, wl.normal, wl.diffuse)]
+    rsms = [[pin(a) for a in r] for r in wl.rsms]
+    out = torch.full((wl.height, wl.width, 4), 7.0, dtype=torch.float16).pin_memory()
+    for bands in (0, 1, 5, 32):
+        out.fill_(7.0)
+        g.ctx.draw_host_frame(gb[0], gb[1], gb[2], rsms, out, bands)
+        assert torch.equal(out, ref), bands
+    g.close()
+
+
 def test_renderer_mirror_draw(cuda_device):
     """The reference-shaped host interface (Renderer::Draw, renderer.cpp:501-594) drives the same frame."""
     import torch
