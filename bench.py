@@ -18,8 +18,8 @@ e2e     = the same frame through the host-buffer C-ABI call (drv_draw_host_frame
 N > 1   = one process per GPU (torchrun). Allocation is replicated (deterministic scan => identical entry
           indices on every rank, no communication); the cache x VPL gather is sharded over contiguous
           cell-ordered entry ranges; finished SH entries are stored to every peer over NVLink from inside the
-          gather epilogue (fused all-gather), an NCCL all-reduce of one word is the cross-GPU barrier; apply is
-          replicated. One frame is split over N GPUs => "scaling": "strong".
+          gather epilogue (fused all-gather); the cross-GPU barrier is a flag exchange in peer memory
+          (drv_peer_barrier; --barrier nccl uses a one-word all-reduce instead); apply is replicated. One frame is split over N GPUs => "scaling": "strong".
 """
 import argparse
 import json
@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps (profiling runs)")
     ap.add_argument("--no-microbench", action="store_true")
     ap.add_argument("--stages", action="store_true", help="print the per-stage table to stderr")
+    ap.add_argument("--barrier", choices=["peer", "nccl"], default="peer",
+                    help="cross-GPU barrier of sharded runs: flags in NVLink peer memory (drv_peer_barrier) or an NCCL all-reduce")
     return ap.parse_args()
 
 
@@ -218,6 +220,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: keep NCCL's own banner / debug output on stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     wl = workload_for(args.config).build()
@@ -238,6 +242,12 @@ def run_b200(args):
             if r != rank:
                 ctx.import_peer_entries(r, h)
 
+    def xbarrier():
+        if args.barrier == "peer":
+            ctx.peer_barrier()
+        else:
+            dist.all_reduce(barrier_word)
+
     def frame_device():
         with torch.cuda.stream(stream):
             for i in range(len(g.rsms)):
@@ -249,9 +259,9 @@ def run_b200(args):
                 ctx.draw(hdr16, abi.DRV_HDR_RGBA16F_ADD)
             else:
                 ctx.allocate_caches()          # replicated; clears this rank's SH
-                dist.all_reduce(barrier_word)  # every rank has finished clearing before any peer stores arrive
+                xbarrier()                     # every rank has finished clearing before any peer stores arrive
                 ctx.light_caches()             # own shard; epilogue stores finished entries to all peers
-                dist.all_reduce(barrier_word)  # all peers' stores have landed
+                xbarrier()                     # all peers' stores have landed
                 ctx.apply_caches(hdr16, abi.DRV_HDR_RGBA16F_ADD)
 
     # ---- warm-up + timed region: CUDA events on the context's stream around every step ----
@@ -325,9 +335,9 @@ def run_b200(args):
             with torch.cuda.stream(stream):
                 hdr16.zero_()
                 ctx.allocate_caches()
-                dist.all_reduce(barrier_word)
+                xbarrier()
                 ctx.light_caches()
-                dist.all_reduce(barrier_word)
+                xbarrier()
                 ctx.apply_caches(hdr16, abi.DRV_HDR_RGBA16F_ADD)
                 if rank == 0:
                     h_out.copy_(hdr16, non_blocking=True)

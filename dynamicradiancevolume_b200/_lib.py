@@ -47,6 +47,7 @@ SYMBOLS = [
     ("drv_shard_range", None, [_u32, _u32, _u32, C.POINTER(_u32), C.POINTER(_u32)]),
     ("drv_export_entries_ipc", _st, [_P, C.POINTER(C.c_uint8 * abi.DRV_IPC_HANDLE_BYTES)]),
     ("drv_import_peer_entries", _st, [_P, _u32, C.POINTER(C.c_uint8 * abi.DRV_IPC_HANDLE_BYTES)]),
+    ("drv_peer_barrier", _st, [_P]),
     ("drv_enable_stage_timers", _st, [_P, C.c_int]),
     ("drv_stage_ms", _st, [_P, C.c_int, C.POINTER(_f32)]),
     ("drv_stage_name", C.c_char_p, [C.c_int]),

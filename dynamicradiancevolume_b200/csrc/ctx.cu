@@ -77,8 +77,9 @@ extern "C" drv_status drv_create(const drv_config* cfg, drv_ctx** out) {
 
   ctx->entry_stride = c.sh_order == 2 ? 128 : 64;
   // "Maximum size per cache": the buffer is max * 128 B whatever the mode (renderer.cpp:266-269)
-  CREATE_CUDA(dmalloc(&ctx->entries, (size_t)c.max_cache_count * 128));
-  CREATE_CUDA(cudaMemsetAsync(ctx->entries, 0, (size_t)c.max_cache_count * 128, ctx->stream));
+  CREATE_CUDA(dmalloc(&ctx->entries, (size_t)c.max_cache_count * 128 + kSyncBytes));
+  CREATE_CUDA(cudaMemsetAsync(ctx->entries, 0, (size_t)c.max_cache_count * 128 + kSyncBytes, ctx->stream));
+  ctx->sync_flags = reinterpret_cast<uint32_t*>(ctx->entries + (size_t)c.max_cache_count * 128);
   CREATE_CUDA(dmalloc(&ctx->counter, sizeof(drv_cache_counter)));
   CREATE_CUDA(cudaMemsetAsync(ctx->counter, 0, sizeof(drv_cache_counter), ctx->stream));
   CREATE_CUDA(dmalloc(&ctx->stats, 2 * sizeof(uint32_t)));
@@ -372,6 +373,15 @@ extern "C" drv_status drv_import_peer_entries(drv_ctx* ctx, uint32_t peer_rank, 
   ctx->peer_entries[peer_rank] = p;
   ctx->peers_open = true;
   return DRV_OK;
+}
+
+extern "C" drv_status drv_peer_barrier(drv_ctx* ctx) {
+  NEED_CTX();
+  if (ctx->shard_world <= 1) return DRV_OK;
+  if (!ctx->peers_open) return ctx->fail(DRV_ERR_NOT_BOUND, "drv_peer_barrier: peers not imported");
+  for (uint32_t r = 0; r < ctx->shard_world; ++r)
+    if (r != ctx->shard_rank && !ctx->peer_entries[r]) return ctx->fail(DRV_ERR_NOT_BOUND, "drv_peer_barrier: a peer is missing");
+  return drv_impl_peer_barrier(ctx);
 }
 
 static const char* kStageNames[DRV_STAGE_COUNT] = {"VoxelizeScene", "VoxelBlendMipMap", "AllocateCaches", "LightCaches",

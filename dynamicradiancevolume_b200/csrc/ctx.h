@@ -110,6 +110,10 @@ struct drv_ctx {
   uint32_t shard_rank = 0, shard_world = 1;
   void* peer_entries[8] = {nullptr};
   bool peers_open = false;
+  // cross-GPU barrier flags live right behind the entries in the same allocation (one IPC handle maps both):
+  // flags[r] = last epoch rank r has announced to this GPU; flags[8] = time-out marker
+  uint32_t* sync_flags = nullptr;
+  uint32_t barrier_epoch = 0;
 
   // host-frame pipeline (drv_draw_host_frame): copy streams + events
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
@@ -143,6 +147,8 @@ drv_status drv_impl_voxelize(drv_ctx* ctx, const float* tris, uint32_t n, const 
                              uint32_t flags);
 drv_status drv_impl_set_synthetic_entries(drv_ctx* ctx, const float* pos, uint32_t n);
 drv_status drv_impl_set_voxel_volume(drv_ctx* ctx, const uint8_t* level0);
+drv_status drv_impl_peer_barrier(drv_ctx* ctx);
+constexpr size_t kSyncBytes = 256;
 void drv_impl_upload_srgb_lut();
 drv_status drv_impl_build_ndc_tables(drv_ctx* ctx);
 

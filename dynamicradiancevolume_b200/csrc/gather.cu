@@ -841,6 +841,50 @@ drv_status launch_gather(drv_ctx* ctx, K kernel, GatherParams& p, int tile_cache
 
 } // namespace
 
+// ---- cross-GPU barrier over NVLink peer memory ---------------------------------------------------------
+// Every rank stores the new epoch into slot [rank] of every peer's flag block (which sits behind that peer's
+// entries buffer), then spins on its own block until all peers' slots carry the epoch. Kernels launched earlier
+// on the stream — including their peer stores — have completed before this kernel starts, so once a rank leaves
+// the barrier every peer's previous stage is visible to it. Epochs only grow: no reset, no ABA.
+namespace {
+struct BarrierArgs {
+  uint32_t* own;
+  uint32_t* peer[8];
+  uint32_t rank, world, epoch;
+};
+__global__ void peer_barrier_kernel(BarrierArgs a) {
+  const uint32_t t = threadIdx.x;
+  const bool active = t < a.world && t != a.rank;
+  __threadfence_system();
+  if (active) *reinterpret_cast<volatile uint32_t*>(a.peer[t] + a.rank) = a.epoch;
+  __syncwarp(); // all announcements are on their way before anybody starts to wait
+  if (!active) return;
+  const long long t0 = clock64();
+  while ((int32_t)(*reinterpret_cast<volatile uint32_t*>(a.own + t) - a.epoch) < 0) {
+    if (clock64() - t0 > 8000000000ll) { // ~4 s at 2 GHz: a peer died; do not hang the GPU
+      a.own[8] = a.epoch;
+      break;
+    }
+  }
+  __threadfence_system();
+}
+} // namespace
+
+drv_status drv_impl_peer_barrier(drv_ctx* ctx) {
+  BarrierArgs a;
+  memset(&a, 0, sizeof(a));
+  a.own = ctx->sync_flags;
+  const size_t off = (size_t)ctx->cfg.max_cache_count * 128;
+  for (uint32_t r = 0; r < ctx->shard_world && r < 8; ++r)
+    a.peer[r] = r == ctx->shard_rank ? ctx->sync_flags : reinterpret_cast<uint32_t*>((uint8_t*)ctx->peer_entries[r] + off);
+  a.rank = ctx->shard_rank;
+  a.world = ctx->shard_world;
+  a.epoch = ++ctx->barrier_epoch;
+  peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(a);
+  DRV_LAUNCH_CHECK();
+  return DRV_OK;
+}
+
 drv_status drv_impl_gather(drv_ctx* ctx) {
   if (!ctx->have_constant) return ctx->fail(DRV_ERR_NOT_BOUND, "drv_light_caches: Constant block not set");
   const bool shadow = ctx->cfg.indirect_shadow != 0;

@@ -266,6 +266,8 @@ class Context:
         f.bands = bands
         self.check(self.lib.drv_draw_host_frame(self.handle, C.byref(f)))
 
+    def peer_barrier(self): self.check(self.lib.drv_peer_barrier(self.handle))
+
     def export_entries_ipc(self) -> bytes:
         h = (C.c_uint8 * abi.DRV_IPC_HANDLE_BYTES)()
         self.check(self.lib.drv_export_entries_ipc(self.handle, C.byref(h)))

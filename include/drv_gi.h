@@ -339,6 +339,13 @@ void drv_shard_range(uint32_t count, uint32_t rank, uint32_t world, uint32_t* be
 drv_status drv_export_entries_ipc(drv_ctx* ctx, uint8_t handle[DRV_IPC_HANDLE_BYTES]);
 drv_status drv_import_peer_entries(drv_ctx* ctx, uint32_t peer_rank, const uint8_t handle[DRV_IPC_HANDLE_BYTES]);
 
+/* Stream-ordered barrier across the ranks of a sharded run, through flags in NVLink peer memory (no host
+ * round trip, no NCCL call): work enqueued after it on this context's stream starts only when every rank's
+ * work enqueued before its own drv_peer_barrier has finished. Every rank must call it the same number of
+ * times. Requires drv_set_shard + drv_import_peer_entries for all peers (all contexts must share
+ * max_cache_count). A no-op for world == 1. */
+drv_status drv_peer_barrier(drv_ctx* ctx);
+
 /* ≙ FrameProfiler (frameprofiler.hpp:138-148): CUDA-event stage timers with
  * the reference's scope names. Enabled timers record events around each
  * stage; drv_stage_ms synchronises on the stage's end event. */

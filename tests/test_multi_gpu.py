@@ -29,18 +29,19 @@ def _worker(rank, world, port, mode, out_dir):
     stream = torch.cuda.Stream(device=rank)
     g = workloads.DeviceFrame(wl, device=rank, stream=stream)
     word = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % rank)
-    if mode == "fused":
+    if mode.startswith("fused"):
         sharding.connect_peers(g.ctx, rank, world)
     else:
         g.ctx.set_shard(rank, world)
+    bctx = g.ctx if mode == "fused" else None  # "fused": flags in peer memory; otherwise an NCCL all-reduce
     for it in range(2):  # twice: the second frame checks the cross-frame ordering of clears and peer stores
         with torch.cuda.stream(stream):
             g.prepare_inputs()
             g.ctx.allocate_caches()
-            sharding.barrier(word)
+            sharding.barrier(word, ctx=bctx)
             g.ctx.light_caches()
-            if mode == "fused":
-                sharding.barrier(word)
+            if mode.startswith("fused"):
+                sharding.barrier(word, ctx=bctx)
             else:
                 n = g.ctx.active_cache_count()[0]
                 sharding.exchange_entries(g.ctx.entries_tensor(), n, world)
@@ -54,7 +55,7 @@ def _worker(rank, world, port, mode, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["fused", "nccl"])
+@pytest.mark.parametrize("mode", ["fused", "fused_nccl_barrier", "nccl"])
 def test_sharded_gather_matches_oracle(tmp_path, mode):
     import torch
     import torch.multiprocessing as mp
