@@ -19,7 +19,8 @@ N > 1   = one process per GPU (torchrun). Allocation is replicated (deterministi
           indices on every rank, no communication); the cache x VPL gather is sharded over contiguous
           cell-ordered entry ranges; finished SH entries are stored to every peer over NVLink from inside the
           gather epilogue (fused all-gather); the cross-GPU barrier is a flag exchange in peer memory
-          (drv_peer_barrier; --barrier nccl uses a one-word all-reduce instead); apply is replicated. One frame is split over N GPUs => "scaling": "strong".
+          (drv_peer_barrier; --barrier nccl uses a one-word all-reduce instead); the apply pass is split by pixel
+          rows and the RGBA16F bands are gathered on rank 0 with NCCL. One frame is split over N GPUs => "scaling": "strong".
 """
 import argparse
 import json
@@ -230,7 +231,10 @@ def run_b200(args):
     ctx = g.ctx
     dev = "cuda:%d" % local
     px = wl.width * wl.height
-    hdr16 = torch.zeros(wl.height, wl.width, 4, dtype=torch.float16, device=dev)
+    # sharded runs: the apply pass is split by rows (sort-first); the bands are gathered on rank 0
+    band = (wl.height + world - 1) // world
+    hdr16 = torch.zeros(band * world, wl.width, 4, dtype=torch.float16, device=dev)
+    band_views = [hdr16[r * band:(r + 1) * band] for r in range(world)]
     flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     barrier_word = torch.zeros(1, dtype=torch.int32, device=dev)
 
@@ -262,7 +266,8 @@ def run_b200(args):
                 xbarrier()                     # every rank has finished clearing before any peer stores arrive
                 ctx.light_caches()             # own shard; epilogue stores finished entries to all peers
                 xbarrier()                     # all peers' stores have landed
-                ctx.apply_caches(hdr16, abi.DRV_HDR_RGBA16F_ADD)
+                ctx.apply_caches_rows(hdr16, abi.DRV_HDR_RGBA16F_ADD, rank * band, min(wl.height, (rank + 1) * band))
+                dist.gather(band_views[rank], band_views if rank == 0 else None, dst=0)  # the image, on rank 0
 
     # ---- warm-up + timed region: CUDA events on the context's stream around every step ----
     torch.cuda.synchronize()
@@ -338,9 +343,10 @@ def run_b200(args):
                 xbarrier()
                 ctx.light_caches()
                 xbarrier()
-                ctx.apply_caches(hdr16, abi.DRV_HDR_RGBA16F_ADD)
+                ctx.apply_caches_rows(hdr16, abi.DRV_HDR_RGBA16F_ADD, rank * band, min(wl.height, (rank + 1) * band))
+                dist.gather(band_views[rank], band_views if rank == 0 else None, dst=0)
                 if rank == 0:
-                    h_out.copy_(hdr16, non_blocking=True)
+                    h_out.copy_(hdr16[:wl.height], non_blocking=True)
             stream.synchronize()
 
     e2e_ms = []
@@ -451,7 +457,7 @@ def run_b200(args):
                    "pairs_per_frame": n_caches * wl.num_vpls,
                    "l2": "flushed between steps (512 MiB memset outside the event pairs)" if not args.no_flush else "not flushed",
                    "parallelism": "1 GPU" if world == 1 else "gather sharded over %d GPUs by cell-ordered entry range, "
-                                  "allocation + apply replicated, fused P2P all-gather" % world,
+                                  "allocation replicated, fused P2P all-gather of SH, apply row-sharded + NCCL gather of the image" % world,
                    "gather_variant": args.variant},
         "e2e": {"value": e2e_per_step, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,

@@ -36,6 +36,7 @@ SYMBOLS = [
     ("drv_allocate_caches", _st, [_P]),
     ("drv_light_caches", _st, [_P]),
     ("drv_apply_caches", _st, [_P, _P, _u32]),
+    ("drv_apply_caches_rows", _st, [_P, _P, _u32, _u32, _u32]),
     ("drv_draw", _st, [_P, _P, _u32]),
     ("drv_get_buffers", _st, [_P, C.POINTER(abi.Buffers)]),
     ("drv_rsm_level_offset", C.c_uint64, [_u32, _u32]),

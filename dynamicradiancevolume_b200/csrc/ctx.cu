@@ -265,6 +265,11 @@ extern "C" drv_status drv_apply_caches(drv_ctx* ctx, void* hdr_out, uint32_t for
   return drv_impl_apply(ctx, hdr_out, format);
 }
 
+extern "C" drv_status drv_apply_caches_rows(drv_ctx* ctx, void* hdr_out, uint32_t format, uint32_t y0, uint32_t y1) {
+  NEED_CTX();
+  return drv_impl_apply_rows(ctx, hdr_out, format, y0, y1, true);
+}
+
 extern "C" drv_status drv_draw(drv_ctx* ctx, void* hdr_out, uint32_t format) {
   NEED_CTX();
   drv_status st = drv_impl_allocate(ctx); // renderer.cpp:550

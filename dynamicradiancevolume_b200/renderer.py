@@ -217,6 +217,9 @@ class Context:
     def light_caches(self): self.check(self.lib.drv_light_caches(self.handle))
     def apply_caches(self, out, fmt): self.check(self.lib.drv_apply_caches(self.handle, out.data_ptr(), fmt))
     def draw(self, out, fmt): self.check(self.lib.drv_draw(self.handle, out.data_ptr(), fmt))
+
+    def apply_caches_rows(self, out, fmt, y0, y1):
+        self.check(self.lib.drv_apply_caches_rows(self.handle, out.data_ptr(), fmt, y0, y1))
     def set_shard(self, rank, world): self.check(self.lib.drv_set_shard(self.handle, rank, world))
     def enable_stage_timers(self, on=True): self.check(self.lib.drv_enable_stage_timers(self.handle, 1 if on else 0))
     def kernel_launches(self): return int(self.lib.drv_kernel_launches(self.handle))

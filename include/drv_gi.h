@@ -280,6 +280,10 @@ drv_status drv_light_caches(drv_ctx* ctx);
 #define DRV_HDR_RGBA32F_WRITE 1u /* parity readback: overwrite float4 (rgb, 1); discarded pixels get 0 */
 drv_status drv_apply_caches(drv_ctx* ctx, void* hdr_out, uint32_t format);
 
+/* The same for the pixel rows [y_begin, y_end) only — sort-first sharding of the apply pass over GPUs, and the
+ * banded host pipeline of drv_draw_host_frame. */
+drv_status drv_apply_caches_rows(drv_ctx* ctx, void* hdr_out, uint32_t format, uint32_t y_begin, uint32_t y_end);
+
 /* The DYN_RADIANCE_VOLUME case of Renderer::Draw (renderer.cpp:539-570)
  * minus the producers: allocate -> light -> apply, one call. */
 drv_status drv_draw(drv_ctx* ctx, void* hdr_out, uint32_t format);

@@ -409,6 +409,24 @@ def test_apply_isolated(cuda_device, sh_order, transition):
     g.close()
 
 
+def test_apply_rows_bands_equal_full_pass(cuda_device):
+    """drv_apply_caches_rows over disjoint row bands (sort-first sharding) == one full-screen pass."""
+    torch = _torch()
+    wl = workloads.cornell(width=200, height=173, sh_order=2)
+    g, o = _frames(wl)
+    g.prepare_inputs()
+    g.frame()
+    torch.cuda.synchronize()
+    ref = g.out32.clone()
+    g.out32.fill_(-1.0)
+    torch.cuda.synchronize()
+    for y0, y1 in ((0, 1), (1, 64), (64, 65), (65, 170), (170, 173), (173, 400)):
+        g.ctx.apply_caches_rows(g.out32, abi.DRV_HDR_RGBA32F_WRITE, y0, y1)
+    torch.cuda.synchronize()
+    assert torch.equal(g.out32, ref)
+    g.close()
+
+
 def test_apply_additive_rgba16f(cuda_device):
     """Reference blend state: GL_ONE/GL_ONE into RGBA16F, alpha untouched (renderer.cpp:119,480)."""
     torch = _torch()
