@@ -106,9 +106,6 @@ extern "C" drv_status drv_create(const drv_config* cfg, drv_ctx** out) {
   }
   if (ctx->voxel_record_count >= (1ull << 31)) { g_create_error = "drv_create: voxel_resolution too large"; drv_destroy(ctx); return DRV_ERR_INVALID; }
   if (c.indirect_shadow) {
-    CREATE_CUDA(dmalloc(&ctx->voxel_brick_mask, 1024 * sizeof(uint32_t)));
-    CREATE_CUDA(cudaMemsetAsync(ctx->voxel_brick_mask, 0, 1024 * sizeof(uint32_t), ctx->stream));
-    ctx->voxel_brick_shift = ilog2(vr) > 5 ? ilog2(vr) - 5 : 0;
     CREATE_CUDA(dmalloc(&ctx->voxel_records, ctx->voxel_record_count * sizeof(uint2)));
     CREATE_CUDA(cudaMemsetAsync(ctx->voxel_records, 0, ctx->voxel_record_count * sizeof(uint2), ctx->stream));
   }
@@ -142,8 +139,8 @@ extern "C" void drv_destroy(drv_ctx* ctx) {
     for (int r = 0; r < 8; ++r)
       if (ctx->peer_entries[r]) cudaIpcCloseMemHandle(ctx->peer_entries[r]);
   cudaFree(ctx->entries); cudaFree(ctx->counter); cudaFree(ctx->stats); cudaFree(ctx->atlas);
-  cudaFree(ctx->cell_flags); cudaFree(ctx->block_counts); cudaFree(ctx->voxel_chain); cudaFree(ctx->voxel_target); cudaFree(ctx->voxel_records); cudaFree(ctx->voxel_brick_mask);
-  cudaFree(ctx->partials); cudaFree(ctx->st_depth); cudaFree(ctx->st_normal); cudaFree(ctx->st_diffuse);
+  cudaFree(ctx->cell_flags); cudaFree(ctx->block_counts); cudaFree(ctx->voxel_chain); cudaFree(ctx->voxel_target); cudaFree(ctx->voxel_records);
+  cudaFree(ctx->partials); cudaFree(ctx->shadow_table); cudaFree(ctx->st_depth); cudaFree(ctx->st_normal); cudaFree(ctx->st_diffuse);
   cudaFree(ctx->hdr16); cudaFree(ctx->ndc_xy);
   for (auto& S : ctx->lights) {
     cudaFree(S.flux_mips); cudaFree(S.normal_mips); cudaFree(S.depth_mips); cudaFree(S.vpls); cudaFree(S.blocks);

@@ -96,15 +96,13 @@ struct drv_ctx {
   // gather-ready copy of the chain for the cone tracer: per level (r+1)^3 records of 8 bytes, record
   // (x,y,z), x,y,z in [-1, r-1], = the 2x2x2 clamp-to-edge texel neighbourhood whose lower corner is (x,y,z).
   // One 64-bit load fetches a whole trilinear footprint.
-  // 32^3-bit mask over level-0 bricks of (res/32)^3 voxels: bit = 1 when the brick dilated by one voxel holds
-  // only zeros, i.e. every lod-0 trilinear footprint whose sample position lies in the brick is exactly 0
-  uint32_t* voxel_brick_mask = nullptr; // 1024 words, bit index = bx | by << 5 | bz << 10
-  uint32_t voxel_brick_shift = 0;
   uint2* voxel_records = nullptr;
   uint32_t voxel_record_offset[16] = {0};
   uint64_t voxel_record_count = 0;
 
   // gather
+  float* shadow_table = nullptr;     // visibility of (VAL block, cache) for the current chunk of caches (cone_kernel)
+  size_t shadow_table_floats = 0;
   float* partials = nullptr;         // split-VPL partial sums
   uint64_t partial_slots = 0;        // capacity in cache slots
   uint32_t shard_rank = 0, shard_world = 1;

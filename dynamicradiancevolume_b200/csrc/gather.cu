@@ -35,6 +35,8 @@
 #include "ctx.h"
 #include "device_math.cuh"
 
+#include <algorithm>
+
 using namespace drvk;
 
 namespace {
@@ -59,14 +61,12 @@ struct GatherParams {
   uint32_t shard_rank, shard_world;
   uint32_t grid;         // CTAs of the gather launch (the finalize kernel needs it too)
   float f0, f1, f2, f20, f22;
-  // voxel volume (cone tracing): gather-ready records, see voxel.cu
-  const uint2* rec;
-  uint32_t rec_offset[16];
-  const uint32_t* brick_mask; // 1024 words, see voxel.cu: voxel_brick_mask_kernel
-  int brick_shift;
-  int vres, vlevels;
-  float vmin[3];
-  float voxel_size;
+  // indirect shadows: the visibility table written by cone_kernel for the current chunk of caches,
+  // table[(block_offset[light] + k / interval) * shadow_stride + chunk-local cache index]
+  const float* shadow_table;
+  uint32_t shadow_stride;
+  uint32_t block_offset[DRV_MAX_LIGHTS];
+  uint32_t chunk_first, chunk_cap; // the gather works on entries [chunk_first, chunk_first + chunk_cap) of the shard
   // fused all-gather: peer copies of the entries buffer (NVLink P2P)
   uint8_t* peers[8];
   uint32_t num_peers;
@@ -89,6 +89,10 @@ __device__ __forceinline__ Schedule make_schedule(const GatherParams& p, int til
   uint32_t g1 = (uint32_t)(((unsigned long long)groups * (p.shard_rank + 1)) / p.shard_world);
   s.first = min(g0 * 64u, n);
   s.count = min(g1 * 64u, n) - s.first;
+  // restrict to the current chunk of the shard (shadowed gathers walk the shard in chunks, see drv_impl_gather)
+  const uint32_t lo = min(s.count, p.chunk_first), hi = min(s.count, p.chunk_first + min(p.chunk_cap, 0xFFFFFFFFu - p.chunk_first));
+  s.first += lo;
+  s.count = hi - lo;
   s.tiles = (s.count + tile_caches - 1) / tile_caches;
   uint32_t upt = 0;
   for (uint32_t l = 0; l < p.num_lights; ++l) upt += (p.lights[l].num_vpls + p.granule - 1) / p.granule;
@@ -123,8 +127,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
 struct VoxelVol {
   const uint2* rec;
   const uint32_t* rec_offset; // GatherParams::rec_offset in the kernel's constant bank (LDC with a register index)
-  const uint32_t* brick_mask; // shared-memory copy of the empty-brick mask
-  int brick_shift;
   int res, levels;
   float vmin[3];
   float voxel_size;
@@ -195,7 +197,6 @@ struct ConeSample {
   float tx1, ty1, tz1;   // ... in level l0 + 1
   float t;               // mip fraction: 0 = level l0 only
   float dist, radius;
-  bool skip;             // sample position lies in an empty brick: the sample is exactly 0, nothing was fetched
 };
 
 // cacheLightingRSM.comp:195-230 for one cache and one shadow block. Distances, step sizes and the break test
@@ -204,7 +205,6 @@ struct ConeSample {
 // on what it sampled, so the fetch of step s+1 is issued before step s is filtered and the L1/L2 latency of
 // the dependent chain position -> index -> load -> filter -> occlusion overlaps with useful work.
 // A cone also stops once occlusion reached 1: later samples would add (1 - 1) * x = 0.
-template <bool ZSKIP>
 __device__ __forceinline__ float cone_trace(const VoxelVol& V, float wx, float wy, float wz, float4 blk) {
   // :104 voxelPos, kept in level-0 texel units minus the half-texel shift (q = voxelPos * res - 0.5), so that a
   // step of `stepSize` voxels along the unit direction is q += dir * stepSize (:197-198, 213)
@@ -230,50 +230,42 @@ __device__ __forceinline__ float cone_trace(const VoxelVol& V, float wx, float w
     S.dist = dist;
     S.radius = ex_mul(dist, kk);                                                    // :216
     S.t = 0.0f;
-    S.skip = false;
     int l0 = 0;
     if (S.radius > 1.0f) {
       // lod = log2(radius) clamped to the chain. radius <= 1 — the first stretch of every cone, a VAL block
       // subtends ~1/32 rad — is level 0 exactly, without the log. fmaxf(NaN, 0) = 0.
       const float l = fminf(__log2f(S.radius), maxLod);
       floor_frac(l, l0, S.t);
-    } else if (ZSKIP) {
-      // lod 0: inside a brick whose one-voxel neighbourhood is empty the footprint is all zeros
-      const int vx = __float_as_int(cx + kMagic) - 0x4B400000; // round(q) = floor(q + .5) = voxel of the position
-      const int vy = __float_as_int(cy + kMagic) - 0x4B400000;
-      const int vz = __float_as_int(cz + kMagic) - 0x4B400000;
-      if ((uint32_t)(vx | vy | vz) < (uint32_t)V.res) {
-        const int sh = V.brick_shift;
-        S.skip = (V.brick_mask[(vy >> sh) + 32 * (vz >> sh)] >> (vx >> sh)) & 1u;
-      }
     }
-    if (!S.skip) {
-      const Footprint f0 = footprint(V, l0, cx, cy, cz);
-      S.r0 = __ldg(V.rec + f0.index);
-      S.tx0 = f0.tx; S.ty0 = f0.ty; S.tz0 = f0.tz;
-      if (S.t != 0.0f) { // mip-linear: also the next coarser level
-        const Footprint f1 = footprint(V, min(l0 + 1, V.levels - 1), cx, cy, cz);
-        S.r1 = __ldg(V.rec + f1.index);
-        S.tx1 = f1.tx; S.ty1 = f1.ty; S.tz1 = f1.tz;
-      }
+    const Footprint f0 = footprint(V, l0, cx, cy, cz);
+    S.r0 = __ldg(V.rec + f0.index);
+    S.tx0 = f0.tx; S.ty0 = f0.ty; S.tz0 = f0.tz;
+    if (S.t != 0.0f) { // mip-linear: also the next coarser level
+      const Footprint f1 = footprint(V, min(l0 + 1, V.levels - 1), cx, cy, cz);
+      S.r1 = __ldg(V.rec + f1.index);
+      S.tx1 = f1.tx; S.ty1 = f1.ty; S.tz1 = f1.tz;
     }
     return S;
   };
 
+  auto filter = [&](const ConeSample& S) -> float {
+    float o = trilinear(S.r0, S.tx0, S.ty0, S.tz0);
+    if (S.t != 0.0f) o = fmaf(S.t, trilinear(S.r1, S.tx1, S.ty1, S.tz1) - o, o);
+    return o;
+  };
+  // two steps per trip so that the in-flight sample alternates between A and B without register copies
   float occ = 0.0f;
-  ConeSample cur = fetch(1.0f);
-  for (int s = 0; s < 32; ++s) {
-    const bool last = (cur.dist >= goal) || (s == 31);                              // :211, :222
-    ConeSample nxt = cur;
-    if (!last) nxt = fetch(fmaxf(1.0f, ex_mul(cur.radius, radToStep)));             // :225, one step ahead
-    float o = 0.0f;
-    if (!cur.skip) {
-      o = trilinear(cur.r0, cur.tx0, cur.ty0, cur.tz0);
-      if (cur.t != 0.0f) o = fmaf(cur.t, trilinear(cur.r1, cur.tx1, cur.ty1, cur.tz1) - o, o);
-    }
-    occ = fmaf(1.0f - occ, o, occ);                                                 // :220
-    if (last || occ >= 1.0f) break;
-    cur = nxt;
+  ConeSample A = fetch(1.0f), B;
+#pragma unroll 1
+  for (int s = 0; s < 32; s += 2) {
+    const bool lastA = A.dist >= goal;                                              // :222 (s <= 30 here)
+    if (!lastA) B = fetch(fmaxf(1.0f, ex_mul(A.radius, radToStep)));                // :225, one step ahead
+    occ = fmaf(1.0f - occ, filter(A), occ);                                         // :220
+    if (lastA || occ >= 1.0f) break;
+    const bool lastB = (B.dist >= goal) || (s == 30);                               // :211
+    if (!lastB) A = fetch(fmaxf(1.0f, ex_mul(B.radius, radToStep)));
+    occ = fmaf(1.0f - occ, filter(B), occ);
+    if (lastB || occ >= 1.0f) break;
   }
   return saturatef(1.0f - occ);                                                     // :230
 }
@@ -402,12 +394,6 @@ struct ScalarMath {
     slot[0] = r0; slot[1] = r1; slot[2] = r2;
   }
   // CPT cones (one per cache of this thread) x up to NB consecutive shadow blocks, marched in lock step
-  // one cone per cache of this thread towards shadow block `blk` (cacheLightingRSM.comp:169-232)
-  template <bool ZSKIP>
-  __device__ __forceinline__ void trace(const VoxelVol& V, const float4* blk) {
-    static_assert(CPT == 1, "shadowed gathers keep one cache per thread");
-    shadow[0] = live[0] ? cone_trace<ZSKIP>(V, px[0], py[0], pz[0], *blk) : 0.0f;
-  }
   __device__ __forceinline__ void set_shadow(const float (&v)[CPT]) {
 #pragma unroll
     for (int j = 0; j < CPT; ++j) shadow[j] = v[j];
@@ -461,8 +447,6 @@ struct PackedMath {
     d[3] = make_float4(r1.z, r1.z, r2.x, r2.x);
     d[4] = make_float4(r2.y, r2.y, r2.z, r2.z);
   }
-  template <bool ZSKIP>
-  __device__ __forceinline__ void trace(const VoxelVol&, const float4*) {} // unshadowed only
   __device__ __forceinline__ void set_shadow(const float (&v)[CPT]) {
 #pragma unroll
     for (int j = 0; j < PAIRS; ++j) { shadow[j].x = v[2 * j]; shadow[j].y = v[2 * j + 1]; }
@@ -584,8 +568,8 @@ __device__ __forceinline__ void advance(const GatherParams& p, const Schedule& S
   if (c.base >= c.v_end) start_run(p, S, c, c.u_next, u1);
 }
 
-// CONES: 1 = plain cone march, 2 = skipping samples inside empty bricks (shadowed kernels only)
-template <int ORDER, bool SHADOW, typename Math, bool USE_TMA, int CONES = 1, int MINB = 1>
+// SHADOW: every pair is scaled by the visibility of its (cache, VAL block), read from the table cone_kernel wrote.
+template <int ORDER, bool SHADOW, typename Math, bool USE_TMA, int MINB = 1>
 __global__ void __launch_bounds__(kThreads, MINB) gather_kernel(const __grid_constant__ GatherParams p) {
   constexpr int CPT = Math::CPT;
   constexpr int TILE = kThreads * CPT;
@@ -594,24 +578,12 @@ __global__ void __launch_bounds__(kThreads, MINB) gather_kernel(const __grid_con
   constexpr int SPV = Math::kSmemPerVpl;
   constexpr int STAGES = USE_TMA ? 2 : 1;
   __shared__ __align__(128) float4 s_vpl[STAGES][kVplTile * SPV];
-  __shared__ float4 s_blk[SHADOW ? kVplTile : 1];
   __shared__ __align__(8) uint64_t s_bar[2];
-  __shared__ uint32_t s_brick_mask[(SHADOW && CONES == 2) ? 1024 : 1];
 
   const Schedule S = make_schedule(p, TILE);
   if (S.units == 0) return;
   const unsigned long long u0 = range_begin(S, gridDim.x, blockIdx.x), u1 = range_begin(S, gridDim.x, blockIdx.x + 1);
   if (u0 >= u1) return;
-  VoxelVol V;
-  if (SHADOW) {
-    V.rec = p.rec; V.rec_offset = p.rec_offset; V.res = p.vres; V.levels = p.vlevels; V.voxel_size = p.voxel_size;
-    V.vmin[0] = p.vmin[0]; V.vmin[1] = p.vmin[1]; V.vmin[2] = p.vmin[2];
-    V.brick_mask = s_brick_mask; V.brick_shift = p.brick_shift;
-    if (CONES == 2) {
-      for (int i = threadIdx.x; i < 1024; i += kThreads) s_brick_mask[i] = __ldg(p.brick_mask + i);
-      __syncthreads();
-    }
-  }
   uint32_t phase[2] = {0u, 0u};
   if (USE_TMA) {
     if (threadIdx.x == 0) {
@@ -623,8 +595,8 @@ __global__ void __launch_bounds__(kThreads, MINB) gather_kernel(const __grid_con
   }
 
   Math M;
-  float4 r0, r1, r2, rb; // register-prefetched VPL (and shadow block) of the NEXT shared-memory tile
-  r0 = r1 = r2 = rb = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 r0, r1, r2; // register-prefetched VPL of the NEXT shared-memory tile
+  r0 = r1 = r2 = make_float4(0.f, 0.f, 0.f, 0.f);
   auto prefetch = [&](const Cursor& c) {
     const GatherLight& L = p.lights[c.light];
     uint32_t v = c.base + threadIdx.x;
@@ -633,10 +605,6 @@ __global__ void __launch_bounds__(kThreads, MINB) gather_kernel(const __grid_con
     r0 = ok ? __ldg(L.vpls + (size_t)v * 3) : make_float4(0.f, 0.f, 0.f, 1.f);
     r1 = ok ? __ldg(L.vpls + (size_t)v * 3 + 1) : z;
     r2 = ok ? __ldg(L.vpls + (size_t)v * 3 + 2) : z;
-    if (SHADOW) {
-      uint32_t b = c.base / L.interval + threadIdx.x;
-      rb = ((unsigned long long)b * L.interval < c.v_end) ? __ldg(L.blocks + b) : z;
-    }
   };
   auto tma_issue = [&](const Cursor& c, int st) {
     const GatherLight& L = p.lights[c.light];
@@ -678,24 +646,33 @@ __global__ void __launch_bounds__(kThreads, MINB) gather_kernel(const __grid_con
     } else {
       __syncthreads(); // previous tile fully consumed
       Math::stage(&s_vpl[0][threadIdx.x * SPV], r0, r1, r2);
-      if (SHADOW) s_blk[threadIdx.x] = rb;
       __syncthreads();
       if (nxt.valid) prefetch(nxt);
     }
     const int n = (int)min((uint32_t)kVplTile, cur.v_end - cur.base);
     const float4* sv = &s_vpl[st][0];
     if constexpr (SHADOW) {
-      // :169 — a new shadow value every `interval` VPLs. A tile starts on a multiple of the granule, which is
-      // a multiple of every interval <= granule; for longer intervals the value carries over.
+      // :169 — a new shadow value every `interval` VPLs: one table read per cache per block.
+      // A tile starts on a multiple of the granule, itself a multiple of every interval <= granule.
       const uint32_t interval = p.lights[cur.light].interval;
-      constexpr bool ZSKIP = CONES == 2;
-      if (interval > (uint32_t)kVplTile) {
-        if ((cur.base & (interval - 1u)) == 0u) M.template trace<ZSKIP>(V, s_blk);
+      const float* col = p.shadow_table + (size_t)p.block_offset[cur.light] * p.shadow_stride + cur.tile * TILE + threadIdx.x;
+      auto load_shadow = [&](uint32_t blk) {
+        float v[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+          v[j] = (cur.tile * TILE + j * kThreads + threadIdx.x < S.count) ? __ldg(col + (size_t)blk * p.shadow_stride + j * kThreads) : 0.0f;
+        M.set_shadow(v);
+      };
+      if (interval >= (uint32_t)kVplTile) {
+        load_shadow(cur.base / interval);
+#pragma unroll 4
         for (int i = 0; i < n; ++i) M.eval(sv + i * SPV);
       } else {
-        for (int i = 0, b = 0; i < n; ++b) {
-          M.template trace<ZSKIP>(V, s_blk + b);
+        uint32_t blk = cur.base / interval;
+        for (int i = 0; i < n; ++blk) {
+          load_shadow(blk);
           const int end = min(n, i + (int)interval);
+#pragma unroll 4
           for (; i < end; ++i) M.eval(sv + i * SPV);
         }
       }
@@ -731,6 +708,67 @@ __global__ void __launch_bounds__(kThreads, MINB) gather_kernel(const __grid_con
       seg_open = false;
     }
     cur = nxt;
+  }
+}
+
+// ------------------------------------------------------------ pass 1: the visibility table
+// cacheLightingRSM.comp:167-232 hoisted out of the pair loop: the reference traces a cone for every
+// (cache, VAL block) inside its VPL loop; here all cones of a chunk of caches are traced first, by a kernel
+// whose register budget is the cone march alone (so ~3x the warps per SM of a fused kernel hide the L1/L2
+// latency of the dependent fetches), into table[block][cache] — 25 MB for the 1080p / 16 k-VPL frame, resident
+// in B200's 126 MB L2 until the pair kernel (pass 2) reads every value exactly once, coalesced.
+struct ConeParams {
+  GatherLight lights[DRV_MAX_LIGHTS];
+  uint32_t block_offset[DRV_MAX_LIGHTS + 1]; // prefix sum of the lights' block counts
+  uint32_t num_lights;
+  const uint8_t* entries;
+  uint32_t entry_stride;
+  const drv_cache_counter* counter;
+  uint32_t shard_rank, shard_world;
+  uint32_t chunk_first, chunk_cap;
+  float* table;
+  uint32_t stride;
+  const uint2* rec;
+  uint32_t rec_offset[16];
+  int vres, vlevels;
+  float vmin[3];
+  float voxel_size;
+};
+
+constexpr int kConeThreads = 128;
+constexpr int kBlocksPerItem = 8;
+
+__global__ void __launch_bounds__(kConeThreads) cone_kernel(const __grid_constant__ ConeParams p) {
+  // this shard's chunk, as make_schedule derives it
+  const uint32_t n = (uint32_t)max(p.counter->TotalLightCacheCount, 0);
+  const uint32_t groups64 = (n + 63u) / 64u;
+  const uint32_t g0 = (uint32_t)(((unsigned long long)groups64 * p.shard_rank) / p.shard_world);
+  const uint32_t g1 = (uint32_t)(((unsigned long long)groups64 * (p.shard_rank + 1)) / p.shard_world);
+  uint32_t first = min(g0 * 64u, n), count = min(g1 * 64u, n) - first;
+  const uint32_t lo = min(count, p.chunk_first), hi = min(count, p.chunk_first + min(p.chunk_cap, 0xFFFFFFFFu - p.chunk_first));
+  first += lo;
+  count = hi - lo;
+  if (count == 0) return;
+  VoxelVol V;
+  V.rec = p.rec; V.rec_offset = p.rec_offset; V.res = p.vres; V.levels = p.vlevels; V.voxel_size = p.voxel_size;
+  V.vmin[0] = p.vmin[0]; V.vmin[1] = p.vmin[1]; V.vmin[2] = p.vmin[2];
+  const uint32_t total_blocks = p.block_offset[p.num_lights];
+  const uint32_t cache_groups = (count + kConeThreads - 1) / kConeThreads;
+  const uint32_t block_groups = (total_blocks + kBlocksPerItem - 1) / kBlocksPerItem;
+  const unsigned long long items = (unsigned long long)cache_groups * block_groups;
+  for (unsigned long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const uint32_t cg = (uint32_t)(item / block_groups), bg = (uint32_t)(item - (unsigned long long)cg * block_groups);
+    const uint32_t local = cg * kConeThreads + threadIdx.x;
+    const bool alive = local < count;
+    float4 pos = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (alive) pos = *reinterpret_cast<const float4*>(p.entries + (size_t)(first + local) * p.entry_stride);
+    const uint32_t b_end = min(total_blocks, (bg + 1) * kBlocksPerItem);
+    uint32_t light = 0;
+    for (uint32_t b = bg * kBlocksPerItem; b < b_end; ++b) {
+      while (b >= p.block_offset[light + 1]) ++light;
+      const float4 blk = __ldg(p.lights[light].blocks + (b - p.block_offset[light]));
+      if (alive) p.table[(size_t)b * p.stride + local] = cone_trace(V, pos.x, pos.y, pos.z, blk);
+    }
   }
 }
 
@@ -811,8 +849,9 @@ __global__ void __launch_bounds__(kFinThreads) gather_finalize_kernel(GatherPara
 // -------------------------------------------------------------------------------- host side
 namespace {
 
-template <typename K>
-drv_status launch_gather(drv_ctx* ctx, K kernel, GatherParams& p, int tile_caches, int order) {
+using GatherFn = void (*)(const GatherParams);
+
+drv_status launch_gather(drv_ctx* ctx, GatherFn kernel, GatherParams& p, int tile_caches, int order) {
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
   if (per_sm < 1) per_sm = 1;
@@ -828,16 +867,45 @@ drv_status launch_gather(drv_ctx* ctx, K kernel, GatherParams& p, int tile_cache
   }
   p.partials = ctx->partials;
   p.grid = (uint32_t)grid;
-  ctx->stage_begin(DRV_STAGE_GATHER_KERNEL);
   kernel<<<grid, kThreads, 0, ctx->stream>>>(p);
   DRV_LAUNCH_CHECK();
-  ctx->stage_end(DRV_STAGE_GATHER_KERNEL);
   const int fin_grid = ctx->num_sms * 4;
   if (order == 1) gather_finalize_kernel<1><<<fin_grid, kFinThreads, 0, ctx->stream>>>(p, tile_caches);
   else gather_finalize_kernel<2><<<fin_grid, kFinThreads, 0, ctx->stream>>>(p, tile_caches);
   DRV_LAUNCH_CHECK();
   return DRV_OK;
 }
+
+// Kernel variants (drv_config.gather_variant; measurements in profiles/):
+//   0  packed FP32x2 maths, 4 caches / thread (SH1) or 2 (SH2)      — default, fastest in the sweep
+//   1  scalar maths, VPL tiles staged with TMA bulk copies + mbarrier, double buffered
+//   3  packed, one pair of caches per thread
+//   4  scalar, 4 caches / thread (SH1)
+//   12 scalar, 2 caches / thread, register-prefetch staging
+// With indirect shadows the same kernels additionally scale every pair by its table visibility.
+template <bool SH>
+GatherFn select_kernel(int order, uint32_t variant, int* tile) {
+#define DRV_PICK(ORD, MATH, TMA) do { *tile = kThreads * MATH::CPT; return gather_kernel<ORD, SH, MATH, TMA>; } while (0)
+  using S1c2 = ScalarMath<1, SH, 2>; using S1c4 = ScalarMath<1, SH, 4>; using S2c2 = ScalarMath<2, SH, 2>;
+  using P1p1 = PackedMath<1, SH, 1>; using P1p2 = PackedMath<1, SH, 2>; using P2p1 = PackedMath<2, SH, 1>;
+  if (order == 1) {
+    switch (variant) {
+      case 1: DRV_PICK(1, S1c2, true);
+      case 3: DRV_PICK(1, P1p1, false);
+      case 4: DRV_PICK(1, S1c4, false);
+      case 12: DRV_PICK(1, S1c2, false);
+      default: DRV_PICK(1, P1p2, false);
+    }
+  }
+  switch (variant) {
+    case 1: DRV_PICK(2, S2c2, true);
+    case 4: case 12: DRV_PICK(2, S2c2, false);
+    default: DRV_PICK(2, P2p1, false);
+  }
+#undef DRV_PICK
+}
+
+constexpr uint32_t kShadowChunk = 65536; // caches per visibility-table chunk
 
 } // namespace
 
@@ -917,14 +985,6 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   p.f2 = ctx->constant.ShEvaFactor2n2_p1_n1;
   p.f20 = ctx->constant.ShEvaFactor20;
   p.f22 = ctx->constant.ShEvaFactor2p2;
-  p.rec = ctx->voxel_records;
-  p.brick_mask = ctx->voxel_brick_mask;
-  p.brick_shift = (int)ctx->voxel_brick_shift;
-  for (int l = 0; l < 16; ++l) p.rec_offset[l] = ctx->voxel_record_offset[l];
-  p.vres = (int)ctx->cfg.voxel_resolution;
-  p.vlevels = (int)ctx->voxel_levels;
-  memcpy(p.vmin, ctx->volume.VolumeWorldMin, 12);
-  p.voxel_size = ctx->volume.VoxelSizeInWorld;
   if (ctx->peers_open) {
     p.num_peers = ctx->shard_world;
     for (uint32_t r = 0; r < ctx->shard_world && r < 8; ++r)
@@ -932,49 +992,68 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   }
   const int order = (int)ctx->cfg.sh_order;
   const uint32_t variant = ctx->cfg.gather_variant;
-#define DRV_GATHER(ORD, SH, MATH, TMA, CONES) \
-  return launch_gather(ctx, gather_kernel<ORD, SH, MATH, TMA, CONES>, p, kThreads * MATH::CPT, ORD)
-  using S1n2 = ScalarMath<1, false, 2>; using S1n4 = ScalarMath<1, false, 4>; using S1s1 = ScalarMath<1, true, 1>;
-  using S2n2 = ScalarMath<2, false, 2>; using S2n1 = ScalarMath<2, false, 1>; using S2s1 = ScalarMath<2, true, 1>;
-  using P1n1 = PackedMath<1, false, 1>; using P1n2 = PackedMath<1, false, 2>;
-  using P2n1 = PackedMath<2, false, 1>;
-  if (shadow) { // variant 6: skip samples whose position lies in an empty brick (exact: such samples add 0)
-    if (variant == 6) { if (order == 1) DRV_GATHER(1, true, S1s1, false, 2); else DRV_GATHER(2, true, S2s1, false, 2); }
-    if (variant == 7) { if (order == 1) DRV_GATHER(1, true, S1s1, false, 1); else DRV_GATHER(2, true, S2s1, false, 1); }
-    // default: register budget for 4 CTAs / SM (128 registers): +14 % over the unconstrained build (profiles/)
-    if (order == 1) return launch_gather(ctx, gather_kernel<1, true, S1s1, false, 1, 4>, p, kThreads, 1);
-    return launch_gather(ctx, gather_kernel<2, true, S2s1, false, 1, 4>, p, kThreads, 2);
+  int tile = 0;
+  const GatherFn kernel = shadow ? select_kernel<true>(order, variant, &tile) : select_kernel<false>(order, variant, &tile);
+  p.chunk_first = 0;
+  p.chunk_cap = 0xFFFFFFFFu;
+  if (!shadow) {
+    ctx->stage_begin(DRV_STAGE_GATHER_KERNEL);
+    drv_status st = launch_gather(ctx, kernel, p, tile, order);
+    ctx->stage_end(DRV_STAGE_GATHER_KERNEL);
+    return st;
   }
-  switch (variant) {
-    case 1: // scalar maths, TMA bulk staging
-      if (order == 1) DRV_GATHER(1, false, S1n2, true, 1); else DRV_GATHER(2, false, S2n2, true, 1);
-    case 2: // packed FP32x2, widest tiling
-      if (order == 1) DRV_GATHER(1, false, P1n2, false, 1); else DRV_GATHER(2, false, P2n1, false, 1);
-    case 3: // packed FP32x2, one pair per thread
-      if (order == 1) DRV_GATHER(1, false, P1n1, false, 1); else DRV_GATHER(2, false, P2n1, false, 1);
-    case 4: // scalar, widest tiling
-      if (order == 1) DRV_GATHER(1, false, S1n4, false, 1); else DRV_GATHER(2, false, S2n2, false, 1);
-    case 5: // scalar, SH2 with one cache per thread
-      if (order == 2) DRV_GATHER(2, false, S2n1, false, 1);
-      break;
-    case 8: // scalar, register budget for 8 CTAs / SM
-      if (order == 1) return launch_gather(ctx, gather_kernel<1, false, S1n2, false, 1, 8>, p, kThreads * 2, 1);
-      return launch_gather(ctx, gather_kernel<2, false, S2n2, false, 1, 5>, p, kThreads * 2, 2);
-    case 9: // TMA staging, register budget for 8 CTAs / SM
-      if (order == 1) return launch_gather(ctx, gather_kernel<1, false, S1n2, true, 1, 8>, p, kThreads * 2, 1);
-      return launch_gather(ctx, gather_kernel<2, false, S2n2, true, 1, 5>, p, kThreads * 2, 2);
-    case 10: // packed, one pair per thread, 8 CTAs / SM
-      if (order == 1) return launch_gather(ctx, gather_kernel<1, false, P1n1, false, 1, 7>, p, kThreads * 2, 1);
-      return launch_gather(ctx, gather_kernel<2, false, P2n1, false, 1, 5>, p, kThreads * 2, 2);
-    case 11: // scalar, one cache per thread (most CTAs / SM)
-      if (order == 1) return launch_gather(ctx, gather_kernel<1, false, ScalarMath<1, false, 1>, false, 1, 10>, p, kThreads, 1);
-      break;
-    default:
-      break;
+
+  // ---- indirect shadows: pass 1 traces every (cache, VAL block) cone of a chunk of caches into the visibility
+  // table, pass 2 is the pair kernel reading it. The cache count lives on the device, so the host walks all
+  // chunks up to max_cache_count; kernels of empty chunks return at once.
+  ConeParams c;
+  memset(&c, 0, sizeof(c));
+  uint32_t total_blocks = 0;
+  for (uint32_t l = 0; l < ctx->num_lights; ++l) {
+    c.lights[l] = p.lights[l];
+    c.block_offset[l] = p.block_offset[l] = total_blocks;
+    total_blocks += (p.lights[l].num_vpls + p.lights[l].interval - 1) / p.lights[l].interval;
   }
-  // variant 0 (default): packed FP32x2 maths (4 caches / thread for SH1, 2 for SH2) — the fastest in the sweep
-  // (profiles/); variant 12 = scalar maths, register-prefetch staging
-  if (variant == 12) { if (order == 1) DRV_GATHER(1, false, S1n2, false, 1); else DRV_GATHER(2, false, S2n2, false, 1); }
-  if (order == 1) DRV_GATHER(1, false, P1n2, false, 1); else DRV_GATHER(2, false, P2n1, false, 1);
-#undef DRV_GATHER
+  c.block_offset[ctx->num_lights] = total_blocks;
+  c.num_lights = ctx->num_lights;
+  c.entries = ctx->entries;
+  c.entry_stride = ctx->entry_stride;
+  c.counter = ctx->counter;
+  c.shard_rank = ctx->shard_rank;
+  c.shard_world = ctx->shard_world;
+  c.rec = ctx->voxel_records;
+  for (int l = 0; l < 16; ++l) c.rec_offset[l] = ctx->voxel_record_offset[l];
+  c.vres = (int)ctx->cfg.voxel_resolution;
+  c.vlevels = (int)ctx->voxel_levels;
+  memcpy(c.vmin, ctx->volume.VolumeWorldMin, 12);
+  c.voxel_size = ctx->volume.VoxelSizeInWorld;
+  const uint32_t chunk = std::min<uint32_t>(kShadowChunk, (ctx->cfg.max_cache_count + 255u) & ~255u);
+  const size_t table_floats = (size_t)total_blocks * chunk;
+  if (table_floats > ctx->shadow_table_floats) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->shadow_table) cudaFree(ctx->shadow_table);
+    ctx->shadow_table = nullptr;
+    ctx->shadow_table_floats = 0;
+    DRV_CUDA(cudaMalloc(&ctx->shadow_table, table_floats * sizeof(float)));
+    ctx->shadow_table_floats = table_floats;
+  }
+  c.table = ctx->shadow_table;
+  c.stride = chunk;
+  p.shadow_table = ctx->shadow_table;
+  p.shadow_stride = chunk;
+  int cone_per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cone_per_sm, cone_kernel, kConeThreads, 0);
+  if (cone_per_sm < 1) cone_per_sm = 1;
+  const int cone_grid = ctx->num_sms * cone_per_sm;
+  ctx->stage_begin(DRV_STAGE_GATHER_KERNEL);
+  for (uint32_t first = 0; first < ctx->cfg.max_cache_count; first += chunk) {
+    c.chunk_first = p.chunk_first = first;
+    c.chunk_cap = p.chunk_cap = chunk;
+    cone_kernel<<<cone_grid, kConeThreads, 0, ctx->stream>>>(c);
+    DRV_LAUNCH_CHECK();
+    drv_status st = launch_gather(ctx, kernel, p, tile, order);
+    if (st != DRV_OK) return st;
+  }
+  ctx->stage_end(DRV_STAGE_GATHER_KERNEL);
+  return DRV_OK;
 }

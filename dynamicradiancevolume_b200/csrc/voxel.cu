@@ -275,34 +275,6 @@ __global__ void __launch_bounds__(256) voxel_records_kernel(RecordLevels L, cons
 
 } // namespace
 
-// Empty-brick mask for the cone tracer's lod-0 stretch: one thread per brick (a warp = 32 bricks along x = one
-// mask word), reading the dilated brick through the level-0 records (each covers 2^3 voxels).
-__global__ void __launch_bounds__(256) voxel_brick_mask_kernel(const uint2* __restrict__ rec0, int res, int shift,
-                                                               uint32_t* __restrict__ mask) {
-  const int bx = threadIdx.x & 31;
-  const int by = blockIdx.x * 8 + (threadIdx.x >> 5), bz = blockIdx.y;
-  const int B = 1 << shift, nb = res >> shift, rp = res + 1;
-  bool empty = false;
-  if (bx < nb && by < nb && bz < nb) {
-    empty = true;
-    // record corners -1+B*i, +2, ... with the last one forced to B*(i+1)-1: together they cover [B*i-1, B*(i+1)]
-    const int n = (B + 2 + 1) / 2;
-    for (int kz = 0; kz < n && empty; ++kz) {
-      const int z = min(B * bz - 1 + 2 * kz, B * (bz + 1) - 1);
-      for (int ky = 0; ky < n && empty; ++ky) {
-        const int y = min(B * by - 1 + 2 * ky, B * (by + 1) - 1);
-        for (int kx = 0; kx < n; ++kx) {
-          const int x = min(B * bx - 1 + 2 * kx, B * (bx + 1) - 1);
-          const uint2 r = __ldg(rec0 + (size_t)(x + 1) + (size_t)rp * ((size_t)(y + 1) + (size_t)rp * (z + 1)));
-          if ((r.x | r.y) != 0u) empty = false;
-        }
-      }
-    }
-  }
-  const uint32_t word = __ballot_sync(0xffffffffu, empty);
-  if (bx == 0 && by < 32 && bz < 32) mask[by + 32 * bz] = word;
-}
-
 // voxelization.cpp:161-171 (mip chain) + the gather-ready records.
 static drv_status drv_impl_voxel_mips_and_records(drv_ctx* ctx) {
   const int res = (int)ctx->cfg.voxel_resolution;
@@ -339,9 +311,7 @@ static drv_status drv_impl_voxel_mips_and_records(drv_ctx* ctx) {
     const uint32_t total = (uint32_t)ctx->voxel_record_count;
     voxel_records_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(L, ctx->voxel_chain, ctx->voxel_records, total);
     DRV_LAUNCH_CHECK();
-    voxel_brick_mask_kernel<<<dim3(4, 32), 256, 0, ctx->stream>>>(ctx->voxel_records, res, (int)ctx->voxel_brick_shift,
-                                                                 ctx->voxel_brick_mask);
-    DRV_LAUNCH_CHECK();
+
   }
   return DRV_OK;
 }
