@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps (profiling runs)")
     ap.add_argument("--no-microbench", action="store_true")
     ap.add_argument("--stages", action="store_true", help="print the per-stage table to stderr")
+    ap.add_argument("--no-graph", action="store_true", help="issue the frame kernel by kernel instead of replaying its CUDA graph")
+    ap.add_argument("--serial", action="store_true", help="reference stage order on one stream (prepare_rsm, clear, drv_draw) "
+                                                          "instead of drv_draw_frame's light-side || camera-side schedule")
     ap.add_argument("--barrier", choices=["peer", "nccl"], default="peer",
                     help="cross-GPU barrier of sharded runs: flags in NVLink peer memory (drv_peer_barrier) or an NCCL all-reduce")
     return ap.parse_args()
@@ -252,12 +255,20 @@ def run_b200(args):
         else:
             dist.all_reduce(barrier_word)
 
+    frame_flags = abi.DRV_FRAME_PREPARE_RSM | (0 if args.no_graph else abi.DRV_FRAME_GRAPH)
+
     def frame_device():
         with torch.cuda.stream(stream):
-            for i in range(len(g.rsms)):
-                ctx.prepare_rsm(i)
             if wl.indirect_shadow:
                 ctx.voxelize(g.tris, None, 1.0)
+            if world == 1 and not args.serial:
+                # one call: (RSM mips + VPLs) || allocate -> gather -> apply; the glClear of the HDR target
+                # (renderer.cpp:562) is fused into the apply pass (DRV_HDR_RGBA16F_WRITE); replayed as a CUDA
+                # graph while stage timers are off
+                ctx.draw_frame(hdr16, abi.DRV_HDR_RGBA16F_WRITE, frame_flags)
+                return
+            for i in range(len(g.rsms)):
+                ctx.prepare_rsm(i)
             hdr16.zero_()  # glClear(GL_COLOR_BUFFER_BIT), renderer.cpp:562
             if world == 1:
                 ctx.draw(hdr16, abi.DRV_HDR_RGBA16F_ADD)
@@ -271,7 +282,6 @@ def run_b200(args):
 
     # ---- warm-up + timed region: CUDA events on the context's stream around every step ----
     torch.cuda.synchronize()
-    ctx.enable_stage_timers(True)
     n_total = args.warmup + args.steps
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_total)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_total)]
@@ -297,17 +307,37 @@ def run_b200(args):
         ev1[i].synchronize()
         if i >= args.warmup:
             step_ms.append(ev0[i].elapsed_time(ev1[i]))
-            for s, name in enumerate(abi.STAGE_NAMES):
-                try:
-                    stage_ms[name].append(ctx.stage_ms(s))
-                except drv.DrvError:
-                    pass
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
     launches = ctx.kernel_launches() - launches0
+    # ---- instrumented pass: the same K steps once more with CUDA events around every stage and around the
+    # gather kernel (stage timers force kernel-by-kernel issue, so the frame graph is not used here); the
+    # clock sampler keeps running: this pass is part of the measured region of the roofline figures
+    ctx.enable_stage_timers(True)
+    inst_ms = []
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    for i in range(args.steps + 1):
+        with torch.cuda.stream(stream):
+            if not args.no_flush:
+                flush_buf.zero_()
+            ev0[i].record(stream)
+        frame_device()
+        with torch.cuda.stream(stream):
+            ev1[i].record(stream)
+        ev1[i].synchronize()
+        if i == 0:
+            continue
+        inst_ms.append(ev0[i].elapsed_time(ev1[i]))
+        for s, name in enumerate(abi.STAGE_NAMES):
+            try:
+                stage_ms[name].append(ctx.stage_ms(s))
+            except drv.DrvError:
+                pass
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
     ctx.enable_stage_timers(False)
     total_ms = sum(step_ms)
     if world > 1:
@@ -387,7 +417,11 @@ def run_b200(args):
     if world > 1:
         b, e = drv.shard_range(n_caches, rank, world)
         shard_caches = e - b
-    pairs_per_launch = shard_caches * wl.num_vpls
+    # units of the roofline: the pairs the kernel EVALUATES (VPLs with zero flux are dropped before the gather;
+    # they add exactly zero) — the reference's own pair count (caches x R^2) is reported beside it
+    live_vpls = sum(ctx.live_vpl_counts()[:len(wl.spot_lights)])
+    pairs_per_launch = shard_caches * live_vpls
+    pairs_reference = shard_caches * wl.num_vpls
     flops = pairs_per_launch * FLOP_PER_PAIR[wl.sh_order]
     peaks = {}
     try:
@@ -414,6 +448,8 @@ def run_b200(args):
             "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS,
             "traffic": None,
             "pairs_per_launch": pairs_per_launch, "flop_per_pair": FLOP_PER_PAIR[wl.sh_order],
+            "live_vpls": live_vpls, "pairs_per_launch_reference": pairs_reference,
+            "frac_counting_reference_pairs": pairs_reference * FLOP_PER_PAIR[wl.sh_order] / (gather_ms * 1e-3) / 1e12 / fp32_peak,
             "pairs_per_s": pairs_per_launch / (gather_ms * 1e-3), "avg_launch_ms": gather_ms,
             "note": ("CUDA-core FP32 roofline (this is not a tensor-core contraction; MEASURED_PEAKS.json has no FP32 "
                      "figure). HBM traffic of the gather is ~0 per pair: the VPL list and entries are L2-resident."),
@@ -453,7 +489,7 @@ def run_b200(args):
         "metric": METRIC, "value": ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(wl), "caches": n_caches, "vpls": wl.num_vpls,
+        "config": {"workload": workload_name(wl), "caches": n_caches, "vpls": wl.num_vpls, "live_vpls": live_vpls,
                    "pairs_per_frame": n_caches * wl.num_vpls,
                    "l2": "flushed between steps (512 MiB memset outside the event pairs)" if not args.no_flush else "not flushed",
                    "parallelism": "1 GPU" if world == 1 else "gather sharded over %d GPUs by cell-ordered entry range, "
@@ -466,6 +502,12 @@ def run_b200(args):
         "roofline_streaming_stages": secondary,
         "cpu_baseline": cpu_baseline,
         "stage_ms": {k: med(v) for k, v in stage_ms.items() if v},
+        "stage_ms_note": "instrumented pass after the timed region: the same steps issued kernel by kernel with CUDA "
+                         "events around every stage (%.4f ms/frame that way); stages of the light side and the camera "
+                         "side overlap" % (sum(inst_ms) / max(len(inst_ms), 1)),
+        "frame_issue": ("serial: prepare_rsm, clear, drv_draw" if (args.serial or world > 1) else
+                        "drv_draw_frame: (RSM mips + VPLs) || allocate -> gather -> apply(+clear)%s"
+                        % ("" if args.no_graph else ", CUDA graph replay")),
         "microbench": micro,
         "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
         "gpu": torch.cuda.get_device_name(local),

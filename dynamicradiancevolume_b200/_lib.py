@@ -38,6 +38,8 @@ SYMBOLS = [
     ("drv_apply_caches", _st, [_P, _P, _u32]),
     ("drv_apply_caches_rows", _st, [_P, _P, _u32, _u32, _u32]),
     ("drv_draw", _st, [_P, _P, _u32]),
+    ("drv_draw_frame", _st, [_P, _P, _u32, _u32]),
+    ("drv_live_vpl_counts", _st, [_P, _P]),
     ("drv_get_buffers", _st, [_P, C.POINTER(abi.Buffers)]),
     ("drv_rsm_level_offset", C.c_uint64, [_u32, _u32]),
     ("drv_voxel_level_offset", C.c_uint64, [_u32, _u32]),

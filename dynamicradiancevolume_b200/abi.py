@@ -25,6 +25,9 @@ DRV_VOXELIZE_CLEAR = 1
 DRV_VOXELIZE_FINISH = 2
 DRV_HDR_RGBA16F_ADD = 0
 DRV_HDR_RGBA32F_WRITE = 1
+DRV_HDR_RGBA16F_WRITE = 2
+DRV_FRAME_PREPARE_RSM = 1
+DRV_FRAME_GRAPH = 2
 
 STAGE_NAMES = ["VoxelizeScene", "VoxelBlendMipMap", "AllocateCaches", "LightCaches", "ApplyCaches",
                "PrepareRSM", "GatherKernel"]

@@ -56,11 +56,13 @@ struct NormalBasis {
   float b2xy, b2yz, b20, b2xz, b2dd;   // band 2
 };
 
-// One corner: entry `address` (already known to exist) weighted by w.
+// One corner: entry `address` weighted by w. Branch-free: a corner without a cache (`valid` false) reads entry 0
+// — always inside the buffer — and selects zero irradiance, so the 24 (56) entry loads of a pixel are independent
+// of each other and of the atlas contents and can all be in flight together.
 template <int ORDER>
 __device__ __forceinline__ void accumulate_corner(const ApplyParams& p, const uint8_t* __restrict__ entries,
-                                                  uint32_t address, const NormalBasis<ORDER>& nb, float w, float& r,
-                                                  float& g, float& b) {
+                                                  uint32_t address, bool valid, const NormalBasis<ORDER>& nb, float w,
+                                                  float& r, float& g, float& b) {
   constexpr uint32_t STRIDE = ORDER == 2 ? 128 : 64;
   const float4* e = reinterpret_cast<const float4*>(entries + address * STRIDE); // < 2^31 bytes: checked at create
   float4 q1 = __ldg(e + 1), q2 = __ldg(e + 2), q3 = __ldg(e + 3); // (SH1neg1,SH00_r) (SH10,SH00_g) (SH1pos1,SH00_b)
@@ -77,9 +79,10 @@ __device__ __forceinline__ void accumulate_corner(const ApplyParams& p, const ui
     ir = fmaf(q6.x, nb.b2xz, ir);  ig = fmaf(q6.y, nb.b2xz, ig);  ib = fmaf(q6.z, nb.b2xz, ib);
     ir = fmaf(q7.x, nb.b2dd, ir);  ig = fmaf(q7.y, nb.b2dd, ig);  ib = fmaf(q7.z, nb.b2dd, ib);
   }
-  r = fmaf(fmaxf(ir, 0.0f), w, r); // max(irradiance, 0) then * weight, lightcache.glsl:178, cacheApply.frag:110
-  g = fmaf(fmaxf(ig, 0.0f), w, g);
-  b = fmaf(fmaxf(ib, 0.0f), w, b);
+  // max(irradiance, 0) then * weight, lightcache.glsl:178, cacheApply.frag:110; no cache -> exactly zero
+  r = fmaf(valid ? fmaxf(ir, 0.0f) : 0.0f, w, r);
+  g = fmaf(valid ? fmaxf(ig, 0.0f) : 0.0f, w, g);
+  b = fmaf(valid ? fmaxf(ib, 0.0f) : 0.0f, w, b);
 }
 
 // ComputeLightingFromCaches, cacheApply.frag:28-118 (before the * diffuse / PI).
@@ -120,12 +123,13 @@ __device__ __forceinline__ void lighting_from_caches(const ApplyParams& p, const
   for (int i = 0; i < 8; ++i) { // offsets in cacheApply.frag:43-54 order: x fastest, then y, then z
     const float w = wxy[i & 3] * ((i >> 2) ? fz : gz);
     const uint32_t address = addr[i] - 1u; // atlas 0 -> 0xFFFFFFFF: no cache, contributes zero
-    if (address < p.max_caches) accumulate_corner<ORDER>(p, entries, address, nb, w, r, g, b);
+    const bool valid = address < p.max_caches;
+    accumulate_corner<ORDER>(p, entries, valid ? address : 0u, valid, nb, w, r, g, b);
   }
 }
 
-template <int ORDER>
-__global__ void __launch_bounds__(256) apply_kernel(ApplyParams p, const float* __restrict__ depth,
+template <int ORDER, int MINB>
+__global__ void __launch_bounds__(256, MINB) apply_kernel(ApplyParams p, const float* __restrict__ depth,
                                                     const int* __restrict__ normal, const uchar4* __restrict__ diffuse,
                                                     const uint32_t* __restrict__ atlas, const uint8_t* __restrict__ entries,
                                                     const float* __restrict__ ndc_xy, void* __restrict__ out, int format,
@@ -139,6 +143,7 @@ __global__ void __launch_bounds__(256) apply_kernel(ApplyParams p, const float* 
   const float d = __ldg(depth + t);
   if (d < 0.00001f) { // :128 discard
     if (format == DRV_HDR_RGBA32F_WRITE) reinterpret_cast<float4*>(out)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    else if (format == DRV_HDR_RGBA16F_WRITE) reinterpret_cast<uint2*>(out)[t] = make_uint2(0u, 0u);
     return;
   }
   // gl_FragCoord.xy -> NDC (:134) through the per-context tables
@@ -171,6 +176,13 @@ __global__ void __launch_bounds__(256) apply_kernel(ApplyParams p, const float* 
   r = r * albr * inv_pi; g = g * albg * inv_pi; b = b * albb * inv_pi; // :114
   if (format == DRV_HDR_RGBA32F_WRITE) {
     reinterpret_cast<float4*>(out)[t] = make_float4(r, g, b, 1.0f);
+  } else if (format == DRV_HDR_RGBA16F_WRITE) { // cleared target (0,0,0,0) + additive blend, in one store
+    __half2 nrg = __floats2half2_rn(0.0f + r, 0.0f + g);
+    __half2 nba = __floats2half2_rn(0.0f + b, 0.0f);
+    uint2 nw;
+    nw.x = *reinterpret_cast<uint32_t*>(&nrg);
+    nw.y = *reinterpret_cast<uint32_t*>(&nba);
+    reinterpret_cast<uint2*>(out)[t] = nw;
   } else { // additive blend GL_ONE, GL_ONE into RGBA16F (renderer.cpp:119, 480, 1053)
     uint2* o = reinterpret_cast<uint2*>(out) + t;
     uint2 old = *o;
@@ -208,7 +220,7 @@ drv_status drv_impl_apply_rows(drv_ctx* ctx, void* out, uint32_t format, uint32_
   if (!ctx->gb_depth || !ctx->gb_normal || !ctx->gb_diffuse)
     return ctx->fail(DRV_ERR_NOT_BOUND, "drv_apply_caches: g-buffer not bound");
   if (!out) return ctx->fail(DRV_ERR_INVALID, "drv_apply_caches: null output");
-  if (format != DRV_HDR_RGBA16F_ADD && format != DRV_HDR_RGBA32F_WRITE)
+  if (format != DRV_HDR_RGBA16F_ADD && format != DRV_HDR_RGBA32F_WRITE && format != DRV_HDR_RGBA16F_WRITE)
     return ctx->fail(DRV_ERR_INVALID, "drv_apply_caches: unknown output format");
   ApplyParams p;
   p.W = ctx->constant.BackbufferResolution[0];
@@ -237,14 +249,19 @@ drv_status drv_impl_apply_rows(drv_ctx* ctx, void* out, uint32_t format, uint32_
   if (y_begin >= y_end) return DRV_OK;
   if (timed) ctx->stage_begin(DRV_STAGE_APPLY_CACHES);
   dim3 block(32, 8), grid((p.W + 31) / 32, (y_end - y_begin + 7) / 8);
-  if (ctx->cfg.sh_order == 2)
-    apply_kernel<2><<<grid, block, 0, ctx->stream>>>(p, ctx->gb_depth, (const int*)ctx->gb_normal,
-                                                     (const uchar4*)ctx->gb_diffuse, ctx->atlas, ctx->entries,
-                                                     ctx->ndc_xy, out, (int)format, (int)y_begin, (int)y_end);
-  else
-    apply_kernel<1><<<grid, block, 0, ctx->stream>>>(p, ctx->gb_depth, (const int*)ctx->gb_normal,
-                                                     (const uchar4*)ctx->gb_diffuse, ctx->atlas, ctx->entries,
-                                                     ctx->ndc_xy, out, (int)format, (int)y_begin, (int)y_end);
+  // resident blocks per SM the kernel is compiled for (register budget 64 / 80 / 128 per thread): more registers
+  // keep more of a pixel's entry loads in flight. drv_config.gather_variant bits 8..11 override it (tuning sweeps).
+  const uint32_t tune = (ctx->cfg.gather_variant >> 8) & 0xFu;
+#define DRV_APPLY(ORD, MB)                                                                                      \
+  apply_kernel<ORD, MB><<<grid, block, 0, ctx->stream>>>(p, ctx->gb_depth, (const int*)ctx->gb_normal,            \
+                                                         (const uchar4*)ctx->gb_diffuse, ctx->atlas, ctx->entries, \
+                                                         ctx->ndc_xy, out, (int)format, (int)y_begin, (int)y_end)
+  if (ctx->cfg.sh_order == 2) {
+    if (tune == 2) DRV_APPLY(2, 2); else if (tune == 3) DRV_APPLY(2, 3); else if (tune == 5) DRV_APPLY(2, 5); else DRV_APPLY(2, 4);
+  } else {
+    if (tune == 2) DRV_APPLY(1, 2); else if (tune == 3) DRV_APPLY(1, 3); else if (tune == 5) DRV_APPLY(1, 5); else DRV_APPLY(1, 4);
+  }
+#undef DRV_APPLY
   DRV_LAUNCH_CHECK();
   if (timed) ctx->stage_end(DRV_STAGE_APPLY_CACHES);
   return DRV_OK;

@@ -119,7 +119,12 @@ extern "C" drv_status drv_create(const drv_config* cfg, drv_ctx** out) {
     CREATE_CUDA(dmalloc(&S.depth_mips, mip_texels * 4));
     CREATE_CUDA(dmalloc(&S.vpls, texels * sizeof(drv_vpl)));
     CREATE_CUDA(dmalloc(&S.blocks, texels * sizeof(drv_shadow_block)));
+    CREATE_CUDA(dmalloc(&S.vpls_live, texels * sizeof(drv_vpl)));
+    CREATE_CUDA(dmalloc(&S.chunk_counts, (texels / 256 + 2) * sizeof(uint32_t)));
+    CREATE_CUDA(dmalloc(&S.block_live, texels));
   }
+  CREATE_CUDA(dmalloc(&ctx->live_counts, DRV_MAX_LIGHTS * sizeof(uint32_t)));
+  CREATE_CUDA(cudaMemsetAsync(ctx->live_counts, 0, DRV_MAX_LIGHTS * sizeof(uint32_t), ctx->stream));
   CREATE_CUDA(dmalloc(&ctx->ndc_xy, ((size_t)c.backbuffer_width + c.backbuffer_height) * sizeof(float)));
   if (drv_impl_build_ndc_tables(ctx) != DRV_OK) { g_create_error = ctx->last_error; drv_destroy(ctx); return DRV_ERR_CUDA; }
   for (int s = 0; s < DRV_STAGE_COUNT; ++s) {
@@ -144,12 +149,18 @@ extern "C" void drv_destroy(drv_ctx* ctx) {
   cudaFree(ctx->hdr16); cudaFree(ctx->ndc_xy);
   for (auto& S : ctx->lights) {
     cudaFree(S.flux_mips); cudaFree(S.normal_mips); cudaFree(S.depth_mips); cudaFree(S.vpls); cudaFree(S.blocks);
+    cudaFree(S.vpls_live); cudaFree(S.chunk_counts); cudaFree(S.block_live);
     cudaFree(S.st_flux); cudaFree(S.st_normal); cudaFree(S.st_depth);
   }
   for (int s = 0; s < DRV_STAGE_COUNT; ++s) {
     if (ctx->ev_begin[s]) cudaEventDestroy(ctx->ev_begin[s]);
     if (ctx->ev_end[s]) cudaEventDestroy(ctx->ev_end[s]);
   }
+  cudaFree(ctx->live_counts);
+  if (ctx->frame_graph) cudaGraphExecDestroy(ctx->frame_graph);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
   for (auto& e : ctx->ev_rsm) if (e) cudaEventDestroy(e);
@@ -162,9 +173,12 @@ extern "C" void drv_destroy(drv_ctx* ctx) {
 }
 
 #define NEED_CTX() do { if (!ctx) return DRV_ERR_INVALID; cudaSetDevice(ctx->device); } while (0)
+// calls that change something a kernel takes as an argument invalidate the recorded frame graph
+#define MUTATES() do { ctx->state_gen++; } while (0)
 
 extern "C" drv_status drv_set_constant(drv_ctx* ctx, const drv_constant* b) {
   NEED_CTX();
+  MUTATES();
   if (!b) return ctx->fail(DRV_ERR_INVALID, "drv_set_constant: null block");
   ctx->constant = *b;
   ctx->have_constant = true;
@@ -172,6 +186,7 @@ extern "C" drv_status drv_set_constant(drv_ctx* ctx, const drv_constant* b) {
 }
 extern "C" drv_status drv_set_per_frame(drv_ctx* ctx, const drv_per_frame* b) {
   NEED_CTX();
+  MUTATES();
   if (!b) return ctx->fail(DRV_ERR_INVALID, "drv_set_per_frame: null block");
   ctx->per_frame = *b;
   ctx->have_per_frame = true;
@@ -179,6 +194,7 @@ extern "C" drv_status drv_set_per_frame(drv_ctx* ctx, const drv_per_frame* b) {
 }
 extern "C" drv_status drv_set_volume_info(drv_ctx* ctx, const drv_volume_info* b) {
   NEED_CTX();
+  MUTATES();
   if (!b) return ctx->fail(DRV_ERR_INVALID, "drv_set_volume_info: null block");
   ctx->volume = *b;
   ctx->have_volume = true;
@@ -186,12 +202,14 @@ extern "C" drv_status drv_set_volume_info(drv_ctx* ctx, const drv_volume_info* b
 }
 extern "C" drv_status drv_set_light_count(drv_ctx* ctx, uint32_t n) {
   NEED_CTX();
+  MUTATES();
   if (n > ctx->cfg.max_lights) return ctx->fail(DRV_ERR_INVALID, "drv_set_light_count: more lights than max_lights");
   ctx->num_lights = n;
   return DRV_OK;
 }
 extern "C" drv_status drv_set_spot_light(drv_ctx* ctx, uint32_t light, const drv_spot_light* b) {
   NEED_CTX();
+  MUTATES();
   if (!b || light >= ctx->cfg.max_lights) return ctx->fail(DRV_ERR_INVALID, "drv_set_spot_light: bad light index");
   ctx->lights[light].block = *b;
   ctx->lights[light].block_set = true;
@@ -201,6 +219,7 @@ extern "C" drv_status drv_set_spot_light(drv_ctx* ctx, uint32_t light, const drv
 extern "C" drv_status drv_bind_gbuffer(drv_ctx* ctx, const float* depth, const int16_t* normal, const uint8_t* diffuse,
                                        uint32_t w, uint32_t h) {
   NEED_CTX();
+  MUTATES();
   if (!depth || w != ctx->cfg.backbuffer_width || h != ctx->cfg.backbuffer_height)
     return ctx->fail(DRV_ERR_INVALID, "drv_bind_gbuffer: resolution differs from the configured backbuffer");
   ctx->gb_depth = depth; ctx->gb_normal = normal; ctx->gb_diffuse = diffuse;
@@ -211,6 +230,7 @@ extern "C" drv_status drv_bind_gbuffer(drv_ctx* ctx, const float* depth, const i
 extern "C" drv_status drv_bind_rsm(drv_ctx* ctx, uint32_t light, const uint16_t* flux, const int16_t* normal,
                                    const uint16_t* depth, uint32_t res) {
   NEED_CTX();
+  MUTATES();
   if (light >= ctx->cfg.max_lights || !flux || !normal || !depth || !is_pow2(res) || res > ctx->cfg.max_rsm_resolution)
     return ctx->fail(DRV_ERR_INVALID, "drv_bind_rsm: bad light index or resolution");
   LightState& S = ctx->lights[light];
@@ -248,8 +268,7 @@ extern "C" drv_status drv_light_caches(drv_ctx* ctx) {
   NEED_CTX();
   ctx->stage_begin(DRV_STAGE_LIGHT_CACHES);
   for (uint32_t l = 0; l < ctx->num_lights; ++l) {
-    if (ctx->lights[l].vpls_external) continue;
-    drv_status st = drv_impl_generate_vpls(ctx, l);
+    drv_status st = ctx->lights[l].vpls_external ? drv_impl_compact_vpls(ctx, l) : drv_impl_generate_vpls(ctx, l);
     if (st != DRV_OK) return st;
   }
   drv_status st = drv_impl_gather(ctx);
@@ -274,6 +293,86 @@ extern "C" drv_status drv_draw(drv_ctx* ctx, void* hdr_out, uint32_t format) {
   st = drv_light_caches(ctx);             // renderer.cpp:556
   if (st != DRV_OK) return st;
   return drv_impl_apply(ctx, hdr_out, format); // renderer.cpp:570
+}
+
+// The frame in GPU order: light side (RSM mips, VPLs) on ctx->side || camera side (allocate) on the main
+// stream, join, gather, apply.
+static drv_status frame_body(drv_ctx* ctx, void* hdr_out, uint32_t format, uint32_t flags) {
+  cudaStream_t main_stream = ctx->stream;
+  DRV_CUDA(cudaEventRecord(ctx->ev_fork, main_stream));
+  DRV_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+  ctx->stream = ctx->side; // the stage implementations launch on ctx->stream
+  drv_status st = DRV_OK;
+  for (uint32_t l = 0; l < ctx->num_lights && st == DRV_OK; ++l) {
+    if (ctx->lights[l].vpls_external) { st = drv_impl_compact_vpls(ctx, l); continue; }
+    if (flags & DRV_FRAME_PREPARE_RSM) st = drv_impl_prepare_rsm(ctx, l);
+    if (st == DRV_OK) st = drv_impl_generate_vpls(ctx, l);
+  }
+  cudaError_t e = cudaEventRecord(ctx->ev_join, ctx->side);
+  ctx->stream = main_stream;
+  if (st != DRV_OK) return st;
+  if (e != cudaSuccess) return ctx->fail(DRV_ERR_CUDA, "drv_draw_frame: event record failed");
+  st = drv_impl_allocate(ctx); // renderer.cpp:550
+  if (st != DRV_OK) return st;
+  DRV_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
+  ctx->stage_begin(DRV_STAGE_LIGHT_CACHES);
+  st = drv_impl_gather(ctx);   // renderer.cpp:556
+  ctx->stage_end(DRV_STAGE_LIGHT_CACHES);
+  if (st != DRV_OK) return st;
+  return drv_impl_apply(ctx, hdr_out, format); // renderer.cpp:570
+}
+
+extern "C" drv_status drv_draw_frame(drv_ctx* ctx, void* hdr_out, uint32_t format, uint32_t flags) {
+  NEED_CTX();
+  if (!hdr_out) return ctx->fail(DRV_ERR_INVALID, "drv_draw_frame: null output");
+  if (!ctx->side) {
+    DRV_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    DRV_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    DRV_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  }
+  const bool want_graph = (flags & DRV_FRAME_GRAPH) && !ctx->timers;
+  if (!want_graph) {
+    drv_status st = frame_body(ctx, hdr_out, format, flags);
+    if (st == DRV_OK) ctx->warm_gen = ctx->state_gen;
+    return st;
+  }
+  const bool valid = ctx->frame_graph && ctx->graph_gen == ctx->state_gen && ctx->graph_out == hdr_out &&
+                     ctx->graph_format == format && ctx->graph_flags == flags;
+  if (!valid) {
+    if (ctx->frame_graph) { cudaGraphExecDestroy(ctx->frame_graph); ctx->frame_graph = nullptr; }
+    if (ctx->warm_gen != ctx->state_gen) {
+      // first frame of a new state runs eagerly: it sizes the scratch buffers (no allocation may happen while
+      // a stream is being captured) and reports binding errors the ordinary way
+      drv_status st = frame_body(ctx, hdr_out, format, flags);
+      if (st == DRV_OK) ctx->warm_gen = ctx->state_gen;
+      return st;
+    }
+    const uint64_t launches0 = ctx->launches;
+    DRV_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    drv_status st = frame_body(ctx, hdr_out, format, flags);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    ctx->graph_launches = ctx->launches - launches0;
+    ctx->launches = launches0; // nothing has run yet
+    if (st != DRV_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+    if (e != cudaSuccess || !graph) {
+      cudaGetLastError();
+      return ctx->fail(DRV_ERR_CUDA, std::string("drv_draw_frame: capture failed: ") + cudaGetErrorString(e));
+    }
+    e = cudaGraphInstantiate(&ctx->frame_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      ctx->frame_graph = nullptr;
+      return ctx->fail(DRV_ERR_CUDA, std::string("drv_draw_frame: instantiate failed: ") + cudaGetErrorString(e));
+    }
+    ctx->graph_gen = ctx->state_gen;
+    ctx->graph_out = hdr_out;
+    ctx->graph_format = format;
+    ctx->graph_flags = flags;
+  }
+  DRV_CUDA(cudaGraphLaunch(ctx->frame_graph, ctx->stream));
+  ctx->launches += ctx->graph_launches;
+  return DRV_OK;
 }
 
 extern "C" drv_status drv_get_buffers(drv_ctx* ctx, drv_buffers* out) {
@@ -318,14 +417,25 @@ extern "C" drv_status drv_active_cache_count(drv_ctx* ctx, uint32_t* count, uint
   return stats[0] ? DRV_ERR_CAPACITY : DRV_OK;
 }
 
+extern "C" drv_status drv_live_vpl_counts(drv_ctx* ctx, uint32_t* counts) {
+  NEED_CTX();
+  if (!counts) return ctx->fail(DRV_ERR_INVALID, "drv_live_vpl_counts: null argument");
+  DRV_CUDA(cudaMemcpyAsync(counts, ctx->live_counts, DRV_MAX_LIGHTS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DRV_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (uint32_t l = ctx->num_lights; l < DRV_MAX_LIGHTS; ++l) counts[l] = 0;
+  return DRV_OK;
+}
+
 extern "C" drv_status drv_set_synthetic_entries(drv_ctx* ctx, const float* pos, uint32_t n) {
   NEED_CTX();
+  MUTATES();
   if (n && !pos) return ctx->fail(DRV_ERR_INVALID, "drv_set_synthetic_entries: null positions");
   return drv_impl_set_synthetic_entries(ctx, pos, n);
 }
 
 extern "C" drv_status drv_set_vpls(drv_ctx* ctx, uint32_t light, const drv_vpl* vpls, uint32_t n) {
   NEED_CTX();
+  MUTATES();
   if (light >= ctx->cfg.max_lights || !vpls) return ctx->fail(DRV_ERR_INVALID, "drv_set_vpls: bad argument");
   if ((size_t)n > (size_t)ctx->cfg.max_rsm_resolution * ctx->cfg.max_rsm_resolution)
     return ctx->fail(DRV_ERR_CAPACITY, "drv_set_vpls: more VPLs than max_rsm_resolution^2");
@@ -349,6 +459,7 @@ extern "C" void drv_shard_range(uint32_t count, uint32_t rank, uint32_t world, u
 
 extern "C" drv_status drv_set_shard(drv_ctx* ctx, uint32_t rank, uint32_t world) {
   NEED_CTX();
+  MUTATES();
   if (world == 0 || rank >= world || world > 8) return ctx->fail(DRV_ERR_INVALID, "drv_set_shard: need rank < world <= 8");
   ctx->shard_rank = rank;
   ctx->shard_world = world;
@@ -366,6 +477,7 @@ extern "C" drv_status drv_export_entries_ipc(drv_ctx* ctx, uint8_t handle[DRV_IP
 
 extern "C" drv_status drv_import_peer_entries(drv_ctx* ctx, uint32_t peer_rank, const uint8_t handle[DRV_IPC_HANDLE_BYTES]) {
   NEED_CTX();
+  MUTATES();
   if (peer_rank >= 8 || peer_rank == ctx->shard_rank) return ctx->fail(DRV_ERR_INVALID, "drv_import_peer_entries: bad peer rank");
   cudaIpcMemHandle_t h;
   memcpy(&h, handle, sizeof(h));
@@ -392,6 +504,7 @@ extern "C" const char* drv_stage_name(drv_stage s) { return (s >= 0 && s < DRV_S
 
 extern "C" drv_status drv_enable_stage_timers(drv_ctx* ctx, int enable) {
   NEED_CTX();
+  MUTATES();
   ctx->timers = enable != 0;
   for (auto& v : ctx->ev_valid) v = false;
   return DRV_OK;
@@ -412,6 +525,7 @@ extern "C" uint64_t drv_kernel_launches(const drv_ctx* ctx) { return ctx ? ctx->
 extern "C" drv_status drv_upload_gbuffer(drv_ctx* ctx, const float* depth, const int16_t* normal, const uint8_t* diffuse,
                                          uint32_t w, uint32_t h) {
   NEED_CTX();
+  MUTATES();
   if (!depth || !normal || !diffuse || w != ctx->cfg.backbuffer_width || h != ctx->cfg.backbuffer_height)
     return ctx->fail(DRV_ERR_INVALID, "drv_upload_gbuffer: bad argument");
   const size_t px = (size_t)w * h;
@@ -429,6 +543,7 @@ extern "C" drv_status drv_upload_gbuffer(drv_ctx* ctx, const float* depth, const
 extern "C" drv_status drv_upload_rsm(drv_ctx* ctx, uint32_t light, const uint16_t* flux, const int16_t* normal,
                                      const uint16_t* depth, uint32_t res) {
   NEED_CTX();
+  MUTATES();
   if (light >= ctx->cfg.max_lights || !flux || !normal || !depth || !is_pow2(res) || res > ctx->cfg.max_rsm_resolution)
     return ctx->fail(DRV_ERR_INVALID, "drv_upload_rsm: bad argument");
   LightState& S = ctx->lights[light];

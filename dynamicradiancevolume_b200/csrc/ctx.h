@@ -40,8 +40,13 @@ struct LightState {
   uint16_t* flux_mips = nullptr;     // levels >= 1, owned
   int16_t* normal_mips = nullptr;
   uint16_t* depth_mips = nullptr;
-  drv_vpl* vpls = nullptr;           // owned, max_rsm_resolution^2
+  drv_vpl* vpls = nullptr;           // owned, max_rsm_resolution^2 (Morton order; the list parity tests read)
   drv_shadow_block* blocks = nullptr;
+  // what the gather streams: the VPLs with non-zero flux, order preserved, each tagged with its shadow-block
+  // index (Normal.w); RSM texels that saw no surface carry zero flux and would add exactly zero to every cache
+  drv_vpl* vpls_live = nullptr;
+  uint32_t* chunk_counts = nullptr;  // live VPLs per 256-VPL chunk (compaction scratch)
+  uint8_t* block_live = nullptr;     // 1 = the shadow block has at least one live VPL (cones of dead blocks are skipped)
   // staging for drv_upload_rsm
   uint16_t* st_flux = nullptr;
   int16_t* st_normal = nullptr;
@@ -101,6 +106,7 @@ struct drv_ctx {
   uint64_t voxel_record_count = 0;
 
   // gather
+  uint32_t* live_counts = nullptr;   // [DRV_MAX_LIGHTS] live VPLs per light (device; the gather reads it there)
   float* shadow_table = nullptr;     // visibility of (VAL block, cache) for the current chunk of caches (cone_kernel)
   size_t shadow_table_floats = 0;
   float* partials = nullptr;         // split-VPL partial sums
@@ -116,6 +122,17 @@ struct drv_ctx {
   // host-frame pipeline (drv_draw_host_frame): copy streams + events
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t ev_rsm[DRV_MAX_LIGHTS]{}, ev_depth = nullptr, ev_band_in[32]{}, ev_band_done[32]{}, ev_frame_start = nullptr;
+
+  // drv_draw_frame: light-side stream, fork / join events, recorded frame graph
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  uint64_t state_gen = 1;            // bumped by every call that changes a kernel argument
+  cudaGraphExec_t frame_graph = nullptr;
+  uint64_t graph_gen = 0;            // state_gen the graph was recorded at
+  void* graph_out = nullptr;
+  uint32_t graph_format = 0, graph_flags = 0;
+  uint64_t graph_launches = 0;       // kernels per replay
+  uint64_t warm_gen = 0;             // state_gen of the last eager frame (scratch buffers are sized)
 
   // timers
   bool timers = false;
@@ -138,6 +155,7 @@ struct drv_ctx {
 drv_status drv_impl_allocate(drv_ctx* ctx);
 drv_status drv_impl_prepare_rsm(drv_ctx* ctx, uint32_t light);
 drv_status drv_impl_generate_vpls(drv_ctx* ctx, uint32_t light);
+drv_status drv_impl_compact_vpls(drv_ctx* ctx, uint32_t light);
 drv_status drv_impl_gather(drv_ctx* ctx);
 drv_status drv_impl_apply(drv_ctx* ctx, void* out, uint32_t format);
 drv_status drv_impl_apply_rows(drv_ctx* ctx, void* out, uint32_t format, uint32_t y_begin, uint32_t y_end, bool timed);

@@ -45,16 +45,19 @@ constexpr int kThreads = 128;
 constexpr int kVplTile = 128; // VPLs staged per shared-memory tile
 
 struct GatherLight {
-  const float4* vpls;   // 3 x float4 per VPL: (pos, area) (normal, -) (flux, -)
+  const float4* vpls;   // the LIVE list (rsm.cu): 3 x float4 per VPL: (pos, area) (normal, shadow-block index) (flux, -)
   const float4* blocks; // (avgPos, distToSphereRad) per shadow block
-  uint32_t num_vpls;
+  const uint32_t* live; // device: number of VPLs in the live list
+  const uint8_t* block_live; // 1 = the block has a live VPL
+  uint32_t num_vpls;    // VPLs before compaction (R^2)
   uint32_t interval;    // IndirectShadowComputationSampleInterval
 };
+__device__ __forceinline__ uint32_t live_vpls(const GatherLight& L) { return min(__ldg(L.live), L.num_vpls); }
 
 struct GatherParams {
   GatherLight lights[DRV_MAX_LIGHTS];
   uint32_t num_lights;
-  uint32_t granule;      // VPLs per scheduling unit: a power of two, >= 32 and >= every shadow interval
+  uint32_t granule;      // VPLs per scheduling unit (a power of two)
   uint8_t* entries;
   const drv_cache_counter* counter;
   float* partials;       // [cta][2][coef][tile cache] floats
@@ -95,7 +98,7 @@ __device__ __forceinline__ Schedule make_schedule(const GatherParams& p, int til
   s.count = hi - lo;
   s.tiles = (s.count + tile_caches - 1) / tile_caches;
   uint32_t upt = 0;
-  for (uint32_t l = 0; l < p.num_lights; ++l) upt += (p.lights[l].num_vpls + p.granule - 1) / p.granule;
+  for (uint32_t l = 0; l < p.num_lights; ++l) upt += (live_vpls(p.lights[l]) + p.granule - 1) / p.granule;
   s.units_per_tile = upt;
   s.units = (unsigned long long)s.tiles * upt;
   return s;
@@ -549,9 +552,10 @@ __device__ __forceinline__ void start_run(const GatherParams& p, const Schedule&
   c.valid = u < u1;
   if (!c.valid) return;
   c.tile = (uint32_t)(u / S.units_per_tile);
-  uint32_t j = (uint32_t)(u - (unsigned long long)c.tile * S.units_per_tile), l = 0, ul = 0;
+  uint32_t j = (uint32_t)(u - (unsigned long long)c.tile * S.units_per_tile), l = 0, ul = 0, nv = 0;
   for (;; ++l) {
-    ul = (p.lights[l].num_vpls + p.granule - 1) / p.granule;
+    nv = live_vpls(p.lights[l]);
+    ul = (nv + p.granule - 1) / p.granule;
     if (j < ul || l + 1 >= p.num_lights) break;
     j -= ul;
   }
@@ -560,7 +564,7 @@ __device__ __forceinline__ void start_run(const GatherParams& p, const Schedule&
   const unsigned long long avail = (u1 < tile_end ? u1 : tile_end) - u;
   const uint32_t take = (uint32_t)min((unsigned long long)(ul - j), avail);
   c.base = j * p.granule;
-  c.v_end = min((j + take) * p.granule, p.lights[l].num_vpls);
+  c.v_end = min((j + take) * p.granule, nv);
   c.u_next = u + take;
 }
 __device__ __forceinline__ void advance(const GatherParams& p, const Schedule& S, Cursor& c, unsigned long long u1) {
@@ -579,6 +583,7 @@ __global__ void __launch_bounds__(kThreads, MINB) gather_kernel(const __grid_con
   constexpr int STAGES = USE_TMA ? 2 : 1;
   __shared__ __align__(128) float4 s_vpl[STAGES][kVplTile * SPV];
   __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ uint32_t s_blk[SHADOW ? kVplTile : 1]; // shadow-block index of every staged VPL
 
   const Schedule S = make_schedule(p, TILE);
   if (S.units == 0) return;
@@ -646,15 +651,15 @@ __global__ void __launch_bounds__(kThreads, MINB) gather_kernel(const __grid_con
     } else {
       __syncthreads(); // previous tile fully consumed
       Math::stage(&s_vpl[0][threadIdx.x * SPV], r0, r1, r2);
+      if (SHADOW) s_blk[threadIdx.x] = __float_as_uint(r1.w);
       __syncthreads();
       if (nxt.valid) prefetch(nxt);
     }
     const int n = (int)min((uint32_t)kVplTile, cur.v_end - cur.base);
     const float4* sv = &s_vpl[st][0];
     if constexpr (SHADOW) {
-      // :169 — a new shadow value every `interval` VPLs: one table read per cache per block.
-      // A tile starts on a multiple of the granule, itself a multiple of every interval <= granule.
-      const uint32_t interval = p.lights[cur.light].interval;
+      // :169 — a new shadow value every `interval` VPLs: one table read per cache per block. The
+      // live list keeps the VPL order, so the VPLs of a block are still consecutive; each carries its block index.
       const float* col = p.shadow_table + (size_t)p.block_offset[cur.light] * p.shadow_stride + cur.tile * TILE + threadIdx.x;
       auto load_shadow = [&](uint32_t blk) {
         float v[CPT];
@@ -663,18 +668,12 @@ __global__ void __launch_bounds__(kThreads, MINB) gather_kernel(const __grid_con
           v[j] = (cur.tile * TILE + j * kThreads + threadIdx.x < S.count) ? __ldg(col + (size_t)blk * p.shadow_stride + j * kThreads) : 0.0f;
         M.set_shadow(v);
       };
-      if (interval >= (uint32_t)kVplTile) {
-        load_shadow(cur.base / interval);
+      uint32_t cur_blk = 0xFFFFFFFFu;
 #pragma unroll 4
-        for (int i = 0; i < n; ++i) M.eval(sv + i * SPV);
-      } else {
-        uint32_t blk = cur.base / interval;
-        for (int i = 0; i < n; ++blk) {
-          load_shadow(blk);
-          const int end = min(n, i + (int)interval);
-#pragma unroll 4
-          for (; i < end; ++i) M.eval(sv + i * SPV);
-        }
+      for (int i = 0; i < n; ++i) {
+        const uint32_t blk = USE_TMA ? __float_as_uint(sv[i * SPV + 1].w) : s_blk[i];
+        if (blk != cur_blk) { cur_blk = blk; load_shadow(blk); } // warp-uniform
+        M.eval(sv + i * SPV);
       }
     } else {
 #pragma unroll 4
@@ -766,6 +765,7 @@ __global__ void __launch_bounds__(kConeThreads) cone_kernel(const __grid_constan
     uint32_t light = 0;
     for (uint32_t b = bg * kBlocksPerItem; b < b_end; ++b) {
       while (b >= p.block_offset[light + 1]) ++light;
+      if (!__ldg(p.lights[light].block_live + (b - p.block_offset[light]))) continue; // no live VPL reads this entry
       const float4 blk = __ldg(p.lights[light].blocks + (b - p.block_offset[light]));
       if (alive) p.table[(size_t)b * p.stride + local] = cone_trace(V, pos.x, pos.y, pos.z, blk);
     }
@@ -773,35 +773,36 @@ __global__ void __launch_bounds__(kConeThreads) cone_kernel(const __grid_constan
 }
 
 // ------------------------------------------------------------ finalize: add the partial segments in VPL order
-// One block per 64 consecutive caches of a tile (block-stride loop: the cache count lives on the device).
-// The CTAs that own pieces of the tile are the same for all 64 caches, so their list is derived once per
-// chunk; then every thread sums (coefficient, cache) items over the owners in ascending CTA = ascending VPL
-// order (deterministic, no float atomics) with coalesced loads, and 64 threads apply the SH factors and add
-// the result into the entries with 128-bit accesses (+ the peer stores of the fused all-gather).
-constexpr int kFinChunk = 64;
-constexpr int kFinThreads = 256;
+// One block per 32 consecutive caches of a tile (block-stride loop: the cache count lives on the device).
+// The CTAs that own pieces of the tile are the same for all 32 caches, so their list is derived once per
+// chunk. Thread (y, x) then sums, for cache x, all coefficients over the owners y, y + 8, y + 16, ... — every
+// load of a thread is independent, so a tile split between ~25 CTAs costs one or two L2 round trips instead of
+// a serial chain — and the eight slices are added in a fixed order through shared memory (deterministic — no
+// float atomics). 32 threads apply the SH factors and add the result into the entries with 128-bit accesses
+// (+ the peer stores of the fused all-gather).
+constexpr int kFinChunk = 32;
+constexpr int kFinSlices = 8;
+constexpr int kFinThreads = kFinChunk * kFinSlices;
 
 template <int ORDER>
 __global__ void __launch_bounds__(kFinThreads) gather_finalize_kernel(GatherParams p, int tile_caches) {
   constexpr int NC = num_coefs<ORDER>();
-  constexpr int ITEMS = (NC * kFinChunk + kFinThreads - 1) / kFinThreads;
-  __shared__ float s_raw[NC][kFinChunk];
+  __shared__ float s_part[kFinSlices][NC][kFinChunk];
   __shared__ uint32_t s_list[kFinThreads];
   const Schedule S = make_schedule(p, tile_caches);
   if (S.units == 0) return;
   const uint32_t G = p.grid;
   const uint32_t chunks = (S.count + kFinChunk - 1) / kFinChunk;
+  const uint32_t x = threadIdx.x % kFinChunk, y = threadIdx.x / kFinChunk;
   for (uint32_t chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
     const uint32_t local0 = chunk * kFinChunk;
     const uint32_t tile = local0 / tile_caches, in_tile0 = local0 - tile * tile_caches;
     const unsigned long long ua = (unsigned long long)tile * S.units_per_tile, ub = ua + S.units_per_tile;
     const uint32_t c_lo = owner_of(S, G, ua), c_hi = owner_of(S, G, ub - 1);
     if (c_lo == c_hi) continue; // one CTA covered the whole tile and already wrote it (block-uniform)
-    float acc[ITEMS];
+    float acc[NC];
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) acc[k] = 0.0f;
-    // owners in batches: every thread derives one owner's partial slot (two 64-bit divisions, in parallel),
-    // then all threads walk the list — the loads of successive owners are independent, so several are in flight
+    for (int q = 0; q < NC; ++q) acc[q] = 0.0f;
     for (uint32_t cbase = c_lo; cbase <= c_hi; cbase += kFinThreads) {
       const uint32_t c = cbase + threadIdx.x;
       uint32_t entry = 0xFFFFFFFFu;
@@ -814,29 +815,32 @@ __global__ void __launch_bounds__(kFinThreads) gather_finalize_kernel(GatherPara
       s_list[threadIdx.x] = entry;
       __syncthreads();
       const int cnt = (int)min((uint32_t)kFinThreads, c_hi - cbase + 1u);
-#pragma unroll 4
-      for (int i = 0; i < cnt; ++i) {
+#pragma unroll 2
+      for (int i = (int)y; i < cnt; i += kFinSlices) {
         const uint32_t e = s_list[i];
         if (e == 0xFFFFFFFFu) continue;
-        const float* src = p.partials + (size_t)e * NC * tile_caches + in_tile0;
+        const float* src = p.partials + (size_t)e * NC * tile_caches + in_tile0 + x;
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-          const int item = k * kFinThreads + threadIdx.x;
-          if (item < NC * kFinChunk) acc[k] += __ldcs(src + (size_t)(item / kFinChunk) * tile_caches + (item % kFinChunk));
-        }
+        for (int q = 0; q < NC; ++q) acc[q] += __ldcs(src + (size_t)q * tile_caches);
       }
     }
-    __syncthreads(); // previous chunk's readers are done with s_raw
+    __syncthreads(); // previous chunk's readers are done with s_part
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-      const int item = k * kFinThreads + threadIdx.x;
-      if (item < NC * kFinChunk) s_raw[item / kFinChunk][item % kFinChunk] = acc[k];
+    for (int q = 0; q < NC; ++q) s_part[y][q][x] = acc[q];
+    __syncthreads();
+    // slice-sum in ascending slice order: item = (coefficient, cache)
+    for (int item = threadIdx.x; item < NC * kFinChunk; item += kFinThreads) {
+      const int q = item / kFinChunk, cx = item % kFinChunk;
+      float v = s_part[0][q][cx];
+#pragma unroll
+      for (int sl = 1; sl < kFinSlices; ++sl) v += s_part[sl][q][cx];
+      s_part[0][q][cx] = v;
     }
     __syncthreads();
     if (threadIdx.x < kFinChunk && local0 + threadIdx.x < S.count) {
       float raw[27];
 #pragma unroll
-      for (int q = 0; q < 27; ++q) raw[q] = q < NC ? s_raw[q < NC ? q : 0][threadIdx.x] : 0.0f;
+      for (int q = 0; q < 27; ++q) raw[q] = q < NC ? s_part[0][q < NC ? q : 0][threadIdx.x] : 0.0f;
       float vals[28];
       coef_values<ORDER>(p, raw, vals);
       add_to_entry<ORDER>(p, S.first + local0 + threadIdx.x, vals);
@@ -869,7 +873,7 @@ drv_status launch_gather(drv_ctx* ctx, GatherFn kernel, GatherParams& p, int til
   p.grid = (uint32_t)grid;
   kernel<<<grid, kThreads, 0, ctx->stream>>>(p);
   DRV_LAUNCH_CHECK();
-  const int fin_grid = ctx->num_sms * 4;
+  const int fin_grid = ctx->num_sms * 8;
   if (order == 1) gather_finalize_kernel<1><<<fin_grid, kFinThreads, 0, ctx->stream>>>(p, tile_caches);
   else gather_finalize_kernel<2><<<fin_grid, kFinThreads, 0, ctx->stream>>>(p, tile_caches);
   DRV_LAUNCH_CHECK();
@@ -882,6 +886,7 @@ drv_status launch_gather(drv_ctx* ctx, GatherFn kernel, GatherParams& p, int til
 //   3  packed, one pair of caches per thread
 //   4  scalar, 4 caches / thread (SH1)
 //   12 scalar, 2 caches / thread, register-prefetch staging
+//   6  as 0 for SH1 but compiled for 3 resident CTAs per SM (168 registers)
 // With indirect shadows the same kernels additionally scale every pair by its table visibility.
 template <bool SH>
 GatherFn select_kernel(int order, uint32_t variant, int* tile) {
@@ -894,6 +899,7 @@ GatherFn select_kernel(int order, uint32_t variant, int* tile) {
       case 3: DRV_PICK(1, P1p1, false);
       case 4: DRV_PICK(1, S1c4, false);
       case 12: DRV_PICK(1, S1c2, false);
+      case 6: *tile = kThreads * P1p2::CPT; return gather_kernel<1, SH, P1p2, false, 3>; // 168 registers: 3 CTAs / SM
       default: DRV_PICK(1, P1p2, false);
     }
   }
@@ -961,11 +967,13 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   GatherParams p;
   memset(&p, 0, sizeof(p));
   p.num_lights = ctx->num_lights;
-  uint32_t granule = 32; // scheduling quantum in VPLs (a shared-memory tile still holds up to kVplTile)
+  const uint32_t granule = 32; // scheduling quantum in VPLs (a shared-memory tile still holds up to kVplTile)
   for (uint32_t l = 0; l < ctx->num_lights; ++l) {
     LightState& S = ctx->lights[l];
-    p.lights[l].vpls = (const float4*)S.vpls;
+    p.lights[l].vpls = (const float4*)S.vpls_live;
     p.lights[l].blocks = (const float4*)S.blocks;
+    p.lights[l].live = ctx->live_counts + l;
+    p.lights[l].block_live = S.block_live;
     p.lights[l].num_vpls = S.num_vpls;
     uint32_t interval = shadow ? (uint32_t)S.block.IndirectShadowComputationSampleInterval : 1u;
     if (interval == 0 || (interval & (interval - 1)) != 0)
@@ -973,7 +981,6 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
     if (shadow && S.vpls_external)
       return ctx->fail(DRV_ERR_INVALID, "drv_light_caches: drv_set_vpls cannot be combined with indirect shadows");
     p.lights[l].interval = interval;
-    if (interval > granule) granule = interval;
   }
   p.granule = granule;
   p.entries = ctx->entries;
@@ -991,7 +998,7 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
       p.peers[r] = (r == ctx->shard_rank) ? nullptr : (uint8_t*)ctx->peer_entries[r];
   }
   const int order = (int)ctx->cfg.sh_order;
-  const uint32_t variant = ctx->cfg.gather_variant;
+  const uint32_t variant = ctx->cfg.gather_variant & 0xFFu; // bits 8.. tune other kernels
   int tile = 0;
   const GatherFn kernel = shadow ? select_kernel<true>(order, variant, &tile) : select_kernel<false>(order, variant, &tile);
   p.chunk_first = 0;

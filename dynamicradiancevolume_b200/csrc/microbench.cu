@@ -112,6 +112,58 @@ __global__ void __launch_bounds__(256) l2_read_kernel(const uint4* __restrict__ 
   if (acc == 0xdeadbeefu) out[0] = acc;
 }
 
+// Legacy warp-level tensor-core path: mma.sync.m16n8k8 TF32 with FP32 accumulate, 4 independent accumulator
+// sets per warp (the gather's mma variant feeds its accumulate step through this instruction).
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__global__ void __launch_bounds__(256) mma_tf32_kernel(float* out, float a) {
+  float d[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[i][j] = 0.f;
+  uint32_t A[4] = {__float_as_uint(a), __float_as_uint(a * 1.5f), __float_as_uint(a + threadIdx.x * 1e-3f), __float_as_uint(a * 0.5f)};
+  uint32_t B[2] = {__float_as_uint(0.25f), __float_as_uint(0.5f + threadIdx.x * 1e-3f)};
+  for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mma_tf32(d[i], A, B);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += d[i][0] + d[i][1] + d[i][2] + d[i][3];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// The mma gather's instruction mix per pair-warp: 10 FFMA2 + 2 mma.sync (operands produced by the FFMA2 chain).
+__global__ void __launch_bounds__(256) mma_mix_kernel(float* out, float a) {
+  float d[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[i][j] = 0.f;
+  float2 x[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) x[i] = make_float2(a + i, a - i + threadIdx.x * 1e-6f);
+  const float2 m = make_float2(1.0001f, 0.9999f), c = make_float2(1e-6f, -1e-6f);
+  uint32_t B[2] = {__float_as_uint(0.25f), __float_as_uint(0.5f + threadIdx.x * 1e-3f)};
+  for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) x[i] = __ffma2_rn(x[i], m, c);
+    uint32_t A0[4] = {__float_as_uint(x[0].x), __float_as_uint(x[1].x), __float_as_uint(x[0].y), __float_as_uint(x[1].y)};
+    uint32_t A1[4] = {__float_as_uint(x[2].x), __float_as_uint(x[3].x), __float_as_uint(x[2].y), __float_as_uint(x[3].y)};
+    mma_tf32(d[0], A0, B);
+    mma_tf32(d[1], A1, B);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) s += d[i][0] + d[i][1] + d[i][2] + d[i][3];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) s += x[i].x + x[i].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 struct Timer {
   cudaEvent_t a, b;
   Timer() { cudaEventCreate(&a); cudaEventCreate(&b); }
@@ -144,6 +196,8 @@ const char* kNames[] = {
     "lds128_bcast_tbs",    // broadcast LDS.128: TB/s of register fill (16 B x 32 lanes per instruction)
     "l2_read_gbs",         // L2-resident 128-bit loads: GB/s
     "sm_clock_mhz",        // current SM clock reported by the driver
+    "mma_tf32_tflops",     // mma.sync.m16n8k8 TF32 (legacy tensor path): TFLOP/s (2*16*8*8 flop per instruction)
+    "mma_mix_cyc",         // 10 FFMA2 + 2 mma.sync per iteration: SM cycles per iteration per SM sub-partition warp slot
 };
 
 } // namespace
@@ -187,6 +241,12 @@ extern "C" drv_status drv_microbench(int32_t device, uint32_t which, double* res
       r = (double)bytes * reps / (ms * 1e-3) / 1e9;
       cudaFree(buf); cudaFree(o2);
     } break;
+    case 7: { double ms = best_ms([&] { mma_tf32_kernel<<<blocks, threads>>>(out, 1.0001f); });
+              r = (lanes / 32.0) * kIters * 4 * 2048.0 / (ms * 1e-3) / 1e12; } break;
+    case 8: { double ms = best_ms([&] { mma_mix_kernel<<<blocks, threads>>>(out, 1.0001f); });
+              int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+              // warps per SM sub-partition = blocks/sms * threads/32 / 4; cycles per iteration per warp slot
+              r = (ms * 1e-3) * (khz * 1e3) / kIters / ((double)blocks / sms * threads / 32.0 / 4.0); } break;
     case 6: { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device); r = khz / 1000.0; } break;
   }
   cudaFree(out);

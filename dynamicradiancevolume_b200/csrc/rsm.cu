@@ -179,7 +179,92 @@ __global__ void vplgen_kernel(drv_spot_light L, const uint2* __restrict__ flux, 
   blocks[b] = make_float4(avg.x, avg.y, avg.z, kc);
 }
 
+// ---- live-VPL compaction ------------------------------------------------------------------------------
+// A VPL whose flux is (+-)0 in all three channels adds exactly zero to every accumulator of every cache
+// (cacheLightingRSM.comp:262-277: every term carries the factor Flux), so the gather never needs to see it:
+// RSM texels outside the spot cone or past the scene are such VPLs. Two small kernels keep the order of the
+// survivors (deterministic sums): per-256-chunk counts, then an ordered scatter. NaN flux compares != 0 and
+// stays in. Each survivor is tagged with its shadow-block index so a compacted list still finds its visibility.
+constexpr int kCompactThreads = 256;
+
+__device__ __forceinline__ bool vpl_is_live(const float4 flux) { return flux.x != 0.0f || flux.y != 0.0f || flux.z != 0.0f; }
+
+__global__ void __launch_bounds__(kCompactThreads) vpl_count_kernel(const float4* __restrict__ vpls, uint32_t n,
+                                                                   uint32_t interval, uint32_t* __restrict__ chunk_counts,
+                                                                   uint8_t* __restrict__ block_live) {
+  const uint32_t k = blockIdx.x * kCompactThreads + threadIdx.x;
+  const bool live = k < n && vpl_is_live(__ldg(vpls + (size_t)k * 3 + 2));
+  if (live && block_live) block_live[k / interval] = 1; // benign race: every writer stores 1
+  const int c = __syncthreads_count(live);
+  if (threadIdx.x == 0) chunk_counts[blockIdx.x] = (uint32_t)c;
+}
+
+__global__ void __launch_bounds__(kCompactThreads) vpl_compact_kernel(const float4* __restrict__ vpls, uint32_t n,
+                                                                     uint32_t interval, const uint32_t* __restrict__ chunk_counts,
+                                                                     float4* __restrict__ out, uint32_t* __restrict__ live_count) {
+  __shared__ uint32_t s_warp[kCompactThreads / 32];
+  __shared__ uint32_t s_base;
+  // survivors in the chunks before this one
+  uint32_t part = 0;
+  for (uint32_t c = threadIdx.x; c < blockIdx.x; c += kCompactThreads) part += __ldg(chunk_counts + c);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_warp[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t b = 0;
+    for (int w = 0; w < kCompactThreads / 32; ++w) b += s_warp[w];
+    s_base = b;
+  }
+  __syncthreads();
+  const uint32_t base = s_base;
+  const uint32_t k = blockIdx.x * kCompactThreads + threadIdx.x;
+  float4 q0, q1, q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k < n) q2 = __ldg(vpls + (size_t)k * 3 + 2);
+  const bool live = k < n && vpl_is_live(q2);
+  const uint32_t ballot = __ballot_sync(0xffffffffu, live);
+  __syncthreads(); // s_warp is reused
+  if (lane == 0) s_warp[warp] = __popc(ballot);
+  __syncthreads();
+  uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
+  for (uint32_t w = 0; w < warp; ++w) pos += s_warp[w];
+  if (live) {
+    q0 = __ldg(vpls + (size_t)k * 3);
+    q1 = __ldg(vpls + (size_t)k * 3 + 1);
+    q1.w = __uint_as_float(k / interval); // shadow-block index of this VPL (cacheLightingRSM.comp:169)
+    float4* o = out + (size_t)pos * 3;
+    o[0] = q0; o[1] = q1; o[2] = q2;
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    uint32_t total = base;
+    for (int w = 0; w < kCompactThreads / 32; ++w) total += s_warp[w];
+    *live_count = total;
+  }
+}
+
 } // namespace
+
+drv_status drv_impl_compact_vpls(drv_ctx* ctx, uint32_t li) {
+  LightState& S = ctx->lights[li];
+  const uint32_t n = S.num_vpls;
+  if (n == 0) {
+    DRV_CUDA(cudaMemsetAsync(ctx->live_counts + li, 0, sizeof(uint32_t), ctx->stream));
+    return DRV_OK;
+  }
+  const bool shadow = ctx->cfg.indirect_shadow != 0 && !S.vpls_external;
+  uint32_t interval = shadow ? (uint32_t)S.block.IndirectShadowComputationSampleInterval : 1u;
+  if (interval == 0) interval = 1;
+  if (shadow) DRV_CUDA(cudaMemsetAsync(S.block_live, 0, (n + interval - 1) / interval, ctx->stream));
+  const uint32_t chunks = (n + kCompactThreads - 1) / kCompactThreads;
+  vpl_count_kernel<<<chunks, kCompactThreads, 0, ctx->stream>>>((const float4*)S.vpls, n, interval, S.chunk_counts,
+                                                               shadow ? S.block_live : nullptr);
+  DRV_LAUNCH_CHECK();
+  vpl_compact_kernel<<<chunks, kCompactThreads, 0, ctx->stream>>>((const float4*)S.vpls, n, interval, S.chunk_counts,
+                                                                 (float4*)S.vpls_live, ctx->live_counts + li);
+  DRV_LAUNCH_CHECK();
+  return DRV_OK;
+}
 
 drv_status drv_impl_prepare_rsm(drv_ctx* ctx, uint32_t li) {
   LightState& S = ctx->lights[li];
@@ -251,5 +336,5 @@ drv_status drv_impl_generate_vpls(drv_ctx* ctx, uint32_t li) {
                                                                (float4*)S.vpls, (float4*)S.blocks);
   DRV_LAUNCH_CHECK();
   S.num_vpls = R * R;
-  return DRV_OK;
+  return drv_impl_compact_vpls(ctx, li);
 }

@@ -218,6 +218,16 @@ class Context:
     def apply_caches(self, out, fmt): self.check(self.lib.drv_apply_caches(self.handle, out.data_ptr(), fmt))
     def draw(self, out, fmt): self.check(self.lib.drv_draw(self.handle, out.data_ptr(), fmt))
 
+    def live_vpl_counts(self):
+        """VPLs with non-zero flux per light — what the gather streams (``drv_live_vpl_counts``)."""
+        a = (C.c_uint32 * 16)()
+        self.check(self.lib.drv_live_vpl_counts(self.handle, a))
+        return list(a)
+
+    def draw_frame(self, out, fmt, flags=abi.DRV_FRAME_PREPARE_RSM):
+        """Whole frame in GPU order (``drv_draw_frame``): light side || allocation, join, gather, apply."""
+        self.check(self.lib.drv_draw_frame(self.handle, out.data_ptr(), fmt, flags))
+
     def apply_caches_rows(self, out, fmt, y0, y1):
         self.check(self.lib.drv_apply_caches_rows(self.handle, out.data_ptr(), fmt, y0, y1))
     def set_shard(self, rank, world): self.check(self.lib.drv_set_shard(self.handle, rank, world))

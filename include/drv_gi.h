@@ -278,6 +278,8 @@ drv_status drv_light_caches(drv_ctx* ctx);
 /* ≙ Renderer::ApplyCaches (renderer.cpp:1047-1079): cacheApply.frag. */
 #define DRV_HDR_RGBA16F_ADD 0u   /* reference behaviour: additive blend into RGBA16F (renderer.cpp:119,480) */
 #define DRV_HDR_RGBA32F_WRITE 1u /* parity readback: overwrite float4 (rgb, 1); discarded pixels get 0 */
+#define DRV_HDR_RGBA16F_WRITE 2u /* glClear(0,0,0,0) + additive blend fused: overwrite RGBA16F with (rgb, 0);
+                                    discarded pixels get 0 (renderer.cpp:562 + :1053 in one pass) */
 drv_status drv_apply_caches(drv_ctx* ctx, void* hdr_out, uint32_t format);
 
 /* The same for the pixel rows [y_begin, y_end) only — sort-first sharding of the apply pass over GPUs, and the
@@ -287,6 +289,24 @@ drv_status drv_apply_caches_rows(drv_ctx* ctx, void* hdr_out, uint32_t format, u
 /* The DYN_RADIANCE_VOLUME case of Renderer::Draw (renderer.cpp:539-570)
  * minus the producers: allocate -> light -> apply, one call. */
 drv_status drv_draw(drv_ctx* ctx, void* hdr_out, uint32_t format);
+
+/* One whole frame of the path, scheduled for the GPU rather than in the reference's serial GL order:
+ * the light side (RSM mip chains + VPL generation, ShadowMap::PrepareRSM / cacheLightingRSM.comp:137-163) runs
+ * on a second stream concurrently with the camera side (AllocateCaches), the two join before the gather, then
+ * apply. Results are identical to drv_prepare_rsm (every light) + drv_draw.
+ *   DRV_FRAME_PREPARE_RSM  rebuild the RSM mip chain of every bound light (else they are used as they stand)
+ *   DRV_FRAME_GRAPH        record the frame into a CUDA graph and replay it while nothing that feeds a kernel
+ *                          argument changes (uniform blocks, bindings, shard, hdr_out, format, flags); any
+ *                          drv_set_* / drv_bind_* / drv_upload_* call makes the next frame re-record.
+ *                          Ignored while stage timers are enabled. */
+#define DRV_FRAME_PREPARE_RSM 1u
+#define DRV_FRAME_GRAPH 2u
+drv_status drv_draw_frame(drv_ctx* ctx, void* hdr_out, uint32_t format, uint32_t flags);
+
+/* VPLs the gather actually streams, per light: drv_light_caches drops VPLs whose flux is zero in all channels
+ * (RSM texels that saw no surface; they add exactly zero to every cache) and keeps the order of the rest.
+ * counts[DRV_MAX_LIGHTS]; synchronises. */
+drv_status drv_live_vpl_counts(drv_ctx* ctx, uint32_t* counts);
 
 /* Device pointers for parity readback / interop. Valid until drv_destroy. */
 typedef struct drv_buffers {

@@ -128,6 +128,43 @@ def test_draw_host_frame_pipelined(cuda_device, cfg):
     g.close()
 
 
+@pytest.mark.parametrize("cfg", [0, 2])
+def test_draw_frame_matches_serial_order(cuda_device, cfg):
+    """drv_draw_frame (light side || camera side, fused clear, CUDA-graph replay) against the reference's serial
+    order prepare_rsm -> clear -> drv_draw: bit-identical images and entries, eager and replayed."""
+    import torch
+    wl = workloads.config(cfg).build()
+    g = workloads.DeviceFrame(wl)
+    g.prepare_inputs()
+    hdr = torch.zeros(wl.height, wl.width, 4, dtype=torch.float16, device="cuda")
+    torch.cuda.synchronize()
+    g.frame(hdr, abi.DRV_HDR_RGBA16F_ADD)
+    torch.cuda.synchronize()
+    ref = hdr.cpu()
+    n = g.ctx.active_cache_count()[0]
+    ref_entries = g.ctx.read_entries(n)
+    out = torch.full((wl.height, wl.width, 4), 7.0, dtype=torch.float16, device="cuda")
+    torch.cuda.synchronize()
+    for flags in (abi.DRV_FRAME_PREPARE_RSM, abi.DRV_FRAME_PREPARE_RSM | abi.DRV_FRAME_GRAPH):
+        for rep in range(4):  # graph mode: eager, record + replay, replay, replay
+            out.fill_(7.0)
+            torch.cuda.synchronize()
+            launches = g.ctx.kernel_launches()
+            g.ctx.draw_frame(out, abi.DRV_HDR_RGBA16F_WRITE, flags)
+            torch.cuda.synchronize()
+            assert g.ctx.kernel_launches() > launches
+            assert torch.equal(out.cpu(), ref), (flags, rep)
+            assert np.array_equal(g.ctx.read_entries(n), ref_entries), (flags, rep)
+    # a changed uniform block invalidates the recorded graph: the next frame must see the new camera
+    import copy
+    pf = copy.copy(wl.per_frame)
+    g.ctx.set_per_frame(pf)
+    g.ctx.draw_frame(out, abi.DRV_HDR_RGBA16F_WRITE, abi.DRV_FRAME_PREPARE_RSM | abi.DRV_FRAME_GRAPH)
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), ref)
+    g.close()
+
+
 def test_renderer_mirror_draw(cuda_device):
     """The reference-shaped host interface (Renderer::Draw, renderer.cpp:501-594) drives the same frame."""
     import torch

@@ -241,6 +241,31 @@ def test_gather_unshadowed_variants(cuda_device, variant, sh_order, n_cache, n_v
     ctx.close()
 
 
+@pytest.mark.parametrize("pattern", ["runs", "sparse", "all-dead", "tail"])
+def test_gather_drops_zero_flux_vpls(cuda_device, pattern):
+    """Live-VPL compaction (rsm.cu): VPLs with zero flux are removed before the gather, the order of the rest is
+    kept, and the result equals the oracle's walk over the full list (ragged runs, chunk boundaries, empty list)."""
+    n_cache, n_vpl = 777, 4096
+    pos, vpls = workloads.sweep(n_cache, n_vpl)
+    vpls = vpls.copy()
+    k = np.arange(n_vpl)
+    dead = {"runs": (k // 300) % 2 == 1, "sparse": (k * 2654435761 % 7) != 0, "all-dead": np.ones(n_vpl, bool),
+            "tail": k >= 257}[pattern]
+    vpls["Flux"][dead] = 0.0
+    vpls["Flux"][dead & (k % 2 == 0), 1] = -0.0  # negative zero is zero too
+    for sh_order in (1, 2):
+        ctx, cb, _, _ = _sweep_ctx(n_cache, n_vpl, sh_order, 0)
+        ctx.set_vpls(0, vpls.ctypes.data, n_vpl)
+        ctx.light_caches()
+        assert ctx.live_vpl_counts()[0] == int((~dead).sum())
+        e = ctx.read_entries(n_cache)
+        eo = _sweep_oracle(cb, pos, [vpls], sh_order)
+        ok, ratio = close(e[:, 4:], eo[:, 4:])
+        assert ok, "worst |err|/tol = %.3f" % ratio
+        assert (np.abs(eo[:, 4:]).max() > 0) == (pattern != "all-dead")
+        ctx.close()
+
+
 def test_gather_accumulates_over_lights_and_calls(cuda_device):
     """`entry.SH += acc` per light (cacheLightingRSM.comp:358-373): two lights, then a second call."""
     ctx, cb, pos, vpls = _sweep_ctx(3000, 4096, 2, 0)
