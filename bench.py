@@ -54,12 +54,24 @@ def parse_args():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps (profiling runs)")
     ap.add_argument("--no-microbench", action="store_true")
     ap.add_argument("--stages", action="store_true", help="print the per-stage table to stderr")
+    ap.add_argument("--no-scaling-workload", action="store_true",
+                    help="skip the short run of BASELINE configs[3] (the multi-GPU scaling workload) after the metric's workload")
     ap.add_argument("--no-graph", action="store_true", help="issue the frame kernel by kernel instead of replaying its CUDA graph")
     ap.add_argument("--serial", action="store_true", help="reference stage order on one stream (prepare_rsm, clear, drv_draw) "
                                                           "instead of drv_draw_frame's light-side || camera-side schedule")
     ap.add_argument("--barrier", choices=["peer", "nccl"], default="peer",
                     help="cross-GPU barrier of sharded runs: flags in NVLink peer memory (drv_peer_barrier) or an NCCL all-reduce")
     return ap.parse_args()
+
+
+def traffic_for(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
+    capture of this command (profiles/ncu_traffic.json names the capture); None if there is no capture."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return t[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def workload_for(index):
@@ -205,16 +217,13 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------- this repo's arm
 def run_b200(args):
-    import numpy as np
+    """The metric's workload (BASELINE configs[1] unless --config says otherwise) and, beside it, the workload the
+    north star quotes multi-GPU scaling on (configs[3]: 3840x2160, 4 lights = 64k VPLs, 4 x 128^3, SH2 + cone-traced
+    shadows) as a short device-timed run under "scaling_workload" — the 0.2 ms metric frame is latency-bound and
+    cannot strong-scale; the 12 ms one does."""
     import torch
     import torch.distributed as dist
-
-    import dynamicradiancevolume_b200 as drv
-    import workloads
-    from dynamicradiancevolume_b200 import abi
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
@@ -227,6 +236,47 @@ def run_b200(args):
         # stdout carries exactly one JSON line: keep NCCL's own banner / debug output on stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = measure(args, args.config, args.steps, args.warmup, light=False)
+    if args.config == 1 and not args.no_scaling_workload:
+        k = max(3, min(10, args.steps // 3))
+        extra = measure(args, 3, k, 2, light=True)
+        if line is not None and extra is not None:
+            line["scaling_workload"] = {
+                "workload": extra["config"]["workload"], "ms_per_frame": extra["value"], "steps": k, "warmup": 2,
+                "n_gpus": world, "caches": extra["config"]["caches"], "vpls": extra["config"]["vpls"],
+                "live_vpls": extra["config"]["live_vpls"], "scaling": "strong",
+                "how": "same timing rules as `value` (CUDA events per step, L2 flushed, max over ranks); "
+                       "speed-up at N GPUs = this figure at n_gpus 1 / this figure at N"}
+    if line is not None:
+        if args.stages:
+            for k_, v in line["stage_ms"].items():
+                sys.stderr.write("%-18s %8.4f ms\n" % (k_, v))
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def measure(args, config_index, n_steps, n_warmup, light):
+    """One workload through the C-ABI on this rank's GPU. Returns the JSON line (rank 0) or None. `light`: only
+    the device-timed frame (no instrumented pass, no end-to-end leg, no CPU baseline, no micro-benchmarks)."""
+    import copy
+    args = copy.copy(args)
+    args.steps, args.warmup, args.config = n_steps, n_warmup, config_index
+    if light:
+        args.no_cpu_baseline = args.no_microbench = True
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import dynamicradiancevolume_b200 as drv
+    import workloads
+    from dynamicradiancevolume_b200 import abi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
 
     wl = workload_for(args.config).build()
     stream = torch.cuda.Stream(device=local)
@@ -266,6 +316,13 @@ def run_b200(args):
                 # (renderer.cpp:562) is fused into the apply pass (DRV_HDR_RGBA16F_WRITE); replayed as a CUDA
                 # graph while stage timers are off
                 ctx.draw_frame(hdr16, abi.DRV_HDR_RGBA16F_WRITE, frame_flags)
+                return
+            if world > 1 and not args.serial and args.barrier == "peer":
+                # the same call on every rank: allocation replicated, peer barrier, own shard of the gather with
+                # the fused all-gather of finished entries, peer barrier, this rank's band of the apply pass;
+                # then the image bands are gathered on rank 0
+                ctx.draw_frame(hdr16, abi.DRV_HDR_RGBA16F_WRITE, frame_flags | abi.DRV_FRAME_APPLY_OWN_ROWS)
+                dist.gather(band_views[rank], band_views if rank == 0 else None, dst=0)
                 return
             for i in range(len(g.rsms)):
                 ctx.prepare_rsm(i)
@@ -319,7 +376,7 @@ def run_b200(args):
     inst_ms = []
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    for i in range(args.steps + 1):
+    for i in range(0 if light else args.steps + 1):
         with torch.cuda.stream(stream):
             if not args.no_flush:
                 flush_buf.zero_()
@@ -380,7 +437,7 @@ def run_b200(args):
             stream.synchronize()
 
     e2e_ms = []
-    for i in range(args.warmup + args.steps):
+    for i in range(0 if light else args.warmup + args.steps):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -405,10 +462,8 @@ def run_b200(args):
         ctx.bind_rsm(i, *r)
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return 0
+        g.close()
+        return None
 
     # ---- roofline of the dominant kernel (the cache x VPL gather) ----
     med = lambda v: statistics.median(v) if v else None
@@ -446,7 +501,7 @@ def run_b200(args):
             "peak_source": ("measured on this GPU at bench start: scalar-FFMA micro-kernel (drv_microbench), FMA = 2 flop"
                             if "ffma_tflops" in micro else "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"),
             "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS,
-            "traffic": None,
+            "traffic": traffic_for("gather_kernel<SH%d,%s>" % (wl.sh_order, "shadow" if wl.indirect_shadow else "unshadowed")),
             "pairs_per_launch": pairs_per_launch, "flop_per_pair": FLOP_PER_PAIR[wl.sh_order],
             "live_vpls": live_vpls, "pairs_per_launch_reference": pairs_reference,
             "frac_counting_reference_pairs": pairs_reference * FLOP_PER_PAIR[wl.sh_order] / (gather_ms * 1e-3) / 1e12 / fp32_peak,
@@ -505,28 +560,30 @@ def run_b200(args):
         "stage_ms_note": "instrumented pass after the timed region: the same steps issued kernel by kernel with CUDA "
                          "events around every stage (%.4f ms/frame that way); stages of the light side and the camera "
                          "side overlap" % (sum(inst_ms) / max(len(inst_ms), 1)),
-        "frame_issue": ("serial: prepare_rsm, clear, drv_draw" if (args.serial or world > 1) else
+        "frame_issue": ("serial: prepare_rsm, clear, drv_draw" if (args.serial or (world > 1 and args.barrier != "peer")) else
                         "drv_draw_frame: (RSM mips + VPLs) || allocate -> gather -> apply(+clear)%s"
                         % ("" if args.no_graph else ", CUDA graph replay")),
         "microbench": micro,
         "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
         "gpu": torch.cuda.get_device_name(local),
     }
-    if args.stages:
-        for k, v in line["stage_ms"].items():
-            sys.stderr.write("%-18s %8.4f ms\n" % (k, v))
-    print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+    g.close()
+    return line
 
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE JSON line: libraries that write banners to file descriptor 1 (NCCL's version
+    # line, for one) are sent to stderr for the duration of the run, and print() gets the real stdout back
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
-        return run_reference(args)
-    return run_b200(args)
+        rc = run_reference(args)
+    else:
+        rc = run_b200(args)
+    sys.stdout.flush()
+    return rc
 
 
 if __name__ == "__main__":

@@ -28,6 +28,7 @@ DRV_HDR_RGBA32F_WRITE = 1
 DRV_HDR_RGBA16F_WRITE = 2
 DRV_FRAME_PREPARE_RSM = 1
 DRV_FRAME_GRAPH = 2
+DRV_FRAME_APPLY_OWN_ROWS = 4
 
 STAGE_NAMES = ["VoxelizeScene", "VoxelBlendMipMap", "AllocateCaches", "LightCaches", "ApplyCaches",
                "PrepareRSM", "GatherKernel"]

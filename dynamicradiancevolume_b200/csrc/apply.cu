@@ -128,19 +128,16 @@ __device__ __forceinline__ void lighting_from_caches(const ApplyParams& p, const
   }
 }
 
-template <int ORDER, int MINB>
-__global__ void __launch_bounds__(256, MINB) apply_kernel(ApplyParams p, const float* __restrict__ depth,
-                                                    const int* __restrict__ normal, const uchar4* __restrict__ diffuse,
-                                                    const uint32_t* __restrict__ atlas, const uint8_t* __restrict__ entries,
-                                                    const float* __restrict__ ndc_xy, void* __restrict__ out, int format,
-                                                    int y_begin, int y_end) {
-  __shared__ float s_srgb[256]; // sRGB8 -> linear; shared memory serves divergent indices, constant memory would serialise
-  s_srgb[threadIdx.y * 32 + threadIdx.x] = c_srgb_lut[threadIdx.y * 32 + threadIdx.x];
-  __syncthreads();
-  const int x = blockIdx.x * 32 + threadIdx.x, y = y_begin + blockIdx.y * 8 + threadIdx.y;
-  if (x >= p.W || y >= y_end) return;
+// Pixels per thread: a thread walks kApplyIter rows (8 apart... see the kernel) and fetches the G-buffer texels of
+// its next pixel before it shades the current one, so the DRAM latency of the depth / normal / albedo reads
+// overlaps the atlas + entry gathers of the previous pixel.
+constexpr int kApplyIter = 4;
+
+template <int ORDER>
+__device__ __forceinline__ void shade_pixel(const ApplyParams& p, const float* s_srgb, const uint32_t* __restrict__ atlas,
+                                            const uint8_t* __restrict__ entries, const float* __restrict__ ndc_xy,
+                                            void* __restrict__ out, int format, int x, int y, float d, int pn, uchar4 dc) {
   const uint32_t t = (uint32_t)y * p.W + x;
-  const float d = __ldg(depth + t);
   if (d < 0.00001f) { // :128 discard
     if (format == DRV_HDR_RGBA32F_WRITE) reinterpret_cast<float4*>(out)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     else if (format == DRV_HDR_RGBA16F_WRITE) reinterpret_cast<uint2*>(out)[t] = make_uint2(0u, 0u);
@@ -149,9 +146,7 @@ __global__ void __launch_bounds__(256, MINB) apply_kernel(ApplyParams p, const f
   // gl_FragCoord.xy -> NDC (:134) through the per-context tables
   F3 wp = ex_unproject(p.ivp, __ldg(ndc_xy + x), __ldg(ndc_xy + p.W + y), d);
   const int c = compute_cascade(p, wp); // :138
-  const int pn = __ldg(normal + t);
   F3 n = unpack_normal16i_fast((int)(short)(pn & 0xffff), (int)(short)((uint32_t)pn >> 16)); // :140
-  const uchar4 dc = __ldg(diffuse + t);
   const float albr = s_srgb[dc.x], albg = s_srgb[dc.y], albb = s_srgb[dc.z]; // :144
   NormalBasis<ORDER> nb;
   nb.b1y = p.g1 * n.y; nb.b1z = p.g1 * n.z; nb.b1x = p.g1 * n.x;
@@ -194,6 +189,36 @@ __global__ void __launch_bounds__(256, MINB) apply_kernel(ApplyParams p, const f
     nw.x = *reinterpret_cast<uint32_t*>(&nrg);
     nw.y = *reinterpret_cast<uint32_t*>(&nba);
     *o = nw;
+  }
+}
+
+// Block = 32 x 8 threads = a 32-wide column strip; it walks ITER consecutive 8-row groups.
+template <int ORDER, int MINB, int ITER>
+__global__ void __launch_bounds__(256, MINB) apply_kernel(ApplyParams p, const float* __restrict__ depth,
+                                                          const int* __restrict__ normal, const uchar4* __restrict__ diffuse,
+                                                          const uint32_t* __restrict__ atlas, const uint8_t* __restrict__ entries,
+                                                          const float* __restrict__ ndc_xy, void* __restrict__ out, int format,
+                                                          int y_begin, int y_end) {
+  __shared__ float s_srgb[256]; // sRGB8 -> linear; shared memory serves divergent indices, constant memory would serialise
+  s_srgb[threadIdx.y * 32 + threadIdx.x] = c_srgb_lut[threadIdx.y * 32 + threadIdx.x];
+  __syncthreads();
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  if (x >= p.W) return;
+  int y = y_begin + blockIdx.y * (8 * ITER) + threadIdx.y;
+  float d = 0.f; int pn = 0; uchar4 dc = make_uchar4(0, 0, 0, 0);
+  if (y < y_end) {
+    const uint32_t t = (uint32_t)y * p.W + x;
+    d = __ldg(depth + t); pn = __ldg(normal + t); dc = __ldg(diffuse + t);
+  }
+#pragma unroll 1
+  for (int it = 0; it < ITER; ++it, y += 8) {
+    if (y >= y_end) return;
+    const float d0 = d; const int pn0 = pn; const uchar4 dc0 = dc;
+    if (it + 1 < ITER && y + 8 < y_end) { // next pixel's texels, in flight while this one is shaded
+      const uint32_t t = (uint32_t)(y + 8) * p.W + x;
+      d = __ldg(depth + t); pn = __ldg(normal + t); dc = __ldg(diffuse + t);
+    }
+    shade_pixel<ORDER>(p, s_srgb, atlas, entries, ndc_xy, out, format, x, y, d0, pn0, dc0);
   }
 }
 
@@ -248,19 +273,23 @@ drv_status drv_impl_apply_rows(drv_ctx* ctx, void* out, uint32_t format, uint32_
   if (y_end > (uint32_t)p.H) y_end = (uint32_t)p.H;
   if (y_begin >= y_end) return DRV_OK;
   if (timed) ctx->stage_begin(DRV_STAGE_APPLY_CACHES);
-  dim3 block(32, 8), grid((p.W + 31) / 32, (y_end - y_begin + 7) / 8);
+  const uint32_t tune = (ctx->cfg.gather_variant >> 8) & 0xFu;
+  const uint32_t iter = ((ctx->cfg.gather_variant >> 12) & 0xFu) == 1 ? 1u : (uint32_t)kApplyIter;
+  dim3 block(32, 8), grid((p.W + 31) / 32, (y_end - y_begin + 8 * iter - 1) / (8 * iter));
   // resident blocks per SM the kernel is compiled for (register budget 64 / 80 / 128 per thread): more registers
   // keep more of a pixel's entry loads in flight. drv_config.gather_variant bits 8..11 override it (tuning sweeps).
-  const uint32_t tune = (ctx->cfg.gather_variant >> 8) & 0xFu;
-#define DRV_APPLY(ORD, MB)                                                                                      \
-  apply_kernel<ORD, MB><<<grid, block, 0, ctx->stream>>>(p, ctx->gb_depth, (const int*)ctx->gb_normal,            \
-                                                         (const uchar4*)ctx->gb_diffuse, ctx->atlas, ctx->entries, \
-                                                         ctx->ndc_xy, out, (int)format, (int)y_begin, (int)y_end)
-  if (ctx->cfg.sh_order == 2) {
-    if (tune == 2) DRV_APPLY(2, 2); else if (tune == 3) DRV_APPLY(2, 3); else if (tune == 5) DRV_APPLY(2, 5); else DRV_APPLY(2, 4);
-  } else {
-    if (tune == 2) DRV_APPLY(1, 2); else if (tune == 3) DRV_APPLY(1, 3); else if (tune == 5) DRV_APPLY(1, 5); else DRV_APPLY(1, 4);
-  }
+  // (bits 12..15 = 1: one pixel per thread, no prefetch loop)
+#define DRV_APPLY(ORD, MB, IT)                                                                                       \
+  apply_kernel<ORD, MB, IT><<<grid, block, 0, ctx->stream>>>(p, ctx->gb_depth, (const int*)ctx->gb_normal,            \
+                                                             (const uchar4*)ctx->gb_diffuse, ctx->atlas, ctx->entries, \
+                                                             ctx->ndc_xy, out, (int)format, (int)y_begin, (int)y_end)
+#define DRV_APPLY_MB(ORD, IT)                                                                                   \
+  do {                                                                                                          \
+    if (tune == 4) DRV_APPLY(ORD, 4, IT); else if (tune == 6) DRV_APPLY(ORD, 6, IT); else DRV_APPLY(ORD, 5, IT); \
+  } while (0)
+  if (ctx->cfg.sh_order == 2) { if (iter == 1) DRV_APPLY_MB(2, 1); else DRV_APPLY_MB(2, kApplyIter); }
+  else { if (iter == 1) DRV_APPLY_MB(1, 1); else DRV_APPLY_MB(1, kApplyIter); }
+#undef DRV_APPLY_MB
 #undef DRV_APPLY
   DRV_LAUNCH_CHECK();
   if (timed) ctx->stage_end(DRV_STAGE_APPLY_CACHES);

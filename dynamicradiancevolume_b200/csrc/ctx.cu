@@ -314,11 +314,21 @@ static drv_status frame_body(drv_ctx* ctx, void* hdr_out, uint32_t format, uint3
   if (e != cudaSuccess) return ctx->fail(DRV_ERR_CUDA, "drv_draw_frame: event record failed");
   st = drv_impl_allocate(ctx); // renderer.cpp:550
   if (st != DRV_OK) return st;
+  // sharded frame: every rank has cleared its SH before any peer's gather epilogue stores into it
+  const bool sharded = ctx->shard_world > 1 && ctx->peers_open;
+  if (sharded && (st = drv_impl_peer_barrier(ctx)) != DRV_OK) return st;
   DRV_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
   ctx->stage_begin(DRV_STAGE_LIGHT_CACHES);
   st = drv_impl_gather(ctx);   // renderer.cpp:556
   ctx->stage_end(DRV_STAGE_LIGHT_CACHES);
   if (st != DRV_OK) return st;
+  // ... and all peers' stores have landed before anybody applies
+  if (sharded && (st = drv_impl_peer_barrier(ctx)) != DRV_OK) return st;
+  if (flags & DRV_FRAME_APPLY_OWN_ROWS) {
+    const uint32_t H = ctx->cfg.backbuffer_height, band = (H + ctx->shard_world - 1) / ctx->shard_world;
+    const uint32_t y0 = ctx->shard_rank * band, y1 = y0 + band < H ? y0 + band : H;
+    return drv_impl_apply_rows(ctx, hdr_out, format, y0 < H ? y0 : H, y1, true);
+  }
   return drv_impl_apply(ctx, hdr_out, format); // renderer.cpp:570
 }
 

@@ -41,8 +41,7 @@ using namespace drvk;
 
 namespace {
 
-constexpr int kThreads = 128;
-constexpr int kVplTile = 128; // VPLs staged per shared-memory tile
+constexpr int kThreads = 128; // default CTA size; a shared-memory VPL tile holds one VPL per thread (NT)
 
 struct GatherLight {
   const float4* vpls;   // the LIVE list (rsm.cu): 3 x float4 per VPL: (pos, area) (normal, shadow-block index) (flux, -)
@@ -137,13 +136,26 @@ struct VoxelVol {
 
 constexpr float kMagic = 12582912.0f; // 1.5 * 2^23: (v + kMagic) - kMagic rounds v to the nearest integer
 
-// floor(v) without the XU pipe (FRND / F2I / I2F are quarter rate): round-to-nearest of v - 0.5 via the magic
-// constant. On exact integers ties-to-even may pick v - 1, in which case frac = 1 and the trilinear result is
-// the same (the filter is continuous across texel boundaries). i = floor as int, f = v - floor.
-__device__ __forceinline__ void floor_frac(float v, int& i, float& f) {
-  float m = (v - 0.5f) + kMagic;
+// The cone march is issue-bound (ncu: issue slots 75 % busy, FMA pipe 38 %), so everything that comes in x / y
+// pairs is evaluated with packed FP32x2 instructions (FFMA2 / FADD2: one issue slot for two IEEE-identical
+// results): positions, texel coordinates, floor / fraction, and the x- and y-lerps of the trilinear filter.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+
+// floor(v) without the XU pipe (FRND / F2I / I2F are quarter rate). The caller passes w = v - 0.5; w + kMagic
+// rounds w to the nearest integer = floor(v) (on exact integers ties-to-even may pick v - 1, in which case
+// frac = 1 and the trilinear result is the same: the filter is continuous across texel boundaries).
+// i = floor as int, f = v - floor.
+__device__ __forceinline__ void floor_frac_w(float w, int& i, float& f) {
+  const float m = w + kMagic;
   i = __float_as_int(m) - 0x4B400000;
-  f = v - (m - kMagic);
+  f = (w - (m - kMagic)) + 0.5f;
+}
+__device__ __forceinline__ void floor_frac_w2(float2 w, int& ix, int& iy, float2& f) {
+  const float2 m = __fadd2_rn(w, f2(kMagic));
+  ix = __float_as_int(m.x) - 0x4B400000;
+  iy = __float_as_int(m.y) - 0x4B400000;
+  f = __fadd2_rn(__fadd2_rn(w, __fadd2_rn(f2(kMagic), f2(-m.x, -m.y))), f2(0.5f)); // (w - (m - magic)) + .5
 }
 
 // byte `sel` (0..3) of w as a float, exactly: build 2^23 + byte with one PRMT, subtract 2^23.
@@ -154,23 +166,24 @@ __device__ __forceinline__ float byte_as_float_biased(uint32_t w) {
 
 struct Footprint {
   uint32_t index; // record index
-  float tx, ty, tz;
+  float2 txy;
+  float tz;
 };
 
 // footprint of the sample at q in level `l`; q is given in level-0 texel units with the half-texel shift
 // already applied (q = p * res - 0.5 for p in [0,1]^3), so level l sees q * 2^-l + (2^-(l+1) - 0.5)
-__device__ __forceinline__ Footprint footprint(const VoxelVol& V, int l, float qx, float qy, float qz) {
+__device__ __forceinline__ Footprint footprint(const VoxelVol& V, int l, float2 qxy, float qz) {
   const int r = V.res >> l;
   Footprint F;
   int x, y, z;
   if (l == 0) {
-    floor_frac(qx, x, F.tx); floor_frac(qy, y, F.ty); floor_frac(qz, z, F.tz);
+    floor_frac_w2(__fadd2_rn(qxy, f2(-0.5f)), x, y, F.txy);
+    floor_frac_w(qz - 0.5f, z, F.tz);
   } else {
     const float sc = __int_as_float(0x3f800000 - (l << 23));  // 2^-l
-    const float of = fmaf(sc, 0.5f, -0.5f);
-    floor_frac(fmaf(qx, sc, of), x, F.tx);
-    floor_frac(fmaf(qy, sc, of), y, F.ty);
-    floor_frac(fmaf(qz, sc, of), z, F.tz);
+    const float of = fmaf(sc, 0.5f, -1.0f);                    // the level's half-texel shift, minus the 0.5 of floor
+    floor_frac_w2(__ffma2_rn(qxy, f2(sc), f2(of)), x, y, F.txy);
+    floor_frac_w(fmaf(qz, sc, of), z, F.tz);
   }
   // clamp the lower corner to [-1, r-1]: outside that range both taps of the axis are the same edge texel
   x = min(max(x, -1), r - 1) + 1;
@@ -180,24 +193,28 @@ __device__ __forceinline__ Footprint footprint(const VoxelVol& V, int l, float q
   return F;
 }
 
-__device__ __forceinline__ float trilinear(uint2 rec, float tx, float ty, float tz) {
+// rec.x = texels (x,y,z) 000 100 010 110, rec.y = 001 101 011 111 (one byte each). The pairs are the two z
+// planes, so the x-lerp and the y-lerp are packed and only the z-lerp is scalar.
+__device__ __forceinline__ float trilinear(uint2 rec, float2 txy, float tz) {
   const float B = 8388608.0f;
-  float a000 = byte_as_float_biased<0>(rec.x), a100 = byte_as_float_biased<1>(rec.x);
-  float a010 = byte_as_float_biased<2>(rec.x), a110 = byte_as_float_biased<3>(rec.x);
-  float a001 = byte_as_float_biased<0>(rec.y), a101 = byte_as_float_biased<1>(rec.y);
-  float a011 = byte_as_float_biased<2>(rec.y), a111 = byte_as_float_biased<3>(rec.y);
+  const float2 a00 = f2(byte_as_float_biased<0>(rec.x), byte_as_float_biased<0>(rec.y)); // (x0,y0) at z0 | z1
+  const float2 a10 = f2(byte_as_float_biased<1>(rec.x), byte_as_float_biased<1>(rec.y)); // (x1,y0)
+  const float2 a01 = f2(byte_as_float_biased<2>(rec.x), byte_as_float_biased<2>(rec.y)); // (x0,y1)
+  const float2 a11 = f2(byte_as_float_biased<3>(rec.x), byte_as_float_biased<3>(rec.y)); // (x1,y1)
+  const float2 tx = f2(txy.x), ty = f2(txy.y), one = f2(1.0f), mone = f2(-1.0f), mB = f2(-B);
   // (a1 - a0) is exact on the biased values; only the base needs un-biasing
-  float c00 = fmaf(tx, a100 - a000, a000 - B), c10 = fmaf(tx, a110 - a010, a010 - B);
-  float c01 = fmaf(tx, a101 - a001, a001 - B), c11 = fmaf(tx, a111 - a011, a011 - B);
-  float c0 = fmaf(ty, c10 - c00, c00), c1 = fmaf(ty, c11 - c01, c01);
-  return fmaf(tz, c1 - c0, c0) * (1.0f / 255.0f);
+  const float2 cy0 = __ffma2_rn(tx, __ffma2_rn(a00, mone, a10), __fadd2_rn(a00, mB)); // x-lerp at y0
+  const float2 cy1 = __ffma2_rn(tx, __ffma2_rn(a01, mone, a11), __fadd2_rn(a01, mB)); // x-lerp at y1
+  const float2 c = __ffma2_rn(ty, __ffma2_rn(cy0, mone, cy1), cy0);                   // y-lerp: (z0, z1)
+  (void)one;
+  return fmaf(tz, c.y - c.x, c.x) * (1.0f / 255.0f);
 }
 
 // One sample of the march with its loads in flight.
 struct ConeSample {
   uint2 r0, r1;          // records of level l0 and l0 + 1 (r1 only when t != 0)
-  float tx0, ty0, tz0;   // trilinear fractions in level l0
-  float tx1, ty1, tz1;   // ... in level l0 + 1
+  float2 txy0; float tz0; // trilinear fractions in level l0
+  float2 txy1; float tz1; // ... in level l0 + 1
   float t;               // mip fraction: 0 = level l0 only
   float dist, radius;
 };
@@ -217,9 +234,9 @@ __device__ __forceinline__ float cone_trace(const VoxelVol& V, float wx, float w
   float tx = ex_sub(blk.x, wx), ty = ex_sub(blk.y, wy), tz = ex_sub(blk.z, wz);     // :195
   const float lightDist = ex_sqrt(ex_dot3(tx, ty, tz, tx, ty, tz));                 // :196
   const float inv = 1.0f / lightDist;
-  const float dx = tx * inv, dy = ty * inv, dz = tz * inv;                          // :197-198 (dirInVoxel * res)
-  float cx = fmaf(dx, 2.0f, fmaf(wx - V.vmin[0], inv_voxel, -0.5f));                // :201
-  float cy = fmaf(dy, 2.0f, fmaf(wy - V.vmin[1], inv_voxel, -0.5f));
+  const float2 dxy = f2(tx * inv, ty * inv);                                        // :197-198 (dirInVoxel * res)
+  const float dz = tz * inv;
+  float2 cxy = __ffma2_rn(dxy, f2(2.0f), f2(fmaf(wx - V.vmin[0], inv_voxel, -0.5f), fmaf(wy - V.vmin[1], inv_voxel, -0.5f))); // :201
   float cz = fmaf(dz, 2.0f, fmaf(wz - V.vmin[2], inv_voxel, -0.5f));
   const float goal = ex_sub(ex_div(lightDist, V.voxel_size), 2.0f);                 // :206
   const float radToStep = ex_div(2.0f, ex_sub(1.0f, kk));                           // :209
@@ -228,7 +245,7 @@ __device__ __forceinline__ float cone_trace(const VoxelVol& V, float wx, float w
   // advance by `stepSize` (:213-216) and issue the fetches of that sample (:219)
   auto fetch = [&](float stepSize) -> ConeSample {
     ConeSample S;
-    cx = fmaf(dx, stepSize, cx); cy = fmaf(dy, stepSize, cy); cz = fmaf(dz, stepSize, cz); // :213
+    cxy = __ffma2_rn(dxy, f2(stepSize), cxy); cz = fmaf(dz, stepSize, cz);          // :213
     dist = ex_add(dist, stepSize);                                                  // :214
     S.dist = dist;
     S.radius = ex_mul(dist, kk);                                                    // :216
@@ -238,22 +255,22 @@ __device__ __forceinline__ float cone_trace(const VoxelVol& V, float wx, float w
       // lod = log2(radius) clamped to the chain. radius <= 1 — the first stretch of every cone, a VAL block
       // subtends ~1/32 rad — is level 0 exactly, without the log. fmaxf(NaN, 0) = 0.
       const float l = fminf(__log2f(S.radius), maxLod);
-      floor_frac(l, l0, S.t);
+      floor_frac_w(l - 0.5f, l0, S.t);
     }
-    const Footprint f0 = footprint(V, l0, cx, cy, cz);
+    const Footprint f0 = footprint(V, l0, cxy, cz);
     S.r0 = __ldg(V.rec + f0.index);
-    S.tx0 = f0.tx; S.ty0 = f0.ty; S.tz0 = f0.tz;
+    S.txy0 = f0.txy; S.tz0 = f0.tz;
     if (S.t != 0.0f) { // mip-linear: also the next coarser level
-      const Footprint f1 = footprint(V, min(l0 + 1, V.levels - 1), cx, cy, cz);
+      const Footprint f1 = footprint(V, min(l0 + 1, V.levels - 1), cxy, cz);
       S.r1 = __ldg(V.rec + f1.index);
-      S.tx1 = f1.tx; S.ty1 = f1.ty; S.tz1 = f1.tz;
+      S.txy1 = f1.txy; S.tz1 = f1.tz;
     }
     return S;
   };
 
   auto filter = [&](const ConeSample& S) -> float {
-    float o = trilinear(S.r0, S.tx0, S.ty0, S.tz0);
-    if (S.t != 0.0f) o = fmaf(S.t, trilinear(S.r1, S.tx1, S.ty1, S.tz1) - o, o);
+    float o = trilinear(S.r0, S.txy0, S.tz0);
+    if (S.t != 0.0f) o = fmaf(S.t, trilinear(S.r1, S.txy1, S.tz1) - o, o);
     return o;
   };
   // two steps per trip so that the in-flight sample alternates between A and B without register copies
@@ -567,16 +584,18 @@ __device__ __forceinline__ void start_run(const GatherParams& p, const Schedule&
   c.v_end = min((j + take) * p.granule, nv);
   c.u_next = u + take;
 }
-__device__ __forceinline__ void advance(const GatherParams& p, const Schedule& S, Cursor& c, unsigned long long u1) {
-  c.base += kVplTile;
+__device__ __forceinline__ void advance(const GatherParams& p, const Schedule& S, Cursor& c, unsigned long long u1,
+                                        uint32_t vpl_tile) {
+  c.base += vpl_tile;
   if (c.base >= c.v_end) start_run(p, S, c, c.u_next, u1);
 }
 
 // SHADOW: every pair is scaled by the visibility of its (cache, VAL block), read from the table cone_kernel wrote.
-template <int ORDER, bool SHADOW, typename Math, bool USE_TMA, int MINB = 1>
-__global__ void __launch_bounds__(kThreads, MINB) gather_kernel(const __grid_constant__ GatherParams p) {
+template <int ORDER, bool SHADOW, typename Math, bool USE_TMA, int MINB = 1, int NT = kThreads>
+__global__ void __launch_bounds__(NT, MINB) gather_kernel(const __grid_constant__ GatherParams p) {
   constexpr int CPT = Math::CPT;
-  constexpr int TILE = kThreads * CPT;
+  constexpr int TILE = NT * CPT;
+  constexpr int kVplTile = NT; // VPLs staged per shared-memory tile: one per thread
   constexpr int NC = num_coefs<ORDER>();
   constexpr int STRIDE = ORDER == 2 ? 128 : 64;
   constexpr int SPV = Math::kSmemPerVpl;
@@ -632,7 +651,7 @@ __global__ void __launch_bounds__(kThreads, MINB) gather_kernel(const __grid_con
     if (!seg_open) { // (re)load this thread's caches and clear the accumulators
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
-        uint32_t local = cur.tile * TILE + j * kThreads + threadIdx.x;
+        uint32_t local = cur.tile * TILE + j * NT + threadIdx.x;
         bool alive = local < S.count;
         float4 pos = alive ? *reinterpret_cast<const float4*>(p.entries + (size_t)(S.first + local) * STRIDE)
                            : make_float4(1e30f, 1e30f, 1e30f, 0.f); // :83
@@ -642,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, MINB) gather_kernel(const __grid_con
       seg_open = true;
     }
     Cursor nxt = cur;
-    advance(p, S, nxt, u1);
+    advance(p, S, nxt, u1, kVplTile);
     const int st = USE_TMA ? (int)(step & 1u) : 0;
     if (USE_TMA) {
       if (threadIdx.x == 0 && nxt.valid) tma_issue(nxt, st ^ 1); // stage st^1 was released by the last __syncthreads
@@ -665,7 +684,7 @@ __global__ void __launch_bounds__(kThreads, MINB) gather_kernel(const __grid_con
         float v[CPT];
 #pragma unroll
         for (int j = 0; j < CPT; ++j)
-          v[j] = (cur.tile * TILE + j * kThreads + threadIdx.x < S.count) ? __ldg(col + (size_t)blk * p.shadow_stride + j * kThreads) : 0.0f;
+          v[j] = (cur.tile * TILE + j * NT + threadIdx.x < S.count) ? __ldg(col + (size_t)blk * p.shadow_stride + j * NT) : 0.0f;
         M.set_shadow(v);
       };
       uint32_t cur_blk = 0xFFFFFFFFu;
@@ -688,7 +707,7 @@ __global__ void __launch_bounds__(kThreads, MINB) gather_kernel(const __grid_con
       const int slot = (cur.tile == (uint32_t)(u0 / S.units_per_tile)) ? 0 : 1;
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
-        uint32_t in_tile = j * kThreads + threadIdx.x;
+        uint32_t in_tile = j * NT + threadIdx.x;
         uint32_t local = cur.tile * TILE + in_tile;
         float raw[27];
         M.raw(j, raw);
@@ -737,7 +756,7 @@ struct ConeParams {
 constexpr int kConeThreads = 128;
 constexpr int kBlocksPerItem = 8;
 
-__global__ void __launch_bounds__(kConeThreads) cone_kernel(const __grid_constant__ ConeParams p) {
+__global__ void __launch_bounds__(kConeThreads, 8) cone_kernel(const __grid_constant__ ConeParams p) {
   // this shard's chunk, as make_schedule derives it
   const uint32_t n = (uint32_t)max(p.counter->TotalLightCacheCount, 0);
   const uint32_t groups64 = (n + 63u) / 64u;
@@ -855,9 +874,9 @@ namespace {
 
 using GatherFn = void (*)(const GatherParams);
 
-drv_status launch_gather(drv_ctx* ctx, GatherFn kernel, GatherParams& p, int tile_caches, int order) {
+drv_status launch_gather(drv_ctx* ctx, GatherFn kernel, GatherParams& p, int tile_caches, int order, int threads) {
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
   if (per_sm < 1) per_sm = 1;
   const int grid = ctx->num_sms * per_sm;
   const size_t need = (size_t)grid * 2 * (order == 2 ? 27 : 12) * tile_caches;
@@ -871,7 +890,7 @@ drv_status launch_gather(drv_ctx* ctx, GatherFn kernel, GatherParams& p, int til
   }
   p.partials = ctx->partials;
   p.grid = (uint32_t)grid;
-  kernel<<<grid, kThreads, 0, ctx->stream>>>(p);
+  kernel<<<grid, threads, 0, ctx->stream>>>(p);
   DRV_LAUNCH_CHECK();
   const int fin_grid = ctx->num_sms * 8;
   if (order == 1) gather_finalize_kernel<1><<<fin_grid, kFinThreads, 0, ctx->stream>>>(p, tile_caches);
@@ -887,9 +906,12 @@ drv_status launch_gather(drv_ctx* ctx, GatherFn kernel, GatherParams& p, int til
 //   4  scalar, 4 caches / thread (SH1)
 //   12 scalar, 2 caches / thread, register-prefetch staging
 //   6  as 0 for SH1 but compiled for 3 resident CTAs per SM (168 registers)
+//   7  as 0 with 64-thread CTAs (cache tiles of 256 / 128 entries: less padding when the frame has few caches)
+//   8  as 0 with 32-thread CTAs (cache tiles of 128 / 64 entries)
 // With indirect shadows the same kernels additionally scale every pair by its table visibility.
 template <bool SH>
-GatherFn select_kernel(int order, uint32_t variant, int* tile) {
+GatherFn select_kernel(int order, uint32_t variant, int* tile, int* threads) {
+  *threads = kThreads;
 #define DRV_PICK(ORD, MATH, TMA) do { *tile = kThreads * MATH::CPT; return gather_kernel<ORD, SH, MATH, TMA>; } while (0)
   using S1c2 = ScalarMath<1, SH, 2>; using S1c4 = ScalarMath<1, SH, 4>; using S2c2 = ScalarMath<2, SH, 2>;
   using P1p1 = PackedMath<1, SH, 1>; using P1p2 = PackedMath<1, SH, 2>; using P2p1 = PackedMath<2, SH, 1>;
@@ -900,12 +922,16 @@ GatherFn select_kernel(int order, uint32_t variant, int* tile) {
       case 4: DRV_PICK(1, S1c4, false);
       case 12: DRV_PICK(1, S1c2, false);
       case 6: *tile = kThreads * P1p2::CPT; return gather_kernel<1, SH, P1p2, false, 3>; // 168 registers: 3 CTAs / SM
+      case 7: *threads = 64; *tile = 64 * P1p2::CPT; return gather_kernel<1, SH, P1p2, false, 1, 64>; // 2-warp CTAs, 256-cache tiles
+      case 8: *threads = 32; *tile = 32 * P1p2::CPT; return gather_kernel<1, SH, P1p2, false, 1, 32>; // 1-warp CTAs, 128-cache tiles
       default: DRV_PICK(1, P1p2, false);
     }
   }
   switch (variant) {
     case 1: DRV_PICK(2, S2c2, true);
     case 4: case 12: DRV_PICK(2, S2c2, false);
+    case 7: *threads = 64; *tile = 64 * P2p1::CPT; return gather_kernel<2, SH, P2p1, false, 1, 64>;
+    case 8: *threads = 32; *tile = 32 * P2p1::CPT; return gather_kernel<2, SH, P2p1, false, 1, 32>;
     default: DRV_PICK(2, P2p1, false);
   }
 #undef DRV_PICK
@@ -924,19 +950,25 @@ namespace {
 struct BarrierArgs {
   uint32_t* own;
   uint32_t* peer[8];
-  uint32_t rank, world, epoch;
+  uint32_t rank, world;
 };
+// flags[0..7] = last epoch each rank announced to this GPU, flags[8] = time-out marker, flags[9] = this GPU's
+// own epoch counter. The epoch lives on the device so that the launch has no per-call argument and a recorded
+// frame graph can replay it; all ranks call the barrier equally often, so their counters advance in lock step.
 __global__ void peer_barrier_kernel(BarrierArgs a) {
   const uint32_t t = threadIdx.x;
+  uint32_t epoch = 0;
+  if (t == 0) { epoch = a.own[9] + 1u; a.own[9] = epoch; }
+  epoch = __shfl_sync(0xffffffffu, epoch, 0);
   const bool active = t < a.world && t != a.rank;
   __threadfence_system();
-  if (active) *reinterpret_cast<volatile uint32_t*>(a.peer[t] + a.rank) = a.epoch;
+  if (active) *reinterpret_cast<volatile uint32_t*>(a.peer[t] + a.rank) = epoch;
   __syncwarp(); // all announcements are on their way before anybody starts to wait
   if (!active) return;
   const long long t0 = clock64();
-  while ((int32_t)(*reinterpret_cast<volatile uint32_t*>(a.own + t) - a.epoch) < 0) {
+  while ((int32_t)(*reinterpret_cast<volatile uint32_t*>(a.own + t) - epoch) < 0) {
     if (clock64() - t0 > 8000000000ll) { // ~4 s at 2 GHz: a peer died; do not hang the GPU
-      a.own[8] = a.epoch;
+      a.own[8] = epoch;
       break;
     }
   }
@@ -953,7 +985,6 @@ drv_status drv_impl_peer_barrier(drv_ctx* ctx) {
     a.peer[r] = r == ctx->shard_rank ? ctx->sync_flags : reinterpret_cast<uint32_t*>((uint8_t*)ctx->peer_entries[r] + off);
   a.rank = ctx->shard_rank;
   a.world = ctx->shard_world;
-  a.epoch = ++ctx->barrier_epoch;
   peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(a);
   DRV_LAUNCH_CHECK();
   return DRV_OK;
@@ -999,13 +1030,14 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   }
   const int order = (int)ctx->cfg.sh_order;
   const uint32_t variant = ctx->cfg.gather_variant & 0xFFu; // bits 8.. tune other kernels
-  int tile = 0;
-  const GatherFn kernel = shadow ? select_kernel<true>(order, variant, &tile) : select_kernel<false>(order, variant, &tile);
+  int tile = 0, threads = kThreads;
+  const GatherFn kernel = shadow ? select_kernel<true>(order, variant, &tile, &threads)
+                                 : select_kernel<false>(order, variant, &tile, &threads);
   p.chunk_first = 0;
   p.chunk_cap = 0xFFFFFFFFu;
   if (!shadow) {
     ctx->stage_begin(DRV_STAGE_GATHER_KERNEL);
-    drv_status st = launch_gather(ctx, kernel, p, tile, order);
+    drv_status st = launch_gather(ctx, kernel, p, tile, order, threads);
     ctx->stage_end(DRV_STAGE_GATHER_KERNEL);
     return st;
   }
@@ -1058,7 +1090,7 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
     c.chunk_cap = p.chunk_cap = chunk;
     cone_kernel<<<cone_grid, kConeThreads, 0, ctx->stream>>>(c);
     DRV_LAUNCH_CHECK();
-    drv_status st = launch_gather(ctx, kernel, p, tile, order);
+    drv_status st = launch_gather(ctx, kernel, p, tile, order, threads);
     if (st != DRV_OK) return st;
   }
   ctx->stage_end(DRV_STAGE_GATHER_KERNEL);

@@ -298,9 +298,12 @@ drv_status drv_draw(drv_ctx* ctx, void* hdr_out, uint32_t format);
  *   DRV_FRAME_GRAPH        record the frame into a CUDA graph and replay it while nothing that feeds a kernel
  *                          argument changes (uniform blocks, bindings, shard, hdr_out, format, flags); any
  *                          drv_set_* / drv_bind_* / drv_upload_* call makes the next frame re-record.
- *                          Ignored while stage timers are enabled. */
+ *                          Ignored while stage timers are enabled.
+ * With drv_set_shard + imported peers the frame is the sharded one: allocate (replicated) -> peer barrier ->
+ * gather of the own entry range, finished entries stored to every peer -> peer barrier -> apply. */
 #define DRV_FRAME_PREPARE_RSM 1u
 #define DRV_FRAME_GRAPH 2u
+#define DRV_FRAME_APPLY_OWN_ROWS 4u /* sharded runs: apply only this rank's band of rows, [rank*ceil(H/world), ...) */
 drv_status drv_draw_frame(drv_ctx* ctx, void* hdr_out, uint32_t format, uint32_t flags);
 
 /* VPLs the gather actually streams, per light: drv_light_caches drops VPLs whose flux is zero in all channels

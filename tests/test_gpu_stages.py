@@ -222,7 +222,7 @@ def _sweep_oracle(cb, pos, vpls_list, sh_order, fp64=False):
     return e
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3, 4, 12])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4, 7, 8, 12])
 @pytest.mark.parametrize("sh_order", [1, 2])
 @pytest.mark.parametrize("n_cache,n_vpl", [(1000, 4096), (70000, 1024), (37, 2500), (5000, 16384)])
 def test_gather_unshadowed_variants(cuda_device, variant, sh_order, n_cache, n_vpl):
@@ -363,7 +363,7 @@ def test_cone_trace_extremes(cuda_device):
     g.close()
 
 
-@pytest.mark.parametrize("variant", [0, 12])
+@pytest.mark.parametrize("variant", [0, 7, 8, 12])
 def test_shadowed_gather_variants_agree(cuda_device, variant):
     """Packed (default) and scalar pair kernels reading the same visibility table."""
     wl = workloads.atrium(width=320, height=180, rsm_res=64, read_lod=0, sh_order=2, indirect_shadow=True,

@@ -34,7 +34,20 @@ def _worker(rank, world, port, mode, out_dir):
     else:
         g.ctx.set_shard(rank, world)
     bctx = g.ctx if mode == "fused" else None  # "fused": flags in peer memory; otherwise an NCCL all-reduce
-    for it in range(2):  # twice: the second frame checks the cross-frame ordering of clears and peer stores
+    if mode == "fused_frame":
+        # drv_draw_frame on every rank: replicated allocation || light side, peer barriers, sharded gather with the
+        # fused all-gather, this rank's band of the apply pass; frames 1.. replay the recorded CUDA graph
+        flags = abi.DRV_FRAME_PREPARE_RSM | abi.DRV_FRAME_GRAPH | abi.DRV_FRAME_APPLY_OWN_ROWS
+        for it in range(4):
+            with torch.cuda.stream(stream):
+                g.ctx.voxelize(g.tris, None, 1.0)
+                g.out32.zero_()
+                g.ctx.draw_frame(g.out32, abi.DRV_HDR_RGBA32F_WRITE, flags)
+            torch.cuda.synchronize()
+        bands = [torch.zeros_like(g.out32) for _ in range(world)]
+        dist.all_gather(bands, g.out32)
+        g.out32.copy_(sum(bands))  # bands are disjoint, the rest of every image is zero
+    for it in range(0 if mode == "fused_frame" else 2):  # twice: the second frame checks the cross-frame ordering of clears and peer stores
         with torch.cuda.stream(stream):
             g.prepare_inputs()
             g.ctx.allocate_caches()
@@ -55,7 +68,7 @@ def _worker(rank, world, port, mode, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["fused", "fused_nccl_barrier", "nccl"])
+@pytest.mark.parametrize("mode", ["fused", "fused_nccl_barrier", "nccl", "fused_frame"])
 def test_sharded_gather_matches_oracle(tmp_path, mode):
     import torch
     import torch.multiprocessing as mp
