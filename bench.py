@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps (profiling runs)")
     ap.add_argument("--no-microbench", action="store_true")
     ap.add_argument("--stages", action="store_true", help="print the per-stage table to stderr")
+    ap.add_argument("--image-gather", choices=["p2p", "nccl"], default="p2p",
+                    help="sharded runs: image bands stored into rank 0's target over NVLink by the apply kernel (p2p) or gathered with NCCL")
     ap.add_argument("--no-scaling-workload", action="store_true",
                     help="skip the short run of BASELINE configs[3] (the multi-GPU scaling workload) after the metric's workload")
     ap.add_argument("--no-graph", action="store_true", help="issue the frame kernel by kernel instead of replaying its CUDA graph")
@@ -298,6 +300,8 @@ def measure(args, config_index, n_steps, n_warmup, light):
         for r, h in enumerate(handles):
             if r != rank:
                 ctx.import_peer_entries(r, h)
+        from dynamicradiancevolume_b200 import sharding
+        sharding.connect_image_gather(ctx, rank, world)  # rank 0's RGBA16F target, mapped by every peer
 
     def xbarrier():
         if args.barrier == "peer":
@@ -306,10 +310,14 @@ def measure(args, config_index, n_steps, n_warmup, light):
             dist.all_reduce(barrier_word)
 
     frame_flags = abi.DRV_FRAME_PREPARE_RSM | (0 if args.no_graph else abi.DRV_FRAME_GRAPH)
+    in_frame = not args.serial and (world == 1 or args.barrier == "peer")
+    if wl.indirect_shadow and in_frame:
+        ctx.bind_scene(g.tris, None, 1.0)  # VoxelizeScene runs inside drv_draw_frame, on its own stream
+        frame_flags |= abi.DRV_FRAME_VOXELIZE
 
     def frame_device():
         with torch.cuda.stream(stream):
-            if wl.indirect_shadow:
+            if wl.indirect_shadow and not in_frame:
                 ctx.voxelize(g.tris, None, 1.0)
             if world == 1 and not args.serial:
                 # one call: (RSM mips + VPLs) || allocate -> gather -> apply; the glClear of the HDR target
@@ -321,8 +329,12 @@ def measure(args, config_index, n_steps, n_warmup, light):
                 # the same call on every rank: allocation replicated, peer barrier, own shard of the gather with
                 # the fused all-gather of finished entries, peer barrier, this rank's band of the apply pass;
                 # then the image bands are gathered on rank 0
-                ctx.draw_frame(hdr16, abi.DRV_HDR_RGBA16F_WRITE, frame_flags | abi.DRV_FRAME_APPLY_OWN_ROWS)
-                dist.gather(band_views[rank], band_views if rank == 0 else None, dst=0)
+                if args.image_gather == "p2p":
+                    # ... and every band is stored straight into rank 0's target over NVLink: no collective at all
+                    ctx.draw_frame(None, abi.DRV_HDR_RGBA16F_WRITE, frame_flags | abi.DRV_FRAME_GATHER_IMAGE)
+                else:
+                    ctx.draw_frame(hdr16, abi.DRV_HDR_RGBA16F_WRITE, frame_flags | abi.DRV_FRAME_APPLY_OWN_ROWS)
+                    dist.gather(band_views[rank], band_views if rank == 0 else None, dst=0)
                 return
             for i in range(len(g.rsms)):
                 ctx.prepare_rsm(i)
@@ -548,7 +560,7 @@ def measure(args, config_index, n_steps, n_warmup, light):
                    "pairs_per_frame": n_caches * wl.num_vpls,
                    "l2": "flushed between steps (512 MiB memset outside the event pairs)" if not args.no_flush else "not flushed",
                    "parallelism": "1 GPU" if world == 1 else "gather sharded over %d GPUs by cell-ordered entry range, "
-                                  "allocation replicated, fused P2P all-gather of SH, apply row-sharded + NCCL gather of the image" % world,
+                                  "allocation replicated, fused P2P all-gather of SH, apply row-sharded, image bands %s" % (world, "stored into rank 0's target over NVLink (no collective in the frame)" if (args.image_gather == "p2p" and args.barrier == "peer" and not args.serial) else "gathered on rank 0 with NCCL"),
                    "gather_variant": args.variant},
         "e2e": {"value": e2e_per_step, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
@@ -561,7 +573,7 @@ def measure(args, config_index, n_steps, n_warmup, light):
                          "events around every stage (%.4f ms/frame that way); stages of the light side and the camera "
                          "side overlap" % (sum(inst_ms) / max(len(inst_ms), 1)),
         "frame_issue": ("serial: prepare_rsm, clear, drv_draw" if (args.serial or (world > 1 and args.barrier != "peer")) else
-                        "drv_draw_frame: (RSM mips + VPLs) || allocate -> gather -> apply(+clear)%s"
+                        "drv_draw_frame: (RSM mips + VPLs) || [voxelise] || allocate -> gather -> apply(+clear)%s"
                         % ("" if args.no_graph else ", CUDA graph replay")),
         "microbench": micro,
         "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,

@@ -40,6 +40,9 @@ SYMBOLS = [
     ("drv_draw", _st, [_P, _P, _u32]),
     ("drv_draw_frame", _st, [_P, _P, _u32, _u32]),
     ("drv_live_vpl_counts", _st, [_P, _P]),
+    ("drv_bind_scene", _st, [_P, _P, _u32, _P, C.c_float]),
+    ("drv_export_hdr_ipc", _st, [_P, _P]),
+    ("drv_import_peer_hdr", _st, [_P, _u32, _P]),
     ("drv_get_buffers", _st, [_P, C.POINTER(abi.Buffers)]),
     ("drv_rsm_level_offset", C.c_uint64, [_u32, _u32]),
     ("drv_voxel_level_offset", C.c_uint64, [_u32, _u32]),

@@ -29,6 +29,8 @@ DRV_HDR_RGBA16F_WRITE = 2
 DRV_FRAME_PREPARE_RSM = 1
 DRV_FRAME_GRAPH = 2
 DRV_FRAME_APPLY_OWN_ROWS = 4
+DRV_FRAME_GATHER_IMAGE = 8
+DRV_FRAME_VOXELIZE = 16
 
 STAGE_NAMES = ["VoxelizeScene", "VoxelBlendMipMap", "AllocateCaches", "LightCaches", "ApplyCaches",
                "PrepareRSM", "GatherKernel"]
@@ -123,6 +125,7 @@ class Buffers(C.Structure):
         ("vpls", C.c_void_p * DRV_MAX_LIGHTS), ("shadow_blocks", C.c_void_p * DRV_MAX_LIGHTS),
         ("rsm_flux_mips", C.c_void_p * DRV_MAX_LIGHTS), ("rsm_normal_mips", C.c_void_p * DRV_MAX_LIGHTS),
         ("rsm_depth_mips", C.c_void_p * DRV_MAX_LIGHTS),
+        ("hdr16", C.c_void_p),
     ]
 
 

@@ -140,9 +140,10 @@ extern "C" void drv_destroy(drv_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  if (ctx->peers_open)
-    for (int r = 0; r < 8; ++r)
-      if (ctx->peer_entries[r]) cudaIpcCloseMemHandle(ctx->peer_entries[r]);
+  for (int r = 0; r < 8; ++r) {
+    if (ctx->peer_entries[r]) cudaIpcCloseMemHandle(ctx->peer_entries[r]);
+    if (ctx->peer_hdr[r]) cudaIpcCloseMemHandle(ctx->peer_hdr[r]);
+  }
   cudaFree(ctx->entries); cudaFree(ctx->counter); cudaFree(ctx->stats); cudaFree(ctx->atlas);
   cudaFree(ctx->cell_flags); cudaFree(ctx->block_counts); cudaFree(ctx->voxel_chain); cudaFree(ctx->voxel_target); cudaFree(ctx->voxel_records);
   cudaFree(ctx->partials); cudaFree(ctx->shadow_table); cudaFree(ctx->st_depth); cudaFree(ctx->st_normal); cudaFree(ctx->st_diffuse);
@@ -159,6 +160,8 @@ extern "C" void drv_destroy(drv_ctx* ctx) {
   cudaFree(ctx->live_counts);
   if (ctx->frame_graph) cudaGraphExecDestroy(ctx->frame_graph);
   if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->side2) cudaStreamDestroy(ctx->side2);
+  if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
@@ -300,9 +303,20 @@ extern "C" drv_status drv_draw(drv_ctx* ctx, void* hdr_out, uint32_t format) {
 static drv_status frame_body(drv_ctx* ctx, void* hdr_out, uint32_t format, uint32_t flags) {
   cudaStream_t main_stream = ctx->stream;
   DRV_CUDA(cudaEventRecord(ctx->ev_fork, main_stream));
+  drv_status st = DRV_OK;
+  const bool vox = (flags & DRV_FRAME_VOXELIZE) && ctx->cfg.indirect_shadow;
+  if (vox) { // VoxelizeScene on its own stream
+    DRV_CUDA(cudaStreamWaitEvent(ctx->side2, ctx->ev_fork, 0));
+    ctx->stream = ctx->side2;
+    st = drv_impl_voxelize(ctx, ctx->scene_tris, ctx->scene_num_tris, ctx->scene_world, ctx->scene_adaption,
+                           DRV_VOXELIZE_CLEAR | DRV_VOXELIZE_FINISH);
+    cudaError_t e2 = cudaEventRecord(ctx->ev_join2, ctx->side2);
+    ctx->stream = main_stream;
+    if (st != DRV_OK) return st;
+    if (e2 != cudaSuccess) return ctx->fail(DRV_ERR_CUDA, "drv_draw_frame: event record failed");
+  }
   DRV_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
   ctx->stream = ctx->side; // the stage implementations launch on ctx->stream
-  drv_status st = DRV_OK;
   for (uint32_t l = 0; l < ctx->num_lights && st == DRV_OK; ++l) {
     if (ctx->lights[l].vpls_external) { st = drv_impl_compact_vpls(ctx, l); continue; }
     if (flags & DRV_FRAME_PREPARE_RSM) st = drv_impl_prepare_rsm(ctx, l);
@@ -318,27 +332,52 @@ static drv_status frame_body(drv_ctx* ctx, void* hdr_out, uint32_t format, uint3
   const bool sharded = ctx->shard_world > 1 && ctx->peers_open;
   if (sharded && (st = drv_impl_peer_barrier(ctx)) != DRV_OK) return st;
   DRV_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
+  if (vox) DRV_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join2, 0));
   ctx->stage_begin(DRV_STAGE_LIGHT_CACHES);
   st = drv_impl_gather(ctx);   // renderer.cpp:556
   ctx->stage_end(DRV_STAGE_LIGHT_CACHES);
   if (st != DRV_OK) return st;
   // ... and all peers' stores have landed before anybody applies
   if (sharded && (st = drv_impl_peer_barrier(ctx)) != DRV_OK) return st;
-  if (flags & DRV_FRAME_APPLY_OWN_ROWS) {
+  if (flags & (DRV_FRAME_APPLY_OWN_ROWS | DRV_FRAME_GATHER_IMAGE)) {
     const uint32_t H = ctx->cfg.backbuffer_height, band = (H + ctx->shard_world - 1) / ctx->shard_world;
     const uint32_t y0 = ctx->shard_rank * band, y1 = y0 + band < H ? y0 + band : H;
+    if (flags & DRV_FRAME_GATHER_IMAGE) {
+      // this rank's band goes straight into rank 0's target (NVLink stores from the apply kernel); the closing
+      // barrier orders them before anything rank 0 enqueues after the frame
+      void* target = ctx->shard_rank == 0 ? ctx->hdr16 : ctx->peer_hdr[0];
+      if (!sharded || !target || format != DRV_HDR_RGBA16F_WRITE)
+        return ctx->fail(DRV_ERR_NOT_BOUND, "drv_draw_frame: DRV_FRAME_GATHER_IMAGE needs a sharded context, rank 0's target "
+                                            "(drv_export_hdr_ipc / drv_import_peer_hdr) and DRV_HDR_RGBA16F_WRITE");
+      st = drv_impl_apply_rows(ctx, target, format, y0 < H ? y0 : H, y1, true);
+      if (st != DRV_OK) return st;
+      return drv_impl_peer_barrier(ctx);
+    }
     return drv_impl_apply_rows(ctx, hdr_out, format, y0 < H ? y0 : H, y1, true);
   }
   return drv_impl_apply(ctx, hdr_out, format); // renderer.cpp:570
 }
 
+extern "C" drv_status drv_bind_scene(drv_ctx* ctx, const float* tri_pos, uint32_t num_tris, const float world[16], float adaption) {
+  NEED_CTX();
+  MUTATES();
+  if ((num_tris && !tri_pos) || !world) return ctx->fail(DRV_ERR_INVALID, "drv_bind_scene: null argument");
+  ctx->scene_tris = tri_pos;
+  ctx->scene_num_tris = num_tris;
+  memcpy(ctx->scene_world, world, sizeof(ctx->scene_world));
+  ctx->scene_adaption = adaption;
+  return DRV_OK;
+}
+
 extern "C" drv_status drv_draw_frame(drv_ctx* ctx, void* hdr_out, uint32_t format, uint32_t flags) {
   NEED_CTX();
-  if (!hdr_out) return ctx->fail(DRV_ERR_INVALID, "drv_draw_frame: null output");
+  if (!hdr_out && !(flags & DRV_FRAME_GATHER_IMAGE)) return ctx->fail(DRV_ERR_INVALID, "drv_draw_frame: null output");
   if (!ctx->side) {
     DRV_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    DRV_CUDA(cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking));
     DRV_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     DRV_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    DRV_CUDA(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
   }
   const bool want_graph = (flags & DRV_FRAME_GRAPH) && !ctx->timers;
   if (!want_graph) {
@@ -408,6 +447,7 @@ extern "C" drv_status drv_get_buffers(drv_ctx* ctx, drv_buffers* out) {
     out->rsm_normal_mips[l] = ctx->lights[l].normal_mips;
     out->rsm_depth_mips[l] = ctx->lights[l].depth_mips;
   }
+  out->hdr16 = ctx->hdr16;
   return DRV_OK;
 }
 
@@ -496,6 +536,34 @@ extern "C" drv_status drv_import_peer_entries(drv_ctx* ctx, uint32_t peer_rank, 
   if (e != cudaSuccess) return ctx->fail(DRV_ERR_PEER, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
   ctx->peer_entries[peer_rank] = p;
   ctx->peers_open = true;
+  return DRV_OK;
+}
+
+extern "C" drv_status drv_export_hdr_ipc(drv_ctx* ctx, uint8_t handle[DRV_IPC_HANDLE_BYTES]) {
+  NEED_CTX();
+  MUTATES();
+  const size_t bytes = (size_t)ctx->cfg.backbuffer_width * ctx->cfg.backbuffer_height * 8;
+  if (!ctx->hdr16) {
+    DRV_CUDA(cudaMalloc(&ctx->hdr16, bytes));
+    DRV_CUDA(cudaMemsetAsync(ctx->hdr16, 0, bytes, ctx->stream));
+    DRV_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  cudaIpcMemHandle_t h;
+  DRV_CUDA(cudaIpcGetMemHandle(&h, ctx->hdr16));
+  memcpy(handle, &h, sizeof(h));
+  return DRV_OK;
+}
+
+extern "C" drv_status drv_import_peer_hdr(drv_ctx* ctx, uint32_t peer_rank, const uint8_t handle[DRV_IPC_HANDLE_BYTES]) {
+  NEED_CTX();
+  MUTATES();
+  if (peer_rank >= 8 || peer_rank == ctx->shard_rank) return ctx->fail(DRV_ERR_INVALID, "drv_import_peer_hdr: bad peer rank");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return ctx->fail(DRV_ERR_PEER, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+  ctx->peer_hdr[peer_rank] = p;
   return DRV_OK;
 }
 

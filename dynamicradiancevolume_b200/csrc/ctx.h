@@ -113,6 +113,7 @@ struct drv_ctx {
   uint64_t partial_slots = 0;        // capacity in cache slots
   uint32_t shard_rank = 0, shard_world = 1;
   void* peer_entries[8] = {nullptr};
+  void* peer_hdr[8] = {nullptr};     // peers' context-owned RGBA16F targets (only rank 0's is used)
   bool peers_open = false;
   // cross-GPU barrier flags live right behind the entries in the same allocation (one IPC handle maps both):
   // flags[r] = last epoch rank r has announced to this GPU; flags[8] = time-out marker
@@ -124,8 +125,12 @@ struct drv_ctx {
   cudaEvent_t ev_rsm[DRV_MAX_LIGHTS]{}, ev_depth = nullptr, ev_band_in[32]{}, ev_band_done[32]{}, ev_frame_start = nullptr;
 
   // drv_draw_frame: light-side stream, fork / join events, recorded frame graph
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side = nullptr, side2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+  const float* scene_tris = nullptr; // drv_bind_scene
+  uint32_t scene_num_tris = 0;
+  float scene_world[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  float scene_adaption = 1.0f;
   uint64_t state_gen = 1;            // bumped by every call that changes a kernel argument
   cudaGraphExec_t frame_graph = nullptr;
   uint64_t graph_gen = 0;            // state_gen the graph was recorded at

@@ -937,7 +937,10 @@ GatherFn select_kernel(int order, uint32_t variant, int* tile, int* threads) {
 #undef DRV_PICK
 }
 
-constexpr uint32_t kShadowChunk = 65536; // caches per visibility-table chunk
+// caches per visibility-table chunk: every chunk costs three launches whether it holds caches or not (the count
+// lives on the device), so chunks are as large as a table of at most kShadowTableBytes allows
+constexpr uint32_t kShadowChunk = 262144;
+constexpr size_t kShadowTableBytes = 6ull << 30;
 
 } // namespace
 
@@ -1066,7 +1069,8 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   c.vlevels = (int)ctx->voxel_levels;
   memcpy(c.vmin, ctx->volume.VolumeWorldMin, 12);
   c.voxel_size = ctx->volume.VoxelSizeInWorld;
-  const uint32_t chunk = std::min<uint32_t>(kShadowChunk, (ctx->cfg.max_cache_count + 255u) & ~255u);
+  uint32_t chunk = std::min<uint32_t>(kShadowChunk, (ctx->cfg.max_cache_count + 511u) & ~511u);
+  while (chunk > 8192 && (size_t)total_blocks * chunk * sizeof(float) > kShadowTableBytes) chunk = (chunk / 2 + 511u) & ~511u;
   const size_t table_floats = (size_t)total_blocks * chunk;
   if (table_floats > ctx->shadow_table_floats) {
     cudaStreamSynchronize(ctx->stream);

@@ -218,6 +218,13 @@ class Context:
     def apply_caches(self, out, fmt): self.check(self.lib.drv_apply_caches(self.handle, out.data_ptr(), fmt))
     def draw(self, out, fmt): self.check(self.lib.drv_draw(self.handle, out.data_ptr(), fmt))
 
+    def bind_scene(self, tris, world=None, adaption=1.0):
+        """Geometry for ``DRV_FRAME_VOXELIZE`` (``drv_bind_scene``); ``tris`` is a device tensor of n*9 floats."""
+        w = (C.c_float * 16)(*(world if world is not None else np.eye(4, dtype=np.float32).ravel().tolist()))
+        n = 0 if tris is None else tris.numel() // 9
+        self._keep_scene = tris
+        self.check(self.lib.drv_bind_scene(self.handle, None if tris is None else tris.data_ptr(), n, C.byref(w), adaption))
+
     def live_vpl_counts(self):
         """VPLs with non-zero flux per light — what the gather streams (``drv_live_vpl_counts``)."""
         a = (C.c_uint32 * 16)()
@@ -226,7 +233,7 @@ class Context:
 
     def draw_frame(self, out, fmt, flags=abi.DRV_FRAME_PREPARE_RSM):
         """Whole frame in GPU order (``drv_draw_frame``): light side || allocation, join, gather, apply."""
-        self.check(self.lib.drv_draw_frame(self.handle, out.data_ptr(), fmt, flags))
+        self.check(self.lib.drv_draw_frame(self.handle, None if out is None else out.data_ptr(), fmt, flags))
 
     def apply_caches_rows(self, out, fmt, y0, y1):
         self.check(self.lib.drv_apply_caches_rows(self.handle, out.data_ptr(), fmt, y0, y1))
@@ -289,6 +296,24 @@ class Context:
     def import_peer_entries(self, rank: int, handle: bytes):
         h = (C.c_uint8 * abi.DRV_IPC_HANDLE_BYTES)(*handle)
         self.check(self.lib.drv_import_peer_entries(self.handle, rank, C.byref(h)))
+
+    def export_hdr_ipc(self) -> bytes:
+        h = (C.c_uint8 * abi.DRV_IPC_HANDLE_BYTES)()
+        self.check(self.lib.drv_export_hdr_ipc(self.handle, C.byref(h)))
+        return bytes(h)
+
+    def import_peer_hdr(self, rank: int, handle: bytes):
+        h = (C.c_uint8 * abi.DRV_IPC_HANDLE_BYTES)(*handle)
+        self.check(self.lib.drv_import_peer_hdr(self.handle, rank, C.byref(h)))
+
+    def hdr16_tensor(self):
+        """The context-owned RGBA16F target as a torch tensor [H, W, 4] (rank 0's holds the gathered image)."""
+        import torch
+        b = self.buffers()
+        if not b.hdr16:
+            raise DrvError(abi.DRV_ERR_NOT_BOUND, "no context-owned HDR target yet")
+        w, h = self.cfg.backbuffer_width, self.cfg.backbuffer_height
+        return self.device_view(b.hdr16, w * h * 8).view(torch.float16).view(h, w, 4)
 
     # -- device -> host readback helpers (parity tests) --
     def device_view(self, ptr, nbytes):

@@ -43,6 +43,16 @@ def connect_peers(ctx, rank: int, world: int, group=None):
             ctx.import_peer_entries(r, h)
 
 
+def connect_image_gather(ctx, rank: int, world: int, group=None):
+    """Fused image gather set-up: rank 0 exports its context-owned RGBA16F target, everybody else maps it, so that
+    ``drv_draw_frame(..., DRV_FRAME_GATHER_IMAGE)`` can store every rank's band there over NVLink."""
+    import torch.distributed as dist
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.export_hdr_ipc() if rank == 0 else None, group=group)
+    if rank != 0:
+        ctx.import_peer_hdr(0, handles[0])
+
+
 def barrier(word, group=None, ctx=None):
     """Stream-ordered cross-GPU barrier. With ``ctx`` (peers connected): flags in NVLink peer memory
     (``drv_peer_barrier``, a few microseconds); otherwise an NCCL all-reduce of one int32 on the current stream."""

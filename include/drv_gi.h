@@ -303,8 +303,19 @@ drv_status drv_draw(drv_ctx* ctx, void* hdr_out, uint32_t format);
  * gather of the own entry range, finished entries stored to every peer -> peer barrier -> apply. */
 #define DRV_FRAME_PREPARE_RSM 1u
 #define DRV_FRAME_GRAPH 2u
+#define DRV_FRAME_VOXELIZE 16u      /* start the frame with VoxelizeScene (renderer.cpp:546: clear + raster + blend + mips)
+                                       of the geometry bound with drv_bind_scene, on its own stream, concurrently with
+                                       the light side and the allocation; joined before the gather */
 #define DRV_FRAME_APPLY_OWN_ROWS 4u /* sharded runs: apply only this rank's band of rows, [rank*ceil(H/world), ...) */
+#define DRV_FRAME_GATHER_IMAGE 8u   /* sharded runs (implies APPLY_OWN_ROWS; format DRV_HDR_RGBA16F_WRITE): every rank
+                                       stores its band straight into rank 0's context-owned RGBA16F target over NVLink
+                                       (drv_export_hdr_ipc / drv_import_peer_hdr) and a closing peer barrier makes the
+                                       image complete on rank 0 — the frame contains no collective. hdr_out is ignored;
+                                       the image is drv_buffers.hdr16 of rank 0. */
 drv_status drv_draw_frame(drv_ctx* ctx, void* hdr_out, uint32_t format, uint32_t flags);
+/* Geometry for DRV_FRAME_VOXELIZE: the arguments of drv_voxelize (device pointer to num_tris * 9 floats, borrowed
+ * until replaced; world matrix and adaption factor are copied). */
+drv_status drv_bind_scene(drv_ctx* ctx, const float* tri_pos, uint32_t num_tris, const float world[16], float adaption);
 
 /* VPLs the gather actually streams, per light: drv_light_caches drops VPLs whose flux is zero in all channels
  * (RSM texels that saw no surface; they add exactly zero to every cache) and keeps the order of the rest.
@@ -330,6 +341,7 @@ typedef struct drv_buffers {
   uint16_t* rsm_flux_mips[DRV_MAX_LIGHTS];
   int16_t*  rsm_normal_mips[DRV_MAX_LIGHTS];
   uint16_t* rsm_depth_mips[DRV_MAX_LIGHTS];
+  void*     hdr16;          /* context-owned RGBA16F target (drv_draw_to_host / DRV_FRAME_GATHER_IMAGE); NULL until used */
 } drv_buffers;
 drv_status drv_get_buffers(drv_ctx* ctx, drv_buffers* out);
 /* Texel offset of mip level `level` (>=1) inside a context-owned RSM mip
@@ -365,6 +377,10 @@ void drv_shard_range(uint32_t count, uint32_t rank, uint32_t world, uint32_t* be
 #define DRV_IPC_HANDLE_BYTES 64
 drv_status drv_export_entries_ipc(drv_ctx* ctx, uint8_t handle[DRV_IPC_HANDLE_BYTES]);
 drv_status drv_import_peer_entries(drv_ctx* ctx, uint32_t peer_rank, const uint8_t handle[DRV_IPC_HANDLE_BYTES]);
+
+/* Fused image gather: rank 0 exports its context-owned RGBA16F target, every other rank maps it. */
+drv_status drv_export_hdr_ipc(drv_ctx* ctx, uint8_t handle[DRV_IPC_HANDLE_BYTES]);
+drv_status drv_import_peer_hdr(drv_ctx* ctx, uint32_t peer_rank, const uint8_t handle[DRV_IPC_HANDLE_BYTES]);
 
 /* Stream-ordered barrier across the ranks of a sharded run, through flags in NVLink peer memory (no host
  * round trip, no NCCL call): work enqueued after it on this context's stream starts only when every rank's

@@ -145,7 +145,10 @@ def test_draw_frame_matches_serial_order(cuda_device, cfg):
     ref_entries = g.ctx.read_entries(n)
     out = torch.full((wl.height, wl.width, 4), 7.0, dtype=torch.float16, device="cuda")
     torch.cuda.synchronize()
-    for flags in (abi.DRV_FRAME_PREPARE_RSM, abi.DRV_FRAME_PREPARE_RSM | abi.DRV_FRAME_GRAPH):
+    g.ctx.bind_scene(g.tris, None, 1.0)
+    vox = abi.DRV_FRAME_VOXELIZE if wl.indirect_shadow else 0
+    for flags in (abi.DRV_FRAME_PREPARE_RSM, abi.DRV_FRAME_PREPARE_RSM | abi.DRV_FRAME_GRAPH,
+                  abi.DRV_FRAME_PREPARE_RSM | abi.DRV_FRAME_GRAPH | vox):
         for rep in range(4):  # graph mode: eager, record + replay, replay, replay
             out.fill_(7.0)
             torch.cuda.synchronize()

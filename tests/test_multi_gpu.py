@@ -47,6 +47,17 @@ def _worker(rank, world, port, mode, out_dir):
         bands = [torch.zeros_like(g.out32) for _ in range(world)]
         dist.all_gather(bands, g.out32)
         g.out32.copy_(sum(bands))  # bands are disjoint, the rest of every image is zero
+        # the same frame with the fused image gather: every rank's band lands in rank 0's RGBA16F target over NVLink
+        sharding.connect_image_gather(g.ctx, rank, world)
+        gflags = abi.DRV_FRAME_PREPARE_RSM | abi.DRV_FRAME_GRAPH | abi.DRV_FRAME_GATHER_IMAGE
+        for it in range(3):
+            with torch.cuda.stream(stream):
+                g.ctx.draw_frame(None, abi.DRV_HDR_RGBA16F_WRITE, gflags)
+            torch.cuda.synchronize()
+        if rank == 0:
+            got = g.ctx.hdr16_tensor().float()
+            want = g.out32[..., :3].half().float()
+            assert torch.equal(got[..., :3], want), "fused image gather differs from the banded apply"
     for it in range(0 if mode == "fused_frame" else 2):  # twice: the second frame checks the cross-frame ordering of clears and peer stores
         with torch.cuda.stream(stream):
             g.prepare_inputs()
