@@ -85,7 +85,7 @@ __device__ __forceinline__ Cell cache_cell(const AllocParams& p, F3 wp, int c) {
 
 // cacheGather.comp:32-91 with the index assignment deferred to the scan.
 __device__ __forceinline__ void mark_corners(const AllocParams& p, const Cell& cell, int c, uint8_t* __restrict__ flags,
-                                             uint32_t* __restrict__ stats) {
+                                             uint32_t* __restrict__ oob_accum) {
   const int R = p.R, R2 = R * R;
   uint8_t* f = flags + (uint32_t)(c * R2 * R + cell.x + cell.y * R + cell.z * R2);
   if (cell.x + 1 < R && cell.y + 1 < R && cell.z + 1 < R) {
@@ -102,12 +102,12 @@ __device__ __forceinline__ void mark_corners(const AllocParams& p, const Cell& c
     if (cell.x + ox >= R || cell.y + oy >= R || cell.z + oz >= R) { ++oob; continue; }
     f[ox + oy * R + oz * R2] = 1;
   }
-  atomicAdd(stats + 1, oob);
+  atomicAdd(oob_accum, oob);
 }
 
 __global__ void __launch_bounds__(256) mark_kernel(AllocParams p, const float* __restrict__ depth,
                                                    const float* __restrict__ ndc_xy, uint8_t* __restrict__ flags,
-                                                   uint32_t* __restrict__ stats) {
+                                                   uint32_t* __restrict__ oob_accum) {
   __shared__ int T1[16][17]; // [local x][local y] like cacheList[x][y]; padded against bank conflicts
   __shared__ int T2[16][17];
   const int lx = threadIdx.x, ly = threadIdx.y;
@@ -132,12 +132,12 @@ __global__ void __launch_bounds__(256) mark_kernel(AllocParams p, const float* _
   {
     int ax = max(0, lx - 1), ay = max(0, ly - 1);
     if (((T1[lx][ay] != own.id && T1[ax][ly] != own.id && T1[ax][ay] != own.id) || (ax == lx && ay == ly)) && own.id != -1)
-      mark_corners(p, own, casc, flags, stats);
+      mark_corners(p, own, casc, flags, oob_accum);
   }
   if (p.transitions) {
     int bx = min(15, lx + 1), by = min(15, ly + 1);
     if (((T2[lx][by] != own2.id && T2[bx][ly] != own2.id && T2[bx][by] != own2.id) || (bx == 15 && by == 15)) && own2.id != -1)
-      mark_corners(p, own2, casc + 1, flags, stats);
+      mark_corners(p, own2, casc + 1, flags, oob_accum);
   }
 }
 
@@ -146,82 +146,37 @@ __device__ __forceinline__ uint32_t nonzero_bytes(uint2 v) { // number of non-ze
   return (__popc(a) + __popc(b)) >> 3;
 }
 
-__global__ void __launch_bounds__(kScanThreads) count_kernel(const uint8_t* __restrict__ flags, uint32_t num_cells,
-                                                             uint32_t* __restrict__ block_counts) {
-  __shared__ uint32_t warp_sums[kScanThreads / 32];
-  uint32_t cell = (blockIdx.x * kScanThreads + threadIdx.x) * kCellsPerThread;
-  uint32_t n = 0;
-  if (cell < num_cells) n = nonzero_bytes(*reinterpret_cast<const uint2*>(flags + cell));
-  n = __reduce_add_sync(0xffffffffu, n);
-  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = n;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t s = 0;
-#pragma unroll
-    for (int i = 0; i < kScanThreads / 32; ++i) s += warp_sums[i];
-    block_counts[blockIdx.x] = s;
-  }
-}
-
-// One block. Exclusive scan of block_counts in place; writes the counter
-// (cachePrepareLighting.comp:8-14) and the overflow statistic.
-__global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t* __restrict__ block_counts, uint32_t num_blocks,
-                                                           uint32_t max_caches, drv_cache_counter* __restrict__ counter,
-                                                           uint32_t* __restrict__ stats) {
-  __shared__ uint32_t warp_tot[32];
-  __shared__ uint32_t carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (uint32_t base = 0; base < num_blocks; base += 1024) {
-    uint32_t i = base + threadIdx.x;
-    uint32_t v = i < num_blocks ? block_counts[i] : 0u;
-    uint32_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if ((threadIdx.x & 31) >= o) incl += t;
-    }
-    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      uint32_t w = warp_tot[threadIdx.x];
-      uint32_t wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-        if (threadIdx.x >= o) wi += t;
-      }
-      warp_tot[threadIdx.x] = wi - w; // exclusive
-    }
-    __syncthreads();
-    uint32_t carry = carry_s;
-    uint32_t excl = carry + warp_tot[threadIdx.x >> 5] + incl - v;
-    if (i < num_blocks) block_counts[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = excl + v;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    uint32_t total = carry_s;
-    uint32_t n = total > max_caches ? max_caches : total; // clamp, report
-    stats[0] = total - n;
-    counter->NumCacheLightingThreadGroupsX = (n + DRV_LIGHTING_THREADS_PER_GROUP - 1) / DRV_LIGHTING_THREADS_PER_GROUP;
-    counter->NumCacheLightingThreadGroupsY = 1;
-    counter->NumCacheLightingThreadGroupsZ = 1;
-    counter->TotalLightCacheCount = (int)n;
-  }
-}
+// ---- scan + compact in one pass ---------------------------------------------------------------------------
+// Every block counts the flagged cells of its 2048-cell slice, publishes the count, obtains the number of
+// flagged cells in all earlier slices by decoupled look-back over the published states (aggregate / inclusive
+// prefix), and writes its atlas texels and entries — count, scan and compact of the classic three-kernel scheme
+// in one launch. State words carry a frame epoch kept on the device (so a recorded frame graph replays without
+// per-launch arguments, and nothing needs clearing): a word from the previous frame is simply "not yet there".
+// The kernel also zeroes the flags it has consumed (the next frame's mark kernel starts from a clean slate
+// without a memset) and moves the out-of-range-corner statistic out of its accumulator.
+struct ScanState {
+  unsigned long long* words; // per block: value | (epoch << 2 | flag) << 32
+  uint32_t* epoch;           // [0] epoch of the current frame, [1] blocks done
+  uint32_t* oob_accum;       // mark_kernel's accumulator
+};
+constexpr uint32_t kFlagAggregate = 1u, kFlagPrefix = 2u;
 
 template <int STRIDE>
-__global__ void __launch_bounds__(kScanThreads) compact_kernel(AllocParams p, const uint8_t* __restrict__ flags,
-                                                               uint32_t num_cells,
-                                                               const uint32_t* __restrict__ block_offsets,
-                                                               uint32_t max_caches, uint32_t* __restrict__ atlas,
-                                                               uint8_t* __restrict__ entries) {
+__global__ void __launch_bounds__(kScanThreads) scan_compact_kernel(AllocParams p, uint8_t* __restrict__ flags,
+                                                                    uint32_t num_cells, ScanState st, uint32_t max_caches,
+                                                                    uint32_t* __restrict__ atlas, uint8_t* __restrict__ entries,
+                                                                    drv_cache_counter* __restrict__ counter,
+                                                                    uint32_t* __restrict__ stats) {
   __shared__ uint32_t warp_tot[kScanThreads / 32];
+  __shared__ uint32_t s_prefix;
+  const uint32_t epoch_raw = *reinterpret_cast<volatile uint32_t*>(st.epoch);
+  const uint32_t epoch = epoch_raw & 0x3FFFFFFFu; // 30 bits fit beside the 2 flag bits
   const uint32_t cell0 = (blockIdx.x * kScanThreads + threadIdx.x) * kCellsPerThread;
   uint2 f = make_uint2(0u, 0u);
-  if (cell0 < num_cells) f = *reinterpret_cast<const uint2*>(flags + cell0);
+  if (cell0 < num_cells) {
+    f = *reinterpret_cast<const uint2*>(flags + cell0);
+    if (f.x | f.y) *reinterpret_cast<uint2*>(flags + cell0) = make_uint2(0u, 0u); // consumed
+  }
   const uint32_t mine = nonzero_bytes(f);
   uint32_t incl = mine;
 #pragma unroll
@@ -231,11 +186,66 @@ __global__ void __launch_bounds__(kScanThreads) compact_kernel(AllocParams p, co
   }
   if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
   __syncthreads();
-  uint32_t warp_base = 0;
+  uint32_t warp_base = 0, block_total = 0;
 #pragma unroll
-  for (int w = 0; w < kScanThreads / 32; ++w)
+  for (int w = 0; w < kScanThreads / 32; ++w) {
     if (w < (int)(threadIdx.x >> 5)) warp_base += warp_tot[w];
-  uint32_t index = block_offsets[blockIdx.x] + warp_base + incl - mine;
+    block_total += warp_tot[w];
+  }
+  // publish, then look back (warp 0)
+  if (threadIdx.x < 32) {
+    volatile unsigned long long* W = st.words;
+    const unsigned long long tag = (unsigned long long)(epoch << 2) << 32;
+    if (threadIdx.x == 0) {
+      const uint32_t flag = blockIdx.x == 0 ? kFlagPrefix : kFlagAggregate;
+      W[blockIdx.x] = (unsigned long long)block_total | tag | ((unsigned long long)flag << 32);
+    }
+    uint32_t prefix = 0;
+    int base = (int)blockIdx.x - 1; // nearest predecessor
+    bool done = false;
+    while (base >= 0 && !done) {    // windows of 32 predecessors, lane 0 = the nearest one
+      const int i = base - (int)threadIdx.x;
+      uint32_t flag = kFlagPrefix, val = 0; // below block 0 there is nothing: an inclusive prefix of 0
+      if (i >= 0) {
+        unsigned long long w;
+        do { w = W[i]; } while ((uint32_t)(w >> 34) != epoch || ((uint32_t)(w >> 32) & 3u) == 0u);
+        flag = (uint32_t)(w >> 32) & 3u;
+        val = (uint32_t)w;
+      }
+      const uint32_t pm = __ballot_sync(0xffffffffu, flag == kFlagPrefix);
+      const int first = __ffs(pm) - 1; // nearest lane holding an inclusive prefix (-1: none in this window)
+      const uint32_t take = (first < 0 || (int)threadIdx.x <= first) ? val : 0u;
+      prefix += __reduce_add_sync(0xffffffffu, take);
+      if (first >= 0) done = true; else base -= 32;
+    }
+    if (threadIdx.x == 0) {
+      if (blockIdx.x != 0)
+        W[blockIdx.x] = (unsigned long long)(prefix + block_total) | tag | ((unsigned long long)kFlagPrefix << 32);
+      s_prefix = prefix;
+    }
+  }
+  __syncthreads();
+  uint32_t index = s_prefix + warp_base + incl - mine;
+
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { // the last slice knows the total: cachePrepareLighting.comp:8-14
+    const uint32_t total = s_prefix + block_total;
+    const uint32_t n = total > max_caches ? max_caches : total; // clamp, report
+    stats[0] = total - n;
+    counter->NumCacheLightingThreadGroupsX = (n + DRV_LIGHTING_THREADS_PER_GROUP - 1) / DRV_LIGHTING_THREADS_PER_GROUP;
+    counter->NumCacheLightingThreadGroupsY = 1;
+    counter->NumCacheLightingThreadGroupsZ = 1;
+    counter->TotalLightCacheCount = (int)n;
+  }
+  if (threadIdx.x == 0) { // frame bookkeeping: the block that finishes last opens the next epoch
+    __threadfence();
+    if (atomicAdd(st.epoch + 1, 1u) == gridDim.x - 1) {
+      stats[1] = *st.oob_accum;
+      *st.oob_accum = 0u;
+      st.epoch[1] = 0u;
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(st.epoch) = (epoch_raw + 1u) == 0u ? 1u : epoch_raw + 1u;
+    }
+  }
   if (cell0 >= num_cells) return;
 
   const int R = p.R, R2 = R * R, R3 = R2 * R;
@@ -321,24 +331,21 @@ drv_status drv_impl_allocate(drv_ctx* ctx) {
   }
 
   ctx->stage_begin(DRV_STAGE_ALLOCATE_CACHES);
-  // ≙ m_lightCacheCounter->ClearToZero(); the atlas clear (renderer.cpp:969-970) is folded into compact
-  DRV_CUDA(cudaMemsetAsync(ctx->cell_flags, 0, ctx->num_cells, ctx->stream));
-  DRV_CUDA(cudaMemsetAsync(ctx->stats, 0, 2 * sizeof(uint32_t), ctx->stream));
+  // ≙ m_lightCacheCounter->ClearToZero() and the atlas clear (renderer.cpp:969-970): both folded into the
+  // scan + compact kernel, which also leaves the cell flags zeroed for the next frame — no memset in the frame
   dim3 grid((p.W + 15) / 16, (p.H + 15) / 16); // renderer.cpp:981-985
-  mark_kernel<<<grid, dim3(16, 16), 0, ctx->stream>>>(p, ctx->gb_depth, ctx->ndc_xy, ctx->cell_flags, ctx->stats);
+  mark_kernel<<<grid, dim3(16, 16), 0, ctx->stream>>>(p, ctx->gb_depth, ctx->ndc_xy, ctx->cell_flags, ctx->scan_epoch + 2);
   DRV_LAUNCH_CHECK();
-  count_kernel<<<ctx->num_scan_blocks, kScanThreads, 0, ctx->stream>>>(ctx->cell_flags, ctx->num_cells,
-                                                                      ctx->block_counts);
-  DRV_LAUNCH_CHECK();
-  scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->block_counts, ctx->num_scan_blocks, ctx->cfg.max_cache_count,
-                                                  ctx->counter, ctx->stats);
-  DRV_LAUNCH_CHECK();
+  ScanState st;
+  st.words = ctx->scan_words;
+  st.epoch = ctx->scan_epoch;
+  st.oob_accum = ctx->scan_epoch + 2;
   if (ctx->entry_stride == 64)
-    compact_kernel<64><<<ctx->num_scan_blocks, kScanThreads, 0, ctx->stream>>>(
-        p, ctx->cell_flags, ctx->num_cells, ctx->block_counts, ctx->cfg.max_cache_count, ctx->atlas, ctx->entries);
+    scan_compact_kernel<64><<<ctx->num_scan_blocks, kScanThreads, 0, ctx->stream>>>(
+        p, ctx->cell_flags, ctx->num_cells, st, ctx->cfg.max_cache_count, ctx->atlas, ctx->entries, ctx->counter, ctx->stats);
   else
-    compact_kernel<128><<<ctx->num_scan_blocks, kScanThreads, 0, ctx->stream>>>(
-        p, ctx->cell_flags, ctx->num_cells, ctx->block_counts, ctx->cfg.max_cache_count, ctx->atlas, ctx->entries);
+    scan_compact_kernel<128><<<ctx->num_scan_blocks, kScanThreads, 0, ctx->stream>>>(
+        p, ctx->cell_flags, ctx->num_cells, st, ctx->cfg.max_cache_count, ctx->atlas, ctx->entries, ctx->counter, ctx->stats);
   DRV_LAUNCH_CHECK();
   ctx->stage_end(DRV_STAGE_ALLOCATE_CACHES);
   return DRV_OK;

@@ -87,9 +87,18 @@ extern "C" drv_status drv_create(const drv_config* cfg, drv_ctx** out) {
   ctx->num_cells = c.cav_cascades * c.cav_resolution * c.cav_resolution * c.cav_resolution;
   CREATE_CUDA(dmalloc(&ctx->atlas, (size_t)ctx->num_cells * sizeof(uint32_t))); // renderer.cpp:1179
   CREATE_CUDA(cudaMemsetAsync(ctx->atlas, 0, (size_t)ctx->num_cells * sizeof(uint32_t), ctx->stream));
-  CREATE_CUDA(dmalloc(&ctx->cell_flags, ctx->num_cells));
+  CREATE_CUDA(dmalloc(&ctx->cell_flags, ctx->num_cells + 16));
+  CREATE_CUDA(cudaMemsetAsync(ctx->cell_flags, 0, ctx->num_cells + 16, ctx->stream));
   ctx->num_scan_blocks = (ctx->num_cells + 2047) / 2048;
   CREATE_CUDA(dmalloc(&ctx->block_counts, (size_t)ctx->num_scan_blocks * sizeof(uint32_t)));
+  CREATE_CUDA(dmalloc(&ctx->scan_words, (size_t)ctx->num_scan_blocks * sizeof(unsigned long long)));
+  CREATE_CUDA(cudaMemsetAsync(ctx->scan_words, 0, (size_t)ctx->num_scan_blocks * sizeof(unsigned long long), ctx->stream));
+  CREATE_CUDA(dmalloc(&ctx->scan_epoch, 4 * sizeof(uint32_t)));
+  {
+    const uint32_t init[4] = {1u, 0u, 0u, 0u};
+    CREATE_CUDA(cudaMemcpyAsync(ctx->scan_epoch, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    CREATE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
 
   // voxel volumes (voxelization.cpp:56-66): target (1 level) + persistent (full chain)
   const uint32_t vr = c.voxel_resolution;
@@ -145,7 +154,7 @@ extern "C" void drv_destroy(drv_ctx* ctx) {
     if (ctx->peer_hdr[r]) cudaIpcCloseMemHandle(ctx->peer_hdr[r]);
   }
   cudaFree(ctx->entries); cudaFree(ctx->counter); cudaFree(ctx->stats); cudaFree(ctx->atlas);
-  cudaFree(ctx->cell_flags); cudaFree(ctx->block_counts); cudaFree(ctx->voxel_chain); cudaFree(ctx->voxel_target); cudaFree(ctx->voxel_records);
+  cudaFree(ctx->cell_flags); cudaFree(ctx->block_counts); cudaFree(ctx->scan_words); cudaFree(ctx->scan_epoch); cudaFree(ctx->voxel_chain); cudaFree(ctx->voxel_target); cudaFree(ctx->voxel_records);
   cudaFree(ctx->partials); cudaFree(ctx->shadow_table); cudaFree(ctx->st_depth); cudaFree(ctx->st_normal); cudaFree(ctx->st_diffuse);
   cudaFree(ctx->hdr16); cudaFree(ctx->ndc_xy);
   for (auto& S : ctx->lights) {
@@ -319,7 +328,7 @@ static drv_status frame_body(drv_ctx* ctx, void* hdr_out, uint32_t format, uint3
   ctx->stream = ctx->side; // the stage implementations launch on ctx->stream
   for (uint32_t l = 0; l < ctx->num_lights && st == DRV_OK; ++l) {
     if (ctx->lights[l].vpls_external) { st = drv_impl_compact_vpls(ctx, l); continue; }
-    if (flags & DRV_FRAME_PREPARE_RSM) st = drv_impl_prepare_rsm(ctx, l);
+    if (flags & DRV_FRAME_PREPARE_RSM) st = drv_impl_prepare_rsm(ctx, l, true);
     if (st == DRV_OK) st = drv_impl_generate_vpls(ctx, l);
   }
   cudaError_t e = cudaEventRecord(ctx->ev_join, ctx->side);

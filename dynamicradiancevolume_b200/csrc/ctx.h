@@ -91,6 +91,8 @@ struct drv_ctx {
   uint32_t* atlas = nullptr;
   uint8_t* cell_flags = nullptr;     // one byte per CAV cell, linear-cell-id order
   uint32_t* block_counts = nullptr;
+  unsigned long long* scan_words = nullptr; // decoupled look-back states of the scan + compact kernel
+  uint32_t* scan_epoch = nullptr;           // [0] frame epoch (starts at 1), [1] blocks done, [2] oob-corner accumulator
   uint32_t num_cells = 0, num_scan_blocks = 0;
 
   // voxels
@@ -158,9 +160,9 @@ struct drv_ctx {
 
 // stage implementations (one .cu each)
 drv_status drv_impl_allocate(drv_ctx* ctx);
-drv_status drv_impl_prepare_rsm(drv_ctx* ctx, uint32_t light);
+drv_status drv_impl_prepare_rsm(drv_ctx* ctx, uint32_t light, bool only_consumed = false);
 drv_status drv_impl_generate_vpls(drv_ctx* ctx, uint32_t light);
-drv_status drv_impl_compact_vpls(drv_ctx* ctx, uint32_t light);
+drv_status drv_impl_compact_vpls(drv_ctx* ctx, uint32_t light, bool counted = false);
 drv_status drv_impl_gather(drv_ctx* ctx);
 drv_status drv_impl_apply(drv_ctx* ctx, void* out, uint32_t format);
 drv_status drv_impl_apply_rows(drv_ctx* ctx, void* out, uint32_t format, uint32_t y_begin, uint32_t y_end, bool timed);

@@ -35,9 +35,12 @@
 #include "ctx.h"
 #include "device_math.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 using namespace drvk;
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -62,6 +65,7 @@ struct GatherParams {
   float* partials;       // [cta][2][coef][tile cache] floats
   uint32_t shard_rank, shard_world;
   uint32_t grid;         // CTAs of the gather launch (the finalize kernel needs it too)
+  uint32_t fused_finalize; // 1: cooperative launch — the gather kernel adds the partial segments itself after a grid barrier
   float f0, f1, f2, f20, f22;
   // indirect shadows: the visibility table written by cone_kernel for the current chunk of caches,
   // table[(block_offset[light] + k / interval) * shadow_stride + chunk-local cache index]
@@ -554,6 +558,96 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                : "memory");
 }
 
+// ------------------------------------------------------------ finalize: add the partial segments in VPL order
+// One block per 32 consecutive caches of a tile (block-stride loop: the cache count lives on the device).
+// The CTAs that own pieces of the tile are the same for all 32 caches, so their list is derived once per
+// chunk. Thread (y, x) then sums, for cache x, all coefficients over the owners y, y + 8, y + 16, ... — every
+// load of a thread is independent, so a tile split between ~25 CTAs costs one or two L2 round trips instead of
+// a serial chain — and the eight slices are added in a fixed order through shared memory (deterministic — no
+// float atomics). 32 threads apply the SH factors and add the result into the entries with 128-bit accesses
+// (+ the peer stores of the fused all-gather).
+constexpr int kFinChunk = 32;
+
+template <int ORDER, int NTHREADS>
+struct FinalizeSmem {
+  static constexpr int SLICES = NTHREADS / kFinChunk;
+  float part[SLICES][num_coefs<ORDER>()][kFinChunk];
+  uint32_t list[NTHREADS];
+};
+
+// `first_block` / `num_blocks`: this block's index and the number of blocks that share the chunk loop.
+template <int ORDER, int NTHREADS>
+__device__ __forceinline__ void finalize_phase(const GatherParams& p, int tile_caches, FinalizeSmem<ORDER, NTHREADS>& sm,
+                                               uint32_t first_block, uint32_t num_blocks) {
+  constexpr int NC = num_coefs<ORDER>();
+  constexpr int SLICES = NTHREADS / kFinChunk;
+  static_assert(NTHREADS % kFinChunk == 0 && SLICES >= 1, "one cache per lane, NTHREADS / 32 owner slices");
+  const Schedule S = make_schedule(p, tile_caches);
+  if (S.units == 0) return;
+  const uint32_t G = p.grid;
+  const uint32_t chunks = (S.count + kFinChunk - 1) / kFinChunk;
+  const uint32_t x = threadIdx.x % kFinChunk, y = threadIdx.x / kFinChunk;
+  for (uint32_t chunk = first_block; chunk < chunks; chunk += num_blocks) {
+    const uint32_t local0 = chunk * kFinChunk;
+    const uint32_t tile = local0 / tile_caches, in_tile0 = local0 - tile * tile_caches;
+    const unsigned long long ua = (unsigned long long)tile * S.units_per_tile, ub = ua + S.units_per_tile;
+    const uint32_t c_lo = owner_of(S, G, ua), c_hi = owner_of(S, G, ub - 1);
+    if (c_lo == c_hi) continue; // one CTA covered the whole tile and already wrote it (block-uniform)
+    float acc[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) acc[q] = 0.0f;
+    for (uint32_t cbase = c_lo; cbase <= c_hi; cbase += NTHREADS) {
+      const uint32_t c = cbase + threadIdx.x;
+      uint32_t entry = 0xFFFFFFFFu;
+      if (c <= c_hi) {
+        const unsigned long long cb = range_begin(S, G, c), ce = range_begin(S, G, c + 1);
+        // slot 0 = the CTA's range starts inside this tile (only c_lo can start before it)
+        if (cb < ce) entry = c * 2u + (cb >= ua ? 0u : 1u);
+      }
+      __syncthreads(); // the previous batch has been consumed
+      sm.list[threadIdx.x] = entry;
+      __syncthreads();
+      const int cnt = (int)min((uint32_t)NTHREADS, c_hi - cbase + 1u);
+#pragma unroll 2
+      for (int i = (int)y; i < cnt; i += SLICES) {
+        const uint32_t e = sm.list[i];
+        if (e == 0xFFFFFFFFu) continue;
+        const float* src = p.partials + (size_t)e * NC * tile_caches + in_tile0 + x;
+#pragma unroll
+        for (int q = 0; q < NC; ++q) acc[q] += __ldcg(src + (size_t)q * tile_caches);
+      }
+    }
+    __syncthreads(); // previous chunk's readers are done with sm.part
+#pragma unroll
+    for (int q = 0; q < NC; ++q) sm.part[y][q][x] = acc[q];
+    __syncthreads();
+    // slice-sum in ascending slice order: item = (coefficient, cache)
+    for (int item = threadIdx.x; item < NC * kFinChunk; item += NTHREADS) {
+      const int q = item / kFinChunk, cx = item % kFinChunk;
+      float v = sm.part[0][q][cx];
+#pragma unroll
+      for (int sl = 1; sl < SLICES; ++sl) v += sm.part[sl][q][cx];
+      sm.part[0][q][cx] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kFinChunk && local0 + threadIdx.x < S.count) {
+      float raw[27];
+#pragma unroll
+      for (int q = 0; q < 27; ++q) raw[q] = q < NC ? sm.part[0][q < NC ? q : 0][threadIdx.x] : 0.0f;
+      float vals[28];
+      coef_values<ORDER>(p, raw, vals);
+      add_to_entry<ORDER>(p, S.first + local0 + threadIdx.x, vals);
+    }
+  }
+}
+
+constexpr int kFinThreads = 256;
+template <int ORDER>
+__global__ void __launch_bounds__(kFinThreads) gather_finalize_kernel(GatherParams p, int tile_caches) {
+  __shared__ FinalizeSmem<ORDER, kFinThreads> sm;
+  finalize_phase<ORDER, kFinThreads>(p, tile_caches, sm, blockIdx.x, gridDim.x);
+}
+
 // ------------------------------------------------------------ the gather kernel
 // A cursor over the shared-memory tiles of a CTA's unit range: runs of
 // consecutive units that share (cache tile, light) are contiguous VPL ranges.
@@ -591,8 +685,8 @@ __device__ __forceinline__ void advance(const GatherParams& p, const Schedule& S
 }
 
 // SHADOW: every pair is scaled by the visibility of its (cache, VAL block), read from the table cone_kernel wrote.
-template <int ORDER, bool SHADOW, typename Math, bool USE_TMA, int MINB = 1, int NT = kThreads>
-__global__ void __launch_bounds__(NT, MINB) gather_kernel(const __grid_constant__ GatherParams p) {
+template <int ORDER, bool SHADOW, typename Math, bool USE_TMA, int NT>
+__device__ __forceinline__ void gather_main(const GatherParams& p) {
   constexpr int CPT = Math::CPT;
   constexpr int TILE = NT * CPT;
   constexpr int kVplTile = NT; // VPLs staged per shared-memory tile: one per thread
@@ -729,6 +823,19 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(const __grid_constant_
   }
 }
 
+// The kernel: the pair loop over this CTA's unit range and — when launched cooperatively (fused_finalize) — after a
+// grid-wide barrier the addition of the partial segments by all CTAs together (the finalize pass without a second
+// launch, its prologue and the launch gap; every CTA of the persistent grid is resident by construction).
+template <int ORDER, bool SHADOW, typename Math, bool USE_TMA, int MINB = 1, int NT = kThreads>
+__global__ void __launch_bounds__(NT, MINB) gather_kernel(const __grid_constant__ GatherParams p) {
+  gather_main<ORDER, SHADOW, Math, USE_TMA, NT>(p);
+  if (p.fused_finalize) {
+    __shared__ FinalizeSmem<ORDER, NT> fin;
+    cg::this_grid().sync();
+    finalize_phase<ORDER, NT>(p, NT * Math::CPT, fin, blockIdx.x, gridDim.x);
+  }
+}
+
 // ------------------------------------------------------------ pass 1: the visibility table
 // cacheLightingRSM.comp:167-232 hoisted out of the pair loop: the reference traces a cone for every
 // (cache, VAL block) inside its VPL loop; here all cones of a chunk of caches are traced first, by a kernel
@@ -791,82 +898,6 @@ __global__ void __launch_bounds__(kConeThreads, 8) cone_kernel(const __grid_cons
   }
 }
 
-// ------------------------------------------------------------ finalize: add the partial segments in VPL order
-// One block per 32 consecutive caches of a tile (block-stride loop: the cache count lives on the device).
-// The CTAs that own pieces of the tile are the same for all 32 caches, so their list is derived once per
-// chunk. Thread (y, x) then sums, for cache x, all coefficients over the owners y, y + 8, y + 16, ... — every
-// load of a thread is independent, so a tile split between ~25 CTAs costs one or two L2 round trips instead of
-// a serial chain — and the eight slices are added in a fixed order through shared memory (deterministic — no
-// float atomics). 32 threads apply the SH factors and add the result into the entries with 128-bit accesses
-// (+ the peer stores of the fused all-gather).
-constexpr int kFinChunk = 32;
-constexpr int kFinSlices = 8;
-constexpr int kFinThreads = kFinChunk * kFinSlices;
-
-template <int ORDER>
-__global__ void __launch_bounds__(kFinThreads) gather_finalize_kernel(GatherParams p, int tile_caches) {
-  constexpr int NC = num_coefs<ORDER>();
-  __shared__ float s_part[kFinSlices][NC][kFinChunk];
-  __shared__ uint32_t s_list[kFinThreads];
-  const Schedule S = make_schedule(p, tile_caches);
-  if (S.units == 0) return;
-  const uint32_t G = p.grid;
-  const uint32_t chunks = (S.count + kFinChunk - 1) / kFinChunk;
-  const uint32_t x = threadIdx.x % kFinChunk, y = threadIdx.x / kFinChunk;
-  for (uint32_t chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
-    const uint32_t local0 = chunk * kFinChunk;
-    const uint32_t tile = local0 / tile_caches, in_tile0 = local0 - tile * tile_caches;
-    const unsigned long long ua = (unsigned long long)tile * S.units_per_tile, ub = ua + S.units_per_tile;
-    const uint32_t c_lo = owner_of(S, G, ua), c_hi = owner_of(S, G, ub - 1);
-    if (c_lo == c_hi) continue; // one CTA covered the whole tile and already wrote it (block-uniform)
-    float acc[NC];
-#pragma unroll
-    for (int q = 0; q < NC; ++q) acc[q] = 0.0f;
-    for (uint32_t cbase = c_lo; cbase <= c_hi; cbase += kFinThreads) {
-      const uint32_t c = cbase + threadIdx.x;
-      uint32_t entry = 0xFFFFFFFFu;
-      if (c <= c_hi) {
-        const unsigned long long cb = range_begin(S, G, c), ce = range_begin(S, G, c + 1);
-        // slot 0 = the CTA's range starts inside this tile (only c_lo can start before it)
-        if (cb < ce) entry = c * 2u + (cb >= ua ? 0u : 1u);
-      }
-      __syncthreads(); // the previous batch has been consumed
-      s_list[threadIdx.x] = entry;
-      __syncthreads();
-      const int cnt = (int)min((uint32_t)kFinThreads, c_hi - cbase + 1u);
-#pragma unroll 2
-      for (int i = (int)y; i < cnt; i += kFinSlices) {
-        const uint32_t e = s_list[i];
-        if (e == 0xFFFFFFFFu) continue;
-        const float* src = p.partials + (size_t)e * NC * tile_caches + in_tile0 + x;
-#pragma unroll
-        for (int q = 0; q < NC; ++q) acc[q] += __ldcs(src + (size_t)q * tile_caches);
-      }
-    }
-    __syncthreads(); // previous chunk's readers are done with s_part
-#pragma unroll
-    for (int q = 0; q < NC; ++q) s_part[y][q][x] = acc[q];
-    __syncthreads();
-    // slice-sum in ascending slice order: item = (coefficient, cache)
-    for (int item = threadIdx.x; item < NC * kFinChunk; item += kFinThreads) {
-      const int q = item / kFinChunk, cx = item % kFinChunk;
-      float v = s_part[0][q][cx];
-#pragma unroll
-      for (int sl = 1; sl < kFinSlices; ++sl) v += s_part[sl][q][cx];
-      s_part[0][q][cx] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < kFinChunk && local0 + threadIdx.x < S.count) {
-      float raw[27];
-#pragma unroll
-      for (int q = 0; q < 27; ++q) raw[q] = q < NC ? s_part[0][q < NC ? q : 0][threadIdx.x] : 0.0f;
-      float vals[28];
-      coef_values<ORDER>(p, raw, vals);
-      add_to_entry<ORDER>(p, S.first + local0 + threadIdx.x, vals);
-    }
-  }
-}
-
 } // namespace
 
 // -------------------------------------------------------------------------------- host side
@@ -890,6 +921,18 @@ drv_status launch_gather(drv_ctx* ctx, GatherFn kernel, GatherParams& p, int til
   }
   p.partials = ctx->partials;
   p.grid = (uint32_t)grid;
+  // one cooperative launch (pair loop, grid barrier, finalize) when the device can do it; gather_variant bit 16
+  // forces the two-kernel form
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+  p.fused_finalize = (coop && !(ctx->cfg.gather_variant & 0x10000u)) ? 1u : 0u;
+  if (p.fused_finalize) {
+    void* args[] = {(void*)&p};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(threads), args, 0, ctx->stream);
+    if (e != cudaSuccess) return ctx->fail(DRV_ERR_CUDA, std::string("cooperative gather launch: ") + cudaGetErrorString(e));
+    DRV_LAUNCH_CHECK();
+    return DRV_OK;
+  }
   kernel<<<grid, threads, 0, ctx->stream>>>(p);
   DRV_LAUNCH_CHECK();
   const int fin_grid = ctx->num_sms * 8;

@@ -126,10 +126,25 @@ __device__ __forceinline__ F3 rsm_world_position(const drv_spot_light& L, float 
 // Threads [0, R^2) write VPLs; threads [R^2, R^2 + numBlocks) write shadow-block records.
 __global__ void vplgen_kernel(drv_spot_light L, const uint2* __restrict__ flux, const int* __restrict__ normal,
                               const uint32_t* __restrict__ depth, const uint32_t* __restrict__ depth_lod,
-                              int with_blocks, float4* __restrict__ vpls, float4* __restrict__ blocks) {
+                              int with_blocks, float4* __restrict__ vpls, float4* __restrict__ blocks,
+                              uint32_t* __restrict__ chunk_counts, uint8_t* __restrict__ block_live) {
   const uint32_t R = (uint32_t)L.RSMReadResolution;
   const uint32_t total = R * R;
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  // live-VPL bookkeeping of the compaction (see vpl_compact_kernel), fused in: per-256-chunk counts + block flags
+  {
+    bool live = false;
+    if (k < total) {
+      uint32_t x, y;
+      morton_decode(k, x, y);
+      const uint2 f = __ldg(flux + (size_t)y * R + x);
+      // half bits: zero flux = all three halfs are +-0
+      live = ((f.x & 0x7fff7fffu) | (f.y & 0x7fffu)) != 0u;
+      if (live && with_blocks) block_live[k / (uint32_t)L.IndirectShadowComputationSampleInterval] = 1;
+    }
+    const int c = __syncthreads_count(live);
+    if (threadIdx.x == 0 && blockIdx.x * blockDim.x < total) chunk_counts[blockIdx.x] = (uint32_t)c;
+  }
   if (k < total) {
     uint32_t x, y;
     morton_decode(k, x, y);                                             // :142
@@ -245,7 +260,7 @@ __global__ void __launch_bounds__(kCompactThreads) vpl_compact_kernel(const floa
 
 } // namespace
 
-drv_status drv_impl_compact_vpls(drv_ctx* ctx, uint32_t li) {
+drv_status drv_impl_compact_vpls(drv_ctx* ctx, uint32_t li, bool counted) {
   LightState& S = ctx->lights[li];
   const uint32_t n = S.num_vpls;
   if (n == 0) {
@@ -255,18 +270,22 @@ drv_status drv_impl_compact_vpls(drv_ctx* ctx, uint32_t li) {
   const bool shadow = ctx->cfg.indirect_shadow != 0 && !S.vpls_external;
   uint32_t interval = shadow ? (uint32_t)S.block.IndirectShadowComputationSampleInterval : 1u;
   if (interval == 0) interval = 1;
-  if (shadow) DRV_CUDA(cudaMemsetAsync(S.block_live, 0, (n + interval - 1) / interval, ctx->stream));
   const uint32_t chunks = (n + kCompactThreads - 1) / kCompactThreads;
-  vpl_count_kernel<<<chunks, kCompactThreads, 0, ctx->stream>>>((const float4*)S.vpls, n, interval, S.chunk_counts,
-                                                               shadow ? S.block_live : nullptr);
-  DRV_LAUNCH_CHECK();
+  if (!counted) { // external lists (drv_set_vpls); vplgen_kernel does this itself
+    if (shadow) DRV_CUDA(cudaMemsetAsync(S.block_live, 0, (n + interval - 1) / interval, ctx->stream));
+    vpl_count_kernel<<<chunks, kCompactThreads, 0, ctx->stream>>>((const float4*)S.vpls, n, interval, S.chunk_counts,
+                                                                 shadow ? S.block_live : nullptr);
+    DRV_LAUNCH_CHECK();
+  }
   vpl_compact_kernel<<<chunks, kCompactThreads, 0, ctx->stream>>>((const float4*)S.vpls, n, interval, S.chunk_counts,
                                                                  (float4*)S.vpls_live, ctx->live_counts + li);
   DRV_LAUNCH_CHECK();
   return DRV_OK;
 }
 
-drv_status drv_impl_prepare_rsm(drv_ctx* ctx, uint32_t li) {
+// `only_consumed`: stop after the last level this frame's consumers read (the VPL read level and, with indirect
+// shadows, the shadow-sample level below it) instead of walking the chain down to 2x2.
+drv_status drv_impl_prepare_rsm(drv_ctx* ctx, uint32_t li, bool only_consumed) {
   LightState& S = ctx->lights[li];
   if (!S.rsm_bound) return ctx->fail(DRV_ERR_NOT_BOUND, "drv_prepare_rsm: RSM not bound");
   ctx->stage_begin(DRV_STAGE_PREPARE_RSM);
@@ -277,6 +296,12 @@ drv_status drv_impl_prepare_rsm(drv_ctx* ctx, uint32_t li) {
   // levels 1 .. log2(res)-1: the 1x1 top level is never rendered (renderer.cpp:1293-1297)
   uint32_t last = 0;
   while ((res >> (last + 1)) >= 2) ++last; // last level to produce
+  if (only_consumed && S.block_set && S.block.RSMReadResolution > 0 && (uint32_t)S.block.RSMRenderResolution == res) {
+    uint32_t need = 0;
+    while ((res >> need) > (uint32_t)S.block.RSMReadResolution) ++need; // TEXTURE_BASE_LEVEL = rsmReadLod
+    if (ctx->cfg.indirect_shadow) need += (uint32_t)S.block.IndirectShadowComputationLod;
+    if (need < last) last = need;
+  }
   uint32_t level = 1;                      // next level to produce
   while (level <= last) {
     RsmMipArgs A;
@@ -332,9 +357,12 @@ drv_status drv_impl_generate_vpls(drv_ctx* ctx, uint32_t li) {
     nblocks = R * R / interval;
   }
   uint32_t threads = R * R + nblocks;
+  static_assert(kCompactThreads == 256, "vplgen_kernel's chunks are the compaction's chunks");
+  if (with_blocks) DRV_CUDA(cudaMemsetAsync(S.block_live, 0, nblocks, ctx->stream));
   vplgen_kernel<<<(threads + 255) / 256, 256, 0, ctx->stream>>>(L, flux, normal, depth, depth_lod, with_blocks,
-                                                               (float4*)S.vpls, (float4*)S.blocks);
+                                                               (float4*)S.vpls, (float4*)S.blocks, S.chunk_counts,
+                                                               S.block_live);
   DRV_LAUNCH_CHECK();
   S.num_vpls = R * R;
-  return drv_impl_compact_vpls(ctx, li);
+  return drv_impl_compact_vpls(ctx, li, true);
 }

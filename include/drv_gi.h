@@ -294,7 +294,8 @@ drv_status drv_draw(drv_ctx* ctx, void* hdr_out, uint32_t format);
  * the light side (RSM mip chains + VPL generation, ShadowMap::PrepareRSM / cacheLightingRSM.comp:137-163) runs
  * on a second stream concurrently with the camera side (AllocateCaches), the two join before the gather, then
  * apply. Results are identical to drv_prepare_rsm (every light) + drv_draw.
- *   DRV_FRAME_PREPARE_RSM  rebuild the RSM mip chain of every bound light (else they are used as they stand)
+ *   DRV_FRAME_PREPARE_RSM  rebuild the RSM mip chain of every bound light, down to the last level this frame
+ *                          reads (drv_prepare_rsm builds the whole chain); else the mips are used as they stand
  *   DRV_FRAME_GRAPH        record the frame into a CUDA graph and replay it while nothing that feeds a kernel
  *                          argument changes (uniform blocks, bindings, shard, hdr_out, format, flags); any
  *                          drv_set_* / drv_bind_* / drv_upload_* call makes the next frame re-record.
