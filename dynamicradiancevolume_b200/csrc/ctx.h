@@ -109,6 +109,7 @@ struct drv_ctx {
 
   // gather
   uint32_t* live_counts = nullptr;   // [DRV_MAX_LIGHTS] live VPLs per light (device; the gather reads it there)
+  uint32_t* cone_work = nullptr;     // cone_kernel's work queue: [0] next item, [1] CTAs done
   float* shadow_table = nullptr;     // visibility of (VAL block, cache) for the current chunk of caches (cone_kernel)
   size_t shadow_table_floats = 0;
   float* partials = nullptr;         // split-VPL partial sums

