@@ -448,6 +448,22 @@ def measure(args, config_index, n_steps, n_warmup, light):
                     h_out.copy_(hdr16[:wl.height], non_blocking=True)
             stream.synchronize()
 
+    # what the link gives: one 64 MiB pinned H2D copy and one D2H copy, alone (the floor of the e2e leg is
+    # h2d_bytes / this bandwidth: the frame's compute hides behind the input copies)
+    pcie = {}
+    if not light:
+        probe_h = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+        probe_d = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+        for name, (src, dst) in (("h2d_gbs", (probe_h, probe_d)), ("d2h_gbs", (probe_d, probe_h))):
+            best = 1e30
+            for _ in range(4):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                dst.copy_(src, non_blocking=True)
+                torch.cuda.synchronize()
+                best = min(best, time.perf_counter() - t0)
+            pcie[name] = (64 << 20) / best / 1e9
+        del probe_h, probe_d
     e2e_ms = []
     for i in range(0 if light else args.warmup + args.steps):
         torch.cuda.synchronize()
@@ -562,7 +578,11 @@ def measure(args, config_index, n_steps, n_warmup, light):
                    "parallelism": "1 GPU" if world == 1 else "gather sharded over %d GPUs by cell-ordered entry range, "
                                   "allocation replicated, fused P2P all-gather of SH, apply row-sharded, image bands %s" % (world, "stored into rank 0's target over NVLink (no collective in the frame)" if (args.image_gather == "p2p" and args.barrier == "peer" and not args.serial) else "gathered on rank 0 with NCCL"),
                    "gather_variant": args.variant},
-        "e2e": {"value": e2e_per_step, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_per_step, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "link": pcie, "h2d_floor_ms": (h2d / (pcie["h2d_gbs"] * 1e9) * 1e3) if pcie.get("h2d_gbs") else None,
+                "how": "drv_draw_host_frame: pinned host G-buffer + RSM level 0 -> H2D -> mips, allocate, light, apply per "
+                       "band -> D2H per band, overlapped inside the frame; wall clock around the call, which returns when "
+                       "the RGBA16F image is in host memory"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,

@@ -20,6 +20,8 @@
 #include "ctx.h"
 #include "device_math.cuh"
 
+#include <algorithm>
+
 using namespace drvk;
 
 namespace {
@@ -83,16 +85,27 @@ __device__ __forceinline__ Cell cache_cell(const AllocParams& p, F3 wp, int c) {
   return o;
 }
 
+// Where the flags go: this GPU's flag array and, in a sharded frame (every rank marks only its band of pixel rows),
+// every peer's as well — a flag store is idempotent, so the union of all ranks' stores over NVLink IS the
+// all-reduce of the mark phase.
+struct MarkTargets {
+  uint8_t* flags[8];
+  int n;
+};
+
 // cacheGather.comp:32-91 with the index assignment deferred to the scan.
-__device__ __forceinline__ void mark_corners(const AllocParams& p, const Cell& cell, int c, uint8_t* __restrict__ flags,
+__device__ __forceinline__ void mark_corners(const AllocParams& p, const Cell& cell, int c, const MarkTargets& T,
                                              uint32_t* __restrict__ oob_accum) {
   const int R = p.R, R2 = R * R;
-  uint8_t* f = flags + (uint32_t)(c * R2 * R + cell.x + cell.y * R + cell.z * R2);
+  const uint32_t base = (uint32_t)(c * R2 * R + cell.x + cell.y * R + cell.z * R2);
   if (cell.x + 1 < R && cell.y + 1 < R && cell.z + 1 < R) {
     // offsets (0,0,0)(0,1,0)(0,0,1)(0,1,1)(1,0,0)(1,1,0)(1,0,1)(1,1,1), cacheGather.comp:34-44. Plain idempotent
     // byte stores: no read-before-write, nothing on the critical path waits for memory.
-    f[0] = 1; f[R] = 1; f[R2] = 1; f[R2 + R] = 1;
-    f[1] = 1; f[R + 1] = 1; f[R2 + 1] = 1; f[R2 + R + 1] = 1;
+    for (int t = 0; t < T.n; ++t) {
+      uint8_t* f = T.flags[t] + base;
+      f[0] = 1; f[R] = 1; f[R2] = 1; f[R2 + R] = 1;
+      f[1] = 1; f[R + 1] = 1; f[R2 + 1] = 1; f[R2 + R + 1] = 1;
+    }
     return;
   }
   uint32_t oob = 0; // out-of-range +1 corners are skipped and counted
@@ -100,18 +113,20 @@ __device__ __forceinline__ void mark_corners(const AllocParams& p, const Cell& c
   for (int i = 0; i < 8; ++i) {
     const int ox = i >> 2, oy = i & 1, oz = (i >> 1) & 1;
     if (cell.x + ox >= R || cell.y + oy >= R || cell.z + oz >= R) { ++oob; continue; }
-    f[ox + oy * R + oz * R2] = 1;
+    for (int t = 0; t < T.n; ++t) T.flags[t][base + ox + oy * R + oz * R2] = 1;
   }
   atomicAdd(oob_accum, oob);
 }
 
+// tile_y0: first 16-row tile of this launch (a sharded frame marks one band of tile rows per rank; the tiles are
+// the reference's own whatever the band, so the dedupe predicate sees the same neighbours)
 __global__ void __launch_bounds__(256) mark_kernel(AllocParams p, const float* __restrict__ depth,
-                                                   const float* __restrict__ ndc_xy, uint8_t* __restrict__ flags,
-                                                   uint32_t* __restrict__ oob_accum) {
+                                                   const float* __restrict__ ndc_xy, MarkTargets flags,
+                                                   uint32_t* __restrict__ oob_accum, int tile_y0) {
   __shared__ int T1[16][17]; // [local x][local y] like cacheList[x][y]; padded against bank conflicts
   __shared__ int T2[16][17];
   const int lx = threadIdx.x, ly = threadIdx.y;
-  const int x = blockIdx.x * 16 + lx, y = blockIdx.y * 16 + ly;
+  const int x = blockIdx.x * 16 + lx, y = (blockIdx.y + tile_y0) * 16 + ly;
   Cell own = {-1, 0, 0, 0}, own2 = {-1, 0, 0, 0};
   int casc = -1;
   if (x < p.W && y < p.H) {
@@ -307,11 +322,10 @@ __global__ void synthetic_entries_kernel(const float4* __restrict__ pos, uint32_
 
 } // namespace
 
-drv_status drv_impl_allocate(drv_ctx* ctx) {
+static drv_status alloc_params(drv_ctx* ctx, AllocParams& p) {
   if (!ctx->have_constant || !ctx->have_per_frame || !ctx->have_volume)
     return ctx->fail(DRV_ERR_NOT_BOUND, "drv_allocate_caches: uniform blocks not set");
   if (!ctx->gb_depth) return ctx->fail(DRV_ERR_NOT_BOUND, "drv_allocate_caches: g-buffer not bound");
-  AllocParams p;
   p.W = ctx->constant.BackbufferResolution[0];
   p.H = ctx->constant.BackbufferResolution[1];
   p.R = ctx->constant.AddressVolumeResolution;
@@ -329,13 +343,68 @@ drv_status drv_impl_allocate(drv_ctx* ctx) {
     // exact power of two well inside the normal range: division == multiplication by the reciprocal
     p.inv_voxel[c] = (v > 1e-6f && v < 1e6f && frexpf(v, &e) == 0.5f) ? 1.0f / v : 0.0f;
   }
+  return DRV_OK;
+}
 
+// Sharded frames: after a rank has marked its band into its own flag array, the flags that are set — a few
+// thousand bytes — are stored into every peer's array (8-byte scan, one remote byte store per set flag and peer).
+// Marking straight into the peers costs a remote store per triggering PIXEL instead and was slower than not
+// sharding at all. Flags a peer has already pushed here are pushed again: harmless, the stores are idempotent.
+__global__ void __launch_bounds__(256) push_flags_kernel(const uint8_t* __restrict__ flags, uint32_t num_cells, MarkTargets peers) {
+  const uint32_t words = num_cells / 8;
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
+    const uint2 f = __ldcg(reinterpret_cast<const uint2*>(flags + (size_t)w * 8));
+    if (!(f.x | f.y)) continue;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t word = i < 4 ? f.x : f.y;
+      if (((word >> ((i & 3) * 8)) & 0xffu) == 0u) continue;
+      for (int t = 0; t < peers.n; ++t) peers.flags[t][(size_t)w * 8 + i] = 1;
+    }
+  }
+}
+
+// Mark phase. `sharded`: only this rank's band of 16-row tiles, then the set flags are pushed to every peer.
+drv_status drv_impl_allocate_mark(drv_ctx* ctx, bool sharded) {
+  AllocParams p;
+  drv_status st = alloc_params(ctx, p);
+  if (st != DRV_OK) return st;
   ctx->stage_begin(DRV_STAGE_ALLOCATE_CACHES);
   // ≙ m_lightCacheCounter->ClearToZero() and the atlas clear (renderer.cpp:969-970): both folded into the
   // scan + compact kernel, which also leaves the cell flags zeroed for the next frame — no memset in the frame
-  dim3 grid((p.W + 15) / 16, (p.H + 15) / 16); // renderer.cpp:981-985
-  mark_kernel<<<grid, dim3(16, 16), 0, ctx->stream>>>(p, ctx->gb_depth, ctx->ndc_xy, ctx->cell_flags, ctx->scan_epoch + 2);
-  DRV_LAUNCH_CHECK();
+  MarkTargets T, P;
+  memset(&T, 0, sizeof(T));
+  memset(&P, 0, sizeof(P));
+  T.flags[0] = ctx->cell_flags;
+  T.n = 1;
+  int tiles_y = (p.H + 15) / 16, tile_y0 = 0;
+  if (sharded) {
+    const size_t off = (size_t)ctx->cfg.max_cache_count * 128 + kSyncBytes; // the flags sit behind entries + sync block
+    for (uint32_t r = 0; r < ctx->shard_world && r < 8; ++r)
+      if (r != ctx->shard_rank) P.flags[P.n++] = (uint8_t*)ctx->peer_entries[r] + off;
+    const int band = (tiles_y + (int)ctx->shard_world - 1) / (int)ctx->shard_world;
+    tile_y0 = std::min(tiles_y, (int)ctx->shard_rank * band);
+    tiles_y = std::min(tiles_y, tile_y0 + band) - tile_y0;
+  }
+  if (tiles_y > 0) {
+    dim3 grid((p.W + 15) / 16, tiles_y); // renderer.cpp:981-985
+    mark_kernel<<<grid, dim3(16, 16), 0, ctx->stream>>>(p, ctx->gb_depth, ctx->ndc_xy, T, ctx->scan_epoch + 2, tile_y0);
+    DRV_LAUNCH_CHECK();
+  }
+  if (sharded && P.n > 0) {
+    const uint32_t words = ctx->num_cells / 8;
+    const uint32_t blocks = std::min<uint32_t>((words + 255) / 256, (uint32_t)ctx->num_sms * 8);
+    push_flags_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->cell_flags, ctx->num_cells, P);
+    DRV_LAUNCH_CHECK();
+  }
+  return DRV_OK;
+}
+
+// Scan + compact phase (replicated on every rank of a sharded frame: deterministic, identical indices).
+drv_status drv_impl_allocate_compact(drv_ctx* ctx) {
+  AllocParams p;
+  drv_status st0 = alloc_params(ctx, p);
+  if (st0 != DRV_OK) return st0;
   ScanState st;
   st.words = ctx->scan_words;
   st.epoch = ctx->scan_epoch;
@@ -349,6 +418,12 @@ drv_status drv_impl_allocate(drv_ctx* ctx) {
   DRV_LAUNCH_CHECK();
   ctx->stage_end(DRV_STAGE_ALLOCATE_CACHES);
   return DRV_OK;
+}
+
+drv_status drv_impl_allocate(drv_ctx* ctx) {
+  drv_status st = drv_impl_allocate_mark(ctx, false);
+  if (st != DRV_OK) return st;
+  return drv_impl_allocate_compact(ctx);
 }
 
 drv_status drv_impl_set_synthetic_entries(drv_ctx* ctx, const float* pos, uint32_t n) {

@@ -77,9 +77,12 @@ extern "C" drv_status drv_create(const drv_config* cfg, drv_ctx** out) {
 
   ctx->entry_stride = c.sh_order == 2 ? 128 : 64;
   // "Maximum size per cache": the buffer is max * 128 B whatever the mode (renderer.cpp:266-269)
-  CREATE_CUDA(dmalloc(&ctx->entries, (size_t)c.max_cache_count * 128 + kSyncBytes));
-  CREATE_CUDA(cudaMemsetAsync(ctx->entries, 0, (size_t)c.max_cache_count * 128 + kSyncBytes, ctx->stream));
+  ctx->num_cells = c.cav_cascades * c.cav_resolution * c.cav_resolution * c.cav_resolution;
+  const size_t entries_bytes = (size_t)c.max_cache_count * 128 + kSyncBytes + ctx->num_cells + 16;
+  CREATE_CUDA(dmalloc(&ctx->entries, entries_bytes));
+  CREATE_CUDA(cudaMemsetAsync(ctx->entries, 0, entries_bytes, ctx->stream));
   ctx->sync_flags = reinterpret_cast<uint32_t*>(ctx->entries + (size_t)c.max_cache_count * 128);
+  ctx->cell_flags = ctx->entries + (size_t)c.max_cache_count * 128 + kSyncBytes;
   CREATE_CUDA(dmalloc(&ctx->counter, sizeof(drv_cache_counter)));
   CREATE_CUDA(cudaMemsetAsync(ctx->counter, 0, sizeof(drv_cache_counter), ctx->stream));
   CREATE_CUDA(dmalloc(&ctx->stats, 2 * sizeof(uint32_t)));
@@ -87,8 +90,6 @@ extern "C" drv_status drv_create(const drv_config* cfg, drv_ctx** out) {
   ctx->num_cells = c.cav_cascades * c.cav_resolution * c.cav_resolution * c.cav_resolution;
   CREATE_CUDA(dmalloc(&ctx->atlas, (size_t)ctx->num_cells * sizeof(uint32_t))); // renderer.cpp:1179
   CREATE_CUDA(cudaMemsetAsync(ctx->atlas, 0, (size_t)ctx->num_cells * sizeof(uint32_t), ctx->stream));
-  CREATE_CUDA(dmalloc(&ctx->cell_flags, ctx->num_cells + 16));
-  CREATE_CUDA(cudaMemsetAsync(ctx->cell_flags, 0, ctx->num_cells + 16, ctx->stream));
   ctx->num_scan_blocks = (ctx->num_cells + 2047) / 2048;
   CREATE_CUDA(dmalloc(&ctx->block_counts, (size_t)ctx->num_scan_blocks * sizeof(uint32_t)));
   CREATE_CUDA(dmalloc(&ctx->scan_words, (size_t)ctx->num_scan_blocks * sizeof(unsigned long long)));
@@ -156,7 +157,7 @@ extern "C" void drv_destroy(drv_ctx* ctx) {
     if (ctx->peer_hdr[r]) cudaIpcCloseMemHandle(ctx->peer_hdr[r]);
   }
   cudaFree(ctx->entries); cudaFree(ctx->counter); cudaFree(ctx->stats); cudaFree(ctx->atlas);
-  cudaFree(ctx->cell_flags); cudaFree(ctx->block_counts); cudaFree(ctx->scan_words); cudaFree(ctx->scan_epoch); cudaFree(ctx->voxel_chain); cudaFree(ctx->voxel_target); cudaFree(ctx->voxel_records);
+  cudaFree(ctx->block_counts); cudaFree(ctx->scan_words); cudaFree(ctx->scan_epoch); cudaFree(ctx->voxel_chain); cudaFree(ctx->voxel_target); cudaFree(ctx->voxel_records);
   cudaFree(ctx->partials); cudaFree(ctx->shadow_table); cudaFree(ctx->st_depth); cudaFree(ctx->st_normal); cudaFree(ctx->st_diffuse);
   cudaFree(ctx->hdr16); cudaFree(ctx->ndc_xy);
   for (auto& S : ctx->lights) {
@@ -337,10 +338,16 @@ static drv_status frame_body(drv_ctx* ctx, void* hdr_out, uint32_t format, uint3
   ctx->stream = main_stream;
   if (st != DRV_OK) return st;
   if (e != cudaSuccess) return ctx->fail(DRV_ERR_CUDA, "drv_draw_frame: event record failed");
-  st = drv_impl_allocate(ctx); // renderer.cpp:550
-  if (st != DRV_OK) return st;
-  // sharded frame: every rank has cleared its SH before any peer's gather epilogue stores into it
+  // renderer.cpp:550. Sharded frame: every rank marks its band of pixel rows and stores the flags to all ranks
+  // (idempotent byte stores over NVLink = the all-reduce of the mark phase); after the barrier every rank holds the
+  // complete flag set and runs the deterministic scan + compact itself (identical indices, no communication)
   const bool sharded = ctx->shard_world > 1 && ctx->peers_open;
+  st = drv_impl_allocate_mark(ctx, sharded);
+  if (st != DRV_OK) return st;
+  if (sharded && (st = drv_impl_peer_barrier(ctx)) != DRV_OK) return st;
+  st = drv_impl_allocate_compact(ctx);
+  if (st != DRV_OK) return st;
+  // ... and every rank has cleared its SH before any peer's gather epilogue stores into it
   if (sharded && (st = drv_impl_peer_barrier(ctx)) != DRV_OK) return st;
   DRV_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
   if (vox) DRV_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join2, 0));

@@ -89,7 +89,8 @@ struct drv_ctx {
   drv_cache_counter* counter = nullptr;
   uint32_t* stats = nullptr;         // [0] overflow, [1] oob corners
   uint32_t* atlas = nullptr;
-  uint8_t* cell_flags = nullptr;     // one byte per CAV cell, linear-cell-id order
+  uint8_t* cell_flags = nullptr;     // one byte per CAV cell, linear-cell-id order; lives behind the entries + sync
+                                     // block in the SAME allocation, so a peer that mapped the entries can store flags
   uint32_t* block_counts = nullptr;
   unsigned long long* scan_words = nullptr; // decoupled look-back states of the scan + compact kernel
   uint32_t* scan_epoch = nullptr;           // [0] frame epoch (starts at 1), [1] blocks done, [2] oob-corner accumulator
@@ -161,6 +162,8 @@ struct drv_ctx {
 
 // stage implementations (one .cu each)
 drv_status drv_impl_allocate(drv_ctx* ctx);
+drv_status drv_impl_allocate_mark(drv_ctx* ctx, bool sharded);
+drv_status drv_impl_allocate_compact(drv_ctx* ctx);
 drv_status drv_impl_prepare_rsm(drv_ctx* ctx, uint32_t light, bool only_consumed = false);
 drv_status drv_impl_generate_vpls(drv_ctx* ctx, uint32_t light);
 drv_status drv_impl_compact_vpls(drv_ctx* ctx, uint32_t light, bool counted = false);
