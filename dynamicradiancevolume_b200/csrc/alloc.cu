@@ -85,27 +85,23 @@ __device__ __forceinline__ Cell cache_cell(const AllocParams& p, F3 wp, int c) {
   return o;
 }
 
-// Where the flags go: this GPU's flag array and, in a sharded frame (every rank marks only its band of pixel rows),
-// every peer's as well — a flag store is idempotent, so the union of all ranks' stores over NVLink IS the
-// all-reduce of the mark phase.
+// The peers' flag arrays of a sharded frame (every rank marks only its band of pixel rows): a flag store is
+// idempotent, so the union of all ranks' stores over NVLink IS the all-reduce of the mark phase.
 struct MarkTargets {
   uint8_t* flags[8];
   int n;
 };
 
 // cacheGather.comp:32-91 with the index assignment deferred to the scan.
-__device__ __forceinline__ void mark_corners(const AllocParams& p, const Cell& cell, int c, const MarkTargets& T,
+__device__ __forceinline__ void mark_corners(const AllocParams& p, const Cell& cell, int c, uint8_t* __restrict__ flags,
                                              uint32_t* __restrict__ oob_accum) {
   const int R = p.R, R2 = R * R;
-  const uint32_t base = (uint32_t)(c * R2 * R + cell.x + cell.y * R + cell.z * R2);
+  uint8_t* f = flags + (uint32_t)(c * R2 * R + cell.x + cell.y * R + cell.z * R2);
   if (cell.x + 1 < R && cell.y + 1 < R && cell.z + 1 < R) {
     // offsets (0,0,0)(0,1,0)(0,0,1)(0,1,1)(1,0,0)(1,1,0)(1,0,1)(1,1,1), cacheGather.comp:34-44. Plain idempotent
     // byte stores: no read-before-write, nothing on the critical path waits for memory.
-    for (int t = 0; t < T.n; ++t) {
-      uint8_t* f = T.flags[t] + base;
-      f[0] = 1; f[R] = 1; f[R2] = 1; f[R2 + R] = 1;
-      f[1] = 1; f[R + 1] = 1; f[R2 + 1] = 1; f[R2 + R + 1] = 1;
-    }
+    f[0] = 1; f[R] = 1; f[R2] = 1; f[R2 + R] = 1;
+    f[1] = 1; f[R + 1] = 1; f[R2 + 1] = 1; f[R2 + R + 1] = 1;
     return;
   }
   uint32_t oob = 0; // out-of-range +1 corners are skipped and counted
@@ -113,7 +109,7 @@ __device__ __forceinline__ void mark_corners(const AllocParams& p, const Cell& c
   for (int i = 0; i < 8; ++i) {
     const int ox = i >> 2, oy = i & 1, oz = (i >> 1) & 1;
     if (cell.x + ox >= R || cell.y + oy >= R || cell.z + oz >= R) { ++oob; continue; }
-    for (int t = 0; t < T.n; ++t) T.flags[t][base + ox + oy * R + oz * R2] = 1;
+    f[ox + oy * R + oz * R2] = 1;
   }
   atomicAdd(oob_accum, oob);
 }
@@ -121,7 +117,7 @@ __device__ __forceinline__ void mark_corners(const AllocParams& p, const Cell& c
 // tile_y0: first 16-row tile of this launch (a sharded frame marks one band of tile rows per rank; the tiles are
 // the reference's own whatever the band, so the dedupe predicate sees the same neighbours)
 __global__ void __launch_bounds__(256) mark_kernel(AllocParams p, const float* __restrict__ depth,
-                                                   const float* __restrict__ ndc_xy, MarkTargets flags,
+                                                   const float* __restrict__ ndc_xy, uint8_t* __restrict__ flags,
                                                    uint32_t* __restrict__ oob_accum, int tile_y0) {
   __shared__ int T1[16][17]; // [local x][local y] like cacheList[x][y]; padded against bank conflicts
   __shared__ int T2[16][17];
@@ -372,11 +368,8 @@ drv_status drv_impl_allocate_mark(drv_ctx* ctx, bool sharded) {
   ctx->stage_begin(DRV_STAGE_ALLOCATE_CACHES);
   // ≙ m_lightCacheCounter->ClearToZero() and the atlas clear (renderer.cpp:969-970): both folded into the
   // scan + compact kernel, which also leaves the cell flags zeroed for the next frame — no memset in the frame
-  MarkTargets T, P;
-  memset(&T, 0, sizeof(T));
+  MarkTargets P;
   memset(&P, 0, sizeof(P));
-  T.flags[0] = ctx->cell_flags;
-  T.n = 1;
   int tiles_y = (p.H + 15) / 16, tile_y0 = 0;
   if (sharded) {
     const size_t off = (size_t)ctx->cfg.max_cache_count * 128 + kSyncBytes; // the flags sit behind entries + sync block
@@ -388,7 +381,8 @@ drv_status drv_impl_allocate_mark(drv_ctx* ctx, bool sharded) {
   }
   if (tiles_y > 0) {
     dim3 grid((p.W + 15) / 16, tiles_y); // renderer.cpp:981-985
-    mark_kernel<<<grid, dim3(16, 16), 0, ctx->stream>>>(p, ctx->gb_depth, ctx->ndc_xy, T, ctx->scan_epoch + 2, tile_y0);
+    mark_kernel<<<grid, dim3(16, 16), 0, ctx->stream>>>(p, ctx->gb_depth, ctx->ndc_xy, ctx->cell_flags, ctx->scan_epoch + 2,
+                                                        tile_y0);
     DRV_LAUNCH_CHECK();
   }
   if (sharded && P.n > 0) {

@@ -294,6 +294,52 @@ __device__ __forceinline__ float cone_trace(const VoxelVol& V, float wx, float w
   return saturatef(1.0f - occ);                                                     // :230
 }
 
+// The same march without the manual software pipeline: one sample per trip, one branch for the second mip level,
+// no ping-pong state. With the cone pass on its own (8+ CTAs of 4 warps per SM) the other warps of the SM hide the
+// L1/L2 latency of the dependent chain, and the loop spends a quarter fewer instructions on control flow and
+// register moves (ncu: BRA + BSSY + BSYNC + MOV were 18 % of the pipelined kernel's instructions).
+__device__ __forceinline__ float cone_trace_simple(const VoxelVol& V, float wx, float wy, float wz, float4 blk) {
+  const float inv_voxel = 1.0f / V.voxel_size;
+  const float maxLod = (float)(V.levels - 1);
+  const float kk = blk.w;
+  float tx = ex_sub(blk.x, wx), ty = ex_sub(blk.y, wy), tz = ex_sub(blk.z, wz);     // :195
+  const float lightDist = ex_sqrt(ex_dot3(tx, ty, tz, tx, ty, tz));                 // :196
+  const float inv = 1.0f / lightDist;
+  const float2 dxy = f2(tx * inv, ty * inv);                                        // :197-198 (dirInVoxel * res)
+  const float dz = tz * inv;
+  float2 cxy = __ffma2_rn(dxy, f2(2.0f), f2(fmaf(wx - V.vmin[0], inv_voxel, -0.5f), fmaf(wy - V.vmin[1], inv_voxel, -0.5f))); // :201
+  float cz = fmaf(dz, 2.0f, fmaf(wz - V.vmin[2], inv_voxel, -0.5f));
+  const float goal = ex_sub(ex_div(lightDist, V.voxel_size), 2.0f);                 // :206
+  const float radToStep = ex_div(2.0f, ex_sub(1.0f, kk));                           // :209
+  float dist = 0.0f, occ = 0.0f, stepSize = 1.0f;
+#pragma unroll 1
+  for (int s = 0; s < 32; ++s) {                                                    // :211
+    cxy = __ffma2_rn(dxy, f2(stepSize), cxy); cz = fmaf(dz, stepSize, cz);          // :213
+    dist = ex_add(dist, stepSize);                                                  // :214
+    const float radius = ex_mul(dist, kk);                                          // :216
+    // lod = log2(radius) clamped to the chain; radius <= 1 is level 0 exactly. fmaxf(NaN, 0) = 0.
+    const float l = fminf(fmaxf(__log2f(radius), 0.0f), maxLod);
+    int l0; float t;
+    floor_frac_w(l - 0.5f, l0, t);
+    if (!(radius > 1.0f)) { l0 = 0; t = 0.0f; }
+    const Footprint f0 = footprint(V, l0, cxy, cz);
+    const uint2 r0 = __ldg(V.rec + f0.index);
+    float o;
+    if (t != 0.0f) { // mip-linear: also the next coarser level (:219)
+      const Footprint f1 = footprint(V, min(l0 + 1, V.levels - 1), cxy, cz);
+      const uint2 r1 = __ldg(V.rec + f1.index);
+      o = trilinear(r0, f0.txy, f0.tz);
+      o = fmaf(t, trilinear(r1, f1.txy, f1.tz) - o, o);
+    } else {
+      o = trilinear(r0, f0.txy, f0.tz);
+    }
+    occ = fmaf(1.0f - occ, o, occ);                                                 // :220
+    if (dist >= goal || occ >= 1.0f) break;                                         // :222
+    stepSize = fmaxf(1.0f, ex_mul(radius, radToStep));                              // :225
+  }
+  return saturatef(1.0f - occ);                                                     // :230
+}
+
 // ------------------------------------------------------------ epilogue helpers
 template <int ORDER>
 constexpr int num_coefs() { return ORDER == 2 ? 27 : 12; }
@@ -864,7 +910,8 @@ struct ConeParams {
 constexpr int kConeThreads = 128;
 constexpr int kBlocksPerItem = 2; // small items: the queue balances the tail to ~1 / 24 of a CTA's share at 1080p
 
-__global__ void __launch_bounds__(kConeThreads, 8) cone_kernel(const __grid_constant__ ConeParams p) {
+template <bool SIMPLE, int MINB>
+__global__ void __launch_bounds__(kConeThreads, MINB) cone_kernel(const __grid_constant__ ConeParams p) {
   // this shard's chunk, as make_schedule derives it
   const uint32_t n = (uint32_t)max(p.counter->TotalLightCacheCount, 0);
   const uint32_t groups64 = (n + 63u) / 64u;
@@ -901,7 +948,9 @@ __global__ void __launch_bounds__(kConeThreads, 8) cone_kernel(const __grid_cons
       while (b >= p.block_offset[light + 1]) ++light;
       if (!__ldg(p.lights[light].block_live + (b - p.block_offset[light]))) continue; // no live VPL reads this entry
       const float4 blk = __ldg(p.lights[light].blocks + (b - p.block_offset[light]));
-      if (alive) p.table[(size_t)b * p.stride + local] = cone_trace(V, pos.x, pos.y, pos.z, blk);
+      if (alive)
+        p.table[(size_t)b * p.stride + local] = SIMPLE ? cone_trace_simple(V, pos.x, pos.y, pos.z, blk)
+                                                       : cone_trace(V, pos.x, pos.y, pos.z, blk);
     }
   }
   // the last CTA to leave rewinds the queue for the next launch
@@ -1141,15 +1190,18 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   c.work = ctx->cone_work;
   p.shadow_table = ctx->shadow_table;
   p.shadow_stride = chunk;
+  // gather_variant bit 17: the software-pipelined march instead of the plain loop
+  using ConeFn = void (*)(const ConeParams);
+  const ConeFn cone_fn = (ctx->cfg.gather_variant & 0x20000u) ? (ConeFn)cone_kernel<false, 8> : (ConeFn)cone_kernel<true, 10>;
   int cone_per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cone_per_sm, cone_kernel, kConeThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cone_per_sm, cone_fn, kConeThreads, 0);
   if (cone_per_sm < 1) cone_per_sm = 1;
   const int cone_grid = ctx->num_sms * cone_per_sm;
   ctx->stage_begin(DRV_STAGE_GATHER_KERNEL);
   for (uint32_t first = 0; first < ctx->cfg.max_cache_count; first += chunk) {
     c.chunk_first = p.chunk_first = first;
     c.chunk_cap = p.chunk_cap = chunk;
-    cone_kernel<<<cone_grid, kConeThreads, 0, ctx->stream>>>(c);
+    cone_fn<<<cone_grid, kConeThreads, 0, ctx->stream>>>(c);
     DRV_LAUNCH_CHECK();
     drv_status st = launch_gather(ctx, kernel, p, tile, order, threads);
     if (st != DRV_OK) return st;
