@@ -274,7 +274,8 @@ drv_status drv_impl_apply_rows(drv_ctx* ctx, void* out, uint32_t format, uint32_
   if (y_begin >= y_end) return DRV_OK;
   if (timed) ctx->stage_begin(DRV_STAGE_APPLY_CACHES);
   const uint32_t tune = (ctx->cfg.gather_variant >> 8) & 0xFu;
-  const uint32_t iter = ((ctx->cfg.gather_variant >> 12) & 0xFu) == 1 ? 1u : (uint32_t)kApplyIter;
+  const uint32_t iter_sel = (ctx->cfg.gather_variant >> 12) & 0xFu; // tuning sweeps: 1, 2 or 8 rows per thread
+  const uint32_t iter = (iter_sel == 1 || iter_sel == 2 || iter_sel == 8) ? iter_sel : (uint32_t)kApplyIter;
   dim3 block(32, 8), grid((p.W + 31) / 32, (y_end - y_begin + 8 * iter - 1) / (8 * iter));
   // resident blocks per SM the kernel is compiled for (register budget 64 / 80 / 128 per thread): more registers
   // keep more of a pixel's entry loads in flight. drv_config.gather_variant bits 8..11 override it (tuning sweeps).
@@ -287,8 +288,13 @@ drv_status drv_impl_apply_rows(drv_ctx* ctx, void* out, uint32_t format, uint32_
   do {                                                                                                          \
     if (tune == 4) DRV_APPLY(ORD, 4, IT); else if (tune == 6) DRV_APPLY(ORD, 6, IT); else DRV_APPLY(ORD, 5, IT); \
   } while (0)
-  if (ctx->cfg.sh_order == 2) { if (iter == 1) DRV_APPLY_MB(2, 1); else DRV_APPLY_MB(2, kApplyIter); }
-  else { if (iter == 1) DRV_APPLY_MB(1, 1); else DRV_APPLY_MB(1, kApplyIter); }
+  if (ctx->cfg.sh_order == 2) {
+    if (iter == 1) DRV_APPLY_MB(2, 1); else if (iter == 2) DRV_APPLY_MB(2, 2); else if (iter == 8) DRV_APPLY_MB(2, 8);
+    else DRV_APPLY_MB(2, kApplyIter);
+  } else {
+    if (iter == 1) DRV_APPLY_MB(1, 1); else if (iter == 2) DRV_APPLY_MB(1, 2); else if (iter == 8) DRV_APPLY_MB(1, 8);
+    else DRV_APPLY_MB(1, kApplyIter);
+  }
 #undef DRV_APPLY_MB
 #undef DRV_APPLY
   DRV_LAUNCH_CHECK();

@@ -704,10 +704,26 @@ extern "C" drv_status drv_draw_host_frame(drv_ctx* ctx, const drv_host_frame* f)
       DRV_CUDA(dmalloc(&S.st_depth, rsm_cap * 4));
     }
   }
-  uint32_t bands = f->bands ? f->bands : 8;
+  // band boundaries (whole 8-row apply blocks). bands == 0: five bands of decreasing height — the last band's
+  // copy-in, apply and copy-out cannot overlap with anything, so it is the smallest; every band costs ~8 us of
+  // copy / launch latency, so there are few of them
+  uint32_t band_y[34];
+  uint32_t bands = f->bands;
   if (bands > 32) bands = 32;
-  const uint32_t rows_per_band = (((H + bands - 1) / bands) + 7) & ~7u; // whole 8-row apply blocks
-  bands = (H + rows_per_band - 1) / rows_per_band;
+  if (bands == 0) {
+    const float cut[5] = {0.40f, 0.65f, 0.82f, 0.93f, 1.0f};
+    bands = 0;
+    band_y[0] = 0;
+    for (int i = 0; i < 5; ++i) {
+      uint32_t y = i == 4 ? H : (((uint32_t)(cut[i] * (float)H) + 7u) & ~7u);
+      if (y > H) y = H;
+      if (y > band_y[bands]) band_y[++bands] = y;
+    }
+  } else {
+    const uint32_t rows_per_band = (((H + bands - 1) / bands) + 7) & ~7u;
+    bands = (H + rows_per_band - 1) / rows_per_band;
+    for (uint32_t b = 0; b <= bands; ++b) band_y[b] = std::min(H, b * rows_per_band);
+  }
 
   // the copy stream starts after everything already queued on the context's stream (previous users of the staging images)
   DRV_CUDA(cudaEventRecord(ctx->ev_frame_start, ctx->stream));
@@ -724,7 +740,7 @@ extern "C" drv_status drv_draw_host_frame(drv_ctx* ctx, const drv_host_frame* f)
   DRV_CUDA(cudaMemcpyAsync(ctx->st_depth, f->depth, px * 4, cudaMemcpyHostToDevice, ctx->copy_in));
   DRV_CUDA(cudaEventRecord(ctx->ev_depth, ctx->copy_in));
   for (uint32_t b = 0; b < bands; ++b) {
-    const size_t y0 = (size_t)b * rows_per_band, y1 = std::min<size_t>(H, y0 + rows_per_band);
+    const size_t y0 = band_y[b], y1 = band_y[b + 1];
     const size_t off = y0 * W * 4, bytes = (y1 - y0) * W * 4;
     DRV_CUDA(cudaMemcpyAsync((uint8_t*)ctx->st_normal + off, (const uint8_t*)f->normal_rg16i + off, bytes,
                              cudaMemcpyHostToDevice, ctx->copy_in));
@@ -732,14 +748,14 @@ extern "C" drv_status drv_draw_host_frame(drv_ctx* ctx, const drv_host_frame* f)
     DRV_CUDA(cudaEventRecord(ctx->ev_band_in[b], ctx->copy_in));
   }
   // compute, on the context's stream
-  DRV_CUDA(cudaMemsetAsync(ctx->hdr16, 0, px * 8, ctx->stream)); // glClear(GL_COLOR_BUFFER_BIT), renderer.cpp:562
+  // glClear(GL_COLOR_BUFFER_BIT) (renderer.cpp:562) is fused into the apply pass: DRV_HDR_RGBA16F_WRITE
   drv_status st = drv_set_light_count(ctx, f->num_lights);
   if (st != DRV_OK) return st;
   for (uint32_t l = 0; l < f->num_lights; ++l) {
     LightState& S = ctx->lights[l];
     DRV_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_rsm[l], 0));
     st = drv_bind_rsm(ctx, l, S.st_flux, S.st_normal, S.st_depth, f->rsm_resolution[l]);
-    if (st == DRV_OK) st = drv_impl_prepare_rsm(ctx, l);
+    if (st == DRV_OK) st = drv_impl_prepare_rsm(ctx, l, true);
     if (st != DRV_OK) return st;
   }
   DRV_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_depth, 0));
@@ -749,9 +765,9 @@ extern "C" drv_status drv_draw_host_frame(drv_ctx* ctx, const drv_host_frame* f)
   if (st != DRV_OK) return st;
   ctx->stage_begin(DRV_STAGE_APPLY_CACHES);
   for (uint32_t b = 0; b < bands; ++b) {
-    const uint32_t y0 = b * rows_per_band, y1 = std::min(H, y0 + rows_per_band);
+    const uint32_t y0 = band_y[b], y1 = band_y[b + 1];
     DRV_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_band_in[b], 0));
-    st = drv_impl_apply_rows(ctx, ctx->hdr16, DRV_HDR_RGBA16F_ADD, y0, y1, false);
+    st = drv_impl_apply_rows(ctx, ctx->hdr16, DRV_HDR_RGBA16F_WRITE, y0, y1, false);
     if (st != DRV_OK) return st;
     DRV_CUDA(cudaEventRecord(ctx->ev_band_done[b], ctx->stream));
     DRV_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_band_done[b], 0));
