@@ -91,7 +91,6 @@ extern "C" drv_status drv_create(const drv_config* cfg, drv_ctx** out) {
   CREATE_CUDA(dmalloc(&ctx->atlas, (size_t)ctx->num_cells * sizeof(uint32_t))); // renderer.cpp:1179
   CREATE_CUDA(cudaMemsetAsync(ctx->atlas, 0, (size_t)ctx->num_cells * sizeof(uint32_t), ctx->stream));
   ctx->num_scan_blocks = (ctx->num_cells + 2047) / 2048;
-  CREATE_CUDA(dmalloc(&ctx->block_counts, (size_t)ctx->num_scan_blocks * sizeof(uint32_t)));
   CREATE_CUDA(dmalloc(&ctx->scan_words, (size_t)ctx->num_scan_blocks * sizeof(unsigned long long)));
   CREATE_CUDA(cudaMemsetAsync(ctx->scan_words, 0, (size_t)ctx->num_scan_blocks * sizeof(unsigned long long), ctx->stream));
   CREATE_CUDA(dmalloc(&ctx->scan_epoch, 4 * sizeof(uint32_t)));
@@ -157,7 +156,7 @@ extern "C" void drv_destroy(drv_ctx* ctx) {
     if (ctx->peer_hdr[r]) cudaIpcCloseMemHandle(ctx->peer_hdr[r]);
   }
   cudaFree(ctx->entries); cudaFree(ctx->counter); cudaFree(ctx->stats); cudaFree(ctx->atlas);
-  cudaFree(ctx->block_counts); cudaFree(ctx->scan_words); cudaFree(ctx->scan_epoch); cudaFree(ctx->voxel_chain); cudaFree(ctx->voxel_target); cudaFree(ctx->voxel_records);
+  cudaFree(ctx->scan_words); cudaFree(ctx->scan_epoch); cudaFree(ctx->voxel_chain); cudaFree(ctx->voxel_target); cudaFree(ctx->voxel_records);
   cudaFree(ctx->partials); cudaFree(ctx->shadow_table); cudaFree(ctx->st_depth); cudaFree(ctx->st_normal); cudaFree(ctx->st_diffuse);
   cudaFree(ctx->hdr16); cudaFree(ctx->ndc_xy);
   for (auto& S : ctx->lights) {

@@ -91,7 +91,6 @@ struct drv_ctx {
   uint32_t* atlas = nullptr;
   uint8_t* cell_flags = nullptr;     // one byte per CAV cell, linear-cell-id order; lives behind the entries + sync
                                      // block in the SAME allocation, so a peer that mapped the entries can store flags
-  uint32_t* block_counts = nullptr;
   unsigned long long* scan_words = nullptr; // decoupled look-back states of the scan + compact kernel
   uint32_t* scan_epoch = nullptr;           // [0] frame epoch (starts at 1), [1] blocks done, [2] oob-corner accumulator
   uint32_t num_cells = 0, num_scan_blocks = 0;
@@ -122,7 +121,6 @@ struct drv_ctx {
   // cross-GPU barrier flags live right behind the entries in the same allocation (one IPC handle maps both):
   // flags[r] = last epoch rank r has announced to this GPU; flags[8] = time-out marker
   uint32_t* sync_flags = nullptr;
-  uint32_t barrier_epoch = 0;
 
   // host-frame pipeline (drv_draw_host_frame): copy streams + events
   cudaStream_t copy_in = nullptr, copy_out = nullptr;

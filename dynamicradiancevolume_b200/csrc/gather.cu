@@ -8,10 +8,12 @@
 // per light — parallelism = N_cache only (≈600 warps for a 40k-cache frame).
 //
 // B200 shape (this file):
-//  * VPLs and shadow-block records are materialised once per light (rsm.cu).
+//  * VPLs and shadow-block records are materialised once per light (rsm.cu)
+//    and the VPLs with zero flux — which add exactly zero — are dropped there;
+//    the kernels below stream the live list and read its length on the device.
 //  * N-body tiling over BOTH axes. The work is the grid of UNITS
-//    (cache tile of 128*CPT entries) x (VPL tile of >=128 VPLs of one light),
-//    VPL tile fastest. A persistent grid (SM count x resident CTAs) splits the
+//    (cache tile of NT*CPT entries) x (32 VPLs of one light),
+//    VPL unit fastest. A persistent grid (SM count x resident CTAs) splits the
 //    flattened unit list into equal contiguous ranges ("stream-K"), so every
 //    CTA gets the same number of units +-1 whatever N_cache and N_vpl are, and
 //    the range bounds are computed on the device from the live cache counter —
@@ -28,10 +30,13 @@
 //    epilogue: 28 FP32 ops + 2 MUFU per SH1 pair instead of 32 + 2.
 //  * a CTA whose range covers a cache tile completely adds straight into the
 //    entries (`entry.SH += acc`, :358-373). Ranges that start or end inside a
-//    tile write their partial sums to a per-CTA scratch slot; the finalize
-//    kernel adds those in ascending VPL order (deterministic — no float
-//    atomics) and, when peers are mapped, stores the finished entry to every
-//    other GPU over NVLink (fused all-gather).
+//    tile write their partial sums to a per-CTA scratch slot; after a
+//    grid-wide barrier (cooperative launch) all CTAs add those in a fixed order
+//    (deterministic — no float atomics) and, when peers are mapped, store the
+//    finished entry to every other GPU over NVLink (fused all-gather).
+//  * indirect shadows: cone_kernel first traces every (cache, live shadow
+//    block) cone into a visibility table (device-side work queue, packed
+//    FP32x2 texel maths), the pair kernel then reads one value per block.
 #include "ctx.h"
 #include "device_math.cuh"
 
@@ -605,7 +610,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 }
 
 // ------------------------------------------------------------ finalize: add the partial segments in VPL order
-// One block per 32 consecutive caches of a tile (block-stride loop: the cache count lives on the device).
+// One block iteration per 32 consecutive caches of a tile (block-stride loop: the cache count lives on the device).
 // The CTAs that own pieces of the tile are the same for all 32 caches, so their list is derived once per
 // chunk. Thread (y, x) then sums, for cache x, all coefficients over the owners y, y + 8, y + 16, ... — every
 // load of a thread is independent, so a tile split between ~25 CTAs costs one or two L2 round trips instead of
