@@ -703,22 +703,13 @@ extern "C" drv_status drv_draw_host_frame(drv_ctx* ctx, const drv_host_frame* f)
       DRV_CUDA(dmalloc(&S.st_depth, rsm_cap * 4));
     }
   }
-  // band boundaries (whole 8-row apply blocks). bands == 0: five bands of decreasing height — the last band's
-  // copy-in, apply and copy-out cannot overlap with anything, so it is the smallest; every band costs ~8 us of
-  // copy / launch latency, so there are few of them
+  // band boundaries (whole 8-row apply blocks). Every band costs ~8 us of copy / launch latency and its copy-out
+  // competes with the copy-in of the next one; measured at 1080p (tools/e2e_probe.py): 1 band 1.15 ms, 2: 1.05,
+  // 4: 1.03, 8: 1.06, 16: 1.11, 32: 1.28 — the default is 4
   uint32_t band_y[34];
-  uint32_t bands = f->bands;
+  uint32_t bands = f->bands ? f->bands : 4;
   if (bands > 32) bands = 32;
-  if (bands == 0) {
-    const float cut[5] = {0.40f, 0.65f, 0.82f, 0.93f, 1.0f};
-    bands = 0;
-    band_y[0] = 0;
-    for (int i = 0; i < 5; ++i) {
-      uint32_t y = i == 4 ? H : (((uint32_t)(cut[i] * (float)H) + 7u) & ~7u);
-      if (y > H) y = H;
-      if (y > band_y[bands]) band_y[++bands] = y;
-    }
-  } else {
+  {
     const uint32_t rows_per_band = (((H + bands - 1) / bands) + 7) & ~7u;
     bands = (H + rows_per_band - 1) / rows_per_band;
     for (uint32_t b = 0; b <= bands; ++b) band_y[b] = std::min(H, b * rows_per_band);

@@ -736,7 +736,7 @@ __device__ __forceinline__ void advance(const GatherParams& p, const Schedule& S
 }
 
 // SHADOW: every pair is scaled by the visibility of its (cache, VAL block), read from the table cone_kernel wrote.
-template <int ORDER, bool SHADOW, typename Math, bool USE_TMA, int NT>
+template <int ORDER, bool SHADOW, typename Math, bool USE_TMA, int NT, int UNROLL>
 __device__ __forceinline__ void gather_main(const GatherParams& p) {
   constexpr int CPT = Math::CPT;
   constexpr int TILE = NT * CPT;
@@ -833,14 +833,14 @@ __device__ __forceinline__ void gather_main(const GatherParams& p) {
         M.set_shadow(v);
       };
       uint32_t cur_blk = 0xFFFFFFFFu;
-#pragma unroll 4
+#pragma unroll UNROLL
       for (int i = 0; i < n; ++i) {
         const uint32_t blk = USE_TMA ? __float_as_uint(sv[i * SPV + 1].w) : s_blk[i];
         if (blk != cur_blk) { cur_blk = blk; load_shadow(blk); } // warp-uniform
         M.eval(sv + i * SPV);
       }
     } else {
-#pragma unroll 4
+#pragma unroll UNROLL
       for (int i = 0; i < n; ++i) M.eval(sv + i * SPV);
     }
     if (USE_TMA) __syncthreads(); // stage st consumed by every warp
@@ -877,9 +877,9 @@ __device__ __forceinline__ void gather_main(const GatherParams& p) {
 // The kernel: the pair loop over this CTA's unit range and — when launched cooperatively (fused_finalize) — after a
 // grid-wide barrier the addition of the partial segments by all CTAs together (the finalize pass without a second
 // launch, its prologue and the launch gap; every CTA of the persistent grid is resident by construction).
-template <int ORDER, bool SHADOW, typename Math, bool USE_TMA, int MINB = 1, int NT = kThreads>
+template <int ORDER, bool SHADOW, typename Math, bool USE_TMA, int MINB = 1, int NT = kThreads, int UNROLL = 4>
 __global__ void __launch_bounds__(NT, MINB) gather_kernel(const __grid_constant__ GatherParams p) {
-  gather_main<ORDER, SHADOW, Math, USE_TMA, NT>(p);
+  gather_main<ORDER, SHADOW, Math, USE_TMA, NT, UNROLL>(p);
   if (p.fused_finalize) {
     __shared__ FinalizeSmem<ORDER, NT> fin;
     cg::this_grid().sync();
@@ -1018,6 +1018,7 @@ drv_status launch_gather(drv_ctx* ctx, GatherFn kernel, GatherParams& p, int til
 //   6  as 0 for SH1 but compiled for 3 resident CTAs per SM (168 registers)
 //   7  as 0 with 64-thread CTAs (cache tiles of 256 / 128 entries: less padding when the frame has few caches)
 //   8  as 0 with 32-thread CTAs (cache tiles of 128 / 64 entries)
+//   9, 10, 11  the packed kernel with the VPL loop unrolled 2x / 8x / 4x (default: 8x for SH1, 4x for SH2)
 // With indirect shadows the same kernels additionally scale every pair by its table visibility.
 template <bool SH>
 GatherFn select_kernel(int order, uint32_t variant, int* tile, int* threads) {
@@ -1034,7 +1035,10 @@ GatherFn select_kernel(int order, uint32_t variant, int* tile, int* threads) {
       case 6: *tile = kThreads * P1p2::CPT; return gather_kernel<1, SH, P1p2, false, 3>; // 168 registers: 3 CTAs / SM
       case 7: *threads = 64; *tile = 64 * P1p2::CPT; return gather_kernel<1, SH, P1p2, false, 1, 64>; // 2-warp CTAs, 256-cache tiles
       case 8: *threads = 32; *tile = 32 * P1p2::CPT; return gather_kernel<1, SH, P1p2, false, 1, 32>; // 1-warp CTAs, 128-cache tiles
-      default: DRV_PICK(1, P1p2, false);
+      case 9: *tile = kThreads * P1p2::CPT; return gather_kernel<1, SH, P1p2, false, 1, kThreads, 2>;  // VPL loop unrolled 2x
+      case 10: *tile = kThreads * P1p2::CPT; return gather_kernel<1, SH, P1p2, false, 1, kThreads, 8>; // ... 8x
+      case 11: DRV_PICK(1, P1p2, false); // VPL loop unrolled 4x
+      default: *tile = kThreads * P1p2::CPT; return gather_kernel<1, SH, P1p2, false, 1, kThreads, 8>; // 8x: +1.5 % (sweep)
     }
   }
   switch (variant) {
@@ -1042,6 +1046,8 @@ GatherFn select_kernel(int order, uint32_t variant, int* tile, int* threads) {
     case 4: case 12: DRV_PICK(2, S2c2, false);
     case 7: *threads = 64; *tile = 64 * P2p1::CPT; return gather_kernel<2, SH, P2p1, false, 1, 64>;
     case 8: *threads = 32; *tile = 32 * P2p1::CPT; return gather_kernel<2, SH, P2p1, false, 1, 32>;
+    case 9: *tile = kThreads * P2p1::CPT; return gather_kernel<2, SH, P2p1, false, 1, kThreads, 2>;
+    case 10: *tile = kThreads * P2p1::CPT; return gather_kernel<2, SH, P2p1, false, 1, kThreads, 8>;
     default: DRV_PICK(2, P2p1, false);
   }
 #undef DRV_PICK

@@ -437,8 +437,7 @@ typedef struct drv_host_frame {
   const uint16_t* rsm_depthlinsq_rg16f[DRV_MAX_LIGHTS];
   uint32_t rsm_resolution[DRV_MAX_LIGHTS];
   void* hdr_out;                 /* W*H*8 bytes RGBA16F: the cleared target plus the indirect light (clear fused into the apply pass) */
-  uint32_t bands;                /* 0 = default (five bands of decreasing height, so that the tail that cannot
-                                    overlap — last band in, apply, out — is short); else that many equal bands, <= 32 */
+  uint32_t bands;                /* equal bands of rows, <= 32; 0 = default (4) */
 } drv_host_frame;
 drv_status drv_draw_host_frame(drv_ctx* ctx, const drv_host_frame* frame);
 

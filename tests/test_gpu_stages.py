@@ -222,7 +222,7 @@ def _sweep_oracle(cb, pos, vpls_list, sh_order, fp64=False):
     return e
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3, 4, 7, 8, 12])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4, 7, 8, 9, 11, 12])
 @pytest.mark.parametrize("sh_order", [1, 2])
 @pytest.mark.parametrize("n_cache,n_vpl", [(1000, 4096), (70000, 1024), (37, 2500), (5000, 16384)])
 def test_gather_unshadowed_variants(cuda_device, variant, sh_order, n_cache, n_vpl):
