@@ -40,6 +40,11 @@ SYMBOLS = [
     ("drv_draw", _st, [_P, _P, _u32]),
     ("drv_draw_frame", _st, [_P, _P, _u32, _u32]),
     ("drv_live_vpl_counts", _st, [_P, _P]),
+    ("drv_fill_rsm", _st, [_P, _u32, _P, _P, _P, _P, _u32]),
+    ("drv_cone_trace_ao", _st, [_P, _P]),
+    ("drv_tonemap", _st, [_P, _P, C.c_float, C.c_float, _P]),
+    ("drv_write_pfm", _st, [C.c_char_p, _P, _u32, _u32]),
+    ("drv_save_to_pfm", _st, [_P, _P, C.c_char_p]),
     ("drv_bind_scene", _st, [_P, _P, _u32, _P, C.c_float]),
     ("drv_export_hdr_ipc", _st, [_P, _P]),
     ("drv_import_peer_hdr", _st, [_P, _u32, _P]),

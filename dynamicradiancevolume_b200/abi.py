@@ -126,6 +126,8 @@ class Buffers(C.Structure):
         ("rsm_flux_mips", C.c_void_p * DRV_MAX_LIGHTS), ("rsm_normal_mips", C.c_void_p * DRV_MAX_LIGHTS),
         ("rsm_depth_mips", C.c_void_p * DRV_MAX_LIGHTS),
         ("hdr16", C.c_void_p),
+        ("rsm_flux0", C.c_void_p * DRV_MAX_LIGHTS), ("rsm_normal0", C.c_void_p * DRV_MAX_LIGHTS),
+        ("rsm_depth0", C.c_void_p * DRV_MAX_LIGHTS),
     ]
 
 

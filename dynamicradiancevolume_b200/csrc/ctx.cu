@@ -463,6 +463,9 @@ extern "C" drv_status drv_get_buffers(drv_ctx* ctx, drv_buffers* out) {
     out->rsm_flux_mips[l] = ctx->lights[l].flux_mips;
     out->rsm_normal_mips[l] = ctx->lights[l].normal_mips;
     out->rsm_depth_mips[l] = ctx->lights[l].depth_mips;
+    out->rsm_flux0[l] = ctx->lights[l].flux0;
+    out->rsm_normal0[l] = ctx->lights[l].normal0;
+    out->rsm_depth0[l] = ctx->lights[l].depth0;
   }
   out->hdr16 = ctx->hdr16;
   return DRV_OK;

@@ -225,6 +225,25 @@ class Context:
         self._keep_scene = tris
         self.check(self.lib.drv_bind_scene(self.handle, None if tris is None else tris.data_ptr(), n, C.byref(w), adaption))
 
+    # -- rows next to the hot path --
+    def fill_rsm(self, light, position, normal, basecolor, coverage=None):
+        """``drv_fill_rsm``: device tensors [R, R, 3] float32 (+ optional [R, R] uint8 coverage); binds the result."""
+        res = position.shape[0]
+        self._keep_fill = (position, normal, basecolor, coverage)
+        self.check(self.lib.drv_fill_rsm(self.handle, light, position.data_ptr(), normal.data_ptr(), basecolor.data_ptr(),
+                                         None if coverage is None else coverage.data_ptr(), res))
+
+    def cone_trace_ao(self, out):
+        """``drv_cone_trace_ao`` into a device tensor [H, W] float32 (discarded pixels are left untouched)."""
+        self.check(self.lib.drv_cone_trace_ao(self.handle, out.data_ptr()))
+
+    def tonemap(self, hdr16, out32, exposure=1.0, l_max=1.2):
+        """``drv_tonemap``: RGBA16F [H, W, 4] -> float32 [H, W, 4]."""
+        self.check(self.lib.drv_tonemap(self.handle, hdr16.data_ptr(), exposure, l_max, out32.data_ptr()))
+
+    def save_to_pfm(self, hdr16, path):
+        self.check(self.lib.drv_save_to_pfm(self.handle, hdr16.data_ptr(), path.encode()))
+
     def live_vpl_counts(self):
         """VPLs with non-zero flux per light — what the gather streams (``drv_live_vpl_counts``)."""
         a = (C.c_uint32 * 16)()

@@ -323,6 +323,31 @@ drv_status drv_bind_scene(drv_ctx* ctx, const float* tri_pos, uint32_t num_tris,
  * counts[DRV_MAX_LIGHTS]; synchronises. */
 drv_status drv_live_vpl_counts(drv_ctx* ctx, uint32_t* counts);
 
+/* ------------------------------------------------------------------------
+ * Rows next to the hot path, built to the same parity bar.
+ * ------------------------------------------------------------------------ */
+/* f1 ≙ shader/fillrsm.frag:32-61 (the FillRSM pass of Renderer::DrawShadowMaps, renderer.cpp:785-800) minus the
+ * rasteriser: level 0 of light `light`'s RSM — flux RGBX16F, packed normal RG16I, depthLinSq RG16F — from the
+ * per-fragment attributes of the light's view (device pointers, resolution^2 texels, row-major): world position,
+ * shading normal (unnormalised), base colour as sampled (linear RGB). coverage (nullable): 0 = no fragment, the
+ * texel keeps the clear value. The result is bound as the light's RSM (as drv_bind_rsm would);
+ * drv_set_spot_light must have been called. */
+drv_status drv_fill_rsm(drv_ctx* ctx, uint32_t light, const float* position_xyz, const float* normal_xyz,
+                        const float* basecolor_rgb, const uint8_t* coverage, uint32_t resolution);
+
+/* f2 ≙ Renderer::ConeTraceAO (renderer.cpp:936-949) + shader/ambientocclusion.frag:25-89: six voxel cones per
+ * pixel through the voxel chain of the bound G-buffer; one float per pixel, discarded pixels (depth < 1e-6) are
+ * left untouched. Needs a context created with indirect_shadow (the cone tracer's record chain). */
+drv_status drv_cone_trace_ao(drv_ctx* ctx, float* ao_out);
+
+/* f3 ≙ shader/tonemapping.frag:21-31 with Exposure and DragoDivider = log2(l_max + 1) (renderer.cpp:1225-1227):
+ * RGBA16F HDR target -> float4 (rgb, 1). */
+drv_status drv_tonemap(drv_ctx* ctx, const void* hdr_rgba16f, float exposure, float l_max, float* ldr_rgba32f);
+/* ≙ WritePfm (rendering/hdrimage.cpp:6-32): host RGBA float image -> PFM file (pure host code). */
+drv_status drv_write_pfm(const char* path, const float* rgba, uint32_t width, uint32_t height);
+/* ≙ Renderer::SaveToPFM (renderer.cpp:1229-1235): read the RGBA16F HDR target back and write it. Synchronises. */
+drv_status drv_save_to_pfm(drv_ctx* ctx, const void* hdr_rgba16f, const char* path);
+
 /* Device pointers for parity readback / interop. Valid until drv_destroy. */
 typedef struct drv_buffers {
   void*     entries;        /* LightCacheBuffer, stride entry_stride */
@@ -343,6 +368,10 @@ typedef struct drv_buffers {
   int16_t*  rsm_normal_mips[DRV_MAX_LIGHTS];
   uint16_t* rsm_depth_mips[DRV_MAX_LIGHTS];
   void*     hdr16;          /* context-owned RGBA16F target (drv_draw_to_host / DRV_FRAME_GATHER_IMAGE); NULL until used */
+  /* level 0 of every light's RSM as currently bound (drv_bind_rsm / drv_upload_rsm / drv_fill_rsm) */
+  const uint16_t* rsm_flux0[DRV_MAX_LIGHTS];
+  const int16_t*  rsm_normal0[DRV_MAX_LIGHTS];
+  const uint16_t* rsm_depth0[DRV_MAX_LIGHTS];
 } drv_buffers;
 drv_status drv_get_buffers(drv_ctx* ctx, drv_buffers* out);
 /* Texel offset of mip level `level` (>=1) inside a context-owned RSM mip

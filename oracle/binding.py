@@ -182,6 +182,43 @@ def voxel_chain(level0, res):
     return chain
 
 
+def fill_rsm(light, position, normal, basecolor, coverage=None):
+    """shader/fillrsm.frag:32-61 -> (flux[r,r,4] u16, normal[r,r,2] i16, depth[r,r,2] u16)."""
+    lib = load()
+    r = position.shape[0]
+    fo = np.zeros((r, r, 4), np.uint16)
+    no = np.zeros((r, r, 2), np.int16)
+    do = np.zeros((r, r, 2), np.uint16)
+    position, normal, basecolor = (np.ascontiguousarray(a, np.float32) for a in (position, normal, basecolor))
+    cov = None if coverage is None else np.ascontiguousarray(coverage, np.uint8)
+    lib.orc_fill_rsm(C.byref(light), _ptr(position), _ptr(normal), _ptr(basecolor), _ptr(cov), C.c_uint32(r), _ptr(fo),
+                     _ptr(no), _ptr(do))
+    return fo, no, do
+
+
+def cone_trace_ao(pf, vi, chain, res, depth, normal, out=None, threads=0):
+    """shader/ambientocclusion.frag:25-89 -> [H, W] float32 (``out`` keeps its values where the shader discards)."""
+    lib = load()
+    H, W = depth.shape
+    if out is None:
+        out = np.zeros((H, W), np.float32)
+    depth = np.ascontiguousarray(depth, np.float32)
+    normal = np.ascontiguousarray(normal, np.int16)
+    lib.orc_cone_trace_ao(C.byref(pf), C.byref(vi), _ptr(chain), C.c_uint32(res), _ptr(depth), _ptr(normal), C.c_uint32(W),
+                          C.c_uint32(H), _ptr(out), int(threads))
+    return out
+
+
+def tonemap(hdr_rgba, exposure, drago_divider):
+    """shader/tonemapping.frag:21-31: [.., 4] float32 -> [.., 3] float32."""
+    lib = load()
+    hdr = np.ascontiguousarray(hdr_rgba, np.float32)
+    n = hdr.size // 4
+    out = np.zeros(hdr.shape[:-1] + (3,), np.float32)
+    lib.orc_tonemap(_ptr(hdr), C.c_uint32(n), C.c_float(exposure), C.c_float(drago_divider), _ptr(out))
+    return out
+
+
 def half_to_float(h):
     return load().orc_half_to_float(int(h))
 

@@ -101,6 +101,19 @@ void orc_voxel_blend(uint8_t* volume, const uint8_t* target, uint32_t res, float
  * chain from level 0. */
 void orc_voxel_mips(uint8_t* chain, uint32_t res);
 
+/* ---- rows SURVEY.md 8(f) ranks next to the hot path (adjacent.cpp) ---- */
+/* f1, shader/fillrsm.frag:32-61: RSM level 0 (flux RGBX16F, packed normal RG16I, depthLinSq RG16F) from the
+ * rasteriser's per-fragment attributes. coverage NULL = every texel covered. */
+void orc_fill_rsm(const drv_spot_light* light, const float* position_xyz, const float* normal_xyz,
+                  const float* basecolor_rgb, const uint8_t* coverage, uint32_t res, uint16_t* flux_rgbx16f,
+                  int16_t* normal_rg16i, uint16_t* depthlinsq_rg16f);
+/* f2, shader/ambientocclusion.frag:25-89: one float per pixel, discarded pixels untouched. */
+void orc_cone_trace_ao(const drv_per_frame* pf, const drv_volume_info* vi, const uint8_t* voxel_chain,
+                       uint32_t voxel_res, const float* depth, const int16_t* normal_rg16i, uint32_t width,
+                       uint32_t height, float* out, int threads);
+/* f3, shader/tonemapping.frag:21-31. */
+void orc_tonemap(const float* hdr_rgba, uint32_t n, float exposure, float drago_divider, float* out_rgb);
+
 /* Exact helpers shared with tests. */
 float    orc_half_to_float(uint16_t h);
 uint16_t orc_float_to_half(float f);

@@ -371,3 +371,72 @@ def test_sh_reconstruction_vs_bruteforce_point_sum_sanity():
     direct = (vpls["Flux"][None, :, 0] * s * np.clip(t[..., 1], 0, 1)).sum(1)
     # the uploaded band-2 lobe factor is negative (renderer.cpp:298): only a loose agreement holds
     assert np.corrcoef(rec, direct)[0, 1] > 0.9
+
+
+# ---------------------------------------------------------------------------------- rows next to the path
+def test_fill_rsm_closed_form():
+    """fillrsm.frag:32-61: a fragment on the light's axis at distance d with unit base colour gets
+    flux = I * 2 (1 - cosHalf) / R^2 (falloff 1, cos 1, the 1/pi 'preponed'), depthLinSq = (d, d^2); off-axis
+    values follow the float64 restatement; texels without a fragment keep the clear value."""
+    wl = workloads.cornell(rsm_res=16, read_lod=0).build()
+    L = wl.spot_lights[0]
+    R = 16
+    lp = np.array(L.LightPosition[:3], np.float64)
+    ld = np.array(L.LightDirection[:3], np.float64)
+    rng = np.random.default_rng(3)
+    d = rng.uniform(0.5, 5.0, size=(R, R, 1))
+    dirs = ld + rng.normal(size=(R, R, 3)) * 0.35
+    dirs /= np.linalg.norm(dirs, axis=-1, keepdims=True)
+    dirs[0, 0] = ld
+    d[0, 0] = 2.0
+    pos = (lp + dirs * d).astype(np.float32)
+    nrm = np.tile(np.array([0.0, 0.0, 3.0], np.float32), (R, R, 1))
+    base = rng.uniform(0.1, 1.0, size=(R, R, 3)).astype(np.float32)
+    base[0, 0] = 1.0
+    cov = np.ones((R, R), np.uint8); cov[5, 7] = 0
+    fo, no, do = orc.fill_rsm(L, pos, nrm, base, cov)
+    flux = fo.view(np.float16).astype(np.float64)[..., :3]
+    depth = do.view(np.float16).astype(np.float64)
+    I = np.array(L.LightIntensity[:3], np.float64)
+    ch = float(L.LightCosHalfAngle)
+    assert np.allclose(flux[0, 0], I * 2.0 * (1.0 - ch) / R ** 2, rtol=1e-3)
+    assert np.allclose(depth[0, 0], [2.0, 4.0], rtol=1e-3)
+    to_light = lp - pos.astype(np.float64)
+    dist = np.linalg.norm(to_light, axis=-1)
+    cos = np.clip((-to_light / dist[..., None] * ld).sum(-1), 0, 1)
+    k = np.clip(cos - ch, 0, 1) / (1 - ch) * (2 * math.pi * (1 - ch) * cos / R / R) / math.pi
+    want = base.astype(np.float64) * I * k[..., None]
+    want[5, 7] = 0
+    assert np.allclose(flux, want, rtol=2e-3, atol=1e-7)
+    assert (flux == 0).all(-1).sum() > 1  # outside the cone: falloff 0
+    assert not fo[5, 7].any() and not no[5, 7].any() and not do[5, 7].any()
+    covered = cov.astype(bool)
+    assert np.all(no[..., 0][covered] == 0) and np.all(no[..., 1][covered] == 32767)  # normalize((0,0,3)) = +z
+
+
+def test_cone_trace_ao_empty_and_full_volume():
+    """ambientocclusion.frag:25-89: an empty volume leaves AO = 1; a full one stops every cone at its first sample
+    with weight 1, so the occlusion is sum(w) / 6 = (pi/4 + 5 * 3 pi/20) / 6 = pi / 6."""
+    wl = workloads.cornell(width=64, height=64, rsm_res=16, read_lod=0, indirect_shadow=True, voxel_resolution=32).build()
+    res = 32
+    from dynamicradiancevolume_b200 import abi as _abi
+    empty = np.zeros(_abi.voxel_chain_bytes(res), np.uint8)
+    full = np.full(_abi.voxel_chain_bytes(res), 255, np.uint8)
+    out = orc.cone_trace_ao(wl.per_frame, wl.volume, empty, res, wl.depth, wl.normal, out=np.full((64, 64), -1.0, np.float32))
+    shaded = wl.depth >= 1e-6
+    assert shaded.any() and np.all(out[shaded] == 1.0) and np.all(out[~shaded] == -1.0)
+    out = orc.cone_trace_ao(wl.per_frame, wl.volume, full, res, wl.depth, wl.normal, out=np.full((64, 64), -1.0, np.float32))
+    # (a pixel whose start point — 1.6 voxels along the normal — lies outside the volume never enters the loop:
+    # saturate(p) == p fails, :74, and it keeps AO = 1)
+    v = out[shaded]
+    inside = v != 1.0
+    assert inside.mean() > 0.5 and np.allclose(v[inside], 1.0 - math.pi / 6.0, atol=2e-6)
+
+
+def test_tonemap_drago_known_answers():
+    hdr = np.array([[0.0, 1.0, 3.0, 9.0], [0.5, 0.25, 7.0, 0.0]], np.float32)
+    got = orc.tonemap(hdr, 1.0, 1.0)
+    assert np.array_equal(got[0], [0.0, 1.0, 2.0])
+    got = orc.tonemap(hdr, 2.0, math.log2(2.2))
+    want = np.log2(hdr[:, :3].astype(np.float64) * 2.0 + 1.0) / math.log2(2.2)
+    assert np.allclose(got, want, rtol=1e-6)
