@@ -583,6 +583,33 @@ class Renderer:
         self.context().apply_caches(hdr, fmt)
         return hdr
 
+    # -- the passes around the path: ConeTraceAO, tonemap, SaveToPFM --
+    def SetExposure(self, exposure): self.m_tonemapExposure = float(exposure)        # renderer.cpp:1218-1221
+    def GetExposure(self): return getattr(self, "m_tonemapExposure", 1.0)
+    def SetTonemapLMax(self, tonemapLMax): self.m_tonemapLMax = float(tonemapLMax)   # renderer.cpp:1223-1227
+    def GetTonemapLMax(self): return getattr(self, "m_tonemapLMax", 1.2)             # default renderer.cpp:39
+
+    def ConeTraceAO(self, out=None):
+        """Renderer::ConeTraceAO (renderer.cpp:936-949): [H, W] float32, discarded pixels keep 0."""
+        import torch
+        if out is None:
+            out = torch.zeros(self.m_resolution[1], self.m_resolution[0], dtype=torch.float32, device="cuda:%d" % self._device)
+        self.context().cone_trace_ao(out)
+        return out
+
+    def Tonemap(self, hdr=None, out=None):
+        """The tonemap pass of Renderer::Draw (tonemapping.frag): RGBA16F HDR target -> float32 (rgb, 1)."""
+        import torch
+        hdr = self._hdr if hdr is None else hdr
+        if out is None:
+            out = torch.zeros(self.m_resolution[1], self.m_resolution[0], 4, dtype=torch.float32, device="cuda:%d" % self._device)
+        self.context().tonemap(hdr, out, self.GetExposure(), self.GetTonemapLMax())
+        return out
+
+    def SaveToPFM(self, filename, hdr=None):
+        """Renderer::SaveToPFM (renderer.cpp:1229-1235)."""
+        self.context().save_to_pfm(self._hdr if hdr is None else hdr, filename)
+
     def Draw(self, camera: Camera, detachViewFromCameraUpdate: bool = False, timeSinceLastFrame: float = 0.0, hdr=None):
         """The DYN_RADIANCE_VOLUME case of Renderer::Draw (renderer.cpp:501-594) minus rasterisation, direct
         lighting and tonemapping: uniforms, [voxelise], allocate, light, clear HDR, apply."""

@@ -199,3 +199,17 @@ def test_renderer_mirror_draw(cuda_device):
     assert ok, ratio
     r.Draw(wl.camera, False, 0.0)
     assert r.GetLightCacheActiveCount() == o.count  # one frame late, renderer.cpp:960-966
+    # the passes around the path through the same mirror: AO output mode, tonemap, screenshot
+    from oracle import binding as orc
+    ao_t = r.ConeTraceAO()
+    torch.cuda.synchronize()  # the context works on its own stream
+    ao = ao_t.cpu().numpy()
+    ao_ref = orc.cone_trace_ao(wl.per_frame, wl.volume, o.chain, wl.voxel_resolution, wl.depth, wl.normal)
+    assert np.abs(ao - ao_ref).max() <= 2e-3
+    r.SetExposure(3.0)
+    ldr_t = r.Tonemap()
+    torch.cuda.synchronize()
+    ldr = ldr_t.cpu().numpy()
+    hdr_now = r._hdr.float().cpu().numpy()
+    ok, ratio = close(ldr[..., :3], orc.tonemap(hdr_now, 3.0, np.float32(np.log2(r.GetTonemapLMax() + 1.0))))
+    assert ok, ratio
