@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) cone_trace_ao_kernel(const __grid_constan
 
 // ---- f3 ----------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tonemap_kernel(const uint2* __restrict__ hdr16, uint32_t n, float exposure,
-                                                      float inv_divider_unused, float divider, float4* __restrict__ out) {
+                                                      float divider, float4* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint2 v = __ldg(hdr16 + i);
@@ -199,7 +199,7 @@ extern "C" drv_status drv_tonemap(drv_ctx* ctx, const void* hdr_rgba16f, float e
   if (!hdr_rgba16f || !ldr_rgba32f) return ctx->fail(DRV_ERR_INVALID, "drv_tonemap: null argument");
   const uint32_t n = ctx->cfg.backbuffer_width * ctx->cfg.backbuffer_height;
   const float divider = log2f(l_max + 1.0f); // renderer.cpp:1226
-  tonemap_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const uint2*)hdr_rgba16f, n, exposure, 0.0f, divider, (float4*)ldr_rgba32f);
+  tonemap_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const uint2*)hdr_rgba16f, n, exposure, divider, (float4*)ldr_rgba32f);
   DRV_LAUNCH_CHECK();
   return DRV_OK;
 }
