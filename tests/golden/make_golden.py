@@ -54,7 +54,30 @@ def run(wl):
         out["voxel_set"] = np.packbits(o.target > 0)
         out["shadow_blocks"] = o.blocks[0].view(np.float32).reshape(-1, 4).copy()
     out["vpl_head"] = o.vpls[0][:64].view(np.float32).reshape(-1, 12).copy()
+    # rows next to the path: AO through the same voxel chain, tonemap of the frame, RSM fill of seeded
+    # fragment attributes
+    if wl.indirect_shadow:
+        out["ao"] = orc.cone_trace_ao(wl.per_frame, wl.volume, o.chain, wl.voxel_resolution, wl.depth, wl.normal)
+    out["tonemap"] = orc.tonemap(img, 2.0, np.float32(np.log2(2.2)))
+    pos, nrm, base, cov = fill_rsm_inputs(wl)
+    fo, no, do = orc.fill_rsm(wl.spot_lights[0], pos, nrm, base, cov)
+    out["fill_rsm_flux"], out["fill_rsm_normal"], out["fill_rsm_depth"] = fo, no, do
     return out
+
+
+def fill_rsm_inputs(wl):
+    """Seeded per-fragment attributes for light 0 (32 x 32 of its render resolution's pixel solid angle)."""
+    L = wl.spot_lights[0]
+    R = 32
+    rng = np.random.default_rng(0xF111)
+    lp = np.array(L.LightPosition[:3], np.float32)
+    ld = np.array(L.LightDirection[:3], np.float32)
+    d = ld + rng.normal(size=(R, R, 3)).astype(np.float32) * 0.5
+    pos = (lp + d * rng.uniform(0.5, 6.0, size=(R, R, 1)).astype(np.float32)).astype(np.float32)
+    nrm = rng.normal(size=(R, R, 3)).astype(np.float32)
+    base = rng.uniform(0, 1, size=(R, R, 3)).astype(np.float32)
+    cov = (rng.uniform(size=(R, R)) > 0.2).astype(np.uint8)
+    return pos, nrm, base, cov
 
 
 if __name__ == "__main__":

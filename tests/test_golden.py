@@ -70,4 +70,19 @@ def test_gpu_matches_golden(cuda_device, name):
         assert np.array_equal(g.ctx.read_shadow_blocks(0, nb).view(np.float32).reshape(-1, 4), gold["shadow_blocks"])
     v = g.ctx.read_vpls(0, 64).view(np.float32).reshape(-1, 12)
     assert np.array_equal(v[:, :4], gold["vpl_head"][:, :4])
+    # rows next to the path
+    if wl.indirect_shadow:
+        ao = torch.zeros(wl.height, wl.width, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        g.ctx.cone_trace_ao(ao)
+        torch.cuda.synchronize()
+        assert np.abs(ao.cpu().numpy() - gold["ao"]).max() <= 2e-3
+    hdr = torch.zeros(wl.height, wl.width, 4, dtype=torch.float16, device="cuda")
+    ldr = torch.zeros(wl.height, wl.width, 4, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    g.ctx.apply_caches(hdr, 0)
+    g.ctx.tonemap(hdr, ldr, 2.0, 1.2)
+    torch.cuda.synchronize()
+    ok, ratio = close(ldr.cpu().numpy()[..., :3], gold["tonemap"], rtol=2e-3, atol=1e-4)  # through the RGBA16F target
+    assert ok, ratio
     g.close()
