@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs index (0..3); the metric is quoted on 1")
+    ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs index (0..3); the metric is quoted on 1. 5 = the reference author's default settings")
     ap.add_argument("--variant", type=int, default=0, help="gather kernel variant (drv_config.gather_variant)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps (profiling runs)")

@@ -77,6 +77,14 @@ def test_config3_reduced_4_lights_4_cascades(cuda_device):
     g.close()
 
 
+def test_reference_default_settings(cuda_device):
+    """The settings the reference's author ran by default: 1080p, 4096 VPLs, 3 cascades x 32^3 with
+    transitions, 128^3 voxels, SH1 + cone-traced shadows at LOD 2, 16384-cache capacity."""
+    g, o, e, img, img_o = _run(workloads.config(5))
+    _check(g, o, e, img, img_o)
+    g.close()
+
+
 def test_draw_to_host_matches_device_path(cuda_device):
     """drv_upload_* + drv_draw_to_host (the end-to-end entry point bench.py times) against the device path."""
     import torch

@@ -128,7 +128,21 @@ def config(index: int, **kw) -> Workload:
                     name="C4-atrium-4k")
         args.update(kw)
         return atrium(**args)
-    raise ValueError("config index 0..3 (the sweep, index 4, has no scene: see sweep())")
+    if index == 5:
+        return reference_defaults(**kw)
+    raise ValueError("config index 0..3 or 5 (the sweep, index 4, has no scene: see sweep())")
+
+
+def reference_defaults(**kw) -> Workload:
+    """Not a BASELINE config: the settings the reference's author ran by default on the atrium —
+    1920x1080 (outputwindow.cpp:59-60), one light, RSM 1024^2 read at LOD 4 = 64^2 = 4096 VPLs (scene/light.hpp:12-14),
+    3 cascades x 32^3 of 4 / 8 / 16 m with 2-voxel transitions (renderer.cpp:41-48, 1184-1187), 128^3 voxels,
+    at most 16384 caches (renderer.cpp:86-90), SH1, indirect shadows at LOD 2."""
+    args = dict(width=1920, height=1080, rsm_res=1024, read_lod=4, sh_order=1, indirect_shadow=True, cascades=3,
+                cav_resolution=32, first_cascade=4.0, voxel_resolution=128, transition=2.0, max_caches=16384,
+                shadow_lod=2, name="reference-defaults")
+    args.update(kw)
+    return atrium(**args)
 
 
 def sweep(n_cache: int, n_vpl: int, seed: int = 0xD27A0001):
