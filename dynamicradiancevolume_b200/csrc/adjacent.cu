@@ -131,16 +131,25 @@ __global__ void __launch_bounds__(256) cone_trace_ao_kernel(const __grid_constan
 }
 
 // ---- f3 ----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tonemap_kernel(const uint2* __restrict__ hdr16, uint32_t n, float exposure,
-                                                      float divider, float4* __restrict__ out) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint2 v = __ldg(hdr16 + i);
+// Two pixels per thread: one 16-byte load, two 16-byte stores (a streaming pass: 8 B in, 16 B out per pixel).
+__device__ __forceinline__ float4 drago(uint2 v, float exposure, float inv_divider) {
   const float2 rg = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
   const float2 ba = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
   // Drago: log2(exposedColor + 1) / DragoDivider, tonemapping.frag:21-24, 29-31
-  out[i] = make_float4(log2f(fmaf(rg.x, exposure, 1.0f)) / divider, log2f(fmaf(rg.y, exposure, 1.0f)) / divider,
-                       log2f(fmaf(ba.x, exposure, 1.0f)) / divider, 1.0f);
+  return make_float4(log2f(fmaf(rg.x, exposure, 1.0f)) * inv_divider, log2f(fmaf(rg.y, exposure, 1.0f)) * inv_divider,
+                     log2f(fmaf(ba.x, exposure, 1.0f)) * inv_divider, 1.0f);
+}
+__global__ void __launch_bounds__(256) tonemap_kernel(const uint2* __restrict__ hdr16, uint32_t n, float exposure,
+                                                      float divider, float4* __restrict__ out) {
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 2u;
+  const float inv_divider = 1.0f / divider;
+  if (i + 1 < n) {
+    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(hdr16 + i));
+    __stcs(out + i, drago(make_uint2(v.x, v.y), exposure, inv_divider));
+    __stcs(out + i + 1, drago(make_uint2(v.z, v.w), exposure, inv_divider));
+  } else if (i < n) {
+    out[i] = drago(__ldg(hdr16 + i), exposure, inv_divider);
+  }
 }
 
 } // namespace
@@ -199,7 +208,7 @@ extern "C" drv_status drv_tonemap(drv_ctx* ctx, const void* hdr_rgba16f, float e
   if (!hdr_rgba16f || !ldr_rgba32f) return ctx->fail(DRV_ERR_INVALID, "drv_tonemap: null argument");
   const uint32_t n = ctx->cfg.backbuffer_width * ctx->cfg.backbuffer_height;
   const float divider = log2f(l_max + 1.0f); // renderer.cpp:1226
-  tonemap_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const uint2*)hdr_rgba16f, n, exposure, divider, (float4*)ldr_rgba32f);
+  tonemap_kernel<<<((n + 1) / 2 + 255) / 256, 256, 0, ctx->stream>>>((const uint2*)hdr_rgba16f, n, exposure, divider, (float4*)ldr_rgba32f);
   DRV_LAUNCH_CHECK();
   return DRV_OK;
 }

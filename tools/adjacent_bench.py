@@ -64,6 +64,24 @@ def main():
     ms = timed(lambda: ctx.tonemap(hdr, ldr, 1.0, 1.2))
     b = px * (8 + 16)
     out["tonemap"] = {"ms": ms, "pixels": px, "algorithmic_bytes": b, "gbs": b / ms / 1e6, "hbm_frac": (b / ms / 1e6 / hbm) if hbm else None}
+    # the oracle (scalar C++ restatement, all host cores for AO; fill / tonemap are single-threaded loops) beside it
+    import time
+    from oracle import binding as orc
+    from oracle.frame import OracleFrame
+    o = OracleFrame(wl).prepare_inputs()
+    t0 = time.perf_counter()
+    orc.cone_trace_ao(wl.per_frame, wl.volume, o.chain, wl.voxel_resolution, wl.depth, wl.normal)
+    out["cone_trace_ao"]["cpu_oracle_ms"] = (time.perf_counter() - t0) * 1e3
+    out["cone_trace_ao"]["cpu_cores"] = orc.default_threads()
+    t0 = time.perf_counter()
+    orc.fill_rsm(wl.spot_lights[0], pos.cpu().numpy(), nrm.cpu().numpy(), base.cpu().numpy())
+    out["fill_rsm"]["cpu_oracle_ms"] = (time.perf_counter() - t0) * 1e3
+    out["fill_rsm"]["cpu_cores"] = 1
+    h = np.zeros((wl.height, wl.width, 4), np.float32)
+    t0 = time.perf_counter()
+    orc.tonemap(h, 1.0, 1.0)
+    out["tonemap"]["cpu_oracle_ms"] = (time.perf_counter() - t0) * 1e3
+    out["tonemap"]["cpu_cores"] = 1
     print(json.dumps(out))
 
 
