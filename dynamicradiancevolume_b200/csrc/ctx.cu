@@ -362,10 +362,7 @@ static drv_status frame_body(drv_ctx* ctx, void* hdr_out, uint32_t format, uint3
     if (flags & DRV_FRAME_GATHER_IMAGE) {
       // this rank's band goes straight into rank 0's target (NVLink stores from the apply kernel); the closing
       // barrier orders them before anything rank 0 enqueues after the frame
-      void* target = ctx->shard_rank == 0 ? ctx->hdr16 : ctx->peer_hdr[0];
-      if (!sharded || !target || format != DRV_HDR_RGBA16F_WRITE)
-        return ctx->fail(DRV_ERR_NOT_BOUND, "drv_draw_frame: DRV_FRAME_GATHER_IMAGE needs a sharded context, rank 0's target "
-                                            "(drv_export_hdr_ipc / drv_import_peer_hdr) and DRV_HDR_RGBA16F_WRITE");
+      void* target = ctx->shard_rank == 0 ? ctx->hdr16 : ctx->peer_hdr[0]; // validated by drv_draw_frame
       st = drv_impl_apply_rows(ctx, target, format, y0 < H ? y0 : H, y1, true);
       if (st != DRV_OK) return st;
       return drv_impl_peer_barrier(ctx);
@@ -389,6 +386,14 @@ extern "C" drv_status drv_bind_scene(drv_ctx* ctx, const float* tri_pos, uint32_
 extern "C" drv_status drv_draw_frame(drv_ctx* ctx, void* hdr_out, uint32_t format, uint32_t flags) {
   NEED_CTX();
   if (!hdr_out && !(flags & DRV_FRAME_GATHER_IMAGE)) return ctx->fail(DRV_ERR_INVALID, "drv_draw_frame: null output");
+  if (flags & DRV_FRAME_GATHER_IMAGE) { // checked before anything is enqueued: a rank that bails out later would leave its peers in a barrier
+    const bool sharded = ctx->shard_world > 1 && ctx->peers_open;
+    if (!sharded || !(ctx->shard_rank == 0 ? ctx->hdr16 : ctx->peer_hdr[0]) || format != DRV_HDR_RGBA16F_WRITE)
+      return ctx->fail(DRV_ERR_NOT_BOUND, "drv_draw_frame: DRV_FRAME_GATHER_IMAGE needs a sharded context, rank 0's target "
+                                          "(drv_export_hdr_ipc / drv_import_peer_hdr) and DRV_HDR_RGBA16F_WRITE");
+  }
+  if ((flags & DRV_FRAME_VOXELIZE) && ctx->cfg.indirect_shadow && ctx->scene_num_tris && !ctx->scene_tris)
+    return ctx->fail(DRV_ERR_NOT_BOUND, "drv_draw_frame: DRV_FRAME_VOXELIZE needs drv_bind_scene");
   if (!ctx->side) {
     DRV_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
     DRV_CUDA(cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking));
