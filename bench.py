@@ -424,7 +424,40 @@ def measure(args, config_index, n_steps, n_warmup, light):
     h2d = sum(t.numel() * t.element_size() for t in h_gb) + sum(t.numel() * t.element_size() for r in h_rsm for t in r)
     d2h = h_out.numel() * h_out.element_size()
 
+    # sharded e2e: every rank uploads 1/world of every input over its own PCIe link, an NVLink all-gather completes
+    # the images on every GPU (allocation and VPL generation are replicated), then the sharded frame; rank 0 reads
+    # the gathered image back
+    e2e_sharded = world > 1 and in_frame and args.image_gather == "p2p"
+    if e2e_sharded:
+        def padded(t):
+            n = t.numel() * t.element_size()
+            chunk = ((n + world - 1) // world + 255) // 256 * 256
+            return n, chunk
+        host_inputs = list(h_gb) + [t for r in h_rsm for t in r]
+        dev_stage = []
+        for t in host_inputs:
+            n, chunk = padded(t)
+            dev_stage.append(torch.empty(chunk * world, dtype=torch.uint8, device=dev))
+        views = [d[:t.numel() * t.element_size()].view(t.dtype).view(t.shape) for d, t in zip(dev_stage, host_inputs)]
+        # bound once: the staging images live at fixed addresses, so the recorded frame graph stays valid
+        ctx.bind_gbuffer(views[0], views[1], views[2])
+        for i in range(len(h_rsm)):
+            ctx.bind_rsm(i, views[3 + 3 * i], views[4 + 3 * i], views[5 + 3 * i])
+
     def frame_e2e():
+        if e2e_sharded:
+            with torch.cuda.stream(stream):
+                for t, d in zip(host_inputs, dev_stage):
+                    n, chunk = padded(t)
+                    a, b = rank * chunk, min(n, (rank + 1) * chunk)
+                    if b > a:
+                        d[a:b].copy_(t.view(-1).view(torch.uint8)[a:b], non_blocking=True)
+                    dist.all_gather_into_tensor(d, d[rank * chunk:(rank + 1) * chunk])
+                ctx.draw_frame(None, abi.DRV_HDR_RGBA16F_WRITE, frame_flags | abi.DRV_FRAME_GATHER_IMAGE)
+                if rank == 0:
+                    h_out.copy_(ctx.hdr16_tensor(), non_blocking=True)
+            stream.synchronize()
+            return
         if wl.indirect_shadow:
             ctx.voxelize(g.tris, None, 1.0)
         if world == 1:
@@ -578,11 +611,17 @@ def measure(args, config_index, n_steps, n_warmup, light):
                    "parallelism": "1 GPU" if world == 1 else "gather sharded over %d GPUs by cell-ordered entry range, "
                                   "allocation replicated, fused P2P all-gather of SH, apply row-sharded, image bands %s" % (world, "stored into rank 0's target over NVLink (no collective in the frame)" if (args.image_gather == "p2p" and args.barrier == "peer" and not args.serial) else "gathered on rank 0 with NCCL"),
                    "gather_variant": args.variant},
-        "e2e": {"value": e2e_per_step, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "link": pcie, "h2d_floor_ms": (h2d / (pcie["h2d_gbs"] * 1e9) * 1e3) if pcie.get("h2d_gbs") else None,
-                "how": "drv_draw_host_frame: pinned host G-buffer + RSM level 0 -> H2D -> mips, allocate, light, apply per "
-                       "band -> D2H per band, overlapped inside the frame; wall clock around the call, which returns when "
-                       "the RGBA16F image is in host memory"},
+        "e2e": {"value": e2e_per_step, "unit": UNIT, "h2d_bytes_per_step": (h2d // world) if (world > 1 and e2e_sharded) else h2d,
+                "d2h_bytes_per_step": d2h,
+                "link": pcie,
+                "h2d_floor_ms": ((h2d // world if (world > 1 and e2e_sharded) else h2d) / (pcie["h2d_gbs"] * 1e9) * 1e3) if pcie.get("h2d_gbs") else None,
+                "how": ("drv_draw_host_frame: pinned host G-buffer + RSM level 0 -> H2D -> mips, allocate, light, apply per "
+                        "band -> D2H per band, overlapped inside the frame; wall clock around the call, which returns when "
+                        "the RGBA16F image is in host memory") if world == 1 else
+                       ("every rank uploads 1/%d of each input image from pinned host memory (h2d_bytes_per_step is per rank), "
+                        "NCCL all-gather over NVLink completes them on every GPU, sharded drv_draw_frame, rank 0 copies the "
+                        "gathered RGBA16F image to host memory; wall clock, max over ranks" % world if e2e_sharded else
+                        "every rank uploads all inputs, serial sharded stages, NCCL image gather, rank 0 D2H")},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
