@@ -210,7 +210,13 @@ typedef struct drv_config {
   uint32_t max_rsm_resolution;/* largest RSMRenderResolution that will be bound */
   int32_t  device;            /* CUDA device ordinal */
   void*    stream;            /* cudaStream_t; NULL = context creates its own */
-  uint32_t gather_variant;    /* 0 = default; other values select experimental gather kernels */
+  uint32_t gather_variant;    /* 0 = default. Tuning switches measured in profiles/ (DESIGN.md 4.1, 4.5):
+                                 bits 0..7   pair-kernel variant (1 TMA staging, 3/4/12 scalar or single-pair maths,
+                                             6 three CTAs/SM, 7/8 64-/32-thread CTAs, 9/10/11 VPL loop unrolled 2/8/4x)
+                                 bits 8..11  apply: resident blocks/SM the kernel is compiled for (4, 6; default 5)
+                                 bits 12..15 apply: rows per thread (1, 2, 8; default 4)
+                                 bit 16      two-kernel gather + finalize instead of the cooperative launch
+                                 bit 17      software-pipelined cone march instead of the plain loop */
   uint32_t reserved[3];
 } drv_config;
 

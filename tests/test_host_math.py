@@ -104,3 +104,19 @@ def test_spot_light_block_known_answers():
 
 def test_default_cascade_sizes():
     assert drv.default_cascade_world_sizes(4) == [4.0, 8.0, 16.0, 32.0]  # renderer.cpp:1181-1187
+
+
+def test_write_pfm_is_the_reference_format(tmp_path):
+    """drv_write_pfm (pure host code) == WritePfm, rendering/hdrimage.cpp:6-32: "PF\\n", "<w> <h>\\n", "-1.000000\\n",
+    then the RGB floats of the RGBA image in memory order."""
+    import ctypes as C
+    lib = drv.load()
+    w, h = 5, 3
+    rgba = np.arange(w * h * 4, dtype=np.float32).reshape(h, w, 4) * 0.25 - 3.0
+    path = str(tmp_path / "t.pfm")
+    assert lib.drv_write_pfm(path.encode(), rgba.ctypes.data_as(C.c_void_p), w, h) == 0
+    raw = open(path, "rb").read()
+    head = b"PF\n5 3\n-1.000000\n"
+    assert raw[:len(head)] == head
+    assert np.array_equal(np.frombuffer(raw[len(head):], np.float32).reshape(h, w, 3), rgba[..., :3])
+    assert lib.drv_write_pfm(b"/nonexistent-dir/x.pfm", rgba.ctypes.data_as(C.c_void_p), w, h) != 0
