@@ -176,6 +176,66 @@ def test_draw_frame_matches_serial_order(cuda_device, cfg):
     g.close()
 
 
+def test_draw_frame_edge_cases(cuda_device):
+    """drv_draw_frame on degenerate frames, eager and replayed: an empty G-buffer (no caches: every kernel must cope with
+    a zero count read on the device), a frame after it with geometry again (stale scan / queue state must not leak),
+    capacity overflow, and an RSM whose flux is zero everywhere (empty live-VPL list)."""
+    import torch
+    wl = workloads.cornell(width=160, height=96, rsm_res=64, read_lod=1, sh_order=2, indirect_shadow=True,
+                           voxel_resolution=32).build()
+    g = workloads.DeviceFrame(wl)
+    g.prepare_inputs()
+    g.ctx.bind_scene(g.tris, None, 1.0)
+    flags = abi.DRV_FRAME_PREPARE_RSM | abi.DRV_FRAME_VOXELIZE | abi.DRV_FRAME_GRAPH
+    out = torch.zeros(wl.height, wl.width, 4, dtype=torch.float16, device="cuda")
+    ref = torch.zeros_like(out)
+    torch.cuda.synchronize()
+    g.frame(ref, abi.DRV_HDR_RGBA16F_ADD)
+    torch.cuda.synchronize()
+    n_ref = g.ctx.active_cache_count()[0]
+    depth = g.depth.clone()
+    # 1. nothing visible
+    g.depth.zero_()
+    for _ in range(3):
+        out.fill_(3.0)
+        g.ctx.draw_frame(out, abi.DRV_HDR_RGBA16F_WRITE, flags)
+        torch.cuda.synchronize()
+        assert g.ctx.active_cache_count()[:2] == (0, 0)
+        assert float(out.float().abs().max()) == 0.0
+    # 2. geometry is back: same result as before the empty frames, from the same recorded graph
+    g.depth.copy_(depth)
+    for _ in range(2):
+        g.ctx.draw_frame(out, abi.DRV_HDR_RGBA16F_WRITE, flags)
+        torch.cuda.synchronize()
+        assert g.ctx.active_cache_count()[0] == n_ref
+        assert torch.equal(out, ref)
+    # 3. an RSM without flux: no live VPLs, caches are allocated but stay dark
+    flux = g.rsms[0][0].clone()
+    g.rsms[0][0].zero_()
+    for _ in range(2):
+        g.ctx.draw_frame(out, abi.DRV_HDR_RGBA16F_WRITE, flags)
+        torch.cuda.synchronize()
+        assert g.ctx.live_vpl_counts()[0] == 0 and g.ctx.active_cache_count()[0] == n_ref
+        assert float(out.float().abs().max()) == 0.0
+    g.rsms[0][0].copy_(flux)
+    g.ctx.draw_frame(out, abi.DRV_HDR_RGBA16F_WRITE, flags)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    g.close()
+    # 4. capacity overflow through the frame call
+    wl2 = workloads.cornell(max_caches=100).build()
+    g2 = workloads.DeviceFrame(wl2)
+    o = OracleFrame(wl2).allocate()
+    out2 = torch.zeros(wl2.height, wl2.width, 4, dtype=torch.float16, device="cuda")
+    for _ in range(3):
+        g2.ctx.draw_frame(out2, abi.DRV_HDR_RGBA16F_WRITE, abi.DRV_FRAME_PREPARE_RSM | abi.DRV_FRAME_GRAPH)
+    torch.cuda.synchronize()
+    n, overflow, _ = g2.ctx.active_cache_count()
+    assert n == 100 and overflow == o.alloc["overflow"] and overflow > 0
+    assert np.array_equal(g2.ctx.read_atlas(), o.alloc["atlas"])
+    g2.close()
+
+
 def test_renderer_mirror_draw(cuda_device):
     """The reference-shaped host interface (Renderer::Draw, renderer.cpp:501-594) drives the same frame."""
     import torch
