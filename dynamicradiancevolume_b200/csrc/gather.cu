@@ -746,12 +746,35 @@ __device__ __forceinline__ void gather_main(const GatherParams& p) {
           v[j] = (cur.tile * TILE + j * NT + threadIdx.x < S.count) ? __ldg(col + (size_t)blk * p.shadow_stride + j * NT) : 0.0f;
         M.set_shadow(v);
       };
-      uint32_t cur_blk = 0xFFFFFFFFu;
+      if constexpr (USE_TMA) {
+        uint32_t cur_blk = 0xFFFFFFFFu;
 #pragma unroll UNROLL
-      for (int i = 0; i < n; ++i) {
-        const uint32_t blk = USE_TMA ? __float_as_uint(sv[i * SPV + 1].w) : s_blk[i];
-        if (blk != cur_blk) { cur_blk = blk; load_shadow(blk); } // warp-uniform
-        M.eval(sv + i * SPV);
+        for (int i = 0; i < n; ++i) {
+          const uint32_t blk = __float_as_uint(sv[i * SPV + 1].w);
+          if (blk != cur_blk) { cur_blk = blk; load_shadow(blk); } // warp-uniform
+          M.eval(sv + i * SPV);
+        }
+      } else {
+        // Runs of VPLs that share a block, found once per 32 VPLs with a ballot (every warp derives the same masks
+        // from shared memory): the pair loop of a run is then the same branch-free, unrolled loop as without
+        // shadows — a block test inside it (one LDS + compare + branch per VPL) cost the shadowed kernel its
+        // instruction-level parallelism across VPLs.
+        const int lane = threadIdx.x & 31;
+#pragma unroll 1
+        for (int c0 = 0; c0 < n; c0 += 32) {
+          const int idx = c0 + lane;
+          const bool start = idx < n && (lane == 0 || s_blk[idx] != s_blk[idx - 1]);
+          uint32_t m = __ballot_sync(0xffffffffu, start); // bit 0 is always set: a run may continue from the last chunk
+          const int c1 = min(n, c0 + 32);
+          int i = c0;
+          while (m) {
+            m &= m - 1u;                                   // drop this run's start bit
+            const int next = m ? c0 + (__ffs(m) - 1) : c1; // the next run's start, or the end of the chunk
+            load_shadow(s_blk[i]);
+#pragma unroll UNROLL
+            for (; i < next; ++i) M.eval(sv + i * SPV);
+          }
+        }
       }
     } else {
 #pragma unroll UNROLL
