@@ -603,3 +603,73 @@ def test_apply_against_float64_restatement(order):
     # allocated (the trilinear blend is continuous only where all eight corners exist)
     assert good >= 155, good
     assert img[..., :3].max() > 1e-3
+
+
+def _morton(k):
+    x = y = 0
+    for b in range(16):
+        x |= ((k >> (2 * b)) & 1) << b
+        y |= ((k >> (2 * b + 1)) & 1) << b
+    return x, y
+
+
+def test_vpl_list_and_shadow_blocks_against_float64_restatement():
+    """cacheLightingRSM.comp:137-163 (VPL load) and :168-192 (the cache-independent half of the indirect-shadow
+    sample) restated independently in float64 python: Morton order, unprojection along the light ray, disc area,
+    bilinear clamp-to-edge fetch of depthLinSq at the shadow LOD, distToSphereRad."""
+    wl = workloads.atrium(width=64, height=64, rsm_res=128, read_lod=1, sh_order=1, indirect_shadow=True,
+                          voxel_resolution=32, shadow_lod=2).build()
+    o = OracleFrame(wl).prepare_inputs()
+    L = wl.spot_lights[0]
+    R = int(L.RSMReadResolution)
+    read_level = workloads.rsm_read_level(L)
+    flux, normal, depth = (np.asarray(a) for a in o.levels[0][read_level])
+    fl = flux.view(np.float16).astype(np.float64)
+    dp = depth.view(np.float16).astype(np.float64)
+    ilvp = np.array(list(L.InverseLightViewProjection), np.float64).reshape(4, 4)
+    lp = np.array(L.LightPosition[:3], np.float64)
+    PI = 3.14159265358979
+
+    def ray_point(u, v, d):
+        w = ilvp @ np.array([u * 2 - 1, v * 2 - 1, 0.0, 1.0])
+        dirv = w[:3] / w[3] - lp
+        return lp + dirv / np.linalg.norm(dirv) * d
+
+    vpls = o.vpls[0]
+    rng = np.random.default_rng(9)
+    for k in rng.choice(R * R, 300, replace=False):
+        x, y = _morton(int(k))
+        d = dp[y, x, 0]
+        want = ray_point((x + 0.5) / R, (y + 0.5) / R, d)
+        assert np.allclose(vpls["Position"][k], want, rtol=1e-5, atol=1e-5)
+        assert np.isclose(vpls["DiscArea"][k], d * d * L.ValAreaFactor, rtol=1e-5)
+        assert np.array_equal(vpls["Flux"][k], fl[y, x, :3].astype(np.float32))
+        a, z = int(normal[y, x, 0]) * PI / 32768.0, int(normal[y, x, 1]) / 32768.0
+        n = np.array([math.cos(a) * math.sqrt(1 - z * z), math.sin(a) * math.sqrt(1 - z * z), z])
+        assert np.allclose(vpls["Normal"][k], n / np.linalg.norm(n), atol=2e-6)
+    # shadow blocks
+    lod = int(L.IndirectShadowComputationLod)
+    interval = int(L.IndirectShadowComputationSampleInterval)
+    assert interval == 4 ** lod
+    dl = np.asarray(o.levels[0][read_level + lod][2]).view(np.float16).astype(np.float64)  # [Rl, Rl, 2]
+    Rl = R >> lod
+    blocks = o.blocks[0]
+    assert len(blocks) == R * R // interval
+    for b in rng.choice(len(blocks), 120, replace=False):
+        x, y = _morton(int(b) * interval)
+        u, v = (x + L.IndirectShadowSamplingOffset) / R, (y + L.IndirectShadowSamplingOffset) / R
+        fx, fy = u * Rl - 0.5, v * Rl - 0.5
+        x0, y0 = math.floor(fx), math.floor(fy)
+        tx, ty = fx - x0, fy - y0
+        cl = lambda i: min(max(i, 0), Rl - 1)
+        s = lambda c: ((dl[cl(y0), cl(x0), c] * (1 - tx) + dl[cl(y0), cl(x0 + 1), c] * tx) * (1 - ty)
+                       + (dl[cl(y0 + 1), cl(x0), c] * (1 - tx) + dl[cl(y0 + 1), cl(x0 + 1), c] * tx) * ty)
+        m1, m2 = s(0), s(1)
+        want_pos = ray_point(u, v, m1)
+        var = max(m2 - m1 * m1, 0.0)
+        want_k = max(L.IndirectShadowComputationSuperValWidth, math.sqrt(var) * 2.0 / m1) if m1 > 0 else None
+        assert np.allclose(blocks["AverageValPos"][b], want_pos, rtol=2e-5, atol=2e-5)
+        if want_k is not None and var > 1e-4 * m1 * m1:  # away from the cancellation-dominated variance ~ 0 case
+            assert np.isclose(blocks["DistToSphereRad"][b], want_k, rtol=2e-3)
+        elif want_k is not None:
+            assert blocks["DistToSphereRad"][b] >= L.IndirectShadowComputationSuperValWidth * (1 - 1e-6)
