@@ -795,3 +795,88 @@ def test_voxelizer_is_conservative_and_tight():
         n_touched += int(touched.sum())
         n_missed += int((touched & ~vol).sum())
     assert n_missed <= 0.03 * n_touched, (n_missed, n_touched)
+
+
+@pytest.mark.parametrize("name,make", [
+    ("cornell", lambda: workloads.cornell(width=96, height=80, rsm_res=16)),
+    ("atrium-transitions", lambda: workloads.atrium(width=160, height=90, rsm_res=32, read_lod=0, cav_resolution=16,
+                                                    first_cascade=8.0, max_caches=8192)),
+    ("atrium-3casc-ragged", lambda: workloads.atrium(width=150, height=70, rsm_res=32, read_lod=0, cascades=3,
+                                                     cav_resolution=16, first_cascade=4.0, max_caches=8192)),
+])
+def test_allocation_set_against_vectorised_float32_restatement(name, make):
+    """cacheGather.comp:93-164 restated independently as whole-image numpy float32 array code (every * and +
+    rounded separately, like the oracle's policy): world positions, cascade choice, cell ids, the two neighbour
+    dedupe predicates on the shader's 16x16 tiles, the eight corner cells. The allocated cell SET must be identical."""
+    wl = make().build()
+    cb, vi = wl.constant, wl.volume
+    W, H, R, C = cb.BackbufferResolution[0], cb.BackbufferResolution[1], cb.AddressVolumeResolution, cb.NumAddressVolumeCascades
+    f = np.float32
+    d = wl.depth.astype(f)
+    xs, ys = np.meshgrid(np.arange(W, dtype=f), np.arange(H, dtype=f))
+    sx = (xs + f(0.5)) / f(W) * f(2) - f(1)
+    sy = (ys + f(0.5)) / f(H) * f(2) - f(1)
+    m = np.array(list(wl.per_frame.InverseViewProjection), f).reshape(4, 4)
+    one = np.ones_like(d)
+    row = lambda r: ((m[r, 0] * sx + m[r, 1] * sy) + m[r, 2] * d) + m[r, 3] * one
+    w = row(3)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        wp = np.stack([row(0) / w, row(1) / w, row(2) / w], -1)
+    valid = d > f(0.0001)
+
+    def inside(c):
+        k = vi.AddressVolumeCascades[c]
+        return np.all(wp <= np.array(k.DecisionMax[:3], f), -1) & np.all(wp >= np.array(k.DecisionMin[:3], f), -1)
+
+    casc = np.full((H, W), C - 1, int)
+    for c in range(C - 2, -1, -1):
+        casc = np.where(inside(c), c, casc)
+
+    def cell(c_arr):
+        out = np.zeros((H, W), np.int64)
+        for c in range(C):
+            k = vi.AddressVolumeCascades[c]
+            with np.errstate(invalid="ignore"):
+                g = (wp - np.array(k.Min[:3], f)) / f(k.WorldVoxelSize)
+            gi = np.clip(np.trunc(np.nan_to_num(g, nan=0.0, posinf=1e9, neginf=-1e9)), 0, R - 1).astype(np.int64)
+            idc = gi[..., 0] + gi[..., 1] * R + gi[..., 2] * R * R + c * R ** 3
+            out = np.where(c_arr == c, idc, out)
+        return out
+
+    T1 = np.where(valid, cell(casc), -1)
+    T2 = np.full((H, W), -1, np.int64)
+    if wl.transitions:
+        tr = np.zeros((H, W), f)
+        for c in range(C - 1):
+            k = vi.AddressVolumeCascades[c]
+            with np.errstate(invalid="ignore"):
+                md = np.minimum((np.array(k.DecisionMax[:3], f) - wp).min(-1), (wp - np.array(k.DecisionMin[:3], f)).min(-1))
+                t = np.clip(f(1) - md / (f(k.WorldVoxelSize) * f(vi.CAVTransitionZoneSize)), 0, 1)
+            tr = np.where(casc == c, t, tr)
+        second = valid & (tr > 0) & (casc < C - 1)
+        T2 = np.where(second, cell(np.minimum(casc + 1, C - 1)), -1)
+
+    # pad to whole tiles with -1 (threads outside the image leave 0xFFFFFFFF in shared memory)
+    Hp, Wp = (H + 15) // 16 * 16, (W + 15) // 16 * 16
+    pad = lambda a: np.pad(a, ((0, Hp - H), (0, Wp - W)), constant_values=-1)
+    T1p, T2p, cp = pad(T1), pad(T2), pad(casc)
+    ly, lx = np.meshgrid(np.arange(Hp) % 16, np.arange(Wp) % 16, indexing="ij")
+    yy, xx = np.meshgrid(np.arange(Hp), np.arange(Wp), indexing="ij")
+    up, left = np.where(ly > 0, yy - 1, yy), np.where(lx > 0, xx - 1, xx)
+    trig1 = (((T1p[up, xx] != T1p) & (T1p[yy, left] != T1p) & (T1p[up, left] != T1p)) | ((lx == 0) & (ly == 0))) & (T1p != -1)
+    dn, right = np.where(ly < 15, yy + 1, yy), np.where(lx < 15, xx + 1, xx)
+    # `lookUpThread == ivec2(LOCAL_SIZE-1)` holds for the clamped look-up, i.e. for local x and y >= 14 (:157)
+    trig2 = (((T2p[dn, xx] != T2p) & (T2p[yy, right] != T2p) & (T2p[dn, right] != T2p)) | ((lx >= 14) & (ly >= 14))) & (T2p != -1)
+    ids = set()
+    for trig, T, cc in ((trig1, T1p, cp), (trig2, T2p, np.minimum(cp + 1, C - 1))):
+        for coord, c in zip(T[trig], cc[trig]):
+            local = int(coord) - R ** 3 * int(c)
+            bz, by, bx = local // (R * R), (local // R) % R, local % R
+            for ox in (0, 1):
+                for oy in (0, 1):
+                    for oz in (0, 1):
+                        if bx + ox < R and by + oy < R and bz + oz < R:
+                            ids.add((bx + ox) + (by + oy) * R + (bz + oz) * R * R + int(c) * R ** 3)
+    got = orc.allocated_cell_ids(wl.constant, wl.per_frame, wl.volume, wl.transitions, wl.depth)
+    assert len(got) > 50
+    assert np.array_equal(np.array(sorted(ids), np.int32), got)
