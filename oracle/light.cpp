@@ -256,7 +256,9 @@ extern "C" void orc_light_caches(const drv_constant* cb, const drv_volume_info* 
 extern "C" void orc_rsm_downsample(const uint16_t* flux_src, const int16_t* normal_src, const uint16_t* depth_src,
                                    uint32_t res, uint16_t* flux_dst, int16_t* normal_dst, uint16_t* depth_dst) {
   const uint32_t h = res / 2;
-  for (uint32_t y = 0; y < h; ++y)
+  /* rows are independent: all host threads for the large levels (the reference arm of bench.py times this) */
+  parallel_for((int64_t)h, h >= 128 ? 0 : 1, [&](int64_t y0, int64_t y1, int) {
+  for (uint32_t y = (uint32_t)y0; y < (uint32_t)y1; ++y)
     for (uint32_t x = 0; x < h; ++x) {
       /* textureGather at the shared corner of the 2x2 footprint: texels
        * (2x,2y+1) (2x+1,2y+1) (2x+1,2y) (2x,2y) in .xyzw order */
@@ -280,6 +282,7 @@ extern "C" void orc_rsm_downsample(const uint16_t* flux_src, const int16_t* norm
         depth_dst[o * 2 + c] = float_to_half(mixf(a, b, 0.5f));
       }
     }
+  });
 }
 
 extern "C" float orc_half_to_float(uint16_t h) { return half_to_float(h); }
