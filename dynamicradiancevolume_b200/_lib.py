@@ -75,6 +75,7 @@ SYMBOLS = [
     ("drv_microbench", _st, [_i32, _u32, C.POINTER(C.c_double)]),
     ("drv_microbench_name", C.c_char_p, [_u32]),
     ("drv_microbench_count", _u32, []),
+    ("drv_debug_gather_trace", _st, [_P, _P, _u32, C.POINTER(_u32)]),
 ]
 
 _lib = None

@@ -134,6 +134,8 @@ extern "C" drv_status drv_create(const drv_config* cfg, drv_ctx** out) {
   }
   CREATE_CUDA(dmalloc(&ctx->cone_work, 4 * sizeof(uint32_t)));
   CREATE_CUDA(cudaMemsetAsync(ctx->cone_work, 0, 4 * sizeof(uint32_t), ctx->stream));
+  CREATE_CUDA(dmalloc(&ctx->gather_tickets, ((size_t)c.max_cache_count / 64 + 2) * sizeof(uint32_t)));
+  CREATE_CUDA(cudaMemsetAsync(ctx->gather_tickets, 0, ((size_t)c.max_cache_count / 64 + 2) * sizeof(uint32_t), ctx->stream));
   CREATE_CUDA(dmalloc(&ctx->live_counts, DRV_MAX_LIGHTS * sizeof(uint32_t)));
   CREATE_CUDA(cudaMemsetAsync(ctx->live_counts, 0, DRV_MAX_LIGHTS * sizeof(uint32_t), ctx->stream));
   CREATE_CUDA(dmalloc(&ctx->ndc_xy, ((size_t)c.backbuffer_width + c.backbuffer_height) * sizeof(float)));
@@ -168,7 +170,7 @@ extern "C" void drv_destroy(drv_ctx* ctx) {
     if (ctx->ev_begin[s]) cudaEventDestroy(ctx->ev_begin[s]);
     if (ctx->ev_end[s]) cudaEventDestroy(ctx->ev_end[s]);
   }
-  cudaFree(ctx->live_counts); cudaFree(ctx->cone_work);
+  cudaFree(ctx->live_counts); cudaFree(ctx->cone_work); cudaFree(ctx->gather_tickets); cudaFree(ctx->gather_trace);
   if (ctx->frame_graph) cudaGraphExecDestroy(ctx->frame_graph);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->side2) cudaStreamDestroy(ctx->side2);

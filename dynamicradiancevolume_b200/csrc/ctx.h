@@ -112,6 +112,9 @@ struct drv_ctx {
   uint32_t* cone_work = nullptr;     // cone_kernel's work queue: [0] next item, [1] CTAs done
   float* shadow_table = nullptr;     // visibility of (VAL block, cache) for the current chunk of caches (cone_kernel)
   size_t shadow_table_floats = 0;
+  uint32_t* gather_tickets = nullptr; // warp-split gather: arrival counter per cache tile (zero between launches)
+  unsigned long long* gather_trace = nullptr; // diagnostics (gather_variant bit 18)
+  uint32_t gather_trace_ctas = 0;
   float* partials = nullptr;         // split-VPL partial sums
   uint64_t partial_slots = 0;        // capacity in cache slots
   uint32_t shard_rank = 0, shard_world = 1;

@@ -82,7 +82,25 @@ struct GatherParams {
   // fused all-gather: peer copies of the entries buffer (NVLink P2P)
   uint8_t* peers[8];
   uint32_t num_peers;
+  uint32_t* tickets;     // warp-split kernel: one arrival counter per cache tile (zero between launches)
+  unsigned long long* trace; // diagnostics (gather_variant bit 18): %globaltimer at 4 points of every CTA, else null
 };
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_point(const GatherParams& p, int k) {
+  if (p.trace && threadIdx.x == 0) {
+    p.trace[(size_t)blockIdx.x * 8 + k] = global_ns();
+    p.trace[(size_t)blockIdx.x * 8 + 4 + k] = (unsigned long long)clock64();
+    if (k == 0) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.trace[(size_t)blockIdx.x * 8 + 4] = smid;
+    }
+  }
+}
 
 struct Schedule {
   uint32_t first, count;      // entry range of this shard
@@ -816,12 +834,222 @@ __device__ __forceinline__ void gather_main(const GatherParams& p) {
 // launch, its prologue and the launch gap; every CTA of the persistent grid is resident by construction).
 template <int ORDER, bool SHADOW, typename Math, bool USE_TMA, int MINB = 1, int NT = kThreads, int UNROLL = 4>
 __global__ void __launch_bounds__(NT, MINB) gather_kernel(const __grid_constant__ GatherParams p) {
+  trace_point(p, 0);
   gather_main<ORDER, SHADOW, Math, USE_TMA, NT, UNROLL>(p);
+  trace_point(p, 1);
   if (p.fused_finalize) {
     __shared__ FinalizeSmem<ORDER, NT> fin;
     cg::this_grid().sync();
+    trace_point(p, 2);
     finalize_phase<ORDER, NT>(p, NT * Math::CPT, fin, blockIdx.x, gridDim.x);
   }
+  trace_point(p, 3);
+}
+
+// ------------------------------------------------------------ the warp-split gather kernel
+// Same pair maths, staging and stream-K unit schedule as gather_kernel, but the cache tile is what ONE warp holds
+// in registers (32 lanes x CPT entries: 128 for SH1, 64 for SH2) and the NW warps of a CTA split the VPLs of every
+// shared-memory tile between them instead of splitting the caches. What that buys at frame-sized cache counts:
+//  * the tile granularity drops from 512 to 128 entries, so the padded slots of the last tile are ~1 % of a
+//    6 k-cache frame instead of 7 %;
+//  * a tile is split between ~grid / tiles CTAs (6 at 1080p) instead of ~23, each CTA first folds its NW warps
+//    through shared memory, so a partial segment is 6 KB instead of 24 KB;
+//  * the cross-CTA fix-up needs no grid-wide barrier and no cooperative launch: every contributor of a split tile
+//    publishes its partial sums and takes a ticket; whoever draws the last ticket adds all partial segments in CTA
+//    order (deterministic — no float atomics) and writes the entry (+ the peer stores of the fused all-gather).
+template <int ORDER, bool SHADOW, typename Math, int NW, int UNROLL, int KVT = 1>
+__global__ void __launch_bounds__(NW * 32, NW >= 8 ? 1 : 256 / (NW * 32)) gather_ws_kernel(const __grid_constant__ GatherParams p) {
+  constexpr int CPT = Math::CPT;
+  constexpr int TILE = 32 * CPT;
+  constexpr int NT = NW * 32;
+  constexpr int KV = NT * KVT; // VPLs staged per shared-memory tile: KVT per thread
+  constexpr int NC = num_coefs<ORDER>();
+  constexpr int STRIDE = ORDER == 2 ? 128 : 64;
+  constexpr int SPV = Math::kSmemPerVpl;
+  constexpr int FOLD = (TILE + NT - 1) / NT; // caches of the tile a thread folds at a segment end
+  // the staged VPL tile and the cross-warp fold buffer share one allocation (the fold runs between two tiles)
+  constexpr int RW = (NW < 4 ? NW : 4) * NC * TILE * 4 > 40960 ? 2 : (NW < 4 ? NW : 4); // warps folded per round
+  constexpr int kVplBytes = KV * SPV * 16, kRedBytes = RW * NC * TILE * 4;
+  __shared__ __align__(16) unsigned char s_raw[kVplBytes > kRedBytes ? kVplBytes : kRedBytes];
+  float4* const s_vpl = reinterpret_cast<float4*>(s_raw);
+  float (*const s_red)[NC][TILE] = reinterpret_cast<float (*)[NC][TILE]>(s_raw);
+  __shared__ uint32_t s_blk[SHADOW ? KV : 1];
+  __shared__ uint32_t s_last;
+
+  trace_point(p, 0);
+  Schedule S = make_schedule(p, TILE);
+  if (S.units == 0) return;
+  // every CTA of the (effective) grid owns a non-empty unit range
+  const uint32_t G = (uint32_t)min((unsigned long long)gridDim.x, S.units);
+  if (blockIdx.x >= G) return;
+  const unsigned long long u0 = range_begin(S, G, blockIdx.x), u1 = range_begin(S, G, blockIdx.x + 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  Math M;
+  float4 r0[KVT], r1[KVT], r2[KVT];
+#pragma unroll
+  for (int k = 0; k < KVT; ++k) r0[k] = r1[k] = r2[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto prefetch = [&](const Cursor& c) {
+    const GatherLight& L = p.lights[c.light];
+#pragma unroll
+    for (int k = 0; k < KVT; ++k) {
+      const uint32_t v = c.base + k * NT + threadIdx.x;
+      const bool ok = v < c.v_end;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      r0[k] = ok ? __ldg(L.vpls + (size_t)v * 3) : make_float4(0.f, 0.f, 0.f, 1.f);
+      r1[k] = ok ? __ldg(L.vpls + (size_t)v * 3 + 1) : z;
+      r2[k] = ok ? __ldg(L.vpls + (size_t)v * 3 + 2) : z;
+    }
+  };
+  Cursor cur;
+  start_run(p, S, cur, u0, u1);
+  prefetch(cur);
+  bool seg_open = false;
+  uint32_t seg_first_j = 0;
+  bool traced = false;
+  while (cur.valid) {
+    if (!seg_open) {
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const uint32_t local = cur.tile * TILE + j * 32 + lane;
+        const bool alive = local < S.count;
+        const float4 pos = alive ? *reinterpret_cast<const float4*>(p.entries + (size_t)(S.first + local) * STRIDE)
+                                 : make_float4(1e30f, 1e30f, 1e30f, 0.f);
+        M.begin(j, alive, pos);
+      }
+      seg_first_j = (uint32_t)(cur.u - (unsigned long long)cur.tile * S.units_per_tile);
+      seg_open = true;
+    }
+    Cursor nxt = cur;
+    advance(p, S, nxt, u1, KV);
+    __syncthreads(); // previous tile (or fold) fully consumed
+#pragma unroll
+    for (int k = 0; k < KVT; ++k) {
+      Math::stage(&s_vpl[(k * NT + threadIdx.x) * SPV], r0[k], r1[k], r2[k]);
+      if (SHADOW) s_blk[k * NT + threadIdx.x] = __float_as_uint(r1[k].w);
+    }
+    __syncthreads();
+    if (nxt.valid) prefetch(nxt);
+    if (!traced) { trace_point(p, 1); traced = true; } // prologue done: the first tile is staged
+    // this warp's share of the staged VPLs
+    const int n = (int)min((uint32_t)KV, cur.v_end - cur.base);
+    const int share = (n + NW - 1) / NW;
+    const int i0 = min(n, warp * share), i1 = min(n, i0 + share);
+    if constexpr (SHADOW) {
+      const float* col = p.shadow_table + (size_t)p.block_offset[cur.light] * p.shadow_stride + cur.tile * TILE + lane;
+      auto load_shadow = [&](uint32_t blk) {
+        float v[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+          v[j] = (cur.tile * TILE + j * 32 + lane < S.count) ? __ldg(col + (size_t)blk * p.shadow_stride + j * 32) : 0.0f;
+        M.set_shadow(v);
+      };
+      // runs of VPLs sharing a shadow block, found 32 VPLs at a time with one ballot
+#pragma unroll 1
+      for (int c0 = i0; c0 < i1; c0 += 32) {
+        const int idx = c0 + lane, c1 = min(i1, c0 + 32);
+        const bool start = idx < c1 && (lane == 0 || s_blk[idx] != s_blk[idx - 1]);
+        uint32_t m = __ballot_sync(0xffffffffu, start);
+        int i = c0;
+        while (m) {
+          m &= m - 1u;
+          const int next = m ? c0 + (__ffs(m) - 1) : c1;
+          load_shadow(s_blk[i]);
+#pragma unroll UNROLL
+          for (; i < next; ++i) M.eval(s_vpl + i * SPV);
+        }
+      }
+    } else {
+#pragma unroll UNROLL
+      for (int i = i0; i < i1; ++i) M.eval(s_vpl + i * SPV);
+    }
+    if (!nxt.valid) trace_point(p, 2); // pair loop done
+    if (!nxt.valid || nxt.tile != cur.tile) { // segment end: fold the warps, then write or publish
+      const uint32_t last_j = (uint32_t)(cur.u_next - 1ull - (unsigned long long)cur.tile * S.units_per_tile);
+      const bool full = seg_first_j == 0 && last_j == S.units_per_tile - 1;
+      // fold the warps' accumulators through shared memory, RW warps per round, in warp order (deterministic)
+      float folded[FOLD][NC];
+#pragma unroll
+      for (int k = 0; k < FOLD; ++k)
+#pragma unroll
+        for (int q = 0; q < NC; ++q) folded[k][q] = 0.0f;
+#pragma unroll
+      for (int w0 = 0; w0 < NW; w0 += RW) {
+        __syncthreads(); // the staged tile (which the fold buffer aliases) / the previous round has been consumed
+        if (warp >= w0 && warp < w0 + RW) {
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) {
+            float raw[27];
+            M.raw(j, raw);
+#pragma unroll
+            for (int q = 0; q < NC; ++q) s_red[warp - w0][q][j * 32 + lane] = raw[q];
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < FOLD; ++k) {
+          const uint32_t t = threadIdx.x + k * NT;
+          if (t < (uint32_t)TILE) {
+#pragma unroll
+            for (int q = 0; q < NC; ++q)
+#pragma unroll
+              for (int w = 0; w < RW; ++w) folded[k][q] += s_red[w][q][t];
+          }
+        }
+      }
+      // slot 0: the segment in the tile that contains u0; slot 1: the (later) tile this range ends in
+      const unsigned long long ua = (unsigned long long)cur.tile * S.units_per_tile, ub = ua + S.units_per_tile;
+      const int slot = u0 >= ua ? 0 : 1;
+#pragma unroll
+      for (int k = 0; k < FOLD; ++k) { // thread t owns cache t (+ NT, ...) of the tile
+        const uint32_t t = threadIdx.x + k * NT;
+        if (t >= (uint32_t)TILE) break;
+        if (full) {
+          if (cur.tile * TILE + t < S.count) {
+            float raw[27];
+#pragma unroll
+            for (int q = 0; q < 27; ++q) raw[q] = q < NC ? folded[k][q < NC ? q : 0] : 0.0f;
+            float vals[28];
+            coef_values<ORDER>(p, raw, vals);
+            add_to_entry<ORDER>(p, S.first + cur.tile * TILE + t, vals);
+          }
+        } else {
+          float* dst = p.partials + ((size_t)blockIdx.x * 2 + slot) * NC * TILE + t;
+#pragma unroll
+          for (int q = 0; q < NC; ++q) __stcg(dst + (size_t)q * TILE, folded[k][q]);
+        }
+      }
+      if (!full) {
+        const uint32_t c_lo = owner_of(S, G, ua), c_hi = owner_of(S, G, ub - 1);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(p.tickets + cur.tile, 1u) == c_hi - c_lo) ? 1u : 0u;
+        __syncthreads();
+        if (s_last) { // block-uniform: every other contributor's partial segment is visible
+          __threadfence();
+          for (uint32_t t = threadIdx.x; t < (uint32_t)TILE; t += NT) {
+            if (cur.tile * TILE + t >= S.count) break;
+            float raw[27];
+#pragma unroll
+            for (int q = 0; q < 27; ++q) raw[q] = 0.0f;
+            for (uint32_t c = c_lo; c <= c_hi; ++c) {
+              const uint32_t sl = range_begin(S, G, c) >= ua ? 0u : 1u;
+              const float* src = p.partials + ((size_t)c * 2 + sl) * NC * TILE + t;
+#pragma unroll
+              for (int q = 0; q < NC; ++q) raw[q] += __ldcg(src + (size_t)q * TILE);
+            }
+            float vals[28];
+            coef_values<ORDER>(p, raw, vals);
+            add_to_entry<ORDER>(p, S.first + cur.tile * TILE + t, vals);
+          }
+          if (threadIdx.x == 0) p.tickets[cur.tile] = 0u; // rewound for the next launch
+        }
+      }
+      seg_open = false;
+    }
+    cur = nxt;
+  }
+  trace_point(p, 3);
 }
 
 // ------------------------------------------------------------ pass 1: the visibility table
@@ -909,7 +1137,7 @@ namespace {
 
 using GatherFn = void (*)(const GatherParams);
 
-drv_status launch_gather(drv_ctx* ctx, GatherFn kernel, GatherParams& p, int tile_caches, int order, int threads) {
+drv_status launch_gather(drv_ctx* ctx, GatherFn kernel, GatherParams& p, int tile_caches, int order, int threads, bool ws) {
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
   if (per_sm < 1) per_sm = 1;
@@ -925,6 +1153,22 @@ drv_status launch_gather(drv_ctx* ctx, GatherFn kernel, GatherParams& p, int til
   }
   p.partials = ctx->partials;
   p.grid = (uint32_t)grid;
+  p.tickets = ctx->gather_tickets;
+  p.trace = nullptr;
+  if (ctx->cfg.gather_variant & 0x40000u) { // diagnostics: per-CTA timestamps, read with drv_debug_gather_trace
+    if (!ctx->gather_trace) {
+      DRV_CUDA(cudaMalloc(&ctx->gather_trace, (size_t)8192 * 8 * sizeof(unsigned long long)));
+      DRV_CUDA(cudaMemsetAsync(ctx->gather_trace, 0, (size_t)8192 * 8 * sizeof(unsigned long long), ctx->stream));
+    }
+    if (grid <= 8192) p.trace = ctx->gather_trace;
+    ctx->gather_trace_ctas = (uint32_t)grid;
+  }
+  if (ws) { // warp-split kernel: ticketed fix-up inside the one ordinary launch
+    p.fused_finalize = 0u;
+    kernel<<<grid, threads, 0, ctx->stream>>>(p);
+    DRV_LAUNCH_CHECK();
+    return DRV_OK;
+  }
   // one cooperative launch (pair loop, grid barrier, finalize) when the device can do it; gather_variant bit 16
   // forces the two-kernel form
   int coop = 0;
@@ -947,7 +1191,8 @@ drv_status launch_gather(drv_ctx* ctx, GatherFn kernel, GatherParams& p, int til
 }
 
 // Kernel variants (drv_config.gather_variant; measurements in profiles/):
-//   0  packed FP32x2 maths, 4 caches / thread (SH1) or 2 (SH2)      — default, fastest in the sweep
+//   0  = 31: warp-split kernel, one 8-warp CTA per SM, 6 caches / thread (SH1) or 4 (SH2) — default
+//   30 the round-1 default: cooperative stream-K kernel, packed FP32x2 maths, 4 caches / thread (SH1) or 2 (SH2)
 //   1  scalar maths, VPL tiles staged with TMA bulk copies + mbarrier, double buffered
 //   3  packed, one pair of caches per thread
 //   4  scalar, 4 caches / thread (SH1)
@@ -957,9 +1202,62 @@ drv_status launch_gather(drv_ctx* ctx, GatherFn kernel, GatherParams& p, int til
 //   8  as 0 with 32-thread CTAs (cache tiles of 128 / 64 entries)
 //   9, 10, 11  the packed kernel with the VPL loop unrolled 2x / 8x / 4x (default: 8x for SH1, 4x for SH2)
 // With indirect shadows the same kernels additionally scale every pair by its table visibility.
+//   20 warp-split kernel (gather_ws_kernel): 4 warps share a 128- (SH1) / 64-entry (SH2) tile and split the VPLs,
+//      ticketed fix-up, ordinary launch; 21 the same with 2-warp CTAs; 22 / 23 as 20 with the VPL loop unrolled 4x / 2x;
+//      24 / 25 as 20 with 256 / 512 VPLs per shared-memory tile; 26 / 27 ONE 8-warp CTA per SM (256 / 512 VPLs per
+//      tile): the warps of a CTA advance in lock step through the tile barriers, so no SM is left with half its
+//      warps while a co-resident CTA that the scheduler favoured has already finished; 28 one 12-warp CTA per SM
 template <bool SH>
-GatherFn select_kernel(int order, uint32_t variant, int* tile, int* threads) {
+GatherFn select_kernel(int order, uint32_t variant, int* tile, int* threads, bool* ws) {
   *threads = kThreads;
+  *ws = false;
+  if (variant == 0) variant = 31; // the default: fastest at every measured size (profiles/r2_gather_variants.md)
+  if (variant == 31 || variant == 32) { // three (SH1) / two (SH2) packed pairs per thread, one 8-warp CTA per SM
+    using P1 = PackedMath<1, SH, 3>; using P2 = PackedMath<2, SH, 2>;
+    *ws = true;
+    *tile = 32 * (order == 1 ? P1::CPT : P2::CPT);
+    *threads = 256;
+    if (order == 1) return variant == 31 ? gather_ws_kernel<1, SH, P1, 8, 8, 2> : gather_ws_kernel<1, SH, P1, 8, 4, 2>;
+    return variant == 31 ? gather_ws_kernel<2, SH, P2, 8, 4, 2> : gather_ws_kernel<2, SH, P2, 8, 2, 2>;
+  }
+  if (variant == 33 || variant == 34) { // four packed pairs per thread (SH1), 256-entry tiles
+    using P1 = PackedMath<1, SH, 4>; using P2 = PackedMath<2, SH, 2>;
+    *ws = true;
+    *tile = 32 * (order == 1 ? P1::CPT : P2::CPT);
+    *threads = 256;
+    if (order == 1) return variant == 33 ? gather_ws_kernel<1, SH, P1, 8, 4, 2> : gather_ws_kernel<1, SH, P1, 8, 2, 2>;
+    return variant == 33 ? gather_ws_kernel<2, SH, P2, 8, 4, 1> : gather_ws_kernel<2, SH, P2, 8, 8, 2>;
+  }
+  if (variant >= 20 && variant <= 28) {
+    using P1 = PackedMath<1, SH, 2>; using P2 = PackedMath<2, SH, 1>;
+    *ws = true;
+    *tile = 32 * (order == 1 ? P1::CPT : P2::CPT);
+    *threads = variant == 21 ? 64 : variant == 28 ? 384 : variant >= 26 ? 256 : 128;
+    if (order == 1) {
+      switch (variant) {
+        case 21: return gather_ws_kernel<1, SH, P1, 2, 8>;
+        case 22: return gather_ws_kernel<1, SH, P1, 4, 4>;
+        case 23: return gather_ws_kernel<1, SH, P1, 4, 2>;
+        case 24: return gather_ws_kernel<1, SH, P1, 4, 8, 2>;
+        case 25: return gather_ws_kernel<1, SH, P1, 4, 8, 4>;
+        case 26: return gather_ws_kernel<1, SH, P1, 8, 8, 1>;
+        case 27: return gather_ws_kernel<1, SH, P1, 8, 8, 2>;
+        case 28: return gather_ws_kernel<1, SH, P1, 12, 8, 1>;
+        default: return gather_ws_kernel<1, SH, P1, 4, 8>;
+      }
+    }
+    switch (variant) {
+      case 21: return gather_ws_kernel<2, SH, P2, 2, 4>;
+      case 22: return gather_ws_kernel<2, SH, P2, 4, 8>;
+      case 23: return gather_ws_kernel<2, SH, P2, 4, 2>;
+      case 24: return gather_ws_kernel<2, SH, P2, 4, 4, 2>;
+      case 25: return gather_ws_kernel<2, SH, P2, 4, 4, 4>;
+      case 26: return gather_ws_kernel<2, SH, P2, 8, 4, 1>;
+      case 27: return gather_ws_kernel<2, SH, P2, 8, 4, 2>;
+      case 28: return gather_ws_kernel<2, SH, P2, 12, 4, 1>;
+      default: return gather_ws_kernel<2, SH, P2, 4, 4>;
+    }
+  }
 #define DRV_PICK(ORD, MATH, TMA) do { *tile = kThreads * MATH::CPT; return gather_kernel<ORD, SH, MATH, TMA>; } while (0)
   using S1c2 = ScalarMath<1, SH, 2>; using S1c4 = ScalarMath<1, SH, 4>; using S2c2 = ScalarMath<2, SH, 2>;
   using P1p1 = PackedMath<1, SH, 1>; using P1p2 = PackedMath<1, SH, 2>; using P2p1 = PackedMath<2, SH, 1>;
@@ -1087,13 +1385,15 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   const int order = (int)ctx->cfg.sh_order;
   const uint32_t variant = ctx->cfg.gather_variant & 0xFFu; // bits 8.. tune other kernels
   int tile = 0, threads = kThreads;
-  const GatherFn kernel = shadow ? select_kernel<true>(order, variant, &tile, &threads)
-                                 : select_kernel<false>(order, variant, &tile, &threads);
+  bool ws = false;
+  const GatherFn kernel = shadow ? select_kernel<true>(order, variant, &tile, &threads, &ws)
+                                 : select_kernel<false>(order, variant, &tile, &threads, &ws);
+  if (ws) p.granule = 8; // the warps split every staged tile evenly, so a finer quantum only improves the balance
   p.chunk_first = 0;
   p.chunk_cap = 0xFFFFFFFFu;
   if (!shadow) {
     ctx->stage_begin(DRV_STAGE_GATHER_KERNEL);
-    drv_status st = launch_gather(ctx, kernel, p, tile, order, threads);
+    drv_status st = launch_gather(ctx, kernel, p, tile, order, threads, ws);
     ctx->stage_end(DRV_STAGE_GATHER_KERNEL);
     return st;
   }
@@ -1151,9 +1451,22 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
     c.chunk_cap = p.chunk_cap = chunk;
     cone_fn<<<cone_grid, kConeThreads, 0, ctx->stream>>>(c);
     DRV_LAUNCH_CHECK();
-    drv_status st = launch_gather(ctx, kernel, p, tile, order, threads);
+    drv_status st = launch_gather(ctx, kernel, p, tile, order, threads, ws);
     if (st != DRV_OK) return st;
   }
   ctx->stage_end(DRV_STAGE_GATHER_KERNEL);
+  return DRV_OK;
+}
+
+// Diagnostics: what the last gather launch wrote, 8 words per CTA: %globaltimer (ns) at kernel entry, prologue done /
+// pair loop done (the two kernels differ, see trace_point calls), exit; then %smid and clock64 at the last three
+// points. Needs gather_variant bit 18.
+extern "C" drv_status drv_debug_gather_trace(drv_ctx* ctx, uint64_t* out, uint32_t capacity_ctas, uint32_t* num_ctas) {
+  if (!ctx) return DRV_ERR_INVALID;
+  if (!ctx->gather_trace) return ctx->fail(DRV_ERR_NOT_BOUND, "drv_debug_gather_trace: gather_variant bit 18 is not set");
+  const uint32_t n = ctx->gather_trace_ctas < capacity_ctas ? ctx->gather_trace_ctas : capacity_ctas;
+  DRV_CUDA(cudaMemcpyAsync(out, ctx->gather_trace, (size_t)n * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DRV_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (num_ctas) *num_ctas = n;
   return DRV_OK;
 }

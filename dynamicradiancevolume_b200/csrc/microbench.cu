@@ -164,6 +164,61 @@ __global__ void __launch_bounds__(256) mma_mix_kernel(float* out, float a) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Operand-delivery study of the gather's accumulate step: acc[m][c] += f[c] * u[m] over NU basis values and 3
+// colours, packed (FFMA2) or scalar, issued colour-major (consecutive FMAs share f[c]) or basis-major (share
+// u[m]). Every FMA reads three registers, one of them a private accumulator; what fraction of the FP32 pipe's
+// lane-cycles such a stream sustains is what bounds the pair loop.
+template <int NU, bool FMAJOR, bool PACKED>
+__global__ void __launch_bounds__(256) outer_study_kernel(float* out, float a) {
+  float2 acc[NU][3];
+#pragma unroll
+  for (int m = 0; m < NU; ++m)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[m][c] = make_float2(0.f, 0.f);
+  float2 f[3] = {make_float2(a, a * 1.01f), make_float2(a * 1.1f, a * 1.11f), make_float2(a * 1.2f, a * 1.21f)};
+  float2 u[NU];
+#pragma unroll
+  for (int m = 0; m < NU; ++m) u[m] = make_float2(0.3f + 0.1f * m + threadIdx.x * 1e-7f, 0.35f + 0.1f * m);
+  const float2 du = make_float2(1e-6f, 2e-6f);
+  for (int it = 0; it < kIters; ++it) {
+    if (PACKED) {
+      if (FMAJOR) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int m = 0; m < NU; ++m) acc[m][c] = __ffma2_rn(f[c], u[m], acc[m][c]);
+      } else {
+#pragma unroll
+        for (int m = 0; m < NU; ++m)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[m][c] = __ffma2_rn(f[c], u[m], acc[m][c]);
+      }
+#pragma unroll
+      for (int m = 0; m < NU; ++m) u[m] = __fadd2_rn(u[m], du);
+    } else {
+      if (FMAJOR) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int m = 0; m < NU; ++m) acc[m][c].x = fmaf(f[c].x, u[m].x, acc[m][c].x);
+      } else {
+#pragma unroll
+        for (int m = 0; m < NU; ++m)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[m][c].x = fmaf(f[c].x, u[m].x, acc[m][c].x);
+      }
+#pragma unroll
+      for (int m = 0; m < NU; ++m) u[m].x += du.x;
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int m = 0; m < NU; ++m)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s += acc[m][c].x + acc[m][c].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 struct Timer {
   cudaEvent_t a, b;
   Timer() { cudaEventCreate(&a); cudaEventCreate(&b); }
@@ -198,6 +253,11 @@ const char* kNames[] = {
     "sm_clock_mhz",        // current SM clock reported by the driver
     "mma_tf32_tflops",     // mma.sync.m16n8k8 TF32 (legacy tensor path): TFLOP/s (2*16*8*8 flop per instruction)
     "mma_mix_cyc",         // 10 FFMA2 + 2 mma.sync per iteration: SM cycles per iteration per SM sub-partition warp slot
+    // operand-delivery study (outer_study_kernel): fraction of the FP32 pipe's lane-cycles at the current clock;
+    // name = <packed|scalar>_<colour|basis>major_nu<4|8>_w<warps per SM>
+    "study_scalar_cmajor_nu4_w8", "study_scalar_cmajor_nu4_w32", "study_scalar_bmajor_nu4_w32",
+    "study_packed_cmajor_nu4_w8", "study_packed_cmajor_nu4_w32", "study_packed_bmajor_nu4_w8", "study_packed_bmajor_nu4_w32",
+    "study_packed_cmajor_nu8_w8", "study_packed_cmajor_nu8_w16", "study_packed_bmajor_nu8_w8", "study_packed_bmajor_nu8_w16",
 };
 
 } // namespace
@@ -248,6 +308,23 @@ extern "C" drv_status drv_microbench(int32_t device, uint32_t which, double* res
               // warps per SM sub-partition = blocks/sms * threads/32 / 4; cycles per iteration per warp slot
               r = (ms * 1e-3) * (khz * 1e3) / kIters / ((double)blocks / sms * threads / 32.0 / 4.0); } break;
     case 6: { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device); r = khz / 1000.0; } break;
+    default: {
+      int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+      struct Study { int nu; bool cmajor, packed; int warps; };
+      static const Study st[] = {{4, true, false, 8}, {4, true, false, 32}, {4, false, false, 32},
+                                 {4, true, true, 8}, {4, true, true, 32}, {4, false, true, 8}, {4, false, true, 32},
+                                 {8, true, true, 8}, {8, true, true, 16}, {8, false, true, 8}, {8, false, true, 16}};
+      const Study& S = st[which - 9];
+      const int b = sms * S.warps / 8;
+      double ms = 0;
+#define DRV_ST(NU, CM, PK) ms = best_ms([&] { outer_study_kernel<NU, CM, PK><<<b, threads>>>(out, 1.0001f); })
+      if (S.nu == 4) { if (S.packed) { if (S.cmajor) DRV_ST(4, true, true); else DRV_ST(4, false, true); }
+                       else { if (S.cmajor) DRV_ST(4, true, false); else DRV_ST(4, false, false); } }
+      else { if (S.cmajor) DRV_ST(8, true, true); else DRV_ST(8, false, true); }
+#undef DRV_ST
+      const double lane_cycles = (double)b * threads * kIters * (4.0 * S.nu) * (S.packed ? 2.0 : 1.0);
+      r = lane_cycles / (ms * 1e-3) / ((double)sms * 128.0 * khz * 1e3);
+    } break;
   }
   cudaFree(out);
   if (cudaGetLastError() != cudaSuccess) return DRV_ERR_CUDA;

@@ -260,6 +260,14 @@ class Context:
     def enable_stage_timers(self, on=True): self.check(self.lib.drv_enable_stage_timers(self.handle, 1 if on else 0))
     def kernel_launches(self): return int(self.lib.drv_kernel_launches(self.handle))
 
+    def gather_trace(self):
+        """Diagnostics (gather_variant bit 18): [ctas, 8] uint64: 4 %globaltimer stamps, %smid, 3 clock64 values of the last pair-kernel launch."""
+        import numpy as np
+        out = np.zeros((8192, 8), np.uint64)
+        n = C.c_uint32()
+        self.check(self.lib.drv_debug_gather_trace(self.handle, out.ctypes.data, 8192, C.byref(n)))
+        return out[:n.value]
+
     def stage_ms(self, stage: int) -> float:
         ms = C.c_float()
         self.check(self.lib.drv_stage_ms(self.handle, stage, C.byref(ms)))

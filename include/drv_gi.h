@@ -211,12 +211,15 @@ typedef struct drv_config {
   int32_t  device;            /* CUDA device ordinal */
   void*    stream;            /* cudaStream_t; NULL = context creates its own */
   uint32_t gather_variant;    /* 0 = default. Tuning switches measured in profiles/ (DESIGN.md 4.1, 4.5):
-                                 bits 0..7   pair-kernel variant (1 TMA staging, 3/4/12 scalar or single-pair maths,
-                                             6 three CTAs/SM, 7/8 64-/32-thread CTAs, 9/10/11 VPL loop unrolled 2/8/4x)
+                                 bits 0..7   pair-kernel variant (0 = 31 warp-split kernel, one 8-warp CTA per SM;
+                                             30 the cooperative stream-K kernel; 1 TMA staging, 3/4/12 scalar or
+                                             single-pair maths, 6 three CTAs/SM, 7/8 64-/32-thread CTAs, 9/10/11 VPL
+                                             loop unrolled 2/8/4x, 20..28 / 32..34 other warp-split shapes)
                                  bits 8..11  apply: resident blocks/SM the kernel is compiled for (4, 6; default 5)
                                  bits 12..15 apply: rows per thread (1, 2, 8; default 4)
-                                 bit 16      two-kernel gather + finalize instead of the cooperative launch
-                                 bit 17      software-pipelined cone march instead of the plain loop */
+                                 bit 16      variant 30: two-kernel gather + finalize instead of the cooperative launch
+                                 bit 17      software-pipelined cone march instead of the plain loop
+                                 bit 18      per-CTA time stamps of the pair kernel (drv_debug_gather_trace) */
   uint32_t reserved[3];
 } drv_config;
 
@@ -520,6 +523,12 @@ void drv_pack_spot_light(drv_spot_light* out, const drv_light_desc* light);
 drv_status drv_microbench(int32_t device, uint32_t which, double* result);
 const char* drv_microbench_name(uint32_t which);
 uint32_t    drv_microbench_count(void);
+
+/* Diagnostics (drv_config.gather_variant bit 18): %globaltimer stamps in ns of the last cache x VPL kernel launch,
+ * at 4 points of every CTA (entry, prologue done / pair loop done, exit), then %smid and clock64 at the last
+ * three: 8 words per CTA — how the fixed costs and the balance of that kernel are measured
+ * (tools/gather_trace.py). `out` holds 8 * capacity_ctas words. */
+drv_status drv_debug_gather_trace(drv_ctx* ctx, uint64_t* out, uint32_t capacity_ctas, uint32_t* num_ctas);
 
 #ifdef __cplusplus
 }

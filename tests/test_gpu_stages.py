@@ -222,9 +222,9 @@ def _sweep_oracle(cb, pos, vpls_list, sh_order, fp64=False):
     return e
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3, 4, 7, 8, 9, 11, 12])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4, 7, 8, 9, 11, 12, 20, 21, 22, 23, 24, 25, 26, 27, 28, 30, 31, 32, 33, 34])
 @pytest.mark.parametrize("sh_order", [1, 2])
-@pytest.mark.parametrize("n_cache,n_vpl", [(1000, 4096), (70000, 1024), (37, 2500), (5000, 16384)])
+@pytest.mark.parametrize("n_cache,n_vpl", [(1000, 4096), (70000, 1024), (37, 2500), (5000, 16384), (129, 9), (300000, 100)])
 def test_gather_unshadowed_variants(cuda_device, variant, sh_order, n_cache, n_vpl):
     ctx, cb, pos, vpls = _sweep_ctx(n_cache, n_vpl, sh_order, variant)
     ctx.light_caches()
@@ -266,9 +266,10 @@ def test_gather_drops_zero_flux_vpls(cuda_device, pattern):
         ctx.close()
 
 
-def test_gather_accumulates_over_lights_and_calls(cuda_device):
+@pytest.mark.parametrize("variant", [0, 20, 26, 28, 30])
+def test_gather_accumulates_over_lights_and_calls(cuda_device, variant):
     """`entry.SH += acc` per light (cacheLightingRSM.comp:358-373): two lights, then a second call."""
-    ctx, cb, pos, vpls = _sweep_ctx(3000, 4096, 2, 0)
+    ctx, cb, pos, vpls = _sweep_ctx(3000, 4096, 2, variant)
     _, vpls2 = workloads.sweep(1, 1024, seed=77)
     ctx.set_light_count(2)
     ctx.set_vpls(1, vpls2.ctypes.data, 1024)
@@ -363,7 +364,7 @@ def test_cone_trace_extremes(cuda_device):
     g.close()
 
 
-@pytest.mark.parametrize("variant", [0, 7, 8, 12])
+@pytest.mark.parametrize("variant", [0, 7, 8, 12, 20, 21, 25, 26, 27, 28, 30, 31])
 def test_shadowed_gather_variants_agree(cuda_device, variant):
     """Packed (default) and scalar pair kernels reading the same visibility table."""
     wl = workloads.atrium(width=320, height=180, rsm_res=64, read_lod=0, sh_order=2, indirect_shadow=True,
