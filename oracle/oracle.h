@@ -6,11 +6,17 @@
  * cpu_baseline / --impl reference legs may load this library; libdrv_gi never
  * links or calls it.
  *
- * PARITY UNPINNED: the reference ships no golden vectors, known-answer tests
- * or fixtures for this path and cannot be built or run here (GLSL 4.50 on a
- * Win32/OpenGL 4.5 host). The oracle is therefore pinned only
- * by (a) being a line-by-line restatement of the cited shader lines and (b)
- * hand-derived known-answer tests in tests/test_oracle_kat.py.
+ * PARITY PINNED TO THE REFERENCE'S SOURCE TEXT: the reference ships no golden
+ * vectors and its host is Win32/OpenGL, but its shaders are C-like text. A
+ * mechanical GLSL -> C++ rewrite (oracle/ref/glsl2cpp.py + glsl_compat.h: work
+ * groups as fibers, shared memory, barriers, atomics, software samplers)
+ * compiles the UNMODIFIED shader files into oracle/_ref/libdrv_ref.so, and
+ * tests/test_oracle_vs_ref.py requires this restatement to equal it bit for
+ * bit (allocation set, entry positions, VPL list, SH coefficients with and
+ * without cone-traced shadows, applied image, voxel blend / mips, RSM mips).
+ * Not covered by that pin: the voxeliser (fixed-function rasterisation in the
+ * reference; the oracle defines the covered set) and the host-side
+ * uniform packers (float64 restatements in tests/test_host_math.py).
  *
  * Arithmetic policy (what GLSL leaves open is fixed here, DESIGN.md "Parity
  * policy"): IEEE-754 binary32, round-to-nearest-even, every * and + rounded

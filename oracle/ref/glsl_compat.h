@@ -284,6 +284,8 @@ inline vec4 unpackUnorm4x8(uint p) {
 /* ---------------------------------------------------------------- matrices (column-major, as GLSL) */
 struct mat3 {
   vec3 c[3];
+  mat3() {}
+  mat3(const vec3& a, const vec3& b, const vec3& d) { c[0] = a; c[1] = b; c[2] = d; }
   vec3& operator[](int i) { return c[i]; }
   const vec3& operator[](int i) const { return c[i]; }
 };
@@ -446,6 +448,7 @@ inline ivec4 textureLod(const isampler2D& s, const vec2& uv, float lod) { /* int
   int x = clampi(f2i(::floorf(uv.x * (float)L.w)), 0, L.w - 1), y = clampi(f2i(::floorf(uv.y * (float)L.h)), 0, L.h - 1);
   return fetch_i(*s.t, 0, x, y, 0);
 }
+inline ivec4 texture(const isampler2D& s, const vec2& uv) { return textureLod(s, uv, 0.0f); }
 inline vec4 texelFetch(const sampler2D& s, const ivec2& p, int l) {
   const Level& L = s.t->lv[l];
   if (p.x < 0 || p.y < 0 || p.x >= L.w || p.y >= L.h) return vec4(0.0f);
@@ -510,6 +513,21 @@ template <class T, class V>
 inline T atomicAdd(T& mem, V v) { return __atomic_fetch_add(&mem, (T)v, __ATOMIC_SEQ_CST); }
 inline void memoryBarrierImage() {}
 inline void memoryBarrier() {}
+
+/* shader storage block with an unsized array: out-of-range reads return zeros and writes are dropped (robust
+ * buffer access — what cacheApply.frag:91-100 relies on for an unallocated neighbour) */
+template <class T>
+struct ssbo {
+  T* data = nullptr;
+  size_t count = 0;
+  void bind(void* p, size_t n) { data = (T*)p; count = n; }
+  T& operator[](size_t i) const {
+    if (i < count) return data[i];
+    static thread_local T dummy;
+    dummy = T();
+    return dummy;
+  }
+};
 
 /* ---------------------------------------------------------------- work groups as fibers */
 struct FiberGroup {
