@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs index (0..3); the metric is quoted on 1. 5 = the reference author's default settings")
     ap.add_argument("--variant", type=int, default=0, help="gather kernel variant (drv_config.gather_variant)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-timing comparison of the frame with the oracle")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps (profiling runs)")
     ap.add_argument("--no-microbench", action="store_true")
     ap.add_argument("--stages", action="store_true", help="print the per-stage table to stderr")
@@ -246,7 +247,7 @@ def run_b200(args):
             line["scaling_workload"] = {
                 "workload": extra["config"]["workload"], "ms_per_frame": extra["value"], "steps": k, "warmup": 2,
                 "n_gpus": world, "caches": extra["config"]["caches"], "vpls": extra["config"]["vpls"],
-                "live_vpls": extra["config"]["live_vpls"], "scaling": "strong",
+                "live_vpls": extra["config"]["live_vpls"], "scaling": "strong", "parity": extra.get("parity"),
                 "how": "same timing rules as `value` (CUDA events per step, L2 flushed, max over ranks); "
                        "speed-up at N GPUs = this figure at n_gpus 1 / this figure at N"}
     if line is not None:
@@ -522,6 +523,34 @@ def measure(args, config_index, n_steps, n_warmup, light):
     for i, r in enumerate(g.rsms):
         ctx.bind_rsm(i, *r)
 
+    # ---- parity of what was just timed (after the timed regions; the oracle is the checker, never the thing
+    # measured): one more frame through the same call, then rank 0 compares ITS entries / atlas / image — in a
+    # sharded run the product of all ranks' shards — with the oracle: allocation bit-exact on the whole frame, SH on
+    # every `step`-th entry, the whole image through the oracle's apply pass (oracle/subsample.py)
+    parity = None
+    if not args.no_parity:
+        frame_device()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            from oracle.subsample import check_frame
+            n_par = ctx.active_cache_count()[0]
+            sharded_image = world > 1 and not args.serial and args.barrier == "peer" and args.image_gather == "p2p"
+            img_t = ctx.hdr16_tensor() if sharded_image else hdr16
+            img = img_t[:wl.height].float().cpu().numpy()
+            small = (not wl.indirect_shadow) and n_par * wl.num_vpls <= 2e8
+            t0 = time.perf_counter()
+            parity = check_frame(wl, ctx.read_entries(n_par), ctx.read_atlas(), n_par, img, step=1 if small else 64,
+                                 image_is_half=True)
+            parity["seconds"] = time.perf_counter() - t0
+            parity["what"] = ("allocation (cell set, indices, positions) bit-exact on the whole frame; SH of every %d-th "
+                              "entry against the oracle's gather within 1e-5 + 1e-3 rel; the whole RGBA16F image against "
+                              "the oracle's apply pass on the device's entries within that gate + one half rounding"
+                              % parity["step"])
+        if world > 1:
+            dist.barrier()
+
     if rank != 0:
         g.close()
         return None
@@ -623,6 +652,7 @@ def measure(args, config_index, n_steps, n_warmup, light):
                         "gathered RGBA16F image to host memory; wall clock, max over ranks" % world if e2e_sharded else
                         "every rank uploads all inputs, serial sharded stages, NCCL image gather, rank 0 D2H")},
         "gpu_launches": launches,
+        "parity": parity,
         "clocks": clocks,
         "roofline": roofline,
         "roofline_streaming_stages": secondary,

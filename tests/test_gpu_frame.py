@@ -281,3 +281,37 @@ def test_renderer_mirror_draw(cuda_device):
     hdr_now = r._hdr.float().cpu().numpy()
     ok, ratio = close(ldr[..., :3], orc.tonemap(hdr_now, 3.0, np.float32(np.log2(r.GetTonemapLMax() + 1.0))))
     assert ok, ratio
+
+
+def test_config3_full_size_stated_subsample(cuda_device):
+    """BASELINE configs[3] AT FULL SIZE (3840x2160, 4 lights x 128^2 = 65 536 VPLs, 4 cascades x 128^3, SH2 +
+    cone-traced shadows through the 128^3 chain): allocation bit-exact on the whole frame, the SH of every 64th
+    entry against the oracle's gather, the whole image against the oracle's apply pass (oracle/subsample.py) —
+    for the serial stage order into RGBA32F and for drv_draw_frame (graph replay) into RGBA16F."""
+    import torch
+    from oracle.subsample import check_frame
+    wl = workloads.config(3).build()
+    g = workloads.DeviceFrame(wl)
+    g.prepare_inputs()
+    g.frame()
+    torch.cuda.synchronize()
+    n, overflow, _ = g.ctx.active_cache_count()
+    assert overflow == 0 and n > 10000
+    o = OracleFrame(wl).prepare_inputs().allocate()
+    entries, atlas = g.ctx.read_entries(n), g.ctx.read_atlas()
+    assert np.array_equal(g.ctx.read_voxel_chain(), o.chain)
+    r = check_frame(wl, entries, atlas, n, g.out32.cpu().numpy(), step=64, oracle=o)
+    assert r["alloc_exact"], r
+    assert r["checked_entries"] >= n // 64 and r["sh_max_abs"] > 0 and r["image_max"] > 0
+    assert r["sh_ok"] and r["image_ok"], r
+    # the overlapped / graph-replayed frame into the reference's RGBA16F target
+    out16 = torch.zeros(wl.height, wl.width, 4, dtype=torch.float16, device="cuda")
+    g.ctx.bind_scene(g.tris, None, 1.0)
+    for _ in range(3):
+        g.ctx.draw_frame(out16, abi.DRV_HDR_RGBA16F_WRITE,
+                         abi.DRV_FRAME_PREPARE_RSM | abi.DRV_FRAME_VOXELIZE | abi.DRV_FRAME_GRAPH)
+    torch.cuda.synchronize()
+    r16 = check_frame(wl, g.ctx.read_entries(n), g.ctx.read_atlas(), n, out16.float().cpu().numpy(), step=64,
+                      image_is_half=True, oracle=o)
+    assert r16["ok"], r16
+    g.close()
