@@ -59,6 +59,8 @@ def parse_args():
                     help="sharded runs: image bands stored into rank 0's target over NVLink by the apply kernel (p2p) or gathered with NCCL")
     ap.add_argument("--no-scaling-workload", action="store_true",
                     help="skip the short run of BASELINE configs[3] (the multi-GPU scaling workload) after the metric's workload")
+    ap.add_argument("--static-uniforms", action="store_true",
+                    help="do not re-upload PerFrame / VolumeInfo before every frame (a static camera: pure graph replay)")
     ap.add_argument("--no-graph", action="store_true", help="issue the frame kernel by kernel instead of replaying its CUDA graph")
     ap.add_argument("--serial", action="store_true", help="reference stage order on one stream (prepare_rsm, clear, drv_draw) "
                                                           "instead of drv_draw_frame's light-side || camera-side schedule")
@@ -320,6 +322,12 @@ def measure(args, config_index, n_steps, n_warmup, light):
         with torch.cuda.stream(stream):
             if wl.indirect_shadow and not in_frame:
                 ctx.voxelize(g.tris, None, 1.0)
+            if not args.static_uniforms:
+                # an animated frame: the application uploads PerFrame / VolumeInfo every frame
+                # (Renderer::UpdatePerFrameUBO / UpdateVolumeUBO, renderer.cpp:324-431); the recorded frame graph is
+                # patched in place with the new kernel arguments (cudaGraphExecUpdate), not re-instantiated
+                ctx.set_per_frame(wl.per_frame)
+                ctx.set_volume_info(wl.volume)
             if world == 1 and not args.serial:
                 # one call: (RSM mips + VPLs) || allocate -> gather -> apply; the glClear of the HDR target
                 # (renderer.cpp:562) is fused into the apply pass (DRV_HDR_RGBA16F_WRITE); replayed as a CUDA
@@ -663,7 +671,9 @@ def measure(args, config_index, n_steps, n_warmup, light):
                          "side overlap" % (sum(inst_ms) / max(len(inst_ms), 1)),
         "frame_issue": ("serial: prepare_rsm, clear, drv_draw" if (args.serial or (world > 1 and args.barrier != "peer")) else
                         "drv_draw_frame: (RSM mips + VPLs) || [voxelise] || allocate -> gather -> apply(+clear)%s"
-                        % ("" if args.no_graph else ", CUDA graph replay")),
+                        % ("" if args.no_graph else (", CUDA graph replay" if args.static_uniforms else
+                                                     ", CUDA graph patched with the frame's uniforms (cudaGraphExecUpdate) and replayed"))),
+        "graph": dict(zip(("instantiations", "updates"), ctx.graph_stats())),
         "microbench": micro,
         "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
         "gpu": torch.cuda.get_device_name(local),

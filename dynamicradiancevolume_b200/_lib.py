@@ -39,6 +39,7 @@ SYMBOLS = [
     ("drv_apply_caches_rows", _st, [_P, _P, _u32, _u32, _u32]),
     ("drv_draw", _st, [_P, _P, _u32]),
     ("drv_draw_frame", _st, [_P, _P, _u32, _u32]),
+    ("drv_graph_stats", _st, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("drv_live_vpl_counts", _st, [_P, _P]),
     ("drv_fill_rsm", _st, [_P, _u32, _P, _P, _P, _P, _u32]),
     ("drv_cone_trace_ao", _st, [_P, _P]),
@@ -59,6 +60,8 @@ SYMBOLS = [
     ("drv_export_entries_ipc", _st, [_P, C.POINTER(C.c_uint8 * abi.DRV_IPC_HANDLE_BYTES)]),
     ("drv_import_peer_entries", _st, [_P, _u32, C.POINTER(C.c_uint8 * abi.DRV_IPC_HANDLE_BYTES)]),
     ("drv_peer_barrier", _st, [_P]),
+    ("drv_peer_status", _st, [_P, C.POINTER(_u32), C.POINTER(_u32)]),
+    ("drv_peer_reset", _st, [_P]),
     ("drv_enable_stage_timers", _st, [_P, C.c_int]),
     ("drv_stage_ms", _st, [_P, C.c_int, C.POINTER(_f32)]),
     ("drv_stage_name", C.c_char_p, [C.c_int]),

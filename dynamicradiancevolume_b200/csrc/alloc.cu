@@ -37,9 +37,10 @@ struct AllocParams {
   float inv_voxel[DRV_MAX_CASCADES];
 };
 
-constexpr int kCellsPerThread = 8;
+constexpr int kGroups = 2;                    // 8-cell groups per thread of the scan + compact kernel
+constexpr int kCellsPerThread = 8 * kGroups;
 constexpr int kScanThreads = 256;
-constexpr int kCellsPerBlock = kCellsPerThread * kScanThreads; // 2048
+constexpr int kCellsPerBlock = kCellsPerThread * kScanThreads; // 4096
 
 // ndc tables: ((i + .5) / N) * 2 - 1, cacheGather.comp:113-116
 __global__ void ndc_table_kernel(float* __restrict__ out, int W, int H) {
@@ -167,7 +168,7 @@ __device__ __forceinline__ uint32_t nonzero_bytes(uint2 v) { // number of non-ze
 // without a memset) and moves the out-of-range-corner statistic out of its accumulator.
 struct ScanState {
   unsigned long long* words; // per block: value | (epoch << 2 | flag) << 32
-  uint32_t* epoch;           // [0] epoch of the current frame, [1] blocks done
+  uint32_t* epoch;           // [0] epoch of the current frame, [1] blocks done, [2] oob accumulator, [3] tile ticket
   uint32_t* oob_accum;       // mark_kernel's accumulator
 };
 constexpr uint32_t kFlagAggregate = 1u, kFlagPrefix = 2u;
@@ -178,17 +179,31 @@ __global__ void __launch_bounds__(kScanThreads) scan_compact_kernel(AllocParams 
                                                                     uint32_t* __restrict__ atlas, uint8_t* __restrict__ entries,
                                                                     drv_cache_counter* __restrict__ counter,
                                                                     uint32_t* __restrict__ stats) {
-  __shared__ uint32_t warp_tot[kScanThreads / 32];
-  __shared__ uint32_t s_prefix;
+  constexpr int NW = kScanThreads / 32;
+  __shared__ uint32_t warp_tot[NW];
+  __shared__ uint32_t s_prefix, s_tile;
+  __shared__ uint32_t lb_sum[NW];   // look-back: per warp, the values up to (and including) its nearest inclusive prefix
+  __shared__ uint32_t lb_found[NW]; // ... and whether the warp saw one
+  // Tiles are handed out through an atomic ticket, not blockIdx: a block only ever waits for tiles with SMALLER
+  // tickets, whose blocks are already running — forward progress does not depend on the dispatch order of CTAs.
+  if (threadIdx.x == 0) s_tile = atomicAdd(st.epoch + 3, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile, num_tiles = gridDim.x;
   const uint32_t epoch_raw = *reinterpret_cast<volatile uint32_t*>(st.epoch);
   const uint32_t epoch = epoch_raw & 0x3FFFFFFFu; // 30 bits fit beside the 2 flag bits
-  const uint32_t cell0 = (blockIdx.x * kScanThreads + threadIdx.x) * kCellsPerThread;
-  uint2 f = make_uint2(0u, 0u);
-  if (cell0 < num_cells) {
-    f = *reinterpret_cast<const uint2*>(flags + cell0);
-    if (f.x | f.y) *reinterpret_cast<uint2*>(flags + cell0) = make_uint2(0u, 0u); // consumed
+  const uint32_t cell0 = (tile * kScanThreads + threadIdx.x) * kCellsPerThread;
+  uint2 f[kGroups];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int g = 0; g < kGroups; ++g) {
+    f[g] = make_uint2(0u, 0u);
+    const uint32_t c0 = cell0 + g * 8;
+    if (c0 < num_cells) {
+      f[g] = *reinterpret_cast<const uint2*>(flags + c0);
+      if (f[g].x | f[g].y) *reinterpret_cast<uint2*>(flags + c0) = make_uint2(0u, 0u); // consumed
+    }
+    mine += nonzero_bytes(f[g]);
   }
-  const uint32_t mine = nonzero_bytes(f);
   uint32_t incl = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -199,47 +214,46 @@ __global__ void __launch_bounds__(kScanThreads) scan_compact_kernel(AllocParams 
   __syncthreads();
   uint32_t warp_base = 0, block_total = 0;
 #pragma unroll
-  for (int w = 0; w < kScanThreads / 32; ++w) {
+  for (int w = 0; w < NW; ++w) {
     if (w < (int)(threadIdx.x >> 5)) warp_base += warp_tot[w];
     block_total += warp_tot[w];
   }
-  // publish, then look back (warp 0)
-  if (threadIdx.x < 32) {
-    volatile unsigned long long* W = st.words;
-    const unsigned long long tag = (unsigned long long)(epoch << 2) << 32;
-    if (threadIdx.x == 0) {
-      const uint32_t flag = blockIdx.x == 0 ? kFlagPrefix : kFlagAggregate;
-      W[blockIdx.x] = (unsigned long long)block_total | tag | ((unsigned long long)flag << 32);
+  // publish the aggregate, then look back over the predecessors, kScanThreads of them per round (thread 0 = the
+  // nearest): a 1080p frame's 128 tiles resolve in a single round of polls instead of a chain of 32-wide windows
+  volatile unsigned long long* W = st.words;
+  const unsigned long long tag = (unsigned long long)(epoch << 2) << 32;
+  if (threadIdx.x == 0)
+    W[tile] = (unsigned long long)block_total | tag | ((unsigned long long)(tile == 0 ? kFlagPrefix : kFlagAggregate) << 32);
+  uint32_t prefix = 0;
+  for (int base = (int)tile - 1; base >= 0; base -= kScanThreads) {
+    const int i = base - (int)threadIdx.x;
+    uint32_t flag = kFlagPrefix, val = 0; // below tile 0 there is nothing: an inclusive prefix of 0
+    if (i >= 0) {
+      unsigned long long w;
+      do { w = W[i]; } while ((uint32_t)(w >> 34) != epoch || ((uint32_t)(w >> 32) & 3u) == 0u);
+      flag = (uint32_t)(w >> 32) & 3u;
+      val = (uint32_t)w;
     }
-    uint32_t prefix = 0;
-    int base = (int)blockIdx.x - 1; // nearest predecessor
-    bool done = false;
-    while (base >= 0 && !done) {    // windows of 32 predecessors, lane 0 = the nearest one
-      const int i = base - (int)threadIdx.x;
-      uint32_t flag = kFlagPrefix, val = 0; // below block 0 there is nothing: an inclusive prefix of 0
-      if (i >= 0) {
-        unsigned long long w;
-        do { w = W[i]; } while ((uint32_t)(w >> 34) != epoch || ((uint32_t)(w >> 32) & 3u) == 0u);
-        flag = (uint32_t)(w >> 32) & 3u;
-        val = (uint32_t)w;
-      }
-      const uint32_t pm = __ballot_sync(0xffffffffu, flag == kFlagPrefix);
-      const int first = __ffs(pm) - 1; // nearest lane holding an inclusive prefix (-1: none in this window)
-      const uint32_t take = (first < 0 || (int)threadIdx.x <= first) ? val : 0u;
-      prefix += __reduce_add_sync(0xffffffffu, take);
-      if (first >= 0) done = true; else base -= 32;
+    const uint32_t pm = __ballot_sync(0xffffffffu, flag == kFlagPrefix);
+    const int first = __ffs(pm) - 1; // nearest lane of this warp holding an inclusive prefix (-1: none)
+    const uint32_t take = (first < 0 || (int)(threadIdx.x & 31) <= first) ? val : 0u;
+    const uint32_t wsum = __reduce_add_sync(0xffffffffu, take);
+    if ((threadIdx.x & 31) == 0) { lb_sum[threadIdx.x >> 5] = wsum; lb_found[threadIdx.x >> 5] = first >= 0 ? 1u : 0u; }
+    __syncthreads();
+    bool found = false;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      if (!found) { prefix += lb_sum[w]; found = lb_found[w] != 0u; }
     }
-    if (threadIdx.x == 0) {
-      if (blockIdx.x != 0)
-        W[blockIdx.x] = (unsigned long long)(prefix + block_total) | tag | ((unsigned long long)kFlagPrefix << 32);
-      s_prefix = prefix;
-    }
+    __syncthreads(); // lb_* are rewritten by the next round
+    if (found) break;
   }
-  __syncthreads();
-  uint32_t index = s_prefix + warp_base + incl - mine;
+  if (threadIdx.x == 0 && tile != 0)
+    W[tile] = (unsigned long long)(prefix + block_total) | tag | ((unsigned long long)kFlagPrefix << 32);
+  uint32_t index = prefix + warp_base + incl - mine;
 
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { // the last slice knows the total: cachePrepareLighting.comp:8-14
-    const uint32_t total = s_prefix + block_total;
+  if (tile == num_tiles - 1 && threadIdx.x == 0) { // the last slice knows the total: cachePrepareLighting.comp:8-14
+    const uint32_t total = prefix + block_total;
     const uint32_t n = total > max_caches ? max_caches : total; // clamp, report
     stats[0] = total - n;
     counter->NumCacheLightingThreadGroupsX = (n + DRV_LIGHTING_THREADS_PER_GROUP - 1) / DRV_LIGHTING_THREADS_PER_GROUP;
@@ -249,50 +263,55 @@ __global__ void __launch_bounds__(kScanThreads) scan_compact_kernel(AllocParams 
   }
   if (threadIdx.x == 0) { // frame bookkeeping: the block that finishes last opens the next epoch
     __threadfence();
-    if (atomicAdd(st.epoch + 1, 1u) == gridDim.x - 1) {
+    if (atomicAdd(st.epoch + 1, 1u) == num_tiles - 1) {
       stats[1] = *st.oob_accum;
       *st.oob_accum = 0u;
       st.epoch[1] = 0u;
+      st.epoch[3] = 0u; // the ticket counter
       __threadfence();
       *reinterpret_cast<volatile uint32_t*>(st.epoch) = (epoch_raw + 1u) == 0u ? 1u : epoch_raw + 1u;
     }
   }
-  if (cell0 >= num_cells) return;
 
   const int R = p.R, R2 = R * R, R3 = R2 * R;
   const uint32_t atlasW = (uint32_t)(R * p.C);
-  // R is a multiple of 8 (checked at create), so the 8 cells share (c, z, y)
-  const int c = cell0 / R3;
-  const int local = cell0 - c * R3;
-  const int z = local / R2;
-  const int y = (local - z * R2) / R;
-  const int x0 = local - z * R2 - y * R;
-  const drv_cav_cascade& k = p.casc[c];
-  uint32_t out[kCellsPerThread];
 #pragma unroll
-  for (int i = 0; i < kCellsPerThread; ++i) {
-    uint32_t word = i < 4 ? f.x : f.y;
-    bool set = ((word >> ((i & 3) * 8)) & 0xffu) != 0u;
-    uint32_t v = 0u;
-    if (set) {
-      if (index < max_caches) {
-        v = index + 1u; // +1 since zero means "cleared", cacheGather.comp:88
-        float4* e = reinterpret_cast<float4*>(entries + (size_t)index * STRIDE);
-        // Position = cell * WorldVoxelSize + Min, cacheGather.comp:65 (mul and add rounded separately)
-        e[0] = make_float4(ex_add(ex_mul((float)(x0 + i), k.WorldVoxelSize), k.Min[0]),
-                           ex_add(ex_mul((float)y, k.WorldVoxelSize), k.Min[1]),
-                           ex_add(ex_mul((float)z, k.WorldVoxelSize), k.Min[2]), 0.0f);
-        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int g = 0; g < kGroups; ++g) {
+    const uint32_t c0 = cell0 + g * 8;
+    if (c0 >= num_cells) break;
+    // R is a multiple of 8 (checked at create), so the 8 cells of a group share (c, z, y)
+    const int c = c0 / R3;
+    const int local = c0 - c * R3;
+    const int z = local / R2;
+    const int y = (local - z * R2) / R;
+    const int x0 = local - z * R2 - y * R;
+    const drv_cav_cascade& k = p.casc[c];
+    uint32_t out[8];
 #pragma unroll
-        for (int q = 1; q < STRIDE / 16; ++q) e[q] = zero; // cacheGather.comp:68-83
+    for (int i = 0; i < 8; ++i) {
+      uint32_t word = i < 4 ? f[g].x : f[g].y;
+      bool set = ((word >> ((i & 3) * 8)) & 0xffu) != 0u;
+      uint32_t v = 0u;
+      if (set) {
+        if (index < max_caches) {
+          v = index + 1u; // +1 since zero means "cleared", cacheGather.comp:88
+          float4* e = reinterpret_cast<float4*>(entries + (size_t)index * STRIDE);
+          // Position = cell * WorldVoxelSize + Min, cacheGather.comp:65 (mul and add rounded separately)
+          e[0] = make_float4(ex_add(ex_mul((float)(x0 + i), k.WorldVoxelSize), k.Min[0]),
+                             ex_add(ex_mul((float)y, k.WorldVoxelSize), k.Min[1]),
+                             ex_add(ex_mul((float)z, k.WorldVoxelSize), k.Min[2]), 0.0f);
+          const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int q = 1; q < STRIDE / 16; ++q) e[q] = zero; // cacheGather.comp:68-83
+        }
+        ++index;
       }
-      ++index;
+      out[i] = v;
     }
-    out[i] = v;
+    uint4* dst = reinterpret_cast<uint4*>(atlas + (size_t)(x0 + c * R) + (size_t)atlasW * ((size_t)y + (size_t)R * z));
+    dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+    dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
   }
-  uint4* dst = reinterpret_cast<uint4*>(atlas + (size_t)(x0 + c * R) + (size_t)atlasW * ((size_t)y + (size_t)R * z));
-  dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
-  dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
 }
 
 // drv_set_synthetic_entries: positions -> entries with zeroed SH.

@@ -90,7 +90,7 @@ extern "C" drv_status drv_create(const drv_config* cfg, drv_ctx** out) {
   ctx->num_cells = c.cav_cascades * c.cav_resolution * c.cav_resolution * c.cav_resolution;
   CREATE_CUDA(dmalloc(&ctx->atlas, (size_t)ctx->num_cells * sizeof(uint32_t))); // renderer.cpp:1179
   CREATE_CUDA(cudaMemsetAsync(ctx->atlas, 0, (size_t)ctx->num_cells * sizeof(uint32_t), ctx->stream));
-  ctx->num_scan_blocks = (ctx->num_cells + 2047) / 2048;
+  ctx->num_scan_blocks = (ctx->num_cells + 4095) / 4096;
   CREATE_CUDA(dmalloc(&ctx->scan_words, (size_t)ctx->num_scan_blocks * sizeof(unsigned long long)));
   CREATE_CUDA(cudaMemsetAsync(ctx->scan_words, 0, (size_t)ctx->num_scan_blocks * sizeof(unsigned long long), ctx->stream));
   CREATE_CUDA(dmalloc(&ctx->scan_epoch, 4 * sizeof(uint32_t)));
@@ -189,12 +189,16 @@ extern "C" void drv_destroy(drv_ctx* ctx) {
 }
 
 #define NEED_CTX() do { if (!ctx) return DRV_ERR_INVALID; cudaSetDevice(ctx->device); } while (0)
-// calls that change something a kernel takes as an argument invalidate the recorded frame graph
-#define MUTATES() do { ctx->state_gen++; } while (0)
+// calls that change something a kernel takes as an argument invalidate the recorded frame graph: MUTATES() for
+// anything that can change a launch shape or a scratch-buffer size (the next graph frame runs eagerly first),
+// MUTATES_UNIFORMS() for the per-frame uniform blocks (moving camera): kernel arguments only, so the recorded
+// graph is re-captured and patched in place with cudaGraphExecUpdate — no eager frame, no re-instantiation
+#define MUTATES() do { ctx->state_gen++; ctx->shape_gen++; } while (0)
+#define MUTATES_UNIFORMS() do { ctx->state_gen++; } while (0)
 
 extern "C" drv_status drv_set_constant(drv_ctx* ctx, const drv_constant* b) {
   NEED_CTX();
-  MUTATES();
+  MUTATES_UNIFORMS();
   if (!b) return ctx->fail(DRV_ERR_INVALID, "drv_set_constant: null block");
   ctx->constant = *b;
   ctx->have_constant = true;
@@ -202,7 +206,7 @@ extern "C" drv_status drv_set_constant(drv_ctx* ctx, const drv_constant* b) {
 }
 extern "C" drv_status drv_set_per_frame(drv_ctx* ctx, const drv_per_frame* b) {
   NEED_CTX();
-  MUTATES();
+  MUTATES_UNIFORMS();
   if (!b) return ctx->fail(DRV_ERR_INVALID, "drv_set_per_frame: null block");
   ctx->per_frame = *b;
   ctx->have_per_frame = true;
@@ -210,7 +214,7 @@ extern "C" drv_status drv_set_per_frame(drv_ctx* ctx, const drv_per_frame* b) {
 }
 extern "C" drv_status drv_set_volume_info(drv_ctx* ctx, const drv_volume_info* b) {
   NEED_CTX();
-  MUTATES();
+  MUTATES_UNIFORMS();
   if (!b) return ctx->fail(DRV_ERR_INVALID, "drv_set_volume_info: null block");
   ctx->volume = *b;
   ctx->have_volume = true;
@@ -342,7 +346,7 @@ static drv_status frame_body(drv_ctx* ctx, void* hdr_out, uint32_t format, uint3
   // renderer.cpp:550. Sharded frame: every rank marks its band of pixel rows and stores the flags to all ranks
   // (idempotent byte stores over NVLink = the all-reduce of the mark phase); after the barrier every rank holds the
   // complete flag set and runs the deterministic scan + compact itself (identical indices, no communication)
-  const bool sharded = ctx->shard_world > 1 && ctx->peers_open;
+  const bool sharded = drv_peers_complete(ctx);
   st = drv_impl_allocate_mark(ctx, sharded);
   if (st != DRV_OK) return st;
   if (sharded && (st = drv_impl_peer_barrier(ctx)) != DRV_OK) return st;
@@ -388,8 +392,13 @@ extern "C" drv_status drv_bind_scene(drv_ctx* ctx, const float* tri_pos, uint32_
 extern "C" drv_status drv_draw_frame(drv_ctx* ctx, void* hdr_out, uint32_t format, uint32_t flags) {
   NEED_CTX();
   if (!hdr_out && !(flags & DRV_FRAME_GATHER_IMAGE)) return ctx->fail(DRV_ERR_INVALID, "drv_draw_frame: null output");
-  if (flags & DRV_FRAME_GATHER_IMAGE) { // checked before anything is enqueued: a rank that bails out later would leave its peers in a barrier
-    const bool sharded = ctx->shard_world > 1 && ctx->peers_open;
+  // checked before anything is enqueued: a rank that bails out later would leave its peers in a barrier, and a
+  // missing mapping would turn into stores through a null-based pointer
+  if (ctx->shard_world > 1 && ctx->peers_open && !drv_peers_complete(ctx))
+    return ctx->fail(DRV_ERR_NOT_BOUND, "drv_draw_frame: sharded context, but not every peer's entries buffer has been "
+                                        "imported (drv_import_peer_entries for each rank != own)");
+  if (flags & DRV_FRAME_GATHER_IMAGE) {
+    const bool sharded = drv_peers_complete(ctx);
     if (!sharded || !(ctx->shard_rank == 0 ? ctx->hdr16 : ctx->peer_hdr[0]) || format != DRV_HDR_RGBA16F_WRITE)
       return ctx->fail(DRV_ERR_NOT_BOUND, "drv_draw_frame: DRV_FRAME_GATHER_IMAGE needs a sharded context, rank 0's target "
                                           "(drv_export_hdr_ipc / drv_import_peer_hdr) and DRV_HDR_RGBA16F_WRITE");
@@ -406,18 +415,18 @@ extern "C" drv_status drv_draw_frame(drv_ctx* ctx, void* hdr_out, uint32_t forma
   const bool want_graph = (flags & DRV_FRAME_GRAPH) && !ctx->timers;
   if (!want_graph) {
     drv_status st = frame_body(ctx, hdr_out, format, flags);
-    if (st == DRV_OK) ctx->warm_gen = ctx->state_gen;
+    if (st == DRV_OK) ctx->warm_gen = ctx->shape_gen;
     return st;
   }
   const bool valid = ctx->frame_graph && ctx->graph_gen == ctx->state_gen && ctx->graph_out == hdr_out &&
                      ctx->graph_format == format && ctx->graph_flags == flags;
   if (!valid) {
-    if (ctx->frame_graph) { cudaGraphExecDestroy(ctx->frame_graph); ctx->frame_graph = nullptr; }
-    if (ctx->warm_gen != ctx->state_gen) {
-      // first frame of a new state runs eagerly: it sizes the scratch buffers (no allocation may happen while
+    if (ctx->warm_gen != ctx->shape_gen) {
+      // first frame of a new SHAPE runs eagerly: it sizes the scratch buffers (no allocation may happen while
       // a stream is being captured) and reports binding errors the ordinary way
+      if (ctx->frame_graph) { cudaGraphExecDestroy(ctx->frame_graph); ctx->frame_graph = nullptr; }
       drv_status st = frame_body(ctx, hdr_out, format, flags);
-      if (st == DRV_OK) ctx->warm_gen = ctx->state_gen;
+      if (st == DRV_OK) ctx->warm_gen = ctx->shape_gen;
       return st;
     }
     const uint64_t launches0 = ctx->launches;
@@ -432,12 +441,25 @@ extern "C" drv_status drv_draw_frame(drv_ctx* ctx, void* hdr_out, uint32_t forma
       cudaGetLastError();
       return ctx->fail(DRV_ERR_CUDA, std::string("drv_draw_frame: capture failed: ") + cudaGetErrorString(e));
     }
-    e = cudaGraphInstantiate(&ctx->frame_graph, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) {
-      ctx->frame_graph = nullptr;
-      return ctx->fail(DRV_ERR_CUDA, std::string("drv_draw_frame: instantiate failed: ") + cudaGetErrorString(e));
+    // same topology, new kernel arguments (uniform blocks of a moving camera, another output pointer): patch the
+    // instantiated graph in place; anything else: instantiate afresh
+    bool updated = false;
+    if (ctx->frame_graph && ctx->graph_flags == flags && ctx->graph_format == format) {
+      cudaGraphExecUpdateResultInfo info;
+      if (cudaGraphExecUpdate(ctx->frame_graph, graph, &info) == cudaSuccess) { updated = true; ctx->graph_updates++; }
+      else cudaGetLastError();
     }
+    if (!updated) {
+      if (ctx->frame_graph) { cudaGraphExecDestroy(ctx->frame_graph); ctx->frame_graph = nullptr; }
+      e = cudaGraphInstantiate(&ctx->frame_graph, graph, 0);
+      if (e != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        ctx->frame_graph = nullptr;
+        return ctx->fail(DRV_ERR_CUDA, std::string("drv_draw_frame: instantiate failed: ") + cudaGetErrorString(e));
+      }
+      ctx->graph_instantiations++;
+    }
+    cudaGraphDestroy(graph);
     ctx->graph_gen = ctx->state_gen;
     ctx->graph_out = hdr_out;
     ctx->graph_format = format;
@@ -445,6 +467,13 @@ extern "C" drv_status drv_draw_frame(drv_ctx* ctx, void* hdr_out, uint32_t forma
   }
   DRV_CUDA(cudaGraphLaunch(ctx->frame_graph, ctx->stream));
   ctx->launches += ctx->graph_launches;
+  return DRV_OK;
+}
+
+extern "C" drv_status drv_graph_stats(drv_ctx* ctx, uint64_t* instantiations, uint64_t* updates) {
+  NEED_CTX();
+  if (instantiations) *instantiations = ctx->graph_instantiations;
+  if (updates) *updates = ctx->graph_updates;
   return DRV_OK;
 }
 
@@ -491,7 +520,31 @@ extern "C" drv_status drv_active_cache_count(drv_ctx* ctx, uint32_t* count, uint
   if (count) *count = (uint32_t)c.TotalLightCacheCount;
   if (overflow) *overflow = stats[0];
   if (oob) *oob = stats[1];
+  if (ctx->shard_world > 1 && ctx->peers_open) { // a cross-GPU barrier of the frame gave up: the entries are incomplete
+    drv_status ps = drv_peer_status(ctx, nullptr, nullptr);
+    if (ps != DRV_OK) return ps;
+  }
   return stats[0] ? DRV_ERR_CAPACITY : DRV_OK;
+}
+
+extern "C" drv_status drv_peer_status(drv_ctx* ctx, uint32_t* timed_out_epoch, uint32_t* missing_rank) {
+  NEED_CTX();
+  uint32_t w[12] = {0};
+  DRV_CUDA(cudaMemcpyAsync(w, ctx->sync_flags, sizeof(w), cudaMemcpyDeviceToHost, ctx->stream));
+  DRV_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (timed_out_epoch) *timed_out_epoch = w[8];
+  if (missing_rank) *missing_rank = w[10];
+  if (w[8] != 0u)
+    return ctx->fail(DRV_ERR_PEER, "cross-GPU barrier " + std::to_string(w[8]) + " timed out waiting for rank " +
+                                       std::to_string(w[10]) + ": the frame's entries / image are incomplete (drv_peer_reset)");
+  return DRV_OK;
+}
+
+extern "C" drv_status drv_peer_reset(drv_ctx* ctx) {
+  NEED_CTX();
+  DRV_CUDA(cudaMemsetAsync(ctx->sync_flags, 0, kSyncBytes, ctx->stream));
+  DRV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DRV_OK;
 }
 
 extern "C" drv_status drv_live_vpl_counts(drv_ctx* ctx, uint32_t* counts) {

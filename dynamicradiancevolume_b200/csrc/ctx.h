@@ -92,7 +92,7 @@ struct drv_ctx {
   uint8_t* cell_flags = nullptr;     // one byte per CAV cell, linear-cell-id order; lives behind the entries + sync
                                      // block in the SAME allocation, so a peer that mapped the entries can store flags
   unsigned long long* scan_words = nullptr; // decoupled look-back states of the scan + compact kernel
-  uint32_t* scan_epoch = nullptr;           // [0] frame epoch (starts at 1), [1] blocks done, [2] oob-corner accumulator
+  uint32_t* scan_epoch = nullptr;           // [0] frame epoch (starts at 1), [1] blocks done, [2] oob-corner accumulator, [3] tile ticket
   uint32_t num_cells = 0, num_scan_blocks = 0;
 
   // voxels
@@ -137,12 +137,14 @@ struct drv_ctx {
   float scene_world[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   float scene_adaption = 1.0f;
   uint64_t state_gen = 1;            // bumped by every call that changes a kernel argument
+  uint64_t shape_gen = 1;            // ... and this one only by calls that can change launch shapes / scratch sizes
+  uint64_t graph_updates = 0, graph_instantiations = 0; // cudaGraphExecUpdate patches / fresh instantiations
   cudaGraphExec_t frame_graph = nullptr;
   uint64_t graph_gen = 0;            // state_gen the graph was recorded at
   void* graph_out = nullptr;
   uint32_t graph_format = 0, graph_flags = 0;
   uint64_t graph_launches = 0;       // kernels per replay
-  uint64_t warm_gen = 0;             // state_gen of the last eager frame (scratch buffers are sized)
+  uint64_t warm_gen = 0;             // shape_gen of the last eager frame (scratch buffers are sized)
 
   // timers
   bool timers = false;
@@ -160,6 +162,15 @@ struct drv_ctx {
     if (timers) { cudaEventRecord(ev_end[s], stream); ev_valid[s] = true; }
   }
 };
+
+// A sharded frame stores through every peer's mapping (mark flags, barrier words, finished entries): all of them
+// must have been imported.
+inline bool drv_peers_complete(const drv_ctx* ctx) {
+  if (ctx->shard_world <= 1) return false;
+  for (uint32_t r = 0; r < ctx->shard_world && r < 8; ++r)
+    if (r != ctx->shard_rank && !ctx->peer_entries[r]) return false;
+  return true;
+}
 
 // stage implementations (one .cu each)
 drv_status drv_impl_allocate(drv_ctx* ctx);

@@ -1306,8 +1306,9 @@ struct BarrierArgs {
   uint32_t* peer[8];
   uint32_t rank, world;
 };
-// flags[0..7] = last epoch each rank announced to this GPU, flags[8] = time-out marker, flags[9] = this GPU's
-// own epoch counter. The epoch lives on the device so that the launch has no per-call argument and a recorded
+// flags[0..7] = last epoch each rank announced to this GPU, flags[8] = time-out marker (the epoch of the barrier
+// that gave up; read by drv_peer_status), flags[10] = the rank it was waiting for, flags[9] = this GPU's own epoch
+// counter. The epoch lives on the device so that the launch has no per-call argument and a recorded
 // frame graph can replay it; all ranks call the barrier equally often, so their counters advance in lock step.
 __global__ void peer_barrier_kernel(BarrierArgs a) {
   const uint32_t t = threadIdx.x;
@@ -1319,10 +1320,15 @@ __global__ void peer_barrier_kernel(BarrierArgs a) {
   if (active) *reinterpret_cast<volatile uint32_t*>(a.peer[t] + a.rank) = epoch;
   __syncwarp(); // all announcements are on their way before anybody starts to wait
   if (!active) return;
+  // a barrier that timed out earlier poisons the ones behind it: they still announce (so that healthy peers do not
+  // hang on this rank and the epoch counters stay in lock step) but no longer wait — the frame drains at once and
+  // the host sees DRV_ERR_PEER from drv_peer_status / drv_active_cache_count instead of a half-gathered image
+  if (*reinterpret_cast<volatile uint32_t*>(a.own + 8) != 0u) return;
   const long long t0 = clock64();
   while ((int32_t)(*reinterpret_cast<volatile uint32_t*>(a.own + t) - epoch) < 0) {
     if (clock64() - t0 > 8000000000ll) { // ~4 s at 2 GHz: a peer died; do not hang the GPU
       a.own[8] = epoch;
+      a.own[10] = t; // the rank that did not arrive
       break;
     }
   }
@@ -1377,7 +1383,7 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   p.f2 = ctx->constant.ShEvaFactor2n2_p1_n1;
   p.f20 = ctx->constant.ShEvaFactor20;
   p.f22 = ctx->constant.ShEvaFactor2p2;
-  if (ctx->peers_open) {
+  if (drv_peers_complete(ctx)) {
     p.num_peers = ctx->shard_world;
     for (uint32_t r = 0; r < ctx->shard_world && r < 8; ++r)
       p.peers[r] = (r == ctx->shard_rank) ? nullptr : (uint8_t*)ctx->peer_entries[r];

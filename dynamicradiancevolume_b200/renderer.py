@@ -260,6 +260,19 @@ class Context:
     def enable_stage_timers(self, on=True): self.check(self.lib.drv_enable_stage_timers(self.handle, 1 if on else 0))
     def kernel_launches(self): return int(self.lib.drv_kernel_launches(self.handle))
 
+    def graph_stats(self):
+        """(instantiations, in-place updates) of the frame graph of draw_frame(DRV_FRAME_GRAPH)."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self.check(self.lib.drv_graph_stats(self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def peer_status(self):
+        """Raises DrvError(DRV_ERR_PEER) if a cross-GPU barrier of an earlier frame timed out."""
+        e, r = C.c_uint32(), C.c_uint32()
+        self.check(self.lib.drv_peer_status(self.handle, C.byref(e), C.byref(r)))
+
+    def peer_reset(self): self.check(self.lib.drv_peer_reset(self.handle))
+
     def gather_trace(self):
         """Diagnostics (gather_variant bit 18): [ctas, 8] uint64: 4 %globaltimer stamps, %smid, 3 clock64 values of the last pair-kernel launch."""
         import numpy as np

@@ -323,6 +323,10 @@ drv_status drv_draw(drv_ctx* ctx, void* hdr_out, uint32_t format);
                                        image complete on rank 0 — the frame contains no collective. hdr_out is ignored;
                                        the image is drv_buffers.hdr16 of rank 0. */
 drv_status drv_draw_frame(drv_ctx* ctx, void* hdr_out, uint32_t format, uint32_t flags);
+/* How often drv_draw_frame(DRV_FRAME_GRAPH) had to instantiate its frame graph, and how often it patched the
+ * instantiated graph in place (cudaGraphExecUpdate) because only kernel arguments had changed — a moving camera
+ * (drv_set_per_frame / drv_set_volume_info every frame) must show up as updates, not instantiations. */
+drv_status drv_graph_stats(drv_ctx* ctx, uint64_t* instantiations, uint64_t* updates);
 /* Geometry for DRV_FRAME_VOXELIZE: the arguments of drv_voxelize (device pointer to num_tris * 9 floats, borrowed
  * until replaced; world matrix and adaption factor are copied). */
 drv_status drv_bind_scene(drv_ctx* ctx, const float* tri_pos, uint32_t num_tris, const float world[16], float adaption);
@@ -427,6 +431,13 @@ drv_status drv_import_peer_hdr(drv_ctx* ctx, uint32_t peer_rank, const uint8_t h
  * times. Requires drv_set_shard + drv_import_peer_entries for all peers (all contexts must share
  * max_cache_count). A no-op for world == 1. */
 drv_status drv_peer_barrier(drv_ctx* ctx);
+/* Health of the cross-GPU barriers: a barrier gives up after ~4 s (a peer died or left the frame early), later
+ * barriers of this context then no longer wait, and this call — like drv_active_cache_count on a sharded context —
+ * returns DRV_ERR_PEER with the epoch of the barrier that gave up and the rank it was waiting for. */
+drv_status drv_peer_status(drv_ctx* ctx, uint32_t* timed_out_epoch, uint32_t* missing_rank);
+/* Re-arms the barriers after an error: zeroes this context's epoch counter, flags and time-out marker. Call it on
+ * EVERY rank, with a host-side barrier (torch.distributed / MPI) before and after, while no frame is in flight. */
+drv_status drv_peer_reset(drv_ctx* ctx);
 
 /* ≙ FrameProfiler (frameprofiler.hpp:138-148): CUDA-event stage timers with
  * the reference's scope names. Enabled timers record events around each

@@ -315,3 +315,55 @@ def test_config3_full_size_stated_subsample(cuda_device):
                       image_is_half=True, oracle=o)
     assert r16["ok"], r16
     g.close()
+
+
+def test_frame_graph_survives_a_moving_camera(cuda_device):
+    """drv_set_per_frame / drv_set_volume_info every frame (an animated camera): the recorded frame graph is patched
+    in place (cudaGraphExecUpdate), never re-instantiated, and every frame equals the eager frame of the same
+    uniforms bit for bit — and the oracle's frame within the gate."""
+    import copy
+    import torch
+    wl = workloads.atrium(width=640, height=360, rsm_res=256, read_lod=1, cav_resolution=32).build()
+    g = workloads.DeviceFrame(wl)
+    g.prepare_inputs()
+    out_g = torch.zeros(wl.height, wl.width, 4, dtype=torch.float32, device="cuda")
+    out_e = torch.zeros_like(out_g)
+    flags = abi.DRV_FRAME_PREPARE_RSM | abi.DRV_FRAME_GRAPH
+    for _ in range(3):
+        g.ctx.draw_frame(out_g, abi.DRV_HDR_RGBA32F_WRITE, flags)
+    inst0, upd0 = g.ctx.graph_stats()
+    assert inst0 == 1
+    cam = copy.copy(wl.camera)
+    counts = set()
+    for step in range(6):
+        cam.position = (0.15 * step, 2.5 + 0.05 * step, 2.0 - 0.2 * step)
+        pf = drv.pack_per_frame(cam, 0.1 * step)
+        vi = drv.pack_volume_info(cam, wl.bbox[0], wl.bbox[1], wl.voxel_resolution, wl.cav_resolution, wl.cascade_sizes,
+                                  wl.transition)
+        # the G-buffer is that of the original camera: unprojection and cascades move with the uniforms, which is
+        # all this test needs (a different set of cells is allocated every frame)
+        g.ctx.set_per_frame(pf)
+        g.ctx.set_volume_info(vi)
+        g.ctx.draw_frame(out_g, abi.DRV_HDR_RGBA32F_WRITE, flags)
+        torch.cuda.synchronize()
+        n = g.ctx.active_cache_count()[0]
+        counts.add(n)
+        e_g = g.ctx.read_entries(n)
+        g.ctx.draw_frame(out_e, abi.DRV_HDR_RGBA32F_WRITE, abi.DRV_FRAME_PREPARE_RSM)  # eager, same uniforms
+        torch.cuda.synchronize()
+        assert g.ctx.active_cache_count()[0] == n
+        assert np.array_equal(g.ctx.read_entries(n), e_g)
+        assert torch.equal(out_g, out_e)
+        if step == 5:
+            wl2 = copy.copy(wl)
+            wl2.per_frame, wl2.volume = pf, vi
+            o = OracleFrame(wl2).prepare_inputs()
+            img = o.frame()
+            assert o.count == n
+            ok, ratio = close(out_g.cpu().numpy()[..., :3], img[..., :3])
+            assert ok, ratio
+    inst1, upd1 = g.ctx.graph_stats()
+    assert inst1 == inst0, "a uniform change re-instantiated the frame graph"
+    assert upd1 - upd0 == 6
+    assert len(counts) > 1
+    g.close()
