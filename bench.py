@@ -40,6 +40,7 @@ METRIC = "GI ms/frame @1080p,16k VPLs"
 UNIT = "ms/frame"
 FLOP_PER_PAIR = {1: 48.0, 2: 92.0}   # 32 ops = 48 flop (SH1), 59 ops = 92 flop (SH2), FMA = 2
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4: 148 SMs x 128 lanes x FMA at clocks.max.sm
+_MICRO_CACHE = {}
 
 
 def parse_args():
@@ -250,8 +251,20 @@ def run_b200(args):
                 "workload": extra["config"]["workload"], "ms_per_frame": extra["value"], "steps": k, "warmup": 2,
                 "n_gpus": world, "caches": extra["config"]["caches"], "vpls": extra["config"]["vpls"],
                 "live_vpls": extra["config"]["live_vpls"], "scaling": "strong", "parity": extra.get("parity"),
+                "stage_ms": extra["stage_ms"], "roofline_cone": extra["roofline_cone"],
                 "how": "same timing rules as `value` (CUDA events per step, L2 flushed, max over ranks); "
                        "speed-up at N GPUs = this figure at n_gpus 1 / this figure at N"}
+    if args.config == 1 and not args.no_scaling_workload:
+        # the same scene with the cone-traced indirect shadows switched on (BASELINE configs[2]): the cone pass is the
+        # dominant kernel of every shadowed frame, so its roofline record rides in the default line too
+        k = max(3, min(10, args.steps // 3))
+        shadowed = measure(args, 2, k, 2, light=True)
+        if line is not None and shadowed is not None:
+            line["shadowed_workload"] = {
+                "workload": shadowed["config"]["workload"], "ms_per_frame": shadowed["value"], "steps": k, "warmup": 2,
+                "caches": shadowed["config"]["caches"], "live_vpls": shadowed["config"]["live_vpls"],
+                "stage_ms": shadowed["stage_ms"], "roofline_pair_pass": shadowed["roofline"],
+                "roofline_cone": shadowed["roofline_cone"], "parity": shadowed.get("parity")}
     if line is not None:
         if args.stages:
             for k_, v in line["stage_ms"].items():
@@ -395,9 +408,12 @@ def measure(args, config_index, n_steps, n_warmup, light):
     # clock sampler keeps running: this pass is part of the measured region of the roofline figures
     ctx.enable_stage_timers(True)
     inst_ms = []
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    for i in range(0 if light else args.steps + 1):
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 4)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 4)]
+    n_inst = 3 if light else args.steps + 1
+    if wl.indirect_shadow:
+        ctx.cone_steps()  # reset the cone pass's sample counter
+    for i in range(n_inst):
         with torch.cuda.stream(stream):
             if not args.no_flush:
                 flush_buf.zero_()
@@ -415,6 +431,7 @@ def measure(args, config_index, n_steps, n_warmup, light):
             except drv.DrvError:
                 pass
     torch.cuda.synchronize()
+    cone_steps_per_frame = (ctx.cone_steps() / n_inst) if wl.indirect_shadow else 0
     clocks = sampler.stop()
     ctx.enable_stage_timers(False)
     total_ms = sum(step_ms)
@@ -565,7 +582,11 @@ def measure(args, config_index, n_steps, n_warmup, light):
 
     # ---- roofline of the dominant kernel (the cache x VPL gather) ----
     med = lambda v: statistics.median(v) if v else None
-    gather_ms = (sum(stage_ms["GatherKernel"]) / len(stage_ms["GatherKernel"])) if stage_ms["GatherKernel"] else None
+    avg = lambda v: (sum(v) / len(v)) if v else None
+    gather_ms = avg(stage_ms["GatherKernel"])
+    cone_ms = avg(stage_ms["ConeKernel"]) if wl.indirect_shadow else None
+    if gather_ms and cone_ms:
+        gather_ms = max(gather_ms - cone_ms, 1e-6)  # the pair pass alone: GatherKernel brackets cone pass + pair pass
     shard_caches = n_caches
     if world > 1:
         b, e = drv.shard_range(n_caches, rank, world)
@@ -581,25 +602,29 @@ def measure(args, config_index, n_steps, n_warmup, light):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    micro = {}
+    micro = dict(_MICRO_CACHE)  # the light runs appended to the default line reuse the main run's figures
     if not args.no_microbench:
         lib = drv.load()
         import ctypes as C
         for w in range(lib.drv_microbench_count()):
+            name = lib.drv_microbench_name(w).decode()
+            if name.startswith("study_"):
+                continue  # the operand-delivery study is tools/microbench.py's job
             r = C.c_double()
             if lib.drv_microbench(local, w, C.byref(r)) == 0:
-                micro[lib.drv_microbench_name(w).decode()] = r.value
+                micro[name] = r.value
+        _MICRO_CACHE.update(micro)
     fp32_peak = micro.get("ffma_tflops") or NOMINAL_FP32_TFLOPS
     roofline = None
     if gather_ms:
         achieved = flops / (gather_ms * 1e-3) / 1e12
         roofline = {
-            "kernel": "gather_kernel<SH%d,%s>" % (wl.sh_order, "shadow" if wl.indirect_shadow else "unshadowed"),
+            "kernel": "gather_ws_kernel<SH%d,%s>" % (wl.sh_order, "shadow" if wl.indirect_shadow else "unshadowed"),
             "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
             "peak_source": ("measured on this GPU at bench start: scalar-FFMA micro-kernel (drv_microbench), FMA = 2 flop"
                             if "ffma_tflops" in micro else "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"),
             "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS,
-            "traffic": traffic_for("gather_kernel<SH%d,%s>" % (wl.sh_order, "shadow" if wl.indirect_shadow else "unshadowed")),
+            "traffic": traffic_for("gather_ws_kernel<SH%d,%s>" % (wl.sh_order, "shadow" if wl.indirect_shadow else "unshadowed")),
             "pairs_per_launch": pairs_per_launch, "flop_per_pair": FLOP_PER_PAIR[wl.sh_order],
             "live_vpls": live_vpls, "pairs_per_launch_reference": pairs_reference,
             "frac_counting_reference_pairs": pairs_reference * FLOP_PER_PAIR[wl.sh_order] / (gather_ms * 1e-3) / 1e12 / fp32_peak,
@@ -607,11 +632,27 @@ def measure(args, config_index, n_steps, n_warmup, light):
             "note": ("CUDA-core FP32 roofline (this is not a tensor-core contraction; MEASURED_PEAKS.json has no FP32 "
                      "figure). HBM traffic of the gather is ~0 per pair: the VPL list and entries are L2-resident."),
         }
+    # ---- the cone pass (the dominant kernel of the shadowed workloads): SURVEY 8d row "cone trace" ----
+    roofline_cone = None
+    if cone_ms and cone_steps_per_frame:
+        steps_per_s = cone_steps_per_frame / (cone_ms * 1e-3)
+        lane_ops_peak = (micro.get("ffma_tflops") or NOMINAL_FP32_TFLOPS) * 1e12 / 2.0  # lane-ops/s (FMA = 2 flop)
+        l2_peak = micro.get("l2_read_gbs")
+        texel_gbs = steps_per_s * 16.0 / 1e9
+        roofline_cone = {
+            "kernel": "cone_kernel", "unit": "cone steps (voxel samples)", "steps_per_launch": cone_steps_per_frame,
+            "avg_launch_ms": cone_ms, "steps_per_s": steps_per_s,
+            "texel_bytes_per_step": 16, "texel_gbs": texel_gbs, "l2_read_gbs_measured": l2_peak,
+            "frac_of_l2": (texel_gbs / l2_peak) if l2_peak else None,
+            "fp32_ops_per_step": 45, "fp32_frac": steps_per_s * 45.0 / lane_ops_peak,
+            "bound": "issue (instruction count per sample), not bandwidth: see profiles/ ncu summary",
+            "note": "algorithmic figures of SURVEY 8d: 16 UNORM8 texels (2 mips x 8) and ~45 FP32 ops per step; the kernel "
+                    "reads one 8-byte record per mip level per step from the L2-resident record chain"}
     # HBM-side summary of the two streaming stages (algorithmic bytes)
     stride = abi.entry_stride(wl.sh_order)
     cells = wl.cav_cascades * wl.cav_resolution ** 3
     alloc_bytes = 4 * px + cells * (1 + 1 + 1 + 4) + n_caches * stride
-    apply_bytes = px * (4 + 4 + 4 + 16)
+    apply_bytes = px * 24  # depth 4 + normal 4 + diffuse 4 (sRGB8 padded) + RGBA16F 8 (+ 4 of slack it allows)
     hbm_peak = peaks.get("hbm_gbs")
     secondary = {}
     for name, nbytes in (("AllocateCaches", alloc_bytes), ("ApplyCaches", apply_bytes)):
@@ -663,6 +704,7 @@ def measure(args, config_index, n_steps, n_warmup, light):
         "parity": parity,
         "clocks": clocks,
         "roofline": roofline,
+        "roofline_cone": roofline_cone,
         "roofline_streaming_stages": secondary,
         "cpu_baseline": cpu_baseline,
         "stage_ms": {k: med(v) for k, v in stage_ms.items() if v},

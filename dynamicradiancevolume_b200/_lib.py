@@ -79,6 +79,7 @@ SYMBOLS = [
     ("drv_microbench_name", C.c_char_p, [_u32]),
     ("drv_microbench_count", _u32, []),
     ("drv_debug_gather_trace", _st, [_P, _P, _u32, C.POINTER(_u32)]),
+    ("drv_debug_cone_steps", _st, [_P, C.POINTER(C.c_uint64)]),
 ]
 
 _lib = None

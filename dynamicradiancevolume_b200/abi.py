@@ -33,7 +33,7 @@ DRV_FRAME_GATHER_IMAGE = 8
 DRV_FRAME_VOXELIZE = 16
 
 STAGE_NAMES = ["VoxelizeScene", "VoxelBlendMipMap", "AllocateCaches", "LightCaches", "ApplyCaches",
-               "PrepareRSM", "GatherKernel"]
+               "PrepareRSM", "GatherKernel", "ConeKernel"]
 
 f32 = C.c_float
 i32 = C.c_int32

@@ -657,7 +657,7 @@ extern "C" drv_status drv_peer_barrier(drv_ctx* ctx) {
 }
 
 static const char* kStageNames[DRV_STAGE_COUNT] = {"VoxelizeScene", "VoxelBlendMipMap", "AllocateCaches", "LightCaches",
-                                                   "ApplyCaches",   "PrepareRSM",       "GatherKernel"};
+                                                   "ApplyCaches",   "PrepareRSM",       "GatherKernel",     "ConeKernel"};
 extern "C" const char* drv_stage_name(drv_stage s) { return (s >= 0 && s < DRV_STAGE_COUNT) ? kStageNames[s] : "?"; }
 
 extern "C" drv_status drv_enable_stage_timers(drv_ctx* ctx, int enable) {

@@ -166,7 +166,7 @@ struct ConeSample {
 // on what it sampled, so the fetch of step s+1 is issued before step s is filtered and the L1/L2 latency of
 // the dependent chain position -> index -> load -> filter -> occlusion overlaps with useful work.
 // A cone also stops once occlusion reached 1: later samples would add (1 - 1) * x = 0.
-__device__ __forceinline__ float cone_trace(const VoxelVol& V, float wx, float wy, float wz, float4 blk) {
+__device__ __forceinline__ float cone_trace(const VoxelVol& V, float wx, float wy, float wz, float4 blk, uint32_t& steps) {
   // :104 voxelPos, kept in level-0 texel units minus the half-texel shift (q = voxelPos * res - 0.5), so that a
   // step of `stepSize` voxels along the unit direction is q += dir * stepSize (:197-198, 213)
   const float inv_voxel = 1.0f / V.voxel_size;
@@ -186,6 +186,7 @@ __device__ __forceinline__ float cone_trace(const VoxelVol& V, float wx, float w
   // advance by `stepSize` (:213-216) and issue the fetches of that sample (:219)
   auto fetch = [&](float stepSize) -> ConeSample {
     ConeSample S;
+    ++steps;
     cxy = __ffma2_rn(dxy, f2(stepSize), cxy); cz = fmaf(dz, stepSize, cz);          // :213
     dist = ex_add(dist, stepSize);                                                  // :214
     S.dist = dist;
@@ -235,7 +236,8 @@ __device__ __forceinline__ float cone_trace(const VoxelVol& V, float wx, float w
 // no ping-pong state. With the cone pass on its own (8+ CTAs of 4 warps per SM) the other warps of the SM hide the
 // L1/L2 latency of the dependent chain, and the loop spends a quarter fewer instructions on control flow and
 // register moves (ncu: BRA + BSSY + BSYNC + MOV were 18 % of the pipelined kernel's instructions).
-__device__ __forceinline__ float cone_trace_simple(const VoxelVol& V, float wx, float wy, float wz, float4 blk) {
+__device__ __forceinline__ float cone_trace_simple(const VoxelVol& V, float wx, float wy, float wz, float4 blk,
+                                                   uint32_t& steps) {
   const float inv_voxel = 1.0f / V.voxel_size;
   const float maxLod = (float)(V.levels - 1);
   const float kk = blk.w;
@@ -249,10 +251,38 @@ __device__ __forceinline__ float cone_trace_simple(const VoxelVol& V, float wx, 
   const float goal = ex_sub(ex_div(lightDist, V.voxel_size), 2.0f);                 // :206
   const float radToStep = ex_div(2.0f, ex_sub(1.0f, kk));                           // :209
   float dist = 0.0f, occ = 0.0f, stepSize = 1.0f;
+  int s = 0;
+  // First stretch: while the sphere radius is <= 1 voxel, log2(radius) <= 0 selects mip level 0 alone
+  // and the step stays max(1, r * g): no log2, no second level, no level arithmetic. A VAL block subtends ~1/32
+  // rad (SuperValWidth), so this loop is where nearly every sample of a frame is taken.
+  {
 #pragma unroll 1
-  for (int s = 0; s < 32; ++s) {                                                    // :211
+    for (; s < 32; ++s) {
+      const float nd = ex_add(dist, stepSize);
+      const float radius = ex_mul(nd, kk);
+      if (radius > 1.0f) break;                                                     // continue in the general loop
+      cxy = __ffma2_rn(dxy, f2(stepSize), cxy); cz = fmaf(dz, stepSize, cz);        // :213
+      dist = nd;                                                                    // :214
+      ++steps;
+      int x, y, z;
+      float2 txy; float tzf;
+      floor_frac_w2(__fadd2_rn(cxy, f2(-0.5f)), x, y, txy);
+      floor_frac_w(cz - 0.5f, z, tzf);
+      const int r = V.res;
+      x = min(max(x, -1), r - 1) + 1;
+      y = min(max(y, -1), r - 1) + 1;
+      z = min(max(z, -1), r - 1) + 1;
+      const uint2 r0 = __ldg(V.rec + (uint32_t)(x + (r + 1) * (y + (r + 1) * z)));  // level 0 records start at 0
+      occ = fmaf(1.0f - occ, trilinear(r0, txy, tzf), occ);                         // :220
+      if (dist >= goal || occ >= 1.0f) return saturatef(1.0f - occ);                // :222
+      stepSize = fmaxf(1.0f, ex_mul(radius, radToStep));                            // :225
+    }
+  }
+#pragma unroll 1
+  for (; s < 32; ++s) {                                                             // :211
     cxy = __ffma2_rn(dxy, f2(stepSize), cxy); cz = fmaf(dz, stepSize, cz);          // :213
     dist = ex_add(dist, stepSize);                                                  // :214
+    ++steps;
     const float radius = ex_mul(dist, kk);                                          // :216
     // lod = log2(radius) clamped to the chain; radius <= 1 is level 0 exactly. fmaxf(NaN, 0) = 0.
     const float l = fminf(fmaxf(__log2f(radius), 0.0f), maxLod);
@@ -1074,7 +1104,8 @@ struct ConeParams {
   int vres, vlevels;
   float vmin[3];
   float voxel_size;
-  uint32_t* work; // [0] next item, [1] CTAs done — a device-side queue: items differ in cost (dead blocks, trip counts)
+  uint32_t* work; // [0] next item, [1] CTAs done — a device-side queue: items differ in cost (dead blocks, trip counts);
+                  // [2..3] 64-bit count of the samples taken since drv_debug_cone_steps last read it
 };
 
 constexpr int kConeThreads = 128;
@@ -1100,6 +1131,7 @@ __global__ void __launch_bounds__(kConeThreads, MINB) cone_kernel(const __grid_c
   const uint32_t block_groups = (total_blocks + kBlocksPerItem - 1) / kBlocksPerItem;
   const uint32_t items = cache_groups * block_groups; // <= 2048 x 2048
   __shared__ uint32_t s_item;
+  uint32_t steps = 0; // samples this thread takes: the unit of the cone pass's roofline (bench.py)
   for (;;) {
     // items are handed out through an atomic counter: 13 % of the SM cycles were idle with a static round-robin
     if (threadIdx.x == 0) s_item = atomicAdd(p.work, 1u);
@@ -1119,10 +1151,12 @@ __global__ void __launch_bounds__(kConeThreads, MINB) cone_kernel(const __grid_c
       if (!__ldg(p.lights[light].block_live + (b - p.block_offset[light]))) continue; // no live VPL reads this entry
       const float4 blk = __ldg(p.lights[light].blocks + (b - p.block_offset[light]));
       if (alive)
-        p.table[(size_t)b * p.stride + local] = SIMPLE ? cone_trace_simple(V, pos.x, pos.y, pos.z, blk)
-                                                       : cone_trace(V, pos.x, pos.y, pos.z, blk);
+        p.table[(size_t)b * p.stride + local] = SIMPLE ? cone_trace_simple(V, pos.x, pos.y, pos.z, blk, steps)
+                                                       : cone_trace(V, pos.x, pos.y, pos.z, blk, steps);
     }
   }
+  steps = __reduce_add_sync(0xffffffffu, steps);
+  if ((threadIdx.x & 31) == 0 && steps) atomicAdd(reinterpret_cast<unsigned long long*>(p.work + 2), (unsigned long long)steps);
   // the last CTA to leave rewinds the queue for the next launch
   if (threadIdx.x == 0 && atomicAdd(p.work + 1, 1u) == gridDim.x - 1) {
     p.work[0] = 0u;
@@ -1446,7 +1480,8 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   p.shadow_stride = chunk;
   // gather_variant bit 17: the software-pipelined march instead of the plain loop
   using ConeFn = void (*)(const ConeParams);
-  const ConeFn cone_fn = (ctx->cfg.gather_variant & 0x20000u) ? (ConeFn)cone_kernel<false, 8> : (ConeFn)cone_kernel<true, 10>;
+  const ConeFn cone_fn = (ctx->cfg.gather_variant & 0x20000u) ? (ConeFn)cone_kernel<false, 8>
+                         : (ctx->cfg.gather_variant & 0x80000u) ? (ConeFn)cone_kernel<true, 8> : (ConeFn)cone_kernel<true, 10>;
   int cone_per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cone_per_sm, cone_fn, kConeThreads, 0);
   if (cone_per_sm < 1) cone_per_sm = 1;
@@ -1455,8 +1490,10 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   for (uint32_t first = 0; first < ctx->cfg.max_cache_count; first += chunk) {
     c.chunk_first = p.chunk_first = first;
     c.chunk_cap = p.chunk_cap = chunk;
+    if (first == 0) ctx->stage_begin(DRV_STAGE_CONE_KERNEL); // the chunk that holds the caches (<= 262 144 of them)
     cone_fn<<<cone_grid, kConeThreads, 0, ctx->stream>>>(c);
     DRV_LAUNCH_CHECK();
+    if (first == 0) ctx->stage_end(DRV_STAGE_CONE_KERNEL);
     drv_status st = launch_gather(ctx, kernel, p, tile, order, threads, ws);
     if (st != DRV_OK) return st;
   }
@@ -1474,5 +1511,15 @@ extern "C" drv_status drv_debug_gather_trace(drv_ctx* ctx, uint64_t* out, uint32
   DRV_CUDA(cudaMemcpyAsync(out, ctx->gather_trace, (size_t)n * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   DRV_CUDA(cudaStreamSynchronize(ctx->stream));
   if (num_ctas) *num_ctas = n;
+  return DRV_OK;
+}
+
+// Diagnostics: the number of voxel samples (cone steps) cone_kernel has taken since the last call; resets it.
+extern "C" drv_status drv_debug_cone_steps(drv_ctx* ctx, uint64_t* steps) {
+  if (!ctx || !steps) return DRV_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  DRV_CUDA(cudaMemcpyAsync(steps, ctx->cone_work + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DRV_CUDA(cudaMemsetAsync(ctx->cone_work + 2, 0, sizeof(uint64_t), ctx->stream));
+  DRV_CUDA(cudaStreamSynchronize(ctx->stream));
   return DRV_OK;
 }

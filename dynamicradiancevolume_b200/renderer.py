@@ -260,6 +260,12 @@ class Context:
     def enable_stage_timers(self, on=True): self.check(self.lib.drv_enable_stage_timers(self.handle, 1 if on else 0))
     def kernel_launches(self): return int(self.lib.drv_kernel_launches(self.handle))
 
+    def cone_steps(self):
+        """Voxel samples the cone pass has taken since the last call (resets the count)."""
+        n = C.c_uint64()
+        self.check(self.lib.drv_debug_cone_steps(self.handle, C.byref(n)))
+        return n.value
+
     def graph_stats(self):
         """(instantiations, in-place updates) of the frame graph of draw_frame(DRV_FRAME_GRAPH)."""
         a, b = C.c_uint64(), C.c_uint64()

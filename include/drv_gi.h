@@ -219,7 +219,8 @@ typedef struct drv_config {
                                  bits 12..15 apply: rows per thread (1, 2, 8; default 4)
                                  bit 16      variant 30: two-kernel gather + finalize instead of the cooperative launch
                                  bit 17      software-pipelined cone march instead of the plain loop
-                                 bit 18      per-CTA time stamps of the pair kernel (drv_debug_gather_trace) */
+                                 bit 18      per-CTA time stamps of the pair kernel (drv_debug_gather_trace)
+                                 bit 19      cone pass compiled for 8 instead of 10 resident CTAs per SM (64 registers) */
   uint32_t reserved[3];
 } drv_config;
 
@@ -449,7 +450,8 @@ typedef enum drv_stage {
   DRV_STAGE_LIGHT_CACHES,         /* "LightCaches"     renderer.cpp:901 */
   DRV_STAGE_APPLY_CACHES,         /* "ApplyCaches"     renderer.cpp:1049 */
   DRV_STAGE_PREPARE_RSM,          /* RSM mip chain (ShadowMap::PrepareRSM) */
-  DRV_STAGE_GATHER_KERNEL,        /* the cache x VPL kernel alone, inside LightCaches */
+  DRV_STAGE_GATHER_KERNEL,        /* the cache x VPL kernel(s) alone, inside LightCaches (cone pass + pair pass when shadowed) */
+  DRV_STAGE_CONE_KERNEL,          /* the cone pass (visibility table) alone, inside GatherKernel */
   DRV_STAGE_COUNT
 } drv_stage;
 drv_status drv_enable_stage_timers(drv_ctx* ctx, int enable);
@@ -540,6 +542,9 @@ uint32_t    drv_microbench_count(void);
  * three: 8 words per CTA — how the fixed costs and the balance of that kernel are measured
  * (tools/gather_trace.py). `out` holds 8 * capacity_ctas words. */
 drv_status drv_debug_gather_trace(drv_ctx* ctx, uint64_t* out, uint32_t capacity_ctas, uint32_t* num_ctas);
+/* Diagnostics: voxel samples (cone steps) the cone pass has taken since the last call (and resets the count) — the
+ * unit of that kernel's roofline record in bench.py. */
+drv_status drv_debug_cone_steps(drv_ctx* ctx, uint64_t* steps);
 
 #ifdef __cplusplus
 }
