@@ -455,33 +455,46 @@ def measure(args, config_index, n_steps, n_warmup, light):
     # the gathered image back
     e2e_sharded = world > 1 and in_frame and args.image_gather == "p2p"
     if e2e_sharded:
-        def padded(t):
-            n = t.numel() * t.element_size()
-            chunk = ((n + world - 1) // world + 255) // 256 * 256
-            return n, chunk
+        # ONE packed pinned host buffer holds the frame's inputs and ONE device staging buffer receives them: rank r
+        # uploads slice r over its own PCIe link, a single NCCL all-gather over NVLink completes the buffer on every
+        # GPU. Every rank applies its own band of rows and copies it D2H straight into its rows of a host image that
+        # all ranks share (POSIX shared memory, registered with CUDA in every process): no rank-0 funnel.
         host_inputs = list(h_gb) + [t for r in h_rsm for t in r]
-        dev_stage = []
+        offs, total = [], 0
         for t in host_inputs:
-            n, chunk = padded(t)
-            dev_stage.append(torch.empty(chunk * world, dtype=torch.uint8, device=dev))
-        views = [d[:t.numel() * t.element_size()].view(t.dtype).view(t.shape) for d, t in zip(dev_stage, host_inputs)]
+            offs.append(total)
+            total += (t.numel() * t.element_size() + 255) // 256 * 256
+        chunk = ((total + world - 1) // world + 255) // 256 * 256
+        host_pack = torch.zeros(chunk * world, dtype=torch.uint8).pin_memory()
+        for t, o_ in zip(host_inputs, offs):
+            n_ = t.numel() * t.element_size()
+            host_pack[o_:o_ + n_].copy_(t.reshape(-1).view(torch.uint8))
+        dev_pack = torch.empty(chunk * world, dtype=torch.uint8, device=dev)
+        views = [dev_pack[o_:o_ + t.numel() * t.element_size()].view(t.dtype).view(t.shape) for t, o_ in zip(host_inputs, offs)]
         # bound once: the staging images live at fixed addresses, so the recorded frame graph stays valid
         ctx.bind_gbuffer(views[0], views[1], views[2])
         for i in range(len(h_rsm)):
             ctx.bind_rsm(i, views[3 + 3 * i], views[4 + 3 * i], views[5 + 3 * i])
+        from dynamicradiancevolume_b200 import sharding
+        shared = sharding.SharedHostImage("drv_bench_%s" % os.environ.get("MASTER_PORT", "0"), (wl.height, wl.width, 4),
+                                          torch.float16, rank, world)
+        h_img = shared.tensor
+        y0, y1 = min(wl.height, rank * band), min(wl.height, (rank + 1) * band)
+        h2d = chunk
+        d2h = (y1 - y0) * wl.width * 8
 
     def frame_e2e():
         if e2e_sharded:
             with torch.cuda.stream(stream):
-                for t, d in zip(host_inputs, dev_stage):
-                    n, chunk = padded(t)
-                    a, b = rank * chunk, min(n, (rank + 1) * chunk)
-                    if b > a:
-                        d[a:b].copy_(t.view(-1).view(torch.uint8)[a:b], non_blocking=True)
-                    dist.all_gather_into_tensor(d, d[rank * chunk:(rank + 1) * chunk])
-                ctx.draw_frame(None, abi.DRV_HDR_RGBA16F_WRITE, frame_flags | abi.DRV_FRAME_GATHER_IMAGE)
-                if rank == 0:
-                    h_out.copy_(ctx.hdr16_tensor(), non_blocking=True)
+                mine = dev_pack[rank * chunk:(rank + 1) * chunk]
+                mine.copy_(host_pack[rank * chunk:(rank + 1) * chunk], non_blocking=True)
+                dist.all_gather_into_tensor(dev_pack, mine)
+                if not args.static_uniforms:
+                    ctx.set_per_frame(wl.per_frame)
+                    ctx.set_volume_info(wl.volume)
+                ctx.draw_frame(hdr16, abi.DRV_HDR_RGBA16F_WRITE, frame_flags | abi.DRV_FRAME_APPLY_OWN_ROWS)
+                if y1 > y0:
+                    h_img[y0:y1].copy_(hdr16[y0:y1], non_blocking=True)
             stream.synchronize()
             return
         if wl.indirect_shadow:
@@ -543,6 +556,12 @@ def measure(args, config_index, n_steps, n_warmup, light):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_total = float(t.item())
     e2e_per_step = e2e_total / args.steps
+    if e2e_sharded:
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:  # the shared host image holds every rank's band: compare it with rank 0's gathered device image later
+            e2e_image = h_img.clone()
+        shared.close()
     # restore the device-resident bindings (upload_* rebinds to staging copies of the same data)
     ctx.bind_gbuffer(g.depth, g.normal, g.diffuse)
     for i, r in enumerate(g.rsms):
@@ -569,6 +588,9 @@ def measure(args, config_index, n_steps, n_warmup, light):
             parity = check_frame(wl, ctx.read_entries(n_par), ctx.read_atlas(), n_par, img, step=1 if small else 64,
                                  image_is_half=True)
             parity["seconds"] = time.perf_counter() - t0
+            if e2e_sharded:  # the end-to-end leg's host image (bands copied by every rank) against the device frame
+                parity["e2e_host_image_equal"] = bool(torch.equal(e2e_image[:wl.height].float(), img_t[:wl.height].float().cpu()))
+                parity["ok"] = bool(parity["ok"] and parity["e2e_host_image_equal"])
             parity["what"] = ("allocation (cell set, indices, positions) bit-exact on the whole frame; SH of every %d-th "
                               "entry against the oracle's gather within 1e-5 + 1e-3 rel; the whole RGBA16F image against "
                               "the oracle's apply pass on the device's entries within that gate + one half rounding"
@@ -689,16 +711,17 @@ def measure(args, config_index, n_steps, n_warmup, light):
                    "parallelism": "1 GPU" if world == 1 else "gather sharded over %d GPUs by cell-ordered entry range, "
                                   "allocation replicated, fused P2P all-gather of SH, apply row-sharded, image bands %s" % (world, "stored into rank 0's target over NVLink (no collective in the frame)" if (args.image_gather == "p2p" and args.barrier == "peer" and not args.serial) else "gathered on rank 0 with NCCL"),
                    "gather_variant": args.variant},
-        "e2e": {"value": e2e_per_step, "unit": UNIT, "h2d_bytes_per_step": (h2d // world) if (world > 1 and e2e_sharded) else h2d,
+        "e2e": {"value": e2e_per_step, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h,
                 "link": pcie,
-                "h2d_floor_ms": ((h2d // world if (world > 1 and e2e_sharded) else h2d) / (pcie["h2d_gbs"] * 1e9) * 1e3) if pcie.get("h2d_gbs") else None,
+                "h2d_floor_ms": (h2d / (pcie["h2d_gbs"] * 1e9) * 1e3) if pcie.get("h2d_gbs") else None,
                 "how": ("drv_draw_host_frame: pinned host G-buffer + RSM level 0 -> H2D -> mips, allocate, light, apply per "
                         "band -> D2H per band, overlapped inside the frame; wall clock around the call, which returns when "
                         "the RGBA16F image is in host memory") if world == 1 else
-                       ("every rank uploads 1/%d of each input image from pinned host memory (h2d_bytes_per_step is per rank), "
-                        "NCCL all-gather over NVLink completes them on every GPU, sharded drv_draw_frame, rank 0 copies the "
-                        "gathered RGBA16F image to host memory; wall clock, max over ranks" % world if e2e_sharded else
+                       ("every rank uploads slice 1/%d of ONE packed pinned input buffer over its own PCIe link, a single NCCL "
+                        "all-gather over NVLink completes it on every GPU, sharded drv_draw_frame with each rank applying its "
+                        "own band of rows, each rank copies its band D2H straight into a host image shared by all ranks "
+                        "(POSIX shm registered with CUDA); h2d / d2h bytes are PER RANK; wall clock, max over ranks" % world if e2e_sharded else
                         "every rank uploads all inputs, serial sharded stages, NCCL image gather, rank 0 D2H")},
         "gpu_launches": launches,
         "parity": parity,

@@ -173,7 +173,7 @@ struct ScanState {
 };
 constexpr uint32_t kFlagAggregate = 1u, kFlagPrefix = 2u;
 
-template <int STRIDE>
+template <int STRIDE, bool ZERO_SH>
 __global__ void __launch_bounds__(kScanThreads) scan_compact_kernel(AllocParams p, uint8_t* __restrict__ flags,
                                                                     uint32_t num_cells, ScanState st, uint32_t max_caches,
                                                                     uint32_t* __restrict__ atlas, uint8_t* __restrict__ entries,
@@ -300,9 +300,11 @@ __global__ void __launch_bounds__(kScanThreads) scan_compact_kernel(AllocParams 
           e[0] = make_float4(ex_add(ex_mul((float)(x0 + i), k.WorldVoxelSize), k.Min[0]),
                              ex_add(ex_mul((float)y, k.WorldVoxelSize), k.Min[1]),
                              ex_add(ex_mul((float)z, k.WorldVoxelSize), k.Min[2]), 0.0f);
-          const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ZERO_SH) { // cacheGather.comp:68-83 (a sharded frame leaves it to the gather, which overwrites)
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int q = 1; q < STRIDE / 16; ++q) e[q] = zero; // cacheGather.comp:68-83
+            for (int q = 1; q < STRIDE / 16; ++q) e[q] = zero;
+          }
         }
         ++index;
       }
@@ -365,7 +367,17 @@ static drv_status alloc_params(drv_ctx* ctx, AllocParams& p) {
 // thousand bytes — are stored into every peer's array (8-byte scan, one remote byte store per set flag and peer).
 // Marking straight into the peers costs a remote store per triggering PIXEL instead and was slower than not
 // sharding at all. Flags a peer has already pushed here are pushed again: harmless, the stores are idempotent.
-__global__ void __launch_bounds__(256) push_flags_kernel(const uint8_t* __restrict__ flags, uint32_t num_cells, MarkTargets peers) {
+// The push ends in the cross-GPU barrier of the mark phase (the same epoch protocol as peer_barrier_kernel, gather.cu):
+// every block fences its remote stores and takes a ticket; the block that draws the last one announces this rank's
+// new epoch to all peers and waits for theirs — one launch instead of push + barrier.
+struct PushBarrier {
+  uint32_t* own;      // this rank's sync block: [0..7] epochs announced by the ranks, [8] time-out marker, [9] own epoch
+  uint32_t* peer[8];  // every rank's sync block (own included)
+  uint32_t rank, world;
+  uint32_t* done;     // blocks-done ticket (zero between launches)
+};
+__global__ void __launch_bounds__(256) push_flags_kernel(const uint8_t* __restrict__ flags, uint32_t num_cells, MarkTargets peers,
+                                                         PushBarrier B) {
   const uint32_t words = num_cells / 8;
   for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
     const uint2 f = __ldcg(reinterpret_cast<const uint2*>(flags + (size_t)w * 8));
@@ -377,6 +389,28 @@ __global__ void __launch_bounds__(256) push_flags_kernel(const uint8_t* __restri
       for (int t = 0; t < peers.n; ++t) peers.flags[t][(size_t)w * 8 + i] = 1;
     }
   }
+  __threadfence_system(); // this thread's remote flag stores are ordered before the ticket
+  __shared__ uint32_t s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(B.done, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last || threadIdx.x >= 32) return;
+  // the last block: every block's stores are ordered before this point
+  const uint32_t t = threadIdx.x;
+  uint32_t epoch = 0;
+  if (t == 0) { *B.done = 0u; epoch = B.own[9] + 1u; B.own[9] = epoch; }
+  epoch = __shfl_sync(0xffffffffu, epoch, 0);
+  const bool active = t < B.world && t != B.rank;
+  __threadfence_system();
+  if (active) *reinterpret_cast<volatile uint32_t*>(B.peer[t] + B.rank) = epoch;
+  __syncwarp();
+  if (!active) return;
+  if (*reinterpret_cast<volatile uint32_t*>(B.own + 8) != 0u) return; // an earlier barrier timed out: do not wait
+  const long long t0 = clock64();
+  while ((int32_t)(*reinterpret_cast<volatile uint32_t*>(B.own + t) - epoch) < 0) {
+    if (clock64() - t0 > 8000000000ll) { B.own[8] = epoch; B.own[10] = t; break; }
+  }
+  __threadfence_system();
 }
 
 // Mark phase. `sharded`: only this rank's band of 16-row tiles, then the set flags are pushed to every peer.
@@ -407,14 +441,26 @@ drv_status drv_impl_allocate_mark(drv_ctx* ctx, bool sharded) {
   if (sharded && P.n > 0) {
     const uint32_t words = ctx->num_cells / 8;
     const uint32_t blocks = std::min<uint32_t>((words + 255) / 256, (uint32_t)ctx->num_sms * 8);
-    push_flags_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->cell_flags, ctx->num_cells, P);
+    PushBarrier B;
+    memset(&B, 0, sizeof(B));
+    B.own = ctx->sync_flags;
+    const size_t sync_off = (size_t)ctx->cfg.max_cache_count * 128;
+    for (uint32_t r = 0; r < ctx->shard_world && r < 8; ++r)
+      B.peer[r] = r == ctx->shard_rank ? ctx->sync_flags : reinterpret_cast<uint32_t*>((uint8_t*)ctx->peer_entries[r] + sync_off);
+    B.rank = ctx->shard_rank;
+    B.world = ctx->shard_world;
+    B.done = ctx->sync_flags + 12; // a word of the sync block the barrier protocol does not use
+    // ... and the cross-GPU barrier that follows the mark phase rides in the same launch
+    push_flags_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->cell_flags, ctx->num_cells, P, B);
     DRV_LAUNCH_CHECK();
   }
   return DRV_OK;
 }
 
 // Scan + compact phase (replicated on every rank of a sharded frame: deterministic, identical indices).
-drv_status drv_impl_allocate_compact(drv_ctx* ctx) {
+// zero_sh = false: a sharded drv_draw_frame, whose gather OVERWRITES every entry's SH on every rank — zeroing here
+// would race with a faster peer's stores (and would need a barrier of its own).
+drv_status drv_impl_allocate_compact(drv_ctx* ctx, bool zero_sh) {
   AllocParams p;
   drv_status st0 = alloc_params(ctx, p);
   if (st0 != DRV_OK) return st0;
@@ -422,12 +468,11 @@ drv_status drv_impl_allocate_compact(drv_ctx* ctx) {
   st.words = ctx->scan_words;
   st.epoch = ctx->scan_epoch;
   st.oob_accum = ctx->scan_epoch + 2;
-  if (ctx->entry_stride == 64)
-    scan_compact_kernel<64><<<ctx->num_scan_blocks, kScanThreads, 0, ctx->stream>>>(
-        p, ctx->cell_flags, ctx->num_cells, st, ctx->cfg.max_cache_count, ctx->atlas, ctx->entries, ctx->counter, ctx->stats);
-  else
-    scan_compact_kernel<128><<<ctx->num_scan_blocks, kScanThreads, 0, ctx->stream>>>(
-        p, ctx->cell_flags, ctx->num_cells, st, ctx->cfg.max_cache_count, ctx->atlas, ctx->entries, ctx->counter, ctx->stats);
+#define DRV_SCAN(ST, Z) scan_compact_kernel<ST, Z><<<ctx->num_scan_blocks, kScanThreads, 0, ctx->stream>>>( \
+    p, ctx->cell_flags, ctx->num_cells, st, ctx->cfg.max_cache_count, ctx->atlas, ctx->entries, ctx->counter, ctx->stats)
+  if (ctx->entry_stride == 64) { if (zero_sh) DRV_SCAN(64, true); else DRV_SCAN(64, false); }
+  else { if (zero_sh) DRV_SCAN(128, true); else DRV_SCAN(128, false); }
+#undef DRV_SCAN
   DRV_LAUNCH_CHECK();
   ctx->stage_end(DRV_STAGE_ALLOCATE_CACHES);
   return DRV_OK;
@@ -436,7 +481,7 @@ drv_status drv_impl_allocate_compact(drv_ctx* ctx) {
 drv_status drv_impl_allocate(drv_ctx* ctx) {
   drv_status st = drv_impl_allocate_mark(ctx, false);
   if (st != DRV_OK) return st;
-  return drv_impl_allocate_compact(ctx);
+  return drv_impl_allocate_compact(ctx, true);
 }
 
 drv_status drv_impl_set_synthetic_entries(drv_ctx* ctx, const float* pos, uint32_t n) {

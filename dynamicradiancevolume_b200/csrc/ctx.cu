@@ -347,17 +347,16 @@ static drv_status frame_body(drv_ctx* ctx, void* hdr_out, uint32_t format, uint3
   // (idempotent byte stores over NVLink = the all-reduce of the mark phase); after the barrier every rank holds the
   // complete flag set and runs the deterministic scan + compact itself (identical indices, no communication)
   const bool sharded = drv_peers_complete(ctx);
-  st = drv_impl_allocate_mark(ctx, sharded);
+  st = drv_impl_allocate_mark(ctx, sharded); // sharded: + flag push + the cross-GPU barrier, in one launch
   if (st != DRV_OK) return st;
-  if (sharded && (st = drv_impl_peer_barrier(ctx)) != DRV_OK) return st;
-  st = drv_impl_allocate_compact(ctx);
+  // sharded: no SH clear here — every entry's SH is overwritten on every rank by its owner's gather epilogue, so
+  // a fast peer's stores cannot be wiped by this rank's (later) compaction and no second barrier is needed
+  st = drv_impl_allocate_compact(ctx, !sharded);
   if (st != DRV_OK) return st;
-  // ... and every rank has cleared its SH before any peer's gather epilogue stores into it
-  if (sharded && (st = drv_impl_peer_barrier(ctx)) != DRV_OK) return st;
   DRV_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
   if (vox) DRV_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join2, 0));
   ctx->stage_begin(DRV_STAGE_LIGHT_CACHES);
-  st = drv_impl_gather(ctx);   // renderer.cpp:556
+  st = drv_impl_gather(ctx, sharded);   // renderer.cpp:556
   ctx->stage_end(DRV_STAGE_LIGHT_CACHES);
   if (st != DRV_OK) return st;
   // ... and all peers' stores have landed before anybody applies

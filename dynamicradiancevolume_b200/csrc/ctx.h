@@ -175,11 +175,11 @@ inline bool drv_peers_complete(const drv_ctx* ctx) {
 // stage implementations (one .cu each)
 drv_status drv_impl_allocate(drv_ctx* ctx);
 drv_status drv_impl_allocate_mark(drv_ctx* ctx, bool sharded);
-drv_status drv_impl_allocate_compact(drv_ctx* ctx);
+drv_status drv_impl_allocate_compact(drv_ctx* ctx, bool zero_sh = true);
 drv_status drv_impl_prepare_rsm(drv_ctx* ctx, uint32_t light, bool only_consumed = false);
 drv_status drv_impl_generate_vpls(drv_ctx* ctx, uint32_t light);
 drv_status drv_impl_compact_vpls(drv_ctx* ctx, uint32_t light, bool counted = false);
-drv_status drv_impl_gather(drv_ctx* ctx);
+drv_status drv_impl_gather(drv_ctx* ctx, bool overwrite = false);
 drv_status drv_impl_apply(drv_ctx* ctx, void* out, uint32_t format);
 drv_status drv_impl_apply_rows(drv_ctx* ctx, void* out, uint32_t format, uint32_t y_begin, uint32_t y_end, bool timed);
 drv_status drv_impl_voxelize(drv_ctx* ctx, const float* tris, uint32_t n, const float* world, float adaption,

@@ -82,6 +82,7 @@ struct GatherParams {
   // fused all-gather: peer copies of the entries buffer (NVLink P2P)
   uint8_t* peers[8];
   uint32_t num_peers;
+  uint32_t overwrite;    // 1: entry.SH = acc instead of += (sharded frames: the allocation did not clear the SH)
   uint32_t* tickets;     // warp-split kernel: one arrival counter per cache tile (zero between launches)
   unsigned long long* trace; // diagnostics (gather_variant bit 18): %globaltimer at 4 points of every CTA, else null
 };
@@ -348,7 +349,7 @@ __device__ __forceinline__ void add_to_entry(const GatherParams& p, uint32_t ent
   float4 outq[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
-    float4 o = e[1 + q];
+    float4 o = p.overwrite ? make_float4(0.f, 0.f, 0.f, 0.f) : e[1 + q];
     o.x += vals[q * 4 + 0]; o.y += vals[q * 4 + 1]; o.z += vals[q * 4 + 2]; o.w += vals[q * 4 + 3];
     e[1 + q] = o; // entry.SH += acc, :358-373
     outq[q] = o;
@@ -908,7 +909,16 @@ __global__ void __launch_bounds__(NW * 32, NW >= 8 ? 1 : 256 / (NW * 32)) gather
 
   trace_point(p, 0);
   Schedule S = make_schedule(p, TILE);
-  if (S.units == 0) return;
+  if (S.units == 0) {
+    // no live VPL at all: `entry.SH += 0`. In overwrite mode the SH was never cleared, so the zeros are written
+    if (p.overwrite) {
+      float vals[28];
+#pragma unroll
+      for (int q = 0; q < 28; ++q) vals[q] = 0.0f;
+      for (uint32_t i = blockIdx.x * NT + threadIdx.x; i < S.count; i += gridDim.x * NT) add_to_entry<ORDER>(p, S.first + i, vals);
+    }
+    return;
+  }
   // every CTA of the (effective) grid owns a non-empty unit range
   const uint32_t G = (uint32_t)min((unsigned long long)gridDim.x, S.units);
   if (blockIdx.x >= G) return;
@@ -1384,7 +1394,7 @@ drv_status drv_impl_peer_barrier(drv_ctx* ctx) {
   return DRV_OK;
 }
 
-drv_status drv_impl_gather(drv_ctx* ctx) {
+drv_status drv_impl_gather(drv_ctx* ctx, bool overwrite) {
   if (!ctx->have_constant) return ctx->fail(DRV_ERR_NOT_BOUND, "drv_light_caches: Constant block not set");
   const bool shadow = ctx->cfg.indirect_shadow != 0;
   if (shadow && !ctx->have_volume) return ctx->fail(DRV_ERR_NOT_BOUND, "drv_light_caches: VolumeInfo not set");
@@ -1412,6 +1422,7 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   p.counter = ctx->counter;
   p.shard_rank = ctx->shard_rank;
   p.shard_world = ctx->shard_world;
+  p.overwrite = overwrite ? 1u : 0u;
   p.f0 = ctx->constant.ShEvaFactor0;
   p.f1 = ctx->constant.ShEvaFactor1;
   p.f2 = ctx->constant.ShEvaFactor2n2_p1_n1;
@@ -1426,8 +1437,10 @@ drv_status drv_impl_gather(drv_ctx* ctx) {
   const uint32_t variant = ctx->cfg.gather_variant & 0xFFu; // bits 8.. tune other kernels
   int tile = 0, threads = kThreads;
   bool ws = false;
-  const GatherFn kernel = shadow ? select_kernel<true>(order, variant, &tile, &threads, &ws)
-                                 : select_kernel<false>(order, variant, &tile, &threads, &ws);
+  GatherFn kernel = shadow ? select_kernel<true>(order, variant, &tile, &threads, &ws)
+                           : select_kernel<false>(order, variant, &tile, &threads, &ws);
+  if (overwrite && !ws) // only the warp-split kernel writes the zeros of a frame without live VPLs: take the default
+    kernel = shadow ? select_kernel<true>(order, 0, &tile, &threads, &ws) : select_kernel<false>(order, 0, &tile, &threads, &ws);
   if (ws) p.granule = 8; // the warps split every staged tile evenly, so a finer quantum only improves the balance
   p.chunk_first = 0;
   p.chunk_cap = 0xFFFFFFFFu;

@@ -61,3 +61,52 @@ def barrier(word, group=None, ctx=None):
         return
     import torch.distributed as dist
     dist.all_reduce(word, group=group)
+
+
+class SharedHostImage:
+    """A host image every rank of one node can copy into with cudaMemcpyAsync: a POSIX shared-memory segment mapped
+    by all ranks and page-locked (cudaHostRegister) in each process. Rank r copies its band of rows device -> host
+    into it directly, so the end-to-end frame has no single-rank read-back funnel."""
+
+    def __init__(self, name, shape, dtype, rank, world, group=None):
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+        self.rank = rank
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        if rank == 0:
+            try:
+                shared_memory.SharedMemory(name=name).unlink()
+            except FileNotFoundError:
+                pass
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=nbytes)
+        if world > 1:
+            dist.barrier(group=group)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name)
+            try:  # only the creating rank may unlink the segment (Python's tracker would do it at exit of any rank)
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        buf = np.ndarray((nbytes,), dtype=np.uint8, buffer=self.shm.buf)
+        self.tensor = torch.from_numpy(buf).view(dtype).view(*shape)
+        self.registered = False
+        if torch.cuda.is_available():  # page-lock the mapping in THIS process so async copies can target it
+            err = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), nbytes, 0)
+            if int(err) != 0:
+                raise RuntimeError("cudaHostRegister failed: %s" % err)
+            self.registered = True
+        self._nbytes = nbytes
+        if world > 1:
+            dist.barrier(group=group)
+
+    def close(self):
+        import torch
+        if self.registered:
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+        del self.tensor
+        self.shm.close()
+        if self.rank == 0:
+            self.shm.unlink()

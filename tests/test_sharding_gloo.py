@@ -63,3 +63,29 @@ def test_shard_ranges_cover_and_balance():
             assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
             sizes = [e - b for b, e in rs]
             assert max(sizes) - min(sizes) <= 64 + 63
+
+
+def _shm_worker(rank, world, port, name):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dynamicradiancevolume_b200 import sharding
+    H, W = 37, 8
+    img = sharding.SharedHostImage(name, (H, W, 4), torch.float16, rank, world)
+    band = (H + world - 1) // world
+    y0, y1 = min(H, rank * band), min(H, (rank + 1) * band)
+    img.tensor[y0:y1] = float(rank + 1)  # every rank writes its own band of rows
+    dist.barrier()
+    if rank == 0:
+        want = torch.zeros(H, W, 4, dtype=torch.float16)
+        for r in range(world):
+            want[min(H, r * band):min(H, (r + 1) * band)] = float(r + 1)
+        assert torch.equal(img.tensor, want)
+    dist.barrier()
+    img.close()
+    dist.destroy_process_group()
+
+
+def test_shared_host_image_bands_from_every_rank():
+    """The end-to-end leg's host image: one POSIX shm segment, every rank fills its band, rank 0 sees them all."""
+    mp.spawn(_shm_worker, args=(3, _free_port(), "drv_test_shm_%d" % os.getpid()), nprocs=3, join=True)
