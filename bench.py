@@ -65,6 +65,9 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="issue the frame kernel by kernel instead of replaying its CUDA graph")
     ap.add_argument("--serial", action="store_true", help="reference stage order on one stream (prepare_rsm, clear, drv_draw) "
                                                           "instead of drv_draw_frame's light-side || camera-side schedule")
+    ap.add_argument("--shard", choices=["interleaved", "contiguous"], default="interleaved",
+                    help="sharded runs with the fused NVLink exchange: deal 64-entry groups round-robin to the ranks "
+                         "(balances the cone pass) or give every rank one contiguous range of the cell-ordered list")
     ap.add_argument("--barrier", choices=["peer", "nccl"], default="peer",
                     help="cross-GPU barrier of sharded runs: flags in NVLink peer memory (drv_peer_barrier) or an NCCL all-reduce")
     return ap.parse_args()
@@ -318,6 +321,8 @@ def measure(args, config_index, n_steps, n_warmup, light):
                 ctx.import_peer_entries(r, h)
         from dynamicradiancevolume_b200 import sharding
         sharding.connect_image_gather(ctx, rank, world)  # rank 0's RGBA16F target, mapped by every peer
+        if args.shard == "interleaved" and args.barrier == "peer" and not args.serial:
+            ctx.set_shard_interleave(True)
 
     def xbarrier():
         if args.barrier == "peer":
@@ -391,6 +396,8 @@ def measure(args, config_index, n_steps, n_warmup, light):
         with torch.cuda.stream(stream):
             if not args.no_flush:
                 flush_buf.zero_()
+            if world > 1 and args.barrier == "peer":
+                ctx.peer_barrier()  # outside the event pair: every rank starts the step together (no start skew in T)
             ev0[i].record(stream)
         frame_device()
         with torch.cuda.stream(stream):
@@ -453,7 +460,7 @@ def measure(args, config_index, n_steps, n_warmup, light):
     # sharded e2e: every rank uploads 1/world of every input over its own PCIe link, an NVLink all-gather completes
     # the images on every GPU (allocation and VPL generation are replicated), then the sharded frame; rank 0 reads
     # the gathered image back
-    e2e_sharded = world > 1 and in_frame and args.image_gather == "p2p"
+    e2e_sharded = world > 1 and in_frame and args.image_gather == "p2p" and not light
     if e2e_sharded:
         # ONE packed pinned host buffer holds the frame's inputs and ONE device staging buffer receives them: rank r
         # uploads slice r over its own PCIe link, a single NCCL all-gather over NVLink completes the buffer on every
@@ -609,10 +616,8 @@ def measure(args, config_index, n_steps, n_warmup, light):
     cone_ms = avg(stage_ms["ConeKernel"]) if wl.indirect_shadow else None
     if gather_ms and cone_ms:
         gather_ms = max(gather_ms - cone_ms, 1e-6)  # the pair pass alone: GatherKernel brackets cone pass + pair pass
-    shard_caches = n_caches
-    if world > 1:
-        b, e = drv.shard_range(n_caches, rank, world)
-        shard_caches = e - b
+    interleaved = world > 1 and args.shard == "interleaved" and args.barrier == "peer" and not args.serial
+    shard_caches = drv.shard_count(n_caches, rank, world, interleaved)
     # units of the roofline: the pairs the kernel EVALUATES (VPLs with zero flux are dropped before the gather;
     # they add exactly zero) — the reference's own pair count (caches x R^2) is reported beside it
     live_vpls = sum(ctx.live_vpl_counts()[:len(wl.spot_lights)])
@@ -708,8 +713,13 @@ def measure(args, config_index, n_steps, n_warmup, light):
         "config": {"workload": workload_name(wl), "caches": n_caches, "vpls": wl.num_vpls, "live_vpls": live_vpls,
                    "pairs_per_frame": n_caches * wl.num_vpls,
                    "l2": "flushed between steps (512 MiB memset outside the event pairs)" if not args.no_flush else "not flushed",
-                   "parallelism": "1 GPU" if world == 1 else "gather sharded over %d GPUs by cell-ordered entry range, "
-                                  "allocation replicated, fused P2P all-gather of SH, apply row-sharded, image bands %s" % (world, "stored into rank 0's target over NVLink (no collective in the frame)" if (args.image_gather == "p2p" and args.barrier == "peer" and not args.serial) else "gathered on rank 0 with NCCL"),
+                   "parallelism": "1 GPU" if world == 1 else (
+                       "gather sharded over %d GPUs by %s, allocation replicated, fused P2P all-gather of SH, apply "
+                       "row-sharded, image bands %s" % (
+                           world,
+                           "64-entry groups of the cell-ordered list dealt round-robin" if interleaved else "cell-ordered entry range",
+                           "stored into rank 0's target over NVLink (no collective in the frame)"
+                           if (args.image_gather == "p2p" and args.barrier == "peer" and not args.serial) else "gathered on rank 0 with NCCL")),
                    "gather_variant": args.variant},
         "e2e": {"value": e2e_per_step, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h,

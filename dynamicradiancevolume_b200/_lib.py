@@ -57,6 +57,8 @@ SYMBOLS = [
     ("drv_set_vpls", _st, [_P, _u32, _P, _u32]),
     ("drv_set_shard", _st, [_P, _u32, _u32]),
     ("drv_shard_range", None, [_u32, _u32, _u32, C.POINTER(_u32), C.POINTER(_u32)]),
+    ("drv_set_shard_interleave", _st, [_P, _u32]),
+    ("drv_shard_entry", None, [_u32, _u32, _u32, C.POINTER(_u32)]),
     ("drv_export_entries_ipc", _st, [_P, C.POINTER(C.c_uint8 * abi.DRV_IPC_HANDLE_BYTES)]),
     ("drv_import_peer_entries", _st, [_P, _u32, C.POINTER(C.c_uint8 * abi.DRV_IPC_HANDLE_BYTES)]),
     ("drv_peer_barrier", _st, [_P]),

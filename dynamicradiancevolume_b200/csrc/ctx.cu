@@ -595,6 +595,18 @@ extern "C" drv_status drv_set_shard(drv_ctx* ctx, uint32_t rank, uint32_t world)
   return DRV_OK;
 }
 
+extern "C" drv_status drv_set_shard_interleave(drv_ctx* ctx, uint32_t enable) {
+  NEED_CTX();
+  MUTATES();
+  ctx->shard_interleave = enable != 0;
+  return DRV_OK;
+}
+
+extern "C" void drv_shard_entry(uint32_t local, uint32_t rank, uint32_t world, uint32_t* entry) {
+  if (world == 0) world = 1;
+  if (entry) *entry = (((local >> 6) * world + rank) << 6) | (local & 63u);
+}
+
 extern "C" drv_status drv_export_entries_ipc(drv_ctx* ctx, uint8_t handle[DRV_IPC_HANDLE_BYTES]) {
   NEED_CTX();
   static_assert(sizeof(cudaIpcMemHandle_t) == DRV_IPC_HANDLE_BYTES, "IPC handle size");

@@ -118,6 +118,7 @@ struct drv_ctx {
   float* partials = nullptr;         // split-VPL partial sums
   uint64_t partial_slots = 0;        // capacity in cache slots
   uint32_t shard_rank = 0, shard_world = 1;
+  bool shard_interleave = false;     // 64-entry groups dealt round-robin to the ranks instead of contiguous ranges
   void* peer_entries[8] = {nullptr};
   void* peer_hdr[8] = {nullptr};     // peers' context-owned RGBA16F targets (only rank 0's is used)
   bool peers_open = false;

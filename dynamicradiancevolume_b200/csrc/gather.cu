@@ -69,7 +69,7 @@ struct GatherParams {
   uint8_t* entries;
   const drv_cache_counter* counter;
   float* partials;       // [cta][2][coef][tile cache] floats
-  uint32_t shard_rank, shard_world;
+  uint32_t shard_rank, shard_world, shard_interleave;
   uint32_t grid;         // CTAs of the gather launch (the finalize kernel needs it too)
   uint32_t fused_finalize; // 1: cooperative launch — the gather kernel adds the partial segments itself after a grid barrier
   float f0, f1, f2, f20, f22;
@@ -104,32 +104,60 @@ __device__ __forceinline__ void trace_point(const GatherParams& p, int k) {
 }
 
 struct Schedule {
-  uint32_t first, count;      // entry range of this shard
+  uint32_t first, count;      // contiguous shard: first entry / entries of this shard's current chunk
+  uint32_t lo;                // offset of the current chunk inside the shard
+  uint32_t rank, world, inter; // interleaved shard: 64-entry group g of the cell-ordered list belongs to rank g % world
   uint32_t tiles;             // cache tiles
   uint32_t units_per_tile;    // VPL units over all lights
   unsigned long long units;   // tiles * units_per_tile
 };
 
+// The part of the n active entries this rank lights, restricted to the current chunk: `count` entries with local
+// indices [0, count); entry_of() maps a local index to the entry. Contiguous: the range of drv_shard_range (64-entry
+// boundaries of the cell-ordered list). Interleaved: every world-th 64-entry group, so that regions of the scene
+// whose cones are expensive (or cheap) are spread over all ranks.
+__device__ __forceinline__ void shard_span(uint32_t n, uint32_t rank, uint32_t world, uint32_t inter, uint32_t chunk_first,
+                                           uint32_t chunk_cap, uint32_t& first, uint32_t& lo_out, uint32_t& count) {
+  const uint32_t groups = (n + 63u) / 64u;
+  uint32_t total;
+  if (inter) {
+    const uint32_t owned = groups > rank ? (groups - rank + world - 1u) / world : 0u;
+    total = owned * 64u;
+    if (owned && (groups - 1u) % world == rank) total -= groups * 64u - n; // the ragged last group is this rank's
+    first = 0;
+  } else {
+    const uint32_t g0 = (uint32_t)(((unsigned long long)groups * rank) / world);
+    const uint32_t g1 = (uint32_t)(((unsigned long long)groups * (rank + 1)) / world);
+    first = min(g0 * 64u, n);
+    total = min(g1 * 64u, n) - first;
+  }
+  const uint32_t lo = min(total, chunk_first), hi = min(total, chunk_first + min(chunk_cap, 0xFFFFFFFFu - chunk_first));
+  first += lo;
+  lo_out = lo;
+  count = hi - lo;
+}
+__device__ __forceinline__ uint32_t entry_of(uint32_t first, uint32_t lo, uint32_t rank, uint32_t world, uint32_t inter,
+                                             uint32_t local) {
+  if (!inter) return first + local;
+  const uint32_t L = lo + local;
+  return (((L >> 6) * world + rank) << 6) | (L & 63u);
+}
+
 // Same result in every thread of the gather and finalize kernels.
 __device__ __forceinline__ Schedule make_schedule(const GatherParams& p, int tile_caches) {
   Schedule s;
   uint32_t n = (uint32_t)max(p.counter->TotalLightCacheCount, 0);
-  // contiguous ranges on 64-entry boundaries of the cell-ordered list (drv_shard_range)
-  uint32_t groups = (n + 63u) / 64u;
-  uint32_t g0 = (uint32_t)(((unsigned long long)groups * p.shard_rank) / p.shard_world);
-  uint32_t g1 = (uint32_t)(((unsigned long long)groups * (p.shard_rank + 1)) / p.shard_world);
-  s.first = min(g0 * 64u, n);
-  s.count = min(g1 * 64u, n) - s.first;
-  // restrict to the current chunk of the shard (shadowed gathers walk the shard in chunks, see drv_impl_gather)
-  const uint32_t lo = min(s.count, p.chunk_first), hi = min(s.count, p.chunk_first + min(p.chunk_cap, 0xFFFFFFFFu - p.chunk_first));
-  s.first += lo;
-  s.count = hi - lo;
+  s.rank = p.shard_rank; s.world = p.shard_world; s.inter = p.shard_interleave;
+  shard_span(n, p.shard_rank, p.shard_world, p.shard_interleave, p.chunk_first, p.chunk_cap, s.first, s.lo, s.count);
   s.tiles = (s.count + tile_caches - 1) / tile_caches;
   uint32_t upt = 0;
   for (uint32_t l = 0; l < p.num_lights; ++l) upt += (live_vpls(p.lights[l]) + p.granule - 1) / p.granule;
   s.units_per_tile = upt;
   s.units = (unsigned long long)s.tiles * upt;
   return s;
+}
+__device__ __forceinline__ uint32_t entry_of(const Schedule& S, uint32_t local) {
+  return entry_of(S.first, S.lo, S.rank, S.world, S.inter, local);
 }
 __device__ __forceinline__ unsigned long long range_begin(const Schedule& s, uint32_t grid, uint32_t cta) {
   return (s.units * cta) / grid;
@@ -650,7 +678,7 @@ __device__ __forceinline__ void finalize_phase(const GatherParams& p, int tile_c
       for (int q = 0; q < 27; ++q) raw[q] = q < NC ? sm.part[0][q < NC ? q : 0][threadIdx.x] : 0.0f;
       float vals[28];
       coef_values<ORDER>(p, raw, vals);
-      add_to_entry<ORDER>(p, S.first + local0 + threadIdx.x, vals);
+      add_to_entry<ORDER>(p, entry_of(S, local0 + threadIdx.x), vals);
     }
   }
 }
@@ -761,7 +789,7 @@ __device__ __forceinline__ void gather_main(const GatherParams& p) {
       for (int j = 0; j < CPT; ++j) {
         uint32_t local = cur.tile * TILE + j * NT + threadIdx.x;
         bool alive = local < S.count;
-        float4 pos = alive ? *reinterpret_cast<const float4*>(p.entries + (size_t)(S.first + local) * STRIDE)
+        float4 pos = alive ? *reinterpret_cast<const float4*>(p.entries + (size_t)entry_of(S, local) * STRIDE)
                            : make_float4(1e30f, 1e30f, 1e30f, 0.f); // :83
         M.begin(j, alive, pos);
       }
@@ -846,7 +874,7 @@ __device__ __forceinline__ void gather_main(const GatherParams& p) {
           if (local < S.count) {
             float vals[28];
             coef_values<ORDER>(p, raw, vals);
-            add_to_entry<ORDER>(p, S.first + local, vals);
+            add_to_entry<ORDER>(p, entry_of(S, local), vals);
           }
         } else {
           float* dst = p.partials + ((size_t)blockIdx.x * 2 + slot) * NC * TILE + in_tile;
@@ -915,7 +943,7 @@ __global__ void __launch_bounds__(NW * 32, NW >= 8 ? 1 : 256 / (NW * 32)) gather
       float vals[28];
 #pragma unroll
       for (int q = 0; q < 28; ++q) vals[q] = 0.0f;
-      for (uint32_t i = blockIdx.x * NT + threadIdx.x; i < S.count; i += gridDim.x * NT) add_to_entry<ORDER>(p, S.first + i, vals);
+      for (uint32_t i = blockIdx.x * NT + threadIdx.x; i < S.count; i += gridDim.x * NT) add_to_entry<ORDER>(p, entry_of(S, i), vals);
     }
     return;
   }
@@ -953,7 +981,7 @@ __global__ void __launch_bounds__(NW * 32, NW >= 8 ? 1 : 256 / (NW * 32)) gather
       for (int j = 0; j < CPT; ++j) {
         const uint32_t local = cur.tile * TILE + j * 32 + lane;
         const bool alive = local < S.count;
-        const float4 pos = alive ? *reinterpret_cast<const float4*>(p.entries + (size_t)(S.first + local) * STRIDE)
+        const float4 pos = alive ? *reinterpret_cast<const float4*>(p.entries + (size_t)entry_of(S, local) * STRIDE)
                                  : make_float4(1e30f, 1e30f, 1e30f, 0.f);
         M.begin(j, alive, pos);
       }
@@ -1051,7 +1079,7 @@ __global__ void __launch_bounds__(NW * 32, NW >= 8 ? 1 : 256 / (NW * 32)) gather
             for (int q = 0; q < 27; ++q) raw[q] = q < NC ? folded[k][q < NC ? q : 0] : 0.0f;
             float vals[28];
             coef_values<ORDER>(p, raw, vals);
-            add_to_entry<ORDER>(p, S.first + cur.tile * TILE + t, vals);
+            add_to_entry<ORDER>(p, entry_of(S, cur.tile * TILE + t), vals);
           }
         } else {
           float* dst = p.partials + ((size_t)blockIdx.x * 2 + slot) * NC * TILE + t;
@@ -1072,15 +1100,33 @@ __global__ void __launch_bounds__(NW * 32, NW >= 8 ? 1 : 256 / (NW * 32)) gather
             float raw[27];
 #pragma unroll
             for (int q = 0; q < 27; ++q) raw[q] = 0.0f;
-            for (uint32_t c = c_lo; c <= c_hi; ++c) {
-              const uint32_t sl = range_begin(S, G, c) >= ua ? 0u : 1u;
-              const float* src = p.partials + ((size_t)c * 2 + sl) * NC * TILE + t;
+            // only the first contributor can have started before this tile (slot 1); four (SH1) / two (SH2) contributors per trip with
+            // independent accumulators, so their L2 round trips overlap instead of forming a chain (a tile of a small
+            // shard is split between dozens of CTAs); the order of the additions is fixed => deterministic
+            const uint32_t sl_lo = range_begin(S, G, c_lo) >= ua ? 0u : 1u;
+            constexpr int FU = NC > 12 ? 2 : 4;
+            float part[FU][NC];
 #pragma unroll
-              for (int q = 0; q < NC; ++q) raw[q] += __ldcg(src + (size_t)q * TILE);
+            for (int u = 0; u < FU; ++u)
+#pragma unroll
+              for (int q = 0; q < NC; ++q) part[u][q] = 0.0f;
+            for (uint32_t c = c_lo; c <= c_hi; c += FU) {
+#pragma unroll
+              for (int u = 0; u < FU; ++u) {
+                const uint32_t cc = c + u;
+                if (cc <= c_hi) {
+                  const uint32_t sl = cc == c_lo ? sl_lo : 0u;
+                  const float* src = p.partials + ((size_t)cc * 2 + sl) * NC * TILE + t;
+#pragma unroll
+                  for (int q = 0; q < NC; ++q) part[u][q] += __ldcg(src + (size_t)q * TILE);
+                }
+              }
             }
+#pragma unroll
+            for (int q = 0; q < NC; ++q) raw[q] = FU == 4 ? (part[0][q] + part[1][q]) + (part[2 % FU][q] + part[3 % FU][q]) : part[0][q] + part[1][q];
             float vals[28];
             coef_values<ORDER>(p, raw, vals);
-            add_to_entry<ORDER>(p, S.first + cur.tile * TILE + t, vals);
+            add_to_entry<ORDER>(p, entry_of(S, cur.tile * TILE + t), vals);
           }
           if (threadIdx.x == 0) p.tickets[cur.tile] = 0u; // rewound for the next launch
         }
@@ -1105,7 +1151,7 @@ struct ConeParams {
   const uint8_t* entries;
   uint32_t entry_stride;
   const drv_cache_counter* counter;
-  uint32_t shard_rank, shard_world;
+  uint32_t shard_rank, shard_world, shard_interleave;
   uint32_t chunk_first, chunk_cap;
   float* table;
   uint32_t stride;
@@ -1125,13 +1171,8 @@ template <bool SIMPLE, int MINB>
 __global__ void __launch_bounds__(kConeThreads, MINB) cone_kernel(const __grid_constant__ ConeParams p) {
   // this shard's chunk, as make_schedule derives it
   const uint32_t n = (uint32_t)max(p.counter->TotalLightCacheCount, 0);
-  const uint32_t groups64 = (n + 63u) / 64u;
-  const uint32_t g0 = (uint32_t)(((unsigned long long)groups64 * p.shard_rank) / p.shard_world);
-  const uint32_t g1 = (uint32_t)(((unsigned long long)groups64 * (p.shard_rank + 1)) / p.shard_world);
-  uint32_t first = min(g0 * 64u, n), count = min(g1 * 64u, n) - first;
-  const uint32_t lo = min(count, p.chunk_first), hi = min(count, p.chunk_first + min(p.chunk_cap, 0xFFFFFFFFu - p.chunk_first));
-  first += lo;
-  count = hi - lo;
+  uint32_t first, lo, count;
+  shard_span(n, p.shard_rank, p.shard_world, p.shard_interleave, p.chunk_first, p.chunk_cap, first, lo, count);
   if (count == 0) return;
   VoxelVol V;
   V.rec = p.rec; V.rec_offset = p.rec_offset; V.res = p.vres; V.levels = p.vlevels; V.voxel_size = p.voxel_size;
@@ -1153,7 +1194,7 @@ __global__ void __launch_bounds__(kConeThreads, MINB) cone_kernel(const __grid_c
     const uint32_t local = cg * kConeThreads + threadIdx.x;
     const bool alive = local < count;
     float4 pos = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (alive) pos = *reinterpret_cast<const float4*>(p.entries + (size_t)(first + local) * p.entry_stride);
+    if (alive) pos = *reinterpret_cast<const float4*>(p.entries + (size_t)entry_of(first, lo, p.shard_rank, p.shard_world, p.shard_interleave, local) * p.entry_stride);
     const uint32_t b_end = min(total_blocks, (bg + 1) * kBlocksPerItem);
     uint32_t light = 0;
     for (uint32_t b = bg * kBlocksPerItem; b < b_end; ++b) {
@@ -1422,6 +1463,7 @@ drv_status drv_impl_gather(drv_ctx* ctx, bool overwrite) {
   p.counter = ctx->counter;
   p.shard_rank = ctx->shard_rank;
   p.shard_world = ctx->shard_world;
+  p.shard_interleave = (ctx->shard_interleave && ctx->shard_world > 1) ? 1u : 0u;
   p.overwrite = overwrite ? 1u : 0u;
   p.f0 = ctx->constant.ShEvaFactor0;
   p.f1 = ctx->constant.ShEvaFactor1;
@@ -1469,6 +1511,7 @@ drv_status drv_impl_gather(drv_ctx* ctx, bool overwrite) {
   c.counter = ctx->counter;
   c.shard_rank = ctx->shard_rank;
   c.shard_world = ctx->shard_world;
+  c.shard_interleave = p.shard_interleave;
   c.rec = ctx->voxel_records;
   for (int l = 0; l < 16; ++l) c.rec_offset[l] = ctx->voxel_record_offset[l];
   c.vres = (int)ctx->cfg.voxel_resolution;

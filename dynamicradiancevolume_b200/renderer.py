@@ -136,6 +136,21 @@ def shard_range(count: int, rank: int, world: int):
     return b.value, e.value
 
 
+def shard_count(count: int, rank: int, world: int, interleave: bool = False) -> int:
+    """Entries rank `rank` lights: the contiguous range of ``shard_range`` or, interleaved, every world-th 64-entry
+    group of the cell-ordered list (``drv_set_shard_interleave``)."""
+    if not interleave or world <= 1:
+        b, e = shard_range(count, rank, world)
+        return e - b
+    groups = (count + 63) // 64
+    owned = (groups - rank + world - 1) // world if groups > rank else 0
+    n = owned * 64
+    if owned and (groups - 1) % world == rank:
+        n -= groups * 64 - count
+    return n
+
+
+
 class Context:
     """Thin RAII wrapper of ``drv_ctx`` — one per (configuration, device)."""
 
@@ -257,6 +272,7 @@ class Context:
     def apply_caches_rows(self, out, fmt, y0, y1):
         self.check(self.lib.drv_apply_caches_rows(self.handle, out.data_ptr(), fmt, y0, y1))
     def set_shard(self, rank, world): self.check(self.lib.drv_set_shard(self.handle, rank, world))
+    def set_shard_interleave(self, on=True): self.check(self.lib.drv_set_shard_interleave(self.handle, 1 if on else 0))
     def enable_stage_timers(self, on=True): self.check(self.lib.drv_enable_stage_timers(self.handle, 1 if on else 0))
     def kernel_launches(self): return int(self.lib.drv_kernel_launches(self.handle))
 

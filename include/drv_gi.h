@@ -415,6 +415,12 @@ drv_status drv_set_vpls(drv_ctx* ctx, uint32_t light, const drv_vpl* vpls, uint3
 drv_status drv_set_shard(drv_ctx* ctx, uint32_t rank, uint32_t world);
 /* Entry range [begin,end) of `rank` for `count` active entries. Pure host maths. */
 void drv_shard_range(uint32_t count, uint32_t rank, uint32_t world, uint32_t* begin, uint32_t* end);
+/* Interleaved sharding (for the fused NVLink exchange, where no rank needs a contiguous range): the 64-entry groups of
+ * the cell-ordered list are dealt round-robin, group g to rank g % world, so that regions whose cone marches are long
+ * (or short) are spread over all GPUs instead of landing on one. drv_shard_entry maps the local index of a rank's
+ * entry to the entry. */
+drv_status drv_set_shard_interleave(drv_ctx* ctx, uint32_t enable);
+void drv_shard_entry(uint32_t local, uint32_t rank, uint32_t world, uint32_t* entry);
 /* Peer exchange over NVLink: every rank exports an IPC handle of its entries
  * buffer, imports the others', and drv_light_caches then stores each finished
  * entry to all peers from inside the gather epilogue (fused all-gather). */

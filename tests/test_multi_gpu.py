@@ -31,10 +31,12 @@ def _worker(rank, world, port, mode, out_dir):
     word = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % rank)
     if mode.startswith("fused"):
         sharding.connect_peers(g.ctx, rank, world)
+        if mode.endswith("interleaved"):
+            g.ctx.set_shard_interleave(True)  # 64-entry groups dealt round-robin instead of contiguous ranges
     else:
         g.ctx.set_shard(rank, world)
-    bctx = g.ctx if mode == "fused" else None  # "fused": flags in peer memory; otherwise an NCCL all-reduce
-    if mode == "fused_frame":
+    bctx = g.ctx if mode in ("fused", "fused_interleaved") else None  # "fused": flags in peer memory; otherwise an NCCL all-reduce
+    if mode.startswith("fused_frame"):
         # drv_draw_frame on every rank: replicated allocation || light side, peer barriers, sharded gather with the
         # fused all-gather, this rank's band of the apply pass; frames 1.. replay the recorded CUDA graph
         flags = abi.DRV_FRAME_PREPARE_RSM | abi.DRV_FRAME_GRAPH | abi.DRV_FRAME_APPLY_OWN_ROWS
@@ -58,7 +60,7 @@ def _worker(rank, world, port, mode, out_dir):
             got = g.ctx.hdr16_tensor().float()
             want = g.out32[..., :3].half().float()
             assert torch.equal(got[..., :3], want), "fused image gather differs from the banded apply"
-    for it in range(0 if mode == "fused_frame" else 2):  # twice: the second frame checks the cross-frame ordering of clears and peer stores
+    for it in range(0 if mode.startswith("fused_frame") else 2):  # twice: the second frame checks the cross-frame ordering of clears and peer stores
         with torch.cuda.stream(stream):
             g.prepare_inputs()
             g.ctx.allocate_caches()
@@ -79,7 +81,8 @@ def _worker(rank, world, port, mode, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["fused", "fused_nccl_barrier", "nccl", "fused_frame"])
+@pytest.mark.parametrize("mode", ["fused", "fused_nccl_barrier", "nccl", "fused_frame", "fused_frame_interleaved",
+                                  "fused_interleaved"])
 def test_sharded_gather_matches_oracle(tmp_path, mode):
     import torch
     import torch.multiprocessing as mp

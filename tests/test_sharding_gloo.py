@@ -89,3 +89,21 @@ def _shm_worker(rank, world, port, name):
 def test_shared_host_image_bands_from_every_rank():
     """The end-to-end leg's host image: one POSIX shm segment, every rank fills its band, rank 0 sees them all."""
     mp.spawn(_shm_worker, args=(3, _free_port(), "drv_test_shm_%d" % os.getpid()), nprocs=3, join=True)
+
+
+def test_interleaved_shards_partition_the_entries():
+    """drv_set_shard_interleave: group g of 64 entries belongs to rank g % world; local indices are dense."""
+    import ctypes as C
+    import dynamicradiancevolume_b200 as drv
+    lib = drv.load()
+    for count in (0, 1, 63, 64, 65, 6210, 21121):
+        for world in (1, 2, 3, 8):
+            seen = np.zeros(count, np.int32)
+            for rank in range(world):
+                n = drv.shard_count(count, rank, world, True)
+                for local in range(n):
+                    e = C.c_uint32()
+                    lib.drv_shard_entry(local, rank, world, C.byref(e))
+                    assert e.value < count and (e.value // 64) % world == rank
+                    seen[e.value] += 1
+            assert np.all(seen == 1)
