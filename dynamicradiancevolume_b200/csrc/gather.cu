@@ -91,10 +91,12 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ void trace_extra(const GatherParams& p, int k) { // words 5..7: inside the fix-up
+  if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 8 + k] = global_ns();
+}
 __device__ __forceinline__ void trace_point(const GatherParams& p, int k) {
   if (p.trace && threadIdx.x == 0) {
     p.trace[(size_t)blockIdx.x * 8 + k] = global_ns();
-    p.trace[(size_t)blockIdx.x * 8 + 4 + k] = (unsigned long long)clock64();
     if (k == 0) {
       uint32_t smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -905,6 +907,39 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(const __grid_constant_
   trace_point(p, 3);
 }
 
+// Sum of the partial segments the contributors c_lo..c_hi published for cache `t` of a tile, in CTA order (fixed =>
+// deterministic). A function of its own (not inlined) so that it gets a register allocation of its own: inside the
+// kernel the pair loop's live state left room for a dozen loads in flight and every contributor cost a full L2
+// round trip (a tile of a small shard is split between ~30 CTAs: 12 us); here FU contributors x NC coefficients are
+// loaded before the first one is consumed. A contributor past the end is clamped onto the last one and weighted 0.
+template <int NC>
+__device__ __noinline__ void fixup_sum(const float* __restrict__ partials, uint32_t tile_caches, uint32_t t, uint32_t c_lo,
+                                       uint32_t c_hi, uint32_t sl_lo, float* __restrict__ raw) {
+  constexpr int FU = NC > 12 ? 6 : 14;
+  float acc[NC];
+#pragma unroll
+  for (int q = 0; q < NC; ++q) acc[q] = 0.0f;
+  for (uint32_t c = c_lo; c <= c_hi; c += FU) {
+    float v[FU][NC];
+#pragma unroll
+    for (int u = 0; u < FU; ++u) {
+      const uint32_t cc = min(c + u, c_hi);
+      const uint32_t sl = cc == c_lo ? sl_lo : 0u;
+      const float* src = partials + ((size_t)cc * 2 + sl) * NC * tile_caches + t;
+#pragma unroll
+      for (int q = 0; q < NC; ++q) v[u][q] = __ldcg(src + (size_t)q * tile_caches);
+    }
+#pragma unroll
+    for (int u = 0; u < FU; ++u) {
+      const float wgt = (c + u <= c_hi) ? 1.0f : 0.0f;
+#pragma unroll
+      for (int q = 0; q < NC; ++q) acc[q] = fmaf(wgt, v[u][q], acc[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NC; ++q) raw[q] = acc[q];
+}
+
 // ------------------------------------------------------------ the warp-split gather kernel
 // Same pair maths, staging and stream-K unit schedule as gather_kernel, but the cache tile is what ONE warp holds
 // in registers (32 lanes x CPT entries: 128 for SH1, 64 for SH2) and the NW warps of a CTA split the VPLs of every
@@ -1093,41 +1128,23 @@ __global__ void __launch_bounds__(NW * 32, NW >= 8 ? 1 : 256 / (NW * 32)) gather
         __syncthreads();
         if (threadIdx.x == 0) s_last = (atomicAdd(p.tickets + cur.tile, 1u) == c_hi - c_lo) ? 1u : 0u;
         __syncthreads();
+        trace_extra(p, 5);
         if (s_last) { // block-uniform: every other contributor's partial segment is visible
           __threadfence();
+          trace_extra(p, 6);
           for (uint32_t t = threadIdx.x; t < (uint32_t)TILE; t += NT) {
             if (cur.tile * TILE + t >= S.count) break;
             float raw[27];
 #pragma unroll
             for (int q = 0; q < 27; ++q) raw[q] = 0.0f;
-            // only the first contributor can have started before this tile (slot 1); four (SH1) / two (SH2) contributors per trip with
-            // independent accumulators, so their L2 round trips overlap instead of forming a chain (a tile of a small
-            // shard is split between dozens of CTAs); the order of the additions is fixed => deterministic
+            // only the first contributor can have started before this tile (slot 1)
             const uint32_t sl_lo = range_begin(S, G, c_lo) >= ua ? 0u : 1u;
-            constexpr int FU = NC > 12 ? 2 : 4;
-            float part[FU][NC];
-#pragma unroll
-            for (int u = 0; u < FU; ++u)
-#pragma unroll
-              for (int q = 0; q < NC; ++q) part[u][q] = 0.0f;
-            for (uint32_t c = c_lo; c <= c_hi; c += FU) {
-#pragma unroll
-              for (int u = 0; u < FU; ++u) {
-                const uint32_t cc = c + u;
-                if (cc <= c_hi) {
-                  const uint32_t sl = cc == c_lo ? sl_lo : 0u;
-                  const float* src = p.partials + ((size_t)cc * 2 + sl) * NC * TILE + t;
-#pragma unroll
-                  for (int q = 0; q < NC; ++q) part[u][q] += __ldcg(src + (size_t)q * TILE);
-                }
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < NC; ++q) raw[q] = FU == 4 ? (part[0][q] + part[1][q]) + (part[2 % FU][q] + part[3 % FU][q]) : part[0][q] + part[1][q];
+            fixup_sum<NC>(p.partials, (uint32_t)TILE, t, c_lo, c_hi, sl_lo, raw);
             float vals[28];
             coef_values<ORDER>(p, raw, vals);
             add_to_entry<ORDER>(p, entry_of(S, cur.tile * TILE + t), vals);
           }
+          trace_extra(p, 7);
           if (threadIdx.x == 0) p.tickets[cur.tile] = 0u; // rewound for the next launch
         }
       }

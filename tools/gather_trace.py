@@ -16,6 +16,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def _fixup(t, t0):
+    """The CTAs that drew a tile's last ticket: (ticket drawn, partial sums visible, entries written), relative."""
+    last = t[t[:, 7] > t0]
+    if len(last) == 0:
+        return None
+    return [[float((r[5] - t0) / 1e3), float((r[6] - t0) / 1e3), float((r[7] - t0) / 1e3), float((r[3] - t0) / 1e3)] for r in last[:6]]
+
+
 def _pair_gap(t):
     by_sm = {}
     for row in t:
@@ -29,6 +37,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--config", type=int, default=1)
     ap.add_argument("--frames", type=int, default=6)
+    ap.add_argument("--shard-world", type=int, default=1, help="light only shard 0 of this many (no peers: what one rank of a sharded run computes)")
     a = ap.parse_args()
     import torch
     import workloads
@@ -36,6 +45,8 @@ def main():
     wl = workloads.config(a.config).build()
     stream = torch.cuda.Stream()
     g = workloads.DeviceFrame(wl, device=0, stream=stream, gather_variant=a.variant | 0x40000)
+    if a.shard_world > 1:
+        g.ctx.set_shard(0, a.shard_world)
     out16 = torch.zeros(wl.height, wl.width, 4, dtype=torch.float16, device="cuda")
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     if wl.indirect_shadow:
@@ -60,12 +71,13 @@ def main():
                      "exit_us": [float(r[:, 3].min()), float(np.median(r[:, 3])), float(r[:, 3].max())],
                      "cta_busy_us": [float((r[:, 3] - r[:, 0]).min()), float(np.median(r[:, 3] - r[:, 0])),
                                      float((r[:, 3] - r[:, 0]).max())],
+                     "fixup_us": _fixup(t, t0),
                      "sms_used": int(len(set(t[:, 4].tolist()))),
                      "ctas_per_sm_max": int(np.bincount(t[:, 4].astype(np.int64)).max()),
                      # the two CTAs of an SM: how far apart they finish their pair loops
                      "pair_gap_us": _pair_gap(t)})
     for r in rows:
-        print(json.dumps({"variant": a.variant, "config": a.config, **r}))
+        print(json.dumps({"variant": a.variant, "config": a.config, "shard_world": a.shard_world, **r}))
     g.close()
 
 
