@@ -22,6 +22,8 @@
 
 #include <ucontext.h>
 
+#include "../../include/drv_r11g11b10.h"
+
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -342,7 +344,7 @@ inline uint8_t unorm8(float v) { /* store conversion: clamp, scale, round to nea
 }
 
 /* ---------------------------------------------------------------- textures, samplers, images */
-enum Format { F_R32F, F_RG16F, F_RGBA16F, F_RG16I, F_SRGB8_A8, F_RG8, F_R8, F_R32UI, F_RGBA32F };
+enum Format { F_R32F, F_RG16F, F_RGBA16F, F_RG16I, F_SRGB8_A8, F_RG8, F_R8, F_R32UI, F_RGBA32F, F_R11G11B10F };
 struct Level { const void* data; int w, h, d; };
 struct Texture {
   Format fmt = F_R32F;
@@ -368,6 +370,7 @@ inline vec4 fetch_f(const Texture& t, int l, int x, int y, int z) { /* in-range 
                        return vec4(srgb8_to_linear(p[0]), srgb8_to_linear(p[1]), srgb8_to_linear(p[2]), (float)p[3] / 255.0f); }
     case F_RG8: { const uint8_t* p = (const uint8_t*)L.data + i * 2; return vec4((float)p[0] / 255.0f, (float)p[1] / 255.0f, 0.0f, 1.0f); }
     case F_R8: return vec4((float)((const uint8_t*)L.data)[i] / 255.0f, 0.0f, 0.0f, 1.0f);
+    case F_R11G11B10F: { float r, g, b; drv_unpack_r11g11b10(((const uint32_t*)L.data)[i], &r, &g, &b); return vec4(r, g, b, 1.0f); }
     default: return vec4(0.0f);
   }
 }
@@ -488,7 +491,18 @@ inline ivec4 textureGather(const isampler2D& s, const vec2& uv, int comp) {
 /* images: one level, load/store/atomics; out-of-range accesses are dropped / return 0 */
 struct image3D { void* data = nullptr; int w = 0, h = 0, d = 0; Format fmt = F_R8; };
 struct uimage3D { uint32_t* data = nullptr; int w = 0, h = 0, d = 0; };
-struct image2D { float* data = nullptr; int w = 0, h = 0; }; /* r11f_g11f_b10f kept as 3 floats rounded on store */
+struct image2D { uint32_t* data = nullptr; int w = 0, h = 0; }; /* r11f_g11f_b10f texels (include/drv_r11g11b10.h) */
+inline ivec2 imageSize(const image2D& im) { return ivec2(im.w, im.h); }
+inline vec4 imageLoad(const image2D& im, const ivec2& p) {
+  if (p.x < 0 || p.y < 0 || p.x >= im.w || p.y >= im.h) return vec4(0.0f);
+  float r, g, b;
+  drv_unpack_r11g11b10(im.data[(size_t)p.x + (size_t)im.w * (size_t)p.y], &r, &g, &b);
+  return vec4(r, g, b, 1.0f);
+}
+inline void imageStore(const image2D& im, const ivec2& p, const vec4& v) {
+  if (p.x < 0 || p.y < 0 || p.x >= im.w || p.y >= im.h) return;
+  im.data[(size_t)p.x + (size_t)im.w * (size_t)p.y] = drv_pack_r11g11b10(v.x, v.y, v.z);
+}
 inline bool in_range(int w, int h, int d, const ivec3& p) { return p.x >= 0 && p.y >= 0 && p.z >= 0 && p.x < w && p.y < h && p.z < d; }
 inline vec4 imageLoad(const image3D& im, const ivec3& p) {
   if (!in_range(im.w, im.h, im.d, p)) return vec4(0.0f);

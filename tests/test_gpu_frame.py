@@ -367,3 +367,22 @@ def test_frame_graph_survives_a_moving_camera(cuda_device):
     assert upd1 - upd0 == 6
     assert len(counts) > 1
     g.close()
+
+
+def test_config2_with_256_cubed_voxels(cuda_device):
+    """BASELINE configs[2] with the voxel volume at 256^3 (the reference's own sweep goes up to 512^3,
+    application.cpp:296-592): chain and gather-ready records (136 MB, past the 126 MB L2) bit-exact / within the
+    gate, SH on every 16th entry, the whole image through the oracle's apply pass."""
+    import torch
+    from oracle.subsample import check_frame
+    wl = workloads.config(2, voxel_resolution=256).build()
+    g = workloads.DeviceFrame(wl)
+    g.prepare_inputs()
+    g.frame()
+    torch.cuda.synchronize()
+    n = g.ctx.active_cache_count()[0]
+    o = OracleFrame(wl).prepare_inputs().allocate()
+    assert np.array_equal(g.ctx.read_voxel_chain(), o.chain)
+    r = check_frame(wl, g.ctx.read_entries(n), g.ctx.read_atlas(), n, g.out32.cpu().numpy(), step=16, oracle=o)
+    assert r["ok"] and r["sh_max_abs"] > 0, r
+    g.close()

@@ -137,7 +137,7 @@ def test_vpl_generation(cuda_device, shadow):
 
 
 # ---------------------------------------------------------------------------- stage 3: voxels
-@pytest.mark.parametrize("scene,res", [("cornell", 64), ("atrium", 128), ("atrium", 32)])
+@pytest.mark.parametrize("scene,res", [("cornell", 64), ("atrium", 128), ("atrium", 32), ("atrium", 256)])
 def test_voxelize_blend_mips_bit_exact(cuda_device, scene, res):
     wl = (workloads.cornell(indirect_shadow=True, voxel_resolution=res) if scene == "cornell" else
           workloads.atrium(width=64, height=64, rsm_res=64, read_lod=0, indirect_shadow=True, voxel_resolution=res))
