@@ -73,6 +73,7 @@ SYMBOLS = [
     ("drv_draw_to_host", _st, [_P, _P]),
     ("drv_draw_host_frame", _st, [_P, C.POINTER(abi.HostFrame)]),
     ("drv_pack_constant", None, [C.POINTER(abi.Constant), _i32, _i32, _i32, _i32, _i32, _u32]),
+    ("drv_pack_specular", None, [C.POINTER(abi.Constant), _u32, _u32]),
     ("drv_pack_per_frame", None, [C.POINTER(abi.PerFrame), _P, _f32]),
     ("drv_pack_volume_info", None, [C.POINTER(abi.VolumeInfo), _P, C.POINTER(_f32 * 3), C.POINTER(_f32 * 3), _i32, _i32,
                                      _i32, C.POINTER(_f32), _f32]),

@@ -20,6 +20,10 @@ static drv::Camera to_camera(const drv_camera_desc* c) {
   return cam;
 }
 
+extern "C" void drv_pack_specular(drv_constant* inout, uint32_t max_caches, uint32_t per_cache_size) {
+  drv::packSpecular(inout, max_caches, per_cache_size);
+}
+
 extern "C" void drv_pack_per_frame(drv_per_frame* out, const drv_camera_desc* camera, float passed_time) {
   drv::packPerFrame(out, to_camera(camera), passed_time);
 }

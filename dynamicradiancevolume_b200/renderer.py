@@ -96,6 +96,12 @@ def pack_constant(width, height, voxel_res, cav_res, cav_cascades, max_caches) -
     return out
 
 
+def pack_specular(constant: abi.Constant, max_caches: int, per_cache_size: int = 16) -> abi.Constant:
+    """Fills the four specular environment-map fields of a Constant block (renderer.cpp:253, 316-319)."""
+    _lib.load().drv_pack_specular(C.byref(constant), max_caches, per_cache_size)
+    return constant
+
+
 def pack_per_frame(camera: Camera, passed_time: float = 0.0) -> abi.PerFrame:
     """≙ Renderer::UpdatePerFrameUBO (renderer.cpp:324-344)."""
     out = abi.PerFrame()

@@ -530,6 +530,8 @@ typedef struct drv_light_desc { /* scene/light.hpp:8-55, scene/scene.cpp:6-7 */
 
 void drv_pack_constant(drv_constant* out, int32_t width, int32_t height, int32_t voxel_resolution,
                        int32_t cav_resolution, int32_t cav_cascades, uint32_t max_caches);
+/* The specular fields of an already packed Constant block (renderer.cpp:253, 316-319). */
+void drv_pack_specular(drv_constant* inout, uint32_t max_caches, uint32_t per_cache_size);
 void drv_pack_per_frame(drv_per_frame* out, const drv_camera_desc* camera, float passed_time);
 void drv_pack_volume_info(drv_volume_info* out, const drv_camera_desc* camera, const float scene_min[3],
                           const float scene_max[3], int32_t voxel_resolution, int32_t cav_resolution,

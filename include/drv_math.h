@@ -194,6 +194,18 @@ inline void packConstant(drv_constant* c, int width, int height, int voxelRes, i
   c->MaxNumLightCaches = maxCaches;
 }
 
+/* The four specular fields of the Constant block: Renderer::AllocateCacheData sizes the environment-map atlas
+ * (renderer.cpp:253: 2^ceil(log2(ceil(sqrt(maxCaches)) * perCacheSize)), capped at GL_MAX_TEXTURE_SIZE — 16384 here)
+ * and UpdateConstantUBO uploads the derived values (renderer.cpp:316-319). */
+inline void packSpecular(drv_constant* c, unsigned maxCaches, unsigned perCacheSize) {
+  int size = (int)powf(2.0f, ceilf(log2f(ceilf(sqrtf((float)maxCaches)) * (float)perCacheSize)));
+  if (size > 16384) size = 16384;
+  c->SpecularEnvmapTotalSize = size;
+  c->SpecularEnvmapPerCacheSize_Texel = (int)perCacheSize;
+  c->SpecularEnvmapPerCacheSize_Texcoord = (float)perCacheSize / (float)size;
+  c->SpecularEnvmapNumCachesPerDimension = size / (int)perCacheSize;
+}
+
 /* Renderer::UpdatePerFrameUBO, renderer.cpp:324-344. */
 inline void packPerFrame(drv_per_frame* f, const Camera& cam, float passedTime) {
   std::memset(f, 0, sizeof(*f));

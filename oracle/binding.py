@@ -248,3 +248,52 @@ def srgb8_to_linear(v):
 def morton_decode(k):
     lib = load()
     return lib.orc_morton_decode_x(C.c_uint32(k)), lib.orc_morton_decode_y(C.c_uint32(k))
+
+
+# ---- f4: indirect specular (specular.cpp) ------------------------------------------------------------------
+def specular_mip_texels(cb):
+    """Texel count of the whole environment-map chain and the per-level sizes."""
+    sizes, r, per = [], cb.SpecularEnvmapTotalSize, cb.SpecularEnvmapPerCacheSize_Texel
+    while per >= 1:
+        sizes.append(r)
+        r //= 2
+        per //= 2
+    return sum(x * x for x in sizes), sizes
+
+
+def light_caches_specular(cb, pf, vi, lights, vpls, blocks, voxel_chain, entries, count, sh_order, indirect_shadow):
+    """In place on ``entries``; returns the mip chain buffer (uint32 R11G11B10F texels) with level 0 filled."""
+    lib = load()
+    n = len(lights)
+    larr = (abi.SpotLight * n)(*lights)
+    vp = (_P * n)(*[_ptr(v) for v in vpls])
+    bp = (_P * n)(*[(_ptr(b) if b is not None else None) for b in (blocks or [None] * n)])
+    total, _ = specular_mip_texels(cb)
+    mips = np.zeros(total, np.uint32)
+    lib.orc_light_caches_specular(C.byref(cb), C.byref(pf), C.byref(vi), larr, C.c_uint32(n), vp, bp, _ptr(voxel_chain),
+                                  _ptr(entries), C.c_uint32(entries.shape[1] * 4), C.c_uint32(count), int(sh_order),
+                                  int(bool(indirect_shadow)), _ptr(mips))
+    return mips
+
+
+def specular_mips(cb, count, mips):
+    load().orc_specular_mips(C.byref(cb), C.c_uint32(count), _ptr(mips))
+    return mips
+
+
+def specular_fill_holes(cb, count, max_level, mips):
+    load().orc_specular_fill_holes(C.byref(cb), C.c_uint32(count), C.c_uint32(max_level), _ptr(mips))
+    return mips
+
+
+def apply_caches_specular(cb, pf, vi, transitions, sh_order, depth, normal, diffuse, rough_metal, atlas, entries, mips,
+                          threads=0):
+    lib = load()
+    H, W = depth.shape
+    out = np.zeros((H, W, 4), np.float32)
+    depth, normal, diffuse, rough_metal, atlas = (np.ascontiguousarray(a) for a in (depth, normal, diffuse, rough_metal, atlas))
+    lib.orc_apply_caches_specular(C.byref(cb), C.byref(pf), C.byref(vi), int(bool(transitions)), int(sh_order), _ptr(depth),
+                                  _ptr(normal), _ptr(diffuse), _ptr(rough_metal), _ptr(atlas), _ptr(entries),
+                                  C.c_uint32(entries.shape[1] * 4), C.c_uint32(entries.shape[0]), _ptr(mips), _ptr(out),
+                                  int(threads))
+    return out

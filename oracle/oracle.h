@@ -120,6 +120,22 @@ void orc_cone_trace_ao(const drv_per_frame* pf, const drv_volume_info* vi, const
 /* f3, shader/tonemapping.frag:21-31. */
 void orc_tonemap(const float* hdr_rgba, uint32_t n, float exposure, float drago_divider, float* out_rgb);
 
+/* f4, INDIRECT_SPECULAR + DIRECT_SPECULAR_MAP_WRITE (specular.cpp): cacheLightingRSM.comp with the per-cache
+ * hemispherical environment maps (SH + R11F_G11F_B10F atlas of SpecularEnvmapTotalSize^2 texels, cleared first),
+ * Renderer::PrepareSpecularEnvmaps (mip chain, hole filling; `mips` = every level, level 0 first), and
+ * cacheApply.frag with the specular term. */
+void orc_light_caches_specular(const drv_constant* cb, const drv_per_frame* pf, const drv_volume_info* vi,
+                               const drv_spot_light* lights, uint32_t num_lights, const drv_vpl* const* vpls,
+                               const drv_shadow_block* const* blocks, const uint8_t* voxel_chain, void* entries,
+                               uint32_t entry_stride, uint32_t count, int sh_order, int indirect_shadow, uint32_t* atlas);
+void orc_specular_mips(const drv_constant* cb, uint32_t count, uint32_t* mips);
+void orc_specular_fill_holes(const drv_constant* cb, uint32_t count, uint32_t max_level, uint32_t* mips);
+void orc_apply_caches_specular(const drv_constant* cb, const drv_per_frame* pf, const drv_volume_info* vi, int transitions,
+                               int sh_order, const float* depth, const int16_t* normal_rg16i, const uint8_t* diffuse_srgb8x,
+                               const uint8_t* roughness_metallic_rg8, const uint32_t* atlas, const void* entries,
+                               uint32_t entry_stride, uint32_t max_caches, const uint32_t* specular_mips, float* out_rgba,
+                               int threads);
+
 /* Exact helpers shared with tests. */
 float    orc_half_to_float(uint16_t h);
 uint16_t orc_float_to_half(float f);

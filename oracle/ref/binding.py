@@ -168,3 +168,57 @@ def tonemap(hdr_rgba, exposure, drago_divider):
     out = np.zeros(hdr.shape[:-1] + (3,), np.float32)
     lib.ref_tonemap(_ptr(hdr), C.c_uint32(n), C.c_float(exposure), C.c_float(drago_divider), _ptr(out))
     return out
+
+
+# ---- f4: INDIRECT_SPECULAR variants ----------------------------------------------------------------------------
+def light_caches_specular(cb, pf, vi, lights, rsm_levels, read_levels, voxel_chain, voxel_res, entries, count, sh_order,
+                          indirect_shadow, total_texels):
+    """cacheLightingRSM.comp with INDIRECT_SPECULAR + DIRECT_SPECULAR_MAP_WRITE (per-cache size 16), work groups in
+    order on one thread. Built variants: (SH1, unshadowed) and (SH2, shadowed). Returns the mip buffer, level 0 filled."""
+    lib = load()
+    n = len(lights)
+    larr = (abi.SpotLight * n)(*lights)
+    keep = []
+    flux_p, normal_p, depth_pp, nlev = (_P * n)(), (_P * n)(), (_P * n)(), (C.c_uint32 * n)()
+    for i in range(n):
+        lv, rl = rsm_levels[i], read_levels[i]
+        f, nm = np.ascontiguousarray(lv[rl][0]), np.ascontiguousarray(lv[rl][1])
+        ds = [np.ascontiguousarray(l[2]) for l in lv[rl:]]
+        dptr = (_P * len(ds))(*[_ptr(d) for d in ds])
+        keep += [f, nm, ds, dptr]
+        flux_p[i], normal_p[i] = _ptr(f), _ptr(nm)
+        depth_pp[i] = C.cast(dptr, _P)
+        nlev[i] = len(ds)
+    mips = np.zeros(total_texels, np.uint32)
+    lib.ref_light_caches_specular.restype = C.c_int
+    rc = lib.ref_light_caches_specular(C.byref(cb), C.byref(pf), C.byref(vi), larr, C.c_uint32(n), flux_p, normal_p, depth_pp,
+                                       nlev, _ptr(voxel_chain), C.c_uint32(voxel_res), _ptr(entries), C.c_uint32(count),
+                                       int(sh_order), int(bool(indirect_shadow)), _ptr(mips))
+    if rc != 0:
+        raise ValueError("this INDIRECT_SPECULAR variant is not built into oracle/_ref")
+    return mips
+
+
+def specular_mips(cb, count, mips):
+    load().ref_specular_mips(C.byref(cb), C.c_uint32(count), _ptr(mips))
+    return mips
+
+
+def specular_fill_holes(cb, count, max_level, mips):
+    load().ref_specular_fill_holes(C.byref(cb), C.c_uint32(count), C.c_uint32(max_level), _ptr(mips))
+    return mips
+
+
+def apply_caches_specular(cb, pf, vi, transitions, sh_order, depth, normal, diffuse, rough_metal, atlas, entries, mips,
+                          threads=0):
+    lib = load()
+    H, W = depth.shape
+    out = np.zeros((H, W, 4), np.float32)
+    depth, normal, diffuse, rough_metal, atlas = (np.ascontiguousarray(a) for a in (depth, normal, diffuse, rough_metal, atlas))
+    lib.ref_apply_caches_specular.restype = C.c_int
+    rc = lib.ref_apply_caches_specular(C.byref(cb), C.byref(pf), C.byref(vi), int(bool(transitions)), int(sh_order), _ptr(depth),
+                                       _ptr(normal), _ptr(diffuse), _ptr(rough_metal), _ptr(atlas), _ptr(entries),
+                                       C.c_uint32(entries.shape[0]), _ptr(mips), _ptr(out), int(threads))
+    if rc != 0:
+        raise ValueError("this INDIRECT_SPECULAR variant is not built into oracle/_ref")
+    return out

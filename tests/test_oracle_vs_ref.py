@@ -237,3 +237,61 @@ def test_tonemap_matches_the_reference_shader():
     a = orc.tonemap(hdr, 1.7, np.float32(np.log2(1.2 + 1.0)))
     b = ref.tonemap(hdr, 1.7, np.float32(np.log2(1.2 + 1.0)))
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+# ---- indirect specular -------------------------------------------------------------------------
+def _rough_metal(wl, seed=11):
+    """A synthetic roughness / metallic G-buffer plane (RG8, renderer.cpp:469): smooth bands + noise."""
+    rng = np.random.default_rng(seed)
+    H, W = wl.depth.shape
+    y, x = np.mgrid[0:H, 0:W]
+    rough = (40 + 180 * (0.5 + 0.5 * np.sin(x * 0.05)) * (0.5 + 0.5 * np.cos(y * 0.07))).astype(np.uint8)
+    metal = rng.integers(0, 256, size=(H, W), dtype=np.uint8)
+    return np.ascontiguousarray(np.stack([rough, metal], -1))
+
+
+@pytest.mark.parametrize("name,sh_order,shadow", [("spec_a", 1, False), ("spec_b", 2, True)])
+def test_indirect_specular_matches_the_reference_shaders(name, sh_order, shadow):
+    """INDIRECT_SPECULAR + DIRECT_SPECULAR_MAP_WRITE: SH with the flux early-out, the R11F_G11F_B10F environment-map
+    atlas (every texel, including the ones neighbouring maps spill into), its mip chain, the hole filling and the
+    applied image — bit for bit."""
+    import dynamicradiancevolume_b200 as drv
+    if shadow:
+        wl = workloads.atrium(width=200, height=112, rsm_res=128, read_lod=1, cav_resolution=16, sh_order=2, transition=0.0,
+                              indirect_shadow=True, voxel_resolution=32, shadow_lod=1, max_caches=4096).build()
+    else:
+        wl = workloads.atrium(width=200, height=112, rsm_res=128, read_lod=1, cav_resolution=16, sh_order=1,
+                              max_caches=4096).build()
+    drv.pack_specular(wl.constant, wl.max_caches, 16)
+    o = OracleFrame(wl).prepare_inputs().allocate()
+    n = o.count
+    assert 64 < n < wl.max_caches
+    total_texels, sizes = orc.specular_mip_texels(wl.constant)
+    eo = o.alloc["entries"].copy()
+    mo = orc.light_caches_specular(wl.constant, wl.per_frame, wl.volume, wl.spot_lights, o.vpls, o.blocks, o.chain, eo, n,
+                                   wl.sh_order, wl.indirect_shadow)
+    er = o.alloc["entries"].copy()
+    reads = [workloads.rsm_read_level(s) for s in wl.spot_lights]
+    mr = ref.light_caches_specular(wl.constant, wl.per_frame, wl.volume, wl.spot_lights, o.levels, reads, o.chain,
+                                   wl.voxel_resolution, er, n, wl.sh_order, wl.indirect_shadow, total_texels)
+    assert np.array_equal(er[:n].view(np.uint32), eo[:n].view(np.uint32)), "SH with the :241 early-out"
+    lvl0 = sizes[0] ** 2
+    assert np.count_nonzero(mo[:lvl0]) > 1000
+    assert np.array_equal(mo[:lvl0], mr[:lvl0]), "environment-map atlas"
+    # Renderer::PrepareSpecularEnvmaps: mip chain, then two levels of hole filling
+    orc.specular_mips(wl.constant, n, mo)
+    ref.specular_mips(wl.constant, n, mr)
+    assert np.array_equal(mo, mr), "specularenvmap_mipmap.frag"
+    assert np.count_nonzero(mo[lvl0:]) > 100
+    orc.specular_fill_holes(wl.constant, n, 2, mo)
+    ref.specular_fill_holes(wl.constant, n, 2, mr)
+    assert np.array_equal(mo, mr), "specularenvmap_fillholes.frag"
+    rm = _rough_metal(wl)
+    img_o = orc.apply_caches_specular(wl.constant, wl.per_frame, wl.volume, wl.transitions, wl.sh_order, wl.depth, wl.normal,
+                                      wl.diffuse, rm, o.alloc["atlas"], eo, mo)
+    img_r = ref.apply_caches_specular(wl.constant, wl.per_frame, wl.volume, wl.transitions, wl.sh_order, wl.depth, wl.normal,
+                                      wl.diffuse, rm, o.alloc["atlas"], eo, mr)
+    assert np.array_equal(img_r.view(np.uint32), img_o.view(np.uint32)), "cacheApply.frag with INDIRECT_SPECULAR"
+    # the specular term is there: the diffuse-only image differs
+    plain = o.apply(entries=eo)
+    assert np.abs(plain[..., :3] - img_o[..., :3]).max() > 1e-4
