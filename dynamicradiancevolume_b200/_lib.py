@@ -29,6 +29,8 @@ SYMBOLS = [
     ("drv_set_light_count", _st, [_P, _u32]),
     ("drv_set_spot_light", _st, [_P, _u32, C.POINTER(abi.SpotLight)]),
     ("drv_bind_gbuffer", _st, [_P, _P, _P, _P, _u32, _u32]),
+    ("drv_bind_gbuffer_material", _st, [_P, _P]),
+    ("drv_prepare_specular_envmaps", _st, [_P]),
     ("drv_bind_rsm", _st, [_P, _u32, _P, _P, _P, _u32]),
     ("drv_prepare_rsm", _st, [_P, _u32]),
     ("drv_voxelize", _st, [_P, _P, _u32, C.POINTER(_f32 * 16), _f32, _u32]),

@@ -110,7 +110,8 @@ class Config(C.Structure):
         ("voxel_resolution", u32), ("sh_order", u32), ("indirect_shadow", u32),
         ("cascade_transitions", u32), ("backbuffer_width", u32), ("backbuffer_height", u32),
         ("max_lights", u32), ("max_rsm_resolution", u32), ("device", i32),
-        ("stream", C.c_void_p), ("gather_variant", u32), ("reserved", u32 * 3),
+        ("stream", C.c_void_p), ("gather_variant", u32), ("indirect_specular", u32),
+        ("specular_per_cache_size", u32), ("specular_fill_holes_level", u32),
     ]
 
 
@@ -128,6 +129,7 @@ class Buffers(C.Structure):
         ("hdr16", C.c_void_p),
         ("rsm_flux0", C.c_void_p * DRV_MAX_LIGHTS), ("rsm_normal0", C.c_void_p * DRV_MAX_LIGHTS),
         ("rsm_depth0", C.c_void_p * DRV_MAX_LIGHTS),
+        ("specular_mips", C.c_void_p), ("specular_total_size", u32), ("specular_levels", u32),
     ]
 
 

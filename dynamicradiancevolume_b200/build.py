@@ -8,8 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libdrv_gi.so")
-SOURCES = ["ctx.cu", "alloc.cu", "rsm.cu", "voxel.cu", "gather.cu", "apply.cu", "adjacent.cu", "microbench.cu", "host_pack.cpp"]
-HEADERS = ["ctx.h", "device_math.cuh", "voxel_sample.cuh", os.path.join(ROOT, "include", "drv_gi.h"), os.path.join(ROOT, "include", "drv_math.h")]
+SOURCES = ["ctx.cu", "alloc.cu", "rsm.cu", "voxel.cu", "gather.cu", "apply.cu", "adjacent.cu", "specular.cu", "microbench.cu", "host_pack.cpp"]
+HEADERS = ["ctx.h", "device_math.cuh", "voxel_sample.cuh", os.path.join(ROOT, "include", "drv_gi.h"), os.path.join(ROOT, "include", "drv_math.h"), os.path.join(ROOT, "include", "drv_r11g11b10.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]

@@ -270,6 +270,8 @@ drv_status drv_impl_apply_rows(drv_ctx* ctx, void* out, uint32_t format, uint32_
     const float v = p.casc[c].WorldVoxelSize;
     p.inv_voxel[c] = (v > 1e-6f && v < 1e6f && frexpf(v, &e) == 0.5f) ? 1.0f / v : 0.0f;
   }
+  if (ctx->cfg.indirect_specular) // cacheApply.frag with INDIRECT_SPECULAR: its own kernel (specular.cu)
+    return drv_impl_apply_specular(ctx, out, format, y_begin, y_end, timed, ctx->srgb_lut_dev);
   if (y_end > (uint32_t)p.H) y_end = (uint32_t)p.H;
   if (y_begin >= y_end) return DRV_OK;
   if (timed) ctx->stage_begin(DRV_STAGE_APPLY_CACHES);

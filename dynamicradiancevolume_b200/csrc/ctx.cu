@@ -4,8 +4,10 @@
 // glhelper's buffer/texture objects + Renderer's members play in the
 // reference (renderer.hpp:227-352).
 #include "ctx.h"
+#include "../../include/drv_math.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 
@@ -132,6 +134,37 @@ extern "C" drv_status drv_create(const drv_config* cfg, drv_ctx** out) {
     CREATE_CUDA(dmalloc(&S.chunk_counts, (texels / 256 + 2) * sizeof(uint32_t)));
     CREATE_CUDA(dmalloc(&S.block_live, texels));
   }
+  if (c.indirect_specular) { // environment-map atlas (Renderer::AllocateCacheData, renderer.cpp:253, 282)
+    uint32_t S = c.specular_per_cache_size ? c.specular_per_cache_size : 16u;
+    if (!is_pow2(S) || S < 2 || S > 16 || c.specular_fill_holes_level > ilog2(S)) {
+      g_create_error = "drv_create: specular_per_cache_size must be a power of two in 2..16 and specular_fill_holes_level <= log2 of it";
+      drv_destroy(ctx);
+      return DRV_ERR_INVALID;
+    }
+    drv_constant tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    drv::packSpecular(&tmp, c.max_cache_count, S);
+    if ((uint64_t)tmp.SpecularEnvmapNumCachesPerDimension * tmp.SpecularEnvmapNumCachesPerDimension < c.max_cache_count) {
+      g_create_error = "drv_create: max_cache_count does not fit a 16384^2 specular environment-map atlas (renderer.cpp:256-263)";
+      drv_destroy(ctx);
+      return DRV_ERR_CAPACITY;
+    }
+    ctx->spec_S = S;
+    ctx->spec_total = (uint32_t)tmp.SpecularEnvmapTotalSize;
+    ctx->spec_levels = ilog2(S) + 1; // renderer.cpp:282
+    size_t texels = 0;
+    for (uint32_t l = 0, r = ctx->spec_total; l < ctx->spec_levels; ++l, r >>= 1) { ctx->spec_level_offset[l] = (uint32_t)texels; texels += (size_t)r * r; }
+    CREATE_CUDA(dmalloc(&ctx->spec_mips, texels * sizeof(uint32_t)));
+    CREATE_CUDA(cudaMemsetAsync(ctx->spec_mips, 0, texels * sizeof(uint32_t), ctx->stream));
+    CREATE_CUDA(dmalloc(&ctx->spec_patches, (size_t)c.max_cache_count * (S + 1) * (S + 1) * sizeof(uint32_t)));
+    float lut[256];
+    for (int v = 0; v < 256; ++v) {
+      const double cc = (double)v / 255.0;
+      lut[v] = (float)((cc <= 0.04045) ? cc / 12.92 : pow((cc + 0.055) / 1.055, 2.4));
+    }
+    CREATE_CUDA(dmalloc(&ctx->srgb_lut_dev, sizeof(lut)));
+    CREATE_CUDA(cudaMemcpy(ctx->srgb_lut_dev, lut, sizeof(lut), cudaMemcpyHostToDevice));
+  }
   CREATE_CUDA(dmalloc(&ctx->cone_work, 4 * sizeof(uint32_t)));
   CREATE_CUDA(cudaMemsetAsync(ctx->cone_work, 0, 4 * sizeof(uint32_t), ctx->stream));
   CREATE_CUDA(dmalloc(&ctx->gather_tickets, ((size_t)c.max_cache_count / 64 + 2) * sizeof(uint32_t)));
@@ -171,6 +204,7 @@ extern "C" void drv_destroy(drv_ctx* ctx) {
     if (ctx->ev_end[s]) cudaEventDestroy(ctx->ev_end[s]);
   }
   cudaFree(ctx->live_counts); cudaFree(ctx->cone_work); cudaFree(ctx->gather_tickets); cudaFree(ctx->gather_trace);
+  cudaFree(ctx->spec_mips); cudaFree(ctx->spec_patches); cudaFree(ctx->srgb_lut_dev);
   if (ctx->frame_graph) cudaGraphExecDestroy(ctx->frame_graph);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->side2) cudaStreamDestroy(ctx->side2);
@@ -247,6 +281,18 @@ extern "C" drv_status drv_bind_gbuffer(drv_ctx* ctx, const float* depth, const i
   return DRV_OK;
 }
 
+extern "C" drv_status drv_bind_gbuffer_material(drv_ctx* ctx, const uint8_t* roughness_metallic_rg8) {
+  NEED_CTX();
+  MUTATES();
+  ctx->gb_rough_metal = roughness_metallic_rg8;
+  return DRV_OK;
+}
+
+extern "C" drv_status drv_prepare_specular_envmaps(drv_ctx* ctx) {
+  NEED_CTX();
+  return drv_impl_prepare_specular(ctx);
+}
+
 extern "C" drv_status drv_bind_rsm(drv_ctx* ctx, uint32_t light, const uint16_t* flux, const int16_t* normal,
                                    const uint16_t* depth, uint32_t res) {
   NEED_CTX();
@@ -292,6 +338,7 @@ extern "C" drv_status drv_light_caches(drv_ctx* ctx) {
     if (st != DRV_OK) return st;
   }
   drv_status st = drv_impl_gather(ctx);
+  if (st == DRV_OK) st = drv_impl_specular_light(ctx); // INDIRECT_SPECULAR: the environment-map atlas (same dispatch in the reference)
   ctx->stage_end(DRV_STAGE_LIGHT_CACHES);
   return st;
 }
@@ -311,6 +358,8 @@ extern "C" drv_status drv_draw(drv_ctx* ctx, void* hdr_out, uint32_t format) {
   drv_status st = drv_impl_allocate(ctx); // renderer.cpp:550
   if (st != DRV_OK) return st;
   st = drv_light_caches(ctx);             // renderer.cpp:556
+  if (st != DRV_OK) return st;
+  st = drv_impl_prepare_specular(ctx);    // renderer.cpp:557-558
   if (st != DRV_OK) return st;
   return drv_impl_apply(ctx, hdr_out, format); // renderer.cpp:570
 }
@@ -357,7 +406,10 @@ static drv_status frame_body(drv_ctx* ctx, void* hdr_out, uint32_t format, uint3
   if (vox) DRV_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join2, 0));
   ctx->stage_begin(DRV_STAGE_LIGHT_CACHES);
   st = drv_impl_gather(ctx, sharded);   // renderer.cpp:556
+  if (st == DRV_OK) st = drv_impl_specular_light(ctx);
   ctx->stage_end(DRV_STAGE_LIGHT_CACHES);
+  if (st != DRV_OK) return st;
+  st = drv_impl_prepare_specular(ctx);  // renderer.cpp:557-558
   if (st != DRV_OK) return st;
   // ... and all peers' stores have landed before anybody applies
   if (sharded && (st = drv_impl_peer_barrier(ctx)) != DRV_OK) return st;
@@ -503,6 +555,9 @@ extern "C" drv_status drv_get_buffers(drv_ctx* ctx, drv_buffers* out) {
     out->rsm_depth0[l] = ctx->lights[l].depth0;
   }
   out->hdr16 = ctx->hdr16;
+  out->specular_mips = ctx->spec_mips;
+  out->specular_total_size = ctx->spec_total;
+  out->specular_levels = ctx->spec_levels;
   return DRV_OK;
 }
 

@@ -78,6 +78,7 @@ struct drv_ctx {
   float* st_depth = nullptr;
   int16_t* st_normal = nullptr;
   uint8_t* st_diffuse = nullptr;
+  const uint8_t* gb_rough_metal = nullptr; // RG8 plane (drv_bind_gbuffer_material), read only with indirect specular
   void* hdr16 = nullptr; // owned RGBA16F target for drv_draw_to_host
   // ndc_x[x] = ((x + .5) / W) * 2 - 1 and ndc_y[y] likewise (cacheGather.comp:113-116), evaluated once per
   // context with the decision-maths operators instead of two IEEE divisions per pixel per stage
@@ -112,6 +113,13 @@ struct drv_ctx {
   uint32_t* cone_work = nullptr;     // cone_kernel's work queue: [0] next item, [1] CTAs done
   float* shadow_table = nullptr;     // visibility of (VAL block, cache) for the current chunk of caches (cone_kernel)
   size_t shadow_table_floats = 0;
+  // layout of the visibility table the last shadowed gather used (the specular pass reads it)
+  uint32_t shadow_stride = 0, shadow_chunks = 0, shadow_block_offset[DRV_MAX_LIGHTS] = {0};
+  // indirect specular (specular.cu): per-cache patches, the R11F_G11F_B10F atlas with its mip levels
+  uint32_t spec_S = 0, spec_total = 0, spec_levels = 0, spec_level_offset[8] = {0};
+  uint32_t* spec_patches = nullptr;
+  uint32_t* spec_mips = nullptr;
+  float* srgb_lut_dev = nullptr;
   uint32_t* gather_tickets = nullptr; // warp-split gather: arrival counter per cache tile (zero between launches)
   unsigned long long* gather_trace = nullptr; // diagnostics (gather_variant bit 18)
   uint32_t gather_trace_ctas = 0;
@@ -188,6 +196,10 @@ drv_status drv_impl_voxelize(drv_ctx* ctx, const float* tris, uint32_t n, const 
 drv_status drv_impl_set_synthetic_entries(drv_ctx* ctx, const float* pos, uint32_t n);
 drv_status drv_impl_set_voxel_volume(drv_ctx* ctx, const uint8_t* level0);
 drv_status drv_impl_peer_barrier(drv_ctx* ctx);
+drv_status drv_impl_specular_light(drv_ctx* ctx);
+drv_status drv_impl_prepare_specular(drv_ctx* ctx);
+drv_status drv_impl_apply_specular(drv_ctx* ctx, void* out, uint32_t format, uint32_t y_begin, uint32_t y_end, bool timed,
+                                   const float* srgb_lut_dev);
 constexpr size_t kSyncBytes = 256;
 void drv_impl_upload_srgb_lut();
 drv_status drv_impl_build_ndc_tables(drv_ctx* ctx);

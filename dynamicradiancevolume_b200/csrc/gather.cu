@@ -1548,6 +1548,9 @@ drv_status drv_impl_gather(drv_ctx* ctx, bool overwrite) {
   }
   c.table = ctx->shadow_table;
   c.stride = chunk;
+  ctx->shadow_stride = chunk; // what the specular pass needs to read the table after this call
+  ctx->shadow_chunks = (ctx->cfg.max_cache_count + chunk - 1) / chunk;
+  for (uint32_t l = 0; l < ctx->num_lights; ++l) ctx->shadow_block_offset[l] = p.block_offset[l];
   c.work = ctx->cone_work;
   p.shadow_table = ctx->shadow_table;
   p.shadow_stride = chunk;

@@ -127,7 +127,7 @@ __device__ __forceinline__ F3 rsm_world_position(const drv_spot_light& L, float 
 __global__ void vplgen_kernel(drv_spot_light L, const uint2* __restrict__ flux, const int* __restrict__ normal,
                               const uint32_t* __restrict__ depth, const uint32_t* __restrict__ depth_lod,
                               int with_blocks, float4* __restrict__ vpls, float4* __restrict__ blocks,
-                              uint32_t* __restrict__ chunk_counts, uint8_t* __restrict__ block_live) {
+                              uint32_t* __restrict__ chunk_counts, uint8_t* __restrict__ block_live, int specular) {
   const uint32_t R = (uint32_t)L.RSMReadResolution;
   const uint32_t total = R * R;
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,8 +138,12 @@ __global__ void vplgen_kernel(drv_spot_light L, const uint2* __restrict__ flux, 
       uint32_t x, y;
       morton_decode(k, x, y);
       const uint2 f = __ldg(flux + (size_t)y * R + x);
-      // half bits: zero flux = all three halfs are +-0
+      // half bits: zero flux = all three halfs are +-0. With INDIRECT_SPECULAR the shader itself skips a VPL whose
+      // flux sums to less than 0.001 — for the SH as well (cacheLightingRSM.comp:241)
       live = ((f.x & 0x7fff7fffu) | (f.y & 0x7fffu)) != 0u;
+      if (specular)
+        live = !(ex_add(ex_add(half_bits_to_float((uint16_t)(f.x & 0xffffu)), half_bits_to_float((uint16_t)(f.x >> 16))),
+                        half_bits_to_float((uint16_t)(f.y & 0xffffu))) < 0.001f);
       if (live && with_blocks) block_live[k / (uint32_t)L.IndirectShadowComputationSampleInterval] = 1;
     }
     const int c = __syncthreads_count(live);
@@ -202,13 +206,16 @@ __global__ void vplgen_kernel(drv_spot_light L, const uint2* __restrict__ flux, 
 // stays in. Each survivor is tagged with its shadow-block index so a compacted list still finds its visibility.
 constexpr int kCompactThreads = 256;
 
-__device__ __forceinline__ bool vpl_is_live(const float4 flux) { return flux.x != 0.0f || flux.y != 0.0f || flux.z != 0.0f; }
+__device__ __forceinline__ bool vpl_is_live(const float4 flux, int specular) {
+  if (specular) return !(ex_add(ex_add(flux.x, flux.y), flux.z) < 0.001f); // cacheLightingRSM.comp:241
+  return flux.x != 0.0f || flux.y != 0.0f || flux.z != 0.0f;
+}
 
 __global__ void __launch_bounds__(kCompactThreads) vpl_count_kernel(const float4* __restrict__ vpls, uint32_t n,
                                                                    uint32_t interval, uint32_t* __restrict__ chunk_counts,
-                                                                   uint8_t* __restrict__ block_live) {
+                                                                   uint8_t* __restrict__ block_live, int specular) {
   const uint32_t k = blockIdx.x * kCompactThreads + threadIdx.x;
-  const bool live = k < n && vpl_is_live(__ldg(vpls + (size_t)k * 3 + 2));
+  const bool live = k < n && vpl_is_live(__ldg(vpls + (size_t)k * 3 + 2), specular);
   if (live && block_live) block_live[k / interval] = 1; // benign race: every writer stores 1
   const int c = __syncthreads_count(live);
   if (threadIdx.x == 0) chunk_counts[blockIdx.x] = (uint32_t)c;
@@ -216,7 +223,8 @@ __global__ void __launch_bounds__(kCompactThreads) vpl_count_kernel(const float4
 
 __global__ void __launch_bounds__(kCompactThreads) vpl_compact_kernel(const float4* __restrict__ vpls, uint32_t n,
                                                                      uint32_t interval, const uint32_t* __restrict__ chunk_counts,
-                                                                     float4* __restrict__ out, uint32_t* __restrict__ live_count) {
+                                                                     float4* __restrict__ out, uint32_t* __restrict__ live_count,
+                                                                     int specular) {
   __shared__ uint32_t s_warp[kCompactThreads / 32];
   __shared__ uint32_t s_base;
   // survivors in the chunks before this one
@@ -237,7 +245,7 @@ __global__ void __launch_bounds__(kCompactThreads) vpl_compact_kernel(const floa
   const uint32_t k = blockIdx.x * kCompactThreads + threadIdx.x;
   float4 q0, q1, q2 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (k < n) q2 = __ldg(vpls + (size_t)k * 3 + 2);
-  const bool live = k < n && vpl_is_live(q2);
+  const bool live = k < n && vpl_is_live(q2, specular);
   const uint32_t ballot = __ballot_sync(0xffffffffu, live);
   __syncthreads(); // s_warp is reused
   if (lane == 0) s_warp[warp] = __popc(ballot);
@@ -268,17 +276,18 @@ drv_status drv_impl_compact_vpls(drv_ctx* ctx, uint32_t li, bool counted) {
     return DRV_OK;
   }
   const bool shadow = ctx->cfg.indirect_shadow != 0 && !S.vpls_external;
+  const int spec = ctx->cfg.indirect_specular ? 1 : 0;
   uint32_t interval = shadow ? (uint32_t)S.block.IndirectShadowComputationSampleInterval : 1u;
   if (interval == 0) interval = 1;
   const uint32_t chunks = (n + kCompactThreads - 1) / kCompactThreads;
   if (!counted) { // external lists (drv_set_vpls); vplgen_kernel does this itself
     if (shadow) DRV_CUDA(cudaMemsetAsync(S.block_live, 0, (n + interval - 1) / interval, ctx->stream));
     vpl_count_kernel<<<chunks, kCompactThreads, 0, ctx->stream>>>((const float4*)S.vpls, n, interval, S.chunk_counts,
-                                                                 shadow ? S.block_live : nullptr);
+                                                                 shadow ? S.block_live : nullptr, spec);
     DRV_LAUNCH_CHECK();
   }
   vpl_compact_kernel<<<chunks, kCompactThreads, 0, ctx->stream>>>((const float4*)S.vpls, n, interval, S.chunk_counts,
-                                                                 (float4*)S.vpls_live, ctx->live_counts + li);
+                                                                 (float4*)S.vpls_live, ctx->live_counts + li, spec);
   DRV_LAUNCH_CHECK();
   return DRV_OK;
 }
@@ -361,7 +370,7 @@ drv_status drv_impl_generate_vpls(drv_ctx* ctx, uint32_t li) {
   if (with_blocks) DRV_CUDA(cudaMemsetAsync(S.block_live, 0, nblocks, ctx->stream));
   vplgen_kernel<<<(threads + 255) / 256, 256, 0, ctx->stream>>>(L, flux, normal, depth, depth_lod, with_blocks,
                                                                (float4*)S.vpls, (float4*)S.blocks, S.chunk_counts,
-                                                               S.block_live);
+                                                               S.block_live, ctx->cfg.indirect_specular ? 1 : 0);
   DRV_LAUNCH_CHECK();
   S.num_vpls = R * R;
   return drv_impl_compact_vpls(ctx, li, true);

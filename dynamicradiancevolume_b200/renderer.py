@@ -162,9 +162,13 @@ class Context:
 
     def __init__(self, *, max_cache_count=16384, cav_cascades=3, cav_resolution=32, voxel_resolution=128, sh_order=1,
                  indirect_shadow=True, cascade_transitions=True, width=1920, height=1080, max_lights=1,
-                 max_rsm_resolution=1024, device=0, stream=None, gather_variant=0):
+                 max_rsm_resolution=1024, device=0, stream=None, gather_variant=0, indirect_specular=False,
+                 specular_per_cache_size=16, specular_fill_holes_level=0):
         self.lib = _lib.load()
         cfg = abi.Config()
+        cfg.indirect_specular = 1 if indirect_specular else 0
+        cfg.specular_per_cache_size = specular_per_cache_size
+        cfg.specular_fill_holes_level = specular_fill_holes_level
         cfg.max_cache_count = max_cache_count
         cfg.cav_cascades = cav_cascades
         cfg.cav_resolution = cav_resolution
@@ -209,6 +213,19 @@ class Context:
     def set_volume_info(self, b): self.check(self.lib.drv_set_volume_info(self.handle, C.byref(b)))
     def set_light_count(self, n): self.check(self.lib.drv_set_light_count(self.handle, n))
     def set_spot_light(self, i, b): self.check(self.lib.drv_set_spot_light(self.handle, i, C.byref(b)))
+
+    def bind_gbuffer_material(self, rough_metal):
+        """RG8 roughness / metallic plane (device tensor [H, W, 2] uint8): read only with indirect specular."""
+        self._keep_rm = rough_metal
+        self.check(self.lib.drv_bind_gbuffer_material(self.handle, rough_metal.data_ptr()))
+
+    def prepare_specular_envmaps(self): self.check(self.lib.drv_prepare_specular_envmaps(self.handle))
+
+    def read_specular_mips(self):
+        """Every level of the environment-map atlas (uint32 R11F_G11F_B10F texels), level 0 first."""
+        b = self.buffers()
+        n = sum((b.specular_total_size >> l) ** 2 for l in range(b.specular_levels))
+        return self._read(b.specular_mips, n * 4).view(np.uint32).copy()
 
     def bind_gbuffer(self, depth, normal, diffuse):
         h, w = depth.shape[0], depth.shape[1]

@@ -221,7 +221,10 @@ typedef struct drv_config {
                                  bit 17      software-pipelined cone march instead of the plain loop
                                  bit 18      per-CTA time stamps of the pair kernel (drv_debug_gather_trace)
                                  bit 19      cone pass compiled for 8 instead of 10 resident CTAs per SM (64 registers) */
-  uint32_t reserved[3];
+  uint32_t indirect_specular; /* 0/1 = INDIRECT_SPECULAR with DIRECT_SPECULAR_MAP_WRITE (SetIndirectSpecular):
+                                 per-cache hemispherical environment maps in an R11F_G11F_B10F atlas */
+  uint32_t specular_per_cache_size;  /* SetPerCacheSpecularEnvMapSize: power of two, 2..16; 0 = 16 (renderer.cpp:43) */
+  uint32_t specular_fill_holes_level;/* SetSpecularEnvMapHoleFillLevel: 0..log2(per cache size) (renderer.cpp:44) */
 } drv_config;
 
 drv_status drv_create(const drv_config* cfg, drv_ctx** out);
@@ -251,6 +254,9 @@ drv_status drv_bind_gbuffer(drv_ctx* ctx, const float* depth, const int16_t* nor
  * renderer.cpp:1288-1291): level 0 at `resolution` = RSMRenderResolution.
  * flux RGB16F stored as 4 halfs/texel (r,g,b,x); normal RG16I; depthLinSq
  * RG16F = (dist, dist^2) (fillrsm.frag:48). Device pointers. */
+/* The roughness / metallic plane of the G-buffer (RG8, renderer.cpp:469; texture unit 1): read by the apply pass
+ * only with drv_config.indirect_specular. Same resolution as drv_bind_gbuffer. */
+drv_status drv_bind_gbuffer_material(drv_ctx* ctx, const uint8_t* roughness_metallic_rg8);
 drv_status drv_bind_rsm(drv_ctx* ctx, uint32_t light, const uint16_t* flux_rgbx16f,
                         const int16_t* normal_rg16i, const uint16_t* depthlinsq_rg16f,
                         uint32_t resolution);
@@ -290,6 +296,10 @@ drv_status drv_light_caches(drv_ctx* ctx);
 #define DRV_HDR_RGBA32F_WRITE 1u /* parity readback: overwrite float4 (rgb, 1); discarded pixels get 0 */
 #define DRV_HDR_RGBA16F_WRITE 2u /* glClear(0,0,0,0) + additive blend fused: overwrite RGBA16F with (rgb, 0);
                                     discarded pixels get 0 (renderer.cpp:562 + :1053 in one pass) */
+/* ≙ Renderer::PrepareSpecularEnvmaps (renderer.cpp:994-1045): mip chain of the environment-map atlas
+ * (specularenvmap_mipmap.frag) and the hole-filling push-down (specularenvmap_fillholes.frag). drv_draw /
+ * drv_draw_frame call it between lighting and apply when drv_config.indirect_specular is set. */
+drv_status drv_prepare_specular_envmaps(drv_ctx* ctx);
 drv_status drv_apply_caches(drv_ctx* ctx, void* hdr_out, uint32_t format);
 
 /* The same for the pixel rows [y_begin, y_end) only — sort-first sharding of the apply pass over GPUs, and the
@@ -386,6 +396,10 @@ typedef struct drv_buffers {
   const uint16_t* rsm_flux0[DRV_MAX_LIGHTS];
   const int16_t*  rsm_normal0[DRV_MAX_LIGHTS];
   const uint16_t* rsm_depth0[DRV_MAX_LIGHTS];
+  /* indirect specular: every level of the environment-map atlas, level 0 first, R11F_G11F_B10F texels
+   * (include/drv_r11g11b10.h); level l is (specular_total_size >> l)^2; NULL unless drv_config.indirect_specular */
+  uint32_t* specular_mips;
+  uint32_t  specular_total_size, specular_levels;
 } drv_buffers;
 drv_status drv_get_buffers(drv_ctx* ctx, drv_buffers* out);
 /* Texel offset of mip level `level` (>=1) inside a context-owned RSM mip
