@@ -268,6 +268,16 @@ def run_b200(args):
                 "caches": shadowed["config"]["caches"], "live_vpls": shadowed["config"]["live_vpls"],
                 "stage_ms": shadowed["stage_ms"], "roofline_pair_pass": shadowed["roofline"],
                 "roofline_cone": shadowed["roofline_cone"], "parity": shadowed.get("parity")}
+    if args.config == 1 and not args.no_scaling_workload:
+        # the metric's view with a 4x finer address volume (~77 000 caches instead of 6 210): the gather at a cache
+        # count where its fixed costs (launch ramp, partial-tile fix-up) no longer dominate
+        k = max(3, min(10, args.steps // 3))
+        dense = measure(args, 6, k, 2, light=True)
+        if line is not None and dense is not None:
+            line["dense_workload"] = {
+                "workload": dense["config"]["workload"], "ms_per_frame": dense["value"], "steps": k, "warmup": 2,
+                "caches": dense["config"]["caches"], "live_vpls": dense["config"]["live_vpls"],
+                "stage_ms": dense["stage_ms"], "roofline": dense["roofline"], "parity": dense.get("parity")}
     if line is not None:
         if args.stages:
             for k_, v in line["stage_ms"].items():

@@ -87,7 +87,13 @@ SYMBOLS = [
     ("drv_debug_cone_steps", _st, [_P, C.POINTER(C.c_uint64)]),
 ]
 
+# the pure-host part of the C-ABI (uniform-block packers): also built as libdrv_host.so with plain g++, so that host
+# tooling which only prepares inputs — the CPU reference arm of bench.py, the oracle tests — never maps the CUDA library
+HOST_LIB_PATH = os.path.join(_HERE, "libdrv_host.so")
+HOST_SYMBOLS = [s for s in SYMBOLS if s[0].startswith("drv_pack_")]
+
 _lib = None
+_host = None
 
 
 class DrvError(RuntimeError):
@@ -111,6 +117,23 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    return lib
+
+
+def load_host():
+    """Load libdrv_host.so (once): the drv_pack_* entry points compiled without CUDA."""
+    global _host
+    if _host is not None:
+        return _host
+    if not os.path.exists(HOST_LIB_PATH):
+        raise ImportError("libdrv_host.so is missing (%s). Build it with `python -m dynamicradiancevolume_b200.build`."
+                          % HOST_LIB_PATH)
+    lib = C.CDLL(HOST_LIB_PATH)
+    for name, res, args in HOST_SYMBOLS:
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _host = lib
     return lib
 
 

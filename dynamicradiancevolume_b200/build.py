@@ -8,6 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libdrv_gi.so")
+HOST_LIB = os.path.join(HERE, "libdrv_host.so")  # the drv_pack_* entry points alone, plain g++ (see _lib.load_host)
 SOURCES = ["ctx.cu", "alloc.cu", "rsm.cu", "voxel.cu", "gather.cu", "apply.cu", "adjacent.cu", "specular.cu", "microbench.cu", "host_pack.cpp"]
 HEADERS = ["ctx.h", "device_math.cuh", "voxel_sample.cuh", os.path.join(ROOT, "include", "drv_gi.h"), os.path.join(ROOT, "include", "drv_math.h"), os.path.join(ROOT, "include", "drv_r11g11b10.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -48,7 +49,20 @@ def build(verbose=False, force=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    build_host()
     return LIB
+
+
+def build_host():
+    src = os.path.join(CSRC, "host_pack.cpp")
+    deps = [src, os.path.join(ROOT, "include", "drv_gi.h"), os.path.join(ROOT, "include", "drv_math.h")]
+    if _mtime(HOST_LIB) > max(_mtime(d) for d in deps):
+        return HOST_LIB
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-Wall", "-shared", "-o", HOST_LIB, src]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed for libdrv_host.so:\n%s\n%s" % (r.stdout, r.stderr))
+    return HOST_LIB
 
 
 def build_aux():

@@ -92,13 +92,13 @@ class IndirectDiffuseMode:
 def pack_constant(width, height, voxel_res, cav_res, cav_cascades, max_caches) -> abi.Constant:
     """≙ Renderer::UpdateConstantUBO (renderer.cpp:290-322)."""
     out = abi.Constant()
-    _lib.load().drv_pack_constant(C.byref(out), width, height, voxel_res, cav_res, cav_cascades, max_caches)
+    _lib.load_host().drv_pack_constant(C.byref(out), width, height, voxel_res, cav_res, cav_cascades, max_caches)
     return out
 
 
 def pack_specular(constant: abi.Constant, max_caches: int, per_cache_size: int = 16) -> abi.Constant:
     """Fills the four specular environment-map fields of a Constant block (renderer.cpp:253, 316-319)."""
-    _lib.load().drv_pack_specular(C.byref(constant), max_caches, per_cache_size)
+    _lib.load_host().drv_pack_specular(C.byref(constant), max_caches, per_cache_size)
     return constant
 
 
@@ -106,7 +106,7 @@ def pack_per_frame(camera: Camera, passed_time: float = 0.0) -> abi.PerFrame:
     """≙ Renderer::UpdatePerFrameUBO (renderer.cpp:324-344)."""
     out = abi.PerFrame()
     d = camera.desc()
-    _lib.load().drv_pack_per_frame(C.byref(out), C.addressof(d), passed_time)
+    _lib.load_host().drv_pack_per_frame(C.byref(out), C.addressof(d), passed_time)
     return out
 
 
@@ -118,7 +118,7 @@ def pack_volume_info(camera: Camera, bbox_min, bbox_max, voxel_res, cav_res, cas
     mn = (C.c_float * 3)(*bbox_min)
     mx = (C.c_float * 3)(*bbox_max)
     sizes = (C.c_float * len(cascade_world_sizes))(*cascade_world_sizes)
-    _lib.load().drv_pack_volume_info(C.byref(out), C.addressof(d), C.byref(mn), C.byref(mx), voxel_res, cav_res,
+    _lib.load_host().drv_pack_volume_info(C.byref(out), C.addressof(d), C.byref(mn), C.byref(mx), voxel_res, cav_res,
                                      len(cascade_world_sizes), sizes, transition_zone_size)
     return out
 
@@ -127,7 +127,7 @@ def pack_spot_light(light: Light) -> abi.SpotLight:
     """≙ Renderer::PrepareLights (renderer.cpp:664-725)."""
     out = abi.SpotLight()
     d = light.desc()
-    _lib.load().drv_pack_spot_light(C.byref(out), C.addressof(d))
+    _lib.load_host().drv_pack_spot_light(C.byref(out), C.addressof(d))
     return out
 
 

@@ -27,6 +27,17 @@ def test_header_symbols_exported():
     assert set(names) == bound, "binding and header drifted: %s" % (set(names) ^ bound)
 
 
+def test_host_library_exports_the_packers():
+    """libdrv_host.so = host_pack.cpp compiled without CUDA: same drv_pack_* symbols, same results as libdrv_gi.so."""
+    host, full = _lib.load_host(), drv.load()
+    assert [s[0] for s in _lib.HOST_SYMBOLS] == ["drv_pack_constant", "drv_pack_specular", "drv_pack_per_frame",
+                                                 "drv_pack_volume_info", "drv_pack_spot_light"]
+    a, b = abi.Constant(), abi.Constant()
+    host.drv_pack_constant(C.byref(a), 1920, 1080, 128, 64, 2, 65536)
+    full.drv_pack_constant(C.byref(b), 1920, 1080, 128, 64, 2, 65536)
+    assert bytes(a) == bytes(b)
+
+
 def test_struct_sizes_match_std140():
     assert C.sizeof(abi.Constant) == 80
     assert C.sizeof(abi.PerFrame) == 288

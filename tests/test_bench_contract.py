@@ -44,3 +44,18 @@ def test_b200_arm_needs_a_gpu():
         pytest.skip("a CUDA device is present")
     r = _run("--steps", "1", "--warmup", "0")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_never_maps_the_cuda_library():
+    """The CPU arm builds its workload through libdrv_host.so (the packers compiled with g++): libdrv_gi.so, the
+    product, must not be among the objects the process has mapped after a whole reference frame."""
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import workloads\n"
+            "from oracle.frame import OracleFrame\n"
+            "wl = workloads.config(0, width=64, height=64).build()\n"
+            "o = OracleFrame(wl, threads=2); o.prepare_inputs(); o.frame()\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libdrv_host.so' in maps and 'liboracle_drv.so' in maps, 'helper libraries not mapped'\n"
+            "assert 'libdrv_gi.so' not in maps, 'the CUDA library was loaded by the CPU arm'\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]

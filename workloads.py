@@ -130,7 +130,9 @@ def config(index: int, **kw) -> Workload:
         return atrium(**args)
     if index == 5:
         return reference_defaults(**kw)
-    raise ValueError("config index 0..3 or 5 (the sweep, index 4, has no scene: see sweep())")
+    if index == 6:
+        return dense(**kw)
+    raise ValueError("config index 0..3, 5 or 6 (the sweep, index 4, has no scene: see sweep())")
 
 
 def reference_defaults(**kw) -> Workload:
@@ -141,6 +143,15 @@ def reference_defaults(**kw) -> Workload:
     args = dict(width=1920, height=1080, rsm_res=1024, read_lod=4, sh_order=1, indirect_shadow=True, cascades=3,
                 cav_resolution=32, first_cascade=4.0, voxel_resolution=128, transition=2.0, max_caches=16384,
                 shadow_lod=2, name="reference-defaults")
+    args.update(kw)
+    return atrium(**args)
+
+
+def dense(**kw) -> Workload:
+    """Not a BASELINE config: configs[1] with a four times finer address volume (2 x 256^3 instead of 2 x 64^3, 3 cm
+    cells in the first cascade), which allocates ~77 000 caches on the same view instead of 6 210 — the upper half of
+    SURVEY 8a's "10^4-10^5 caches for real frames". bench.py carries it as `dense_workload`."""
+    args = dict(cav_resolution=256, max_caches=1 << 17, name="C2-atrium-dense")
     args.update(kw)
     return atrium(**args)
 
