@@ -267,51 +267,70 @@ __device__ __forceinline__ float cone_trace(const VoxelVol& V, float wx, float w
 // no ping-pong state. With the cone pass on its own (8+ CTAs of 4 warps per SM) the other warps of the SM hide the
 // L1/L2 latency of the dependent chain, and the loop spends a quarter fewer instructions on control flow and
 // register moves (ncu: BRA + BSSY + BSYNC + MOV were 18 % of the pipelined kernel's instructions).
-__device__ __forceinline__ float cone_trace_simple(const VoxelVol& V, float wx, float wy, float wz, float4 blk,
-                                                   uint32_t& steps) {
-  const float inv_voxel = 1.0f / V.voxel_size;
+//
+// The pass is issue-bound, so the march is written for instruction count:
+//  * the position is carried as w = (level-0 texel coordinate) - 1: w + kMagic rounds to the lower corner of the
+//    footprint directly, and level l sees w * 2^-l + (2^-l - 1) — one FFMA, exact for l = 0;
+//  * the "+1" of the record index (records are addressed by lower corner + 1) and the start of the level are one
+//    constant per level (ConeTables::rec_k);
+//  * INSIDE: a cone whose two ends lie inside the volume (by a margin that covers the last step's overshoot) never
+//    leaves it, every lower corner is in [-1, r - 1] at every level, and the clamp disappears: the index is formed
+//    from the raw float bits of the rounded coordinates (the 0x4B400000 bias of all three is folded into
+//    ConeTables::rec_kb). A warp takes this path when all its cones are inside — nearly always: caches and VAL
+//    blocks are surface points of the scene the volume encloses;
+//  * an empty footprint (most of a scene's volume) filters to exactly 0 and occ = fma(1 - occ, 0, occ) is occ, bit
+//    for bit, so unpack + trilinear + blend are skipped.
+struct ConeTables {
+  uint32_t rec_k[16];  // rec_offset[l] + 1 + S + S^2,                     S = (res >> l) + 1
+  uint32_t rec_kb[16]; // rec_k[l] - 0x4B400000 * (1 + S + S^2)  (mod 2^32)
+};
+
+template <bool INSIDE>
+__device__ __forceinline__ uint32_t record_index(const ConeTables& T, int l, int r, float2 mxy, float mz) {
+  const int S = r + 1;
+  if (INSIDE) // raw bits: 0x4B400000 + corner each; the bias is in rec_kb (unsigned: the sum wraps by design)
+    return __float_as_uint(mxy.x) + (uint32_t)S * (__float_as_uint(mxy.y) + (uint32_t)S * __float_as_uint(mz)) + T.rec_kb[l];
+  const int x = min(max(__float_as_int(mxy.x) - 0x4B400000, -1), r - 1);
+  const int y = min(max(__float_as_int(mxy.y) - 0x4B400000, -1), r - 1);
+  const int z = min(max(__float_as_int(mz) - 0x4B400000, -1), r - 1);
+  return (uint32_t)(x + S * (y + S * z)) + T.rec_k[l];
+}
+// fractions of w around its rounded value m: (w - (m - kMagic)) + 0.5
+__device__ __forceinline__ float2 frac_of2(float2 w, float2 m) {
+  return __fadd2_rn(__fadd2_rn(w, __fadd2_rn(f2(kMagic), f2(-m.x, -m.y))), f2(0.5f));
+}
+__device__ __forceinline__ float frac_of(float w, float m) { return (w - (m - kMagic)) + 0.5f; }
+
+template <bool INSIDE>
+__device__ __forceinline__ float cone_march(const VoxelVol& V, const ConeTables& T, float2 dxy, float dz, float2 wxy,
+                                            float wz, float kk, float goal, float radToStep, uint32_t& steps) {
   const float maxLod = (float)(V.levels - 1);
-  const float kk = blk.w;
-  float tx = ex_sub(blk.x, wx), ty = ex_sub(blk.y, wy), tz = ex_sub(blk.z, wz);     // :195
-  const float lightDist = ex_sqrt(ex_dot3(tx, ty, tz, tx, ty, tz));                 // :196
-  const float inv = 1.0f / lightDist;
-  const float2 dxy = f2(tx * inv, ty * inv);                                        // :197-198 (dirInVoxel * res)
-  const float dz = tz * inv;
-  float2 cxy = __ffma2_rn(dxy, f2(2.0f), f2(fmaf(wx - V.vmin[0], inv_voxel, -0.5f), fmaf(wy - V.vmin[1], inv_voxel, -0.5f))); // :201
-  float cz = fmaf(dz, 2.0f, fmaf(wz - V.vmin[2], inv_voxel, -0.5f));
-  const float goal = ex_sub(ex_div(lightDist, V.voxel_size), 2.0f);                 // :206
-  const float radToStep = ex_div(2.0f, ex_sub(1.0f, kk));                           // :209
   float dist = 0.0f, occ = 0.0f, stepSize = 1.0f;
   int s = 0;
   // First stretch: while the sphere radius is <= 1 voxel, log2(radius) <= 0 selects mip level 0 alone
   // and the step stays max(1, r * g): no log2, no second level, no level arithmetic. A VAL block subtends ~1/32
   // rad (SuperValWidth), so this loop is where nearly every sample of a frame is taken.
-  {
 #pragma unroll 1
-    for (; s < 32; ++s) {
-      const float nd = ex_add(dist, stepSize);
-      const float radius = ex_mul(nd, kk);
-      if (radius > 1.0f) break;                                                     // continue in the general loop
-      cxy = __ffma2_rn(dxy, f2(stepSize), cxy); cz = fmaf(dz, stepSize, cz);        // :213
-      dist = nd;                                                                    // :214
-      ++steps;
-      int x, y, z;
-      float2 txy; float tzf;
-      floor_frac_w2(__fadd2_rn(cxy, f2(-0.5f)), x, y, txy);
-      floor_frac_w(cz - 0.5f, z, tzf);
-      const int r = V.res;
-      x = min(max(x, -1), r - 1) + 1;
-      y = min(max(y, -1), r - 1) + 1;
-      z = min(max(z, -1), r - 1) + 1;
-      const uint2 r0 = __ldg(V.rec + (uint32_t)(x + (r + 1) * (y + (r + 1) * z)));  // level 0 records start at 0
-      occ = fmaf(1.0f - occ, trilinear(r0, txy, tzf), occ);                         // :220
-      if (dist >= goal || occ >= 1.0f) return saturatef(1.0f - occ);                // :222
-      stepSize = fmaxf(1.0f, ex_mul(radius, radToStep));                            // :225
+  for (; s < 32; ++s) {
+    const float nd = ex_add(dist, stepSize);
+    const float radius = ex_mul(nd, kk);
+    if (radius > 1.0f) break;                                                       // continue in the general loop
+    wxy = __ffma2_rn(dxy, f2(stepSize), wxy); wz = fmaf(dz, stepSize, wz);          // :213
+    dist = nd;                                                                      // :214
+    ++steps;
+    const float2 mxy = __fadd2_rn(wxy, f2(kMagic));
+    const float mz = wz + kMagic;
+    const uint2 r0 = __ldg(V.rec + record_index<INSIDE>(T, 0, V.res, mxy, mz));
+    if ((r0.x | r0.y) != 0u) {
+      occ = fmaf(1.0f - occ, trilinear(r0, frac_of2(wxy, mxy), frac_of(wz, mz)), occ); // :220
+      if (occ >= 1.0f) return saturatef(1.0f - occ);                                // :222
     }
+    if (dist >= goal) return saturatef(1.0f - occ);                                 // :222
+    stepSize = fmaxf(1.0f, ex_mul(radius, radToStep));                              // :225
   }
 #pragma unroll 1
   for (; s < 32; ++s) {                                                             // :211
-    cxy = __ffma2_rn(dxy, f2(stepSize), cxy); cz = fmaf(dz, stepSize, cz);          // :213
+    wxy = __ffma2_rn(dxy, f2(stepSize), wxy); wz = fmaf(dz, stepSize, wz);          // :213
     dist = ex_add(dist, stepSize);                                                  // :214
     ++steps;
     const float radius = ex_mul(dist, kk);                                          // :216
@@ -320,22 +339,63 @@ __device__ __forceinline__ float cone_trace_simple(const VoxelVol& V, float wx, 
     int l0; float t;
     floor_frac_w(l - 0.5f, l0, t);
     if (!(radius > 1.0f)) { l0 = 0; t = 0.0f; }
-    const Footprint f0 = footprint(V, l0, cxy, cz);
-    const uint2 r0 = __ldg(V.rec + f0.index);
-    float o;
+    const float sc0 = __int_as_float(0x3f800000 - (l0 << 23));                      // 2^-l0
+    const float2 w0xy = __ffma2_rn(wxy, f2(sc0), f2(sc0 - 1.0f));
+    const float w0z = fmaf(wz, sc0, sc0 - 1.0f);
+    const float2 m0xy = __fadd2_rn(w0xy, f2(kMagic));
+    const float m0z = w0z + kMagic;
+    const uint2 r0 = __ldg(V.rec + record_index<INSIDE>(T, l0, V.res >> l0, m0xy, m0z));
+    float o = 0.0f;
     if (t != 0.0f) { // mip-linear: also the next coarser level (:219)
-      const Footprint f1 = footprint(V, min(l0 + 1, V.levels - 1), cxy, cz);
-      const uint2 r1 = __ldg(V.rec + f1.index);
-      o = trilinear(r0, f0.txy, f0.tz);
-      o = fmaf(t, trilinear(r1, f1.txy, f1.tz) - o, o);
-    } else {
-      o = trilinear(r0, f0.txy, f0.tz);
+      const int l1 = min(l0 + 1, V.levels - 1);
+      const float sc1 = __int_as_float(0x3f800000 - (l1 << 23));
+      const float2 w1xy = __ffma2_rn(wxy, f2(sc1), f2(sc1 - 1.0f));
+      const float w1z = fmaf(wz, sc1, sc1 - 1.0f);
+      const float2 m1xy = __fadd2_rn(w1xy, f2(kMagic));
+      const float m1z = w1z + kMagic;
+      const uint2 r1 = __ldg(V.rec + record_index<INSIDE>(T, l1, V.res >> l1, m1xy, m1z));
+      if ((r0.x | r0.y | r1.x | r1.y) != 0u) { // else both footprints empty: 0 + t * (0 - 0), exactly
+        o = trilinear(r0, frac_of2(w0xy, m0xy), frac_of(w0z, m0z));
+        o = fmaf(t, trilinear(r1, frac_of2(w1xy, m1xy), frac_of(w1z, m1z)) - o, o);
+      }
+    } else if ((r0.x | r0.y) != 0u) {
+      o = trilinear(r0, frac_of2(w0xy, m0xy), frac_of(w0z, m0z));
     }
     occ = fmaf(1.0f - occ, o, occ);                                                 // :220
     if (dist >= goal || occ >= 1.0f) break;                                         // :222
     stepSize = fmaxf(1.0f, ex_mul(radius, radToStep));                              // :225
   }
   return saturatef(1.0f - occ);                                                     // :230
+}
+
+__device__ __forceinline__ float cone_trace_simple(const VoxelVol& V, const ConeTables& T, float wx, float wy, float wz,
+                                                   float4 blk, uint32_t& steps) {
+  const float inv_voxel = 1.0f / V.voxel_size;
+  const float kk = blk.w;
+  float tx = ex_sub(blk.x, wx), ty = ex_sub(blk.y, wy), tz = ex_sub(blk.z, wz);     // :195
+  const float lightDist = ex_sqrt(ex_dot3(tx, ty, tz, tx, ty, tz));                 // :196
+  const float inv = 1.0f / lightDist;
+  const float2 dxy = f2(tx * inv, ty * inv);                                        // :197-198 (dirInVoxel * res)
+  const float dz = tz * inv;
+  // the cache in level-0 texel units, minus one (see above); the march starts two voxels along the cone (:201)
+  const float sx = fmaf(wx - V.vmin[0], inv_voxel, -1.0f), sy = fmaf(wy - V.vmin[1], inv_voxel, -1.0f);
+  const float sz = fmaf(wz - V.vmin[2], inv_voxel, -1.0f);
+  const float2 cxy = __ffma2_rn(dxy, f2(2.0f), f2(sx, sy));
+  const float cz = fmaf(dz, 2.0f, sz);
+  const float distVox = ex_div(lightDist, V.voxel_size);
+  const float goal = ex_sub(distVox, 2.0f);                                         // :206
+  const float radToStep = ex_div(2.0f, ex_sub(1.0f, kk));                           // :209
+  // Inside test. The last sample lies less than one step beyond `goal`, and no step is longer than
+  // max(1, goal * kk * radToStep): both ends of [cache, light + overshoot] inside the texel range [0, res] (w in
+  // [-1, res - 1]) by that margin (+1 for rounding) => every sample is. NaN / inf fail the comparisons.
+  const float over = fmaxf(1.0f, distVox * kk * radToStep) + 1.0f;
+  const float hi = (float)V.res - 1.0f - over, lo = over - 1.0f;
+  const float ex = fmaf(dxy.x, distVox, sx), ey = fmaf(dxy.y, distVox, sy), ez = fmaf(dz, distVox, sz);
+  const bool inside = sx >= lo && sx <= hi && sy >= lo && sy <= hi && sz >= lo && sz <= hi &&
+                      ex >= lo && ex <= hi && ey >= lo && ey <= hi && ez >= lo && ez <= hi;
+  if (__all_sync(__activemask(), inside))
+    return cone_march<true>(V, T, dxy, dz, cxy, cz, kk, goal, radToStep, steps);
+  return cone_march<false>(V, T, dxy, dz, cxy, cz, kk, goal, radToStep, steps);
 }
 
 // ------------------------------------------------------------ epilogue helpers
@@ -1174,6 +1234,7 @@ struct ConeParams {
   uint32_t stride;
   const uint2* rec;
   uint32_t rec_offset[16];
+  ConeTables tables;
   int vres, vlevels;
   float vmin[3];
   float voxel_size;
@@ -1219,7 +1280,7 @@ __global__ void __launch_bounds__(kConeThreads, MINB) cone_kernel(const __grid_c
       if (!__ldg(p.lights[light].block_live + (b - p.block_offset[light]))) continue; // no live VPL reads this entry
       const float4 blk = __ldg(p.lights[light].blocks + (b - p.block_offset[light]));
       if (alive)
-        p.table[(size_t)b * p.stride + local] = SIMPLE ? cone_trace_simple(V, pos.x, pos.y, pos.z, blk, steps)
+        p.table[(size_t)b * p.stride + local] = SIMPLE ? cone_trace_simple(V, p.tables, pos.x, pos.y, pos.z, blk, steps)
                                                        : cone_trace(V, pos.x, pos.y, pos.z, blk, steps);
     }
   }
@@ -1530,7 +1591,12 @@ drv_status drv_impl_gather(drv_ctx* ctx, bool overwrite) {
   c.shard_world = ctx->shard_world;
   c.shard_interleave = p.shard_interleave;
   c.rec = ctx->voxel_records;
-  for (int l = 0; l < 16; ++l) c.rec_offset[l] = ctx->voxel_record_offset[l];
+  for (int l = 0; l < 16; ++l) {
+    c.rec_offset[l] = ctx->voxel_record_offset[l];
+    const uint32_t S = ((uint32_t)ctx->cfg.voxel_resolution >> l) + 1u, K = 1u + S + S * S;
+    c.tables.rec_k[l] = c.rec_offset[l] + K;
+    c.tables.rec_kb[l] = c.tables.rec_k[l] - 0x4B400000u * K;
+  }
   c.vres = (int)ctx->cfg.voxel_resolution;
   c.vlevels = (int)ctx->voxel_levels;
   memcpy(c.vmin, ctx->volume.VolumeWorldMin, 12);
