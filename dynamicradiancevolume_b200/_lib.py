@@ -85,6 +85,7 @@ SYMBOLS = [
     ("drv_microbench_count", _u32, []),
     ("drv_debug_gather_trace", _st, [_P, _P, _u32, C.POINTER(_u32)]),
     ("drv_debug_cone_steps", _st, [_P, C.POINTER(C.c_uint64)]),
+    ("drv_debug_host_frame_timeline", _st, [_P, C.POINTER(_f32), _u32, C.POINTER(_u32)]),
 ]
 
 # the pure-host part of the C-ABI (uniform-block packers): also built as libdrv_host.so with plain g++, so that host

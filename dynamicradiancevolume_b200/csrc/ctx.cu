@@ -216,6 +216,8 @@ extern "C" void drv_destroy(drv_ctx* ctx) {
   for (auto& e : ctx->ev_rsm) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->ev_band_in) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->ev_band_done) if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->ev_band_out) if (e) cudaEventDestroy(e);
+  if (ctx->ev_lit) cudaEventDestroy(ctx->ev_lit);
   if (ctx->ev_depth) cudaEventDestroy(ctx->ev_depth);
   if (ctx->ev_frame_start) cudaEventDestroy(ctx->ev_frame_start);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -797,6 +799,27 @@ extern "C" drv_status drv_draw_to_host(drv_ctx* ctx, void* hdr_host) {
   return DRV_OK;
 }
 
+// Diagnostics: when the pieces of the last drv_draw_host_frame finished, in ms after its first copy was queued.
+extern "C" drv_status drv_debug_host_frame_timeline(drv_ctx* ctx, float* out, uint32_t capacity, uint32_t* bands) {
+  NEED_CTX();
+  const uint32_t nb = ctx->host_frame_bands;
+  if (!out || !bands || !nb) return ctx->fail(DRV_ERR_NOT_BOUND, "drv_debug_host_frame_timeline: no host frame drawn yet");
+  if (capacity < 3 + 3 * nb) return ctx->fail(DRV_ERR_INVALID, "drv_debug_host_frame_timeline: capacity < 3 + 3 * bands");
+  DRV_CUDA(cudaStreamSynchronize(ctx->copy_out));
+  DRV_CUDA(cudaStreamSynchronize(ctx->stream));
+  const uint32_t last_light = ctx->num_lights ? ctx->num_lights - 1 : 0;
+  DRV_CUDA(cudaEventElapsedTime(out + 0, ctx->ev_frame_start, ctx->ev_rsm[last_light]));
+  DRV_CUDA(cudaEventElapsedTime(out + 1, ctx->ev_frame_start, ctx->ev_depth));
+  DRV_CUDA(cudaEventElapsedTime(out + 2, ctx->ev_frame_start, ctx->ev_lit));
+  for (uint32_t b = 0; b < nb; ++b) {
+    DRV_CUDA(cudaEventElapsedTime(out + 3 + 3 * b, ctx->ev_frame_start, ctx->ev_band_in[b]));
+    DRV_CUDA(cudaEventElapsedTime(out + 4 + 3 * b, ctx->ev_frame_start, ctx->ev_band_done[b]));
+    DRV_CUDA(cudaEventElapsedTime(out + 5 + 3 * b, ctx->ev_frame_start, ctx->ev_band_out[b]));
+  }
+  *bands = nb;
+  return DRV_OK;
+}
+
 // ---- pipelined end-to-end frame -------------------------------------------------------
 extern "C" drv_status drv_draw_host_frame(drv_ctx* ctx, const drv_host_frame* f) {
   NEED_CTX();
@@ -807,11 +830,14 @@ extern "C" drv_status drv_draw_host_frame(drv_ctx* ctx, const drv_host_frame* f)
   if (!ctx->copy_in) {
     DRV_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
     DRV_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
-    for (auto& e : ctx->ev_rsm) DRV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto& e : ctx->ev_band_in) DRV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto& e : ctx->ev_band_done) DRV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    DRV_CUDA(cudaEventCreateWithFlags(&ctx->ev_depth, cudaEventDisableTiming));
-    DRV_CUDA(cudaEventCreateWithFlags(&ctx->ev_frame_start, cudaEventDisableTiming));
+    // timing events: the same events order the streams and give the frame's timeline (drv_debug_host_frame_timeline)
+    for (auto& e : ctx->ev_rsm) DRV_CUDA(cudaEventCreate(&e));
+    for (auto& e : ctx->ev_band_in) DRV_CUDA(cudaEventCreate(&e));
+    for (auto& e : ctx->ev_band_done) DRV_CUDA(cudaEventCreate(&e));
+    for (auto& e : ctx->ev_band_out) DRV_CUDA(cudaEventCreate(&e));
+    DRV_CUDA(cudaEventCreate(&ctx->ev_depth));
+    DRV_CUDA(cudaEventCreate(&ctx->ev_lit));
+    DRV_CUDA(cudaEventCreate(&ctx->ev_frame_start));
   }
   if (!ctx->st_depth) {
     DRV_CUDA(dmalloc(&ctx->st_depth, px * 4));
@@ -882,6 +908,8 @@ extern "C" drv_status drv_draw_host_frame(drv_ctx* ctx, const drv_host_frame* f)
   if (st == DRV_OK) st = drv_impl_allocate(ctx);
   if (st == DRV_OK) st = drv_light_caches(ctx);
   if (st != DRV_OK) return st;
+  DRV_CUDA(cudaEventRecord(ctx->ev_lit, ctx->stream));
+  ctx->host_frame_bands = bands;
   ctx->stage_begin(DRV_STAGE_APPLY_CACHES);
   for (uint32_t b = 0; b < bands; ++b) {
     const uint32_t y0 = band_y[b], y1 = band_y[b + 1];
@@ -893,6 +921,7 @@ extern "C" drv_status drv_draw_host_frame(drv_ctx* ctx, const drv_host_frame* f)
     const size_t off = (size_t)y0 * W * 8, bytes = (size_t)(y1 - y0) * W * 8;
     DRV_CUDA(cudaMemcpyAsync((uint8_t*)f->hdr_out + off, (const uint8_t*)ctx->hdr16 + off, bytes, cudaMemcpyDeviceToHost,
                              ctx->copy_out));
+    DRV_CUDA(cudaEventRecord(ctx->ev_band_out[b], ctx->copy_out));
   }
   ctx->stage_end(DRV_STAGE_APPLY_CACHES);
   DRV_CUDA(cudaStreamSynchronize(ctx->copy_out));

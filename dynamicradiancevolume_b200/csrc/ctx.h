@@ -137,6 +137,8 @@ struct drv_ctx {
   // host-frame pipeline (drv_draw_host_frame): copy streams + events
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t ev_rsm[DRV_MAX_LIGHTS]{}, ev_depth = nullptr, ev_band_in[32]{}, ev_band_done[32]{}, ev_frame_start = nullptr;
+  cudaEvent_t ev_band_out[32]{}, ev_lit = nullptr; // timeline of the last host frame (drv_debug_host_frame_timeline)
+  uint32_t host_frame_bands = 0;
 
   // drv_draw_frame: light-side stream, fork / join events, recorded frame graph
   cudaStream_t side = nullptr, side2 = nullptr;

@@ -305,6 +305,15 @@ class Context:
         self.check(self.lib.drv_debug_cone_steps(self.handle, C.byref(n)))
         return n.value
 
+    def host_frame_timeline(self):
+        """Timeline of the last draw_host_frame, ms after its first copy was queued: {"rsm_in", "depth_in", "lit",
+        "bands": [(inputs_in, applied, copied_out), ...]}."""
+        buf = (C.c_float * (3 + 3 * 32))()
+        n = C.c_uint32()
+        self.check(self.lib.drv_debug_host_frame_timeline(self.handle, buf, len(buf), C.byref(n)))
+        return {"rsm_in": buf[0], "depth_in": buf[1], "lit": buf[2],
+                "bands": [(buf[3 + 3 * b], buf[4 + 3 * b], buf[5 + 3 * b]) for b in range(n.value)]}
+
     def graph_stats(self):
         """(instantiations, in-place updates) of the frame graph of draw_frame(DRV_FRAME_GRAPH)."""
         a, b = C.c_uint64(), C.c_uint64()

@@ -567,6 +567,11 @@ drv_status drv_debug_gather_trace(drv_ctx* ctx, uint64_t* out, uint32_t capacity
 /* Diagnostics: voxel samples (cone steps) the cone pass has taken since the last call (and resets the count) — the
  * unit of that kernel's roofline record in bench.py. */
 drv_status drv_debug_cone_steps(drv_ctx* ctx, uint64_t* steps);
+/* Diagnostics: timeline of the last drv_draw_host_frame, in ms after its first copy was queued (waits for the
+ * frame): out[0] = RSMs on the device, out[1] = depth on the device, out[2] = caches lit, then for every band b
+ * out[3+3b] = its normals / albedo on the device, out[4+3b] = band applied, out[5+3b] = band back on the host.
+ * capacity >= 3 + 3 * bands (bands <= 32). */
+drv_status drv_debug_host_frame_timeline(drv_ctx* ctx, float* out, uint32_t capacity, uint32_t* bands);
 
 #ifdef __cplusplus
 }

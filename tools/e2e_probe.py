@@ -43,6 +43,10 @@ def main():
             if i >= 3:
                 ts.append(dt)
         out["bands_%d_ms" % bands] = sorted(ts)[len(ts) // 2]
+        if bands in (1, 4):
+            tl = ctx.host_frame_timeline()
+            out["timeline_bands_%d" % bands] = {k: (round(v, 4) if not isinstance(v, list) else [[round(x, 4) for x in b] for b in v])
+                                                for k, v in tl.items()}
     # raw copies of the same buffers, back to back on one stream
     dev = [torch.empty_like(t, device="cuda") for t in h_gb] + [torch.empty_like(t, device="cuda") for r in h_rsm for t in r]
     src = h_gb + [t for r in h_rsm for t in r]
