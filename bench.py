@@ -70,6 +70,8 @@ def parse_args():
                          "(balances the cone pass) or give every rank one contiguous range of the cell-ordered list")
     ap.add_argument("--barrier", choices=["peer", "nccl"], default="peer",
                     help="cross-GPU barrier of sharded runs: flags in NVLink peer memory (drv_peer_barrier) or an NCCL all-reduce")
+    ap.add_argument("--voxel-resolution", type=int, default=0,
+                    help="override the workload's voxel volume resolution (shadowed configs; 256 = the record chain no longer fits L2)")
     return ap.parse_args()
 
 
@@ -83,9 +85,9 @@ def traffic_for(kernel):
         return None
 
 
-def workload_for(index):
+def workload_for(index, voxel_resolution=0):
     import workloads
-    return workloads.config(index)
+    return workloads.config(index, **({"voxel_resolution": voxel_resolution} if voxel_resolution else {}))
 
 
 def workload_name(wl):
@@ -309,7 +311,7 @@ def measure(args, config_index, n_steps, n_warmup, light):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
-    wl = workload_for(args.config).build()
+    wl = workload_for(args.config, args.voxel_resolution).build()
     stream = torch.cuda.Stream(device=local)
     g = workloads.DeviceFrame(wl, device=local, stream=stream, gather_variant=args.variant)
     ctx = g.ctx

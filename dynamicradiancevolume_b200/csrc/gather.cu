@@ -1220,7 +1220,9 @@ __global__ void __launch_bounds__(NW * 32, NW >= 8 ? 1 : 256 / (NW * 32)) gather
 // (cache, VAL block) inside its VPL loop; here all cones of a chunk of caches are traced first, by a kernel
 // whose register budget is the cone march alone (so ~3x the warps per SM of a fused kernel hide the L1/L2
 // latency of the dependent fetches), into table[block][cache] — 25 MB for the 1080p / 16 k-VPL frame, resident
-// in B200's 126 MB L2 until the pair kernel (pass 2) reads every value exactly once, coalesced.
+// in B200's 126 MB L2 until the pair kernel (pass 2) reads every value exactly once, coalesced. Larger frames
+// (configs[3]: 4096 blocks x 21 k caches = 346 MB) spill to HBM: one write and one read of every value, ~0.1 ms of
+// a 7 ms pass at HBM speed.
 struct ConeParams {
   GatherLight lights[DRV_MAX_LIGHTS];
   uint32_t block_offset[DRV_MAX_LIGHTS + 1]; // prefix sum of the lights' block counts

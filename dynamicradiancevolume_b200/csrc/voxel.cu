@@ -209,14 +209,20 @@ struct VoxMipArgs {
 };
 
 __global__ void __launch_bounds__(256) voxel_mip_chain_kernel(VoxMipArgs A) {
-  __shared__ uint8_t s_a[16 * 16 * 16];
+  __shared__ __align__(16) uint8_t s_a[16 * 16 * 16];
   __shared__ uint8_t s_b[8 * 8 * 8];
   const int T = min(A.src_res, 16);
   const int bx = blockIdx.x * T, by = blockIdx.y * T, bz = blockIdx.z * T;
   // stage the tile (rows of T bytes; T is 16 or a smaller power of two)
-  for (int i = threadIdx.x; i < T * T * T; i += blockDim.x) {
-    const int x = i % T, y = (i / T) % T, z = i / (T * T);
-    s_a[i] = A.src[(size_t)(bx + x) + (size_t)A.src_res * ((size_t)(by + y) + (size_t)A.src_res * (bz + z))];
+  if (T == 16) { // a row of the tile is one aligned 16-byte word (every level starts 16-byte aligned: res^3 bytes each)
+    const int y = threadIdx.x & 15, z = threadIdx.x >> 4; // 256 threads = 16 x 16 rows
+    reinterpret_cast<uint4*>(s_a)[threadIdx.x] = *reinterpret_cast<const uint4*>(
+        A.src + (size_t)bx + (size_t)A.src_res * ((size_t)(by + y) + (size_t)A.src_res * (bz + z)));
+  } else {
+    for (int i = threadIdx.x; i < T * T * T; i += blockDim.x) {
+      const int x = i % T, y = (i / T) % T, z = i / (T * T);
+      s_a[i] = A.src[(size_t)(bx + x) + (size_t)A.src_res * ((size_t)(by + y) + (size_t)A.src_res * (bz + z))];
+    }
   }
   __syncthreads();
   uint8_t* cur = s_a;
@@ -252,25 +258,80 @@ struct RecordLevels {
   int levels, res;
 };
 
-__global__ void __launch_bounds__(256) voxel_records_kernel(RecordLevels L, const uint8_t* __restrict__ chain,
-                                                            uint2* __restrict__ records, uint32_t total) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+// Block = 4 record rows (y) x ZB slabs (z) of one level, 64 threads per row. Record x (lower corner x - 1) reads
+// texels max(x-1, 0) and min(x, r-1) per axis: per source row one aligned 32-bit word (texels 4m..4m+3) and the byte
+// before it cover the four records 4m..4m+3, and the ZB slabs share their ZB + 1 source planes — 2 (ZB + 1) x 2 loads,
+// all in flight together, per 4 ZB records (the kernel is latency-bound: a record costs 8 dependent-free byte loads
+// and one store, and 8 000 small blocks ran in ~60 waves). The records pass through shared memory so that the
+// 8-byte stores of a warp are consecutive. blockIdx.y = slab group summed over the levels (RecordRows),
+// blockIdx.x * 4 + threadIdx.y = y; levels with r < 4 take the byte path.
+struct RecordRows {
+  uint32_t z_offset[17]; // first blockIdx.y of level l (level l has ceil((r + 1) / ZB) of them), [levels] = total
+};
+
+template <int ZB>
+__global__ void __launch_bounds__(256) voxel_records_kernel(RecordLevels L, RecordRows R, const uint8_t* __restrict__ chain,
+                                                            uint2* __restrict__ records) {
+  extern __shared__ uint2 s_out[]; // ZB x 4 rows of (level-0 row length + 3) records
   int l = 0;
 #pragma unroll 1
-  while (l + 1 < L.levels && i >= L.offset[l + 1]) ++l;
+  while (l + 1 < L.levels && blockIdx.y >= R.z_offset[l + 1]) ++l;
   const int r = L.res >> l, rp = r + 1;
-  uint32_t j = i - L.offset[l];
-  int x = (int)(j % rp) - 1;
-  int y = (int)((j / rp) % rp) - 1;
-  int z = (int)(j / (rp * rp)) - 1;
+  const int yr = (int)(blockIdx.x * blockDim.y + threadIdx.y), zr0 = (int)(blockIdx.y - R.z_offset[l]) * ZB;
+  if ((int)(blockIdx.x * blockDim.y) >= rp) return; // block-uniform
+  const bool live = yr < rp;
   const uint8_t* lvl = chain + L.chain_offset[l];
-  int x0 = max(x, 0), x1 = min(x + 1, r - 1), y0 = max(y, 0), y1 = min(y + 1, r - 1), z0 = max(z, 0), z1 = min(z + 1, r - 1);
-  auto T = [&](int xx, int yy, int zz) -> uint32_t { return lvl[(size_t)xx + (size_t)r * ((size_t)yy + (size_t)r * zz)]; };
-  uint2 o;
-  o.x = T(x0, y0, z0) | (T(x1, y0, z0) << 8) | (T(x0, y1, z0) << 16) | (T(x1, y1, z0) << 24);
-  o.y = T(x0, y0, z1) | (T(x1, y0, z1) << 8) | (T(x0, y1, z1) << 16) | (T(x1, y1, z1) << 24);
-  records[i] = o;
+  const int ys[2] = {max(yr - 1, 0), min(yr, r - 1)};
+  const int stride = L.res + 4;
+  if (live && r < 4) {
+    for (int zz = 0; zz < ZB && zr0 + zz < rp; ++zz) {
+      const int zr = zr0 + zz, zs[2] = {max(zr - 1, 0), min(zr, r - 1)};
+      for (int x = (int)threadIdx.x; x < rp; x += blockDim.x) {
+        const int x0 = max(x - 1, 0), x1 = min(x, r - 1);
+        auto T = [&](int xx, int k) -> uint32_t { return lvl[(size_t)xx + (size_t)r * ((size_t)ys[k & 1] + (size_t)r * zs[k >> 1])]; };
+        uint2 o;
+        o.x = T(x0, 0) | (T(x1, 0) << 8) | (T(x0, 1) << 16) | (T(x1, 1) << 24);
+        o.y = T(x0, 2) | (T(x1, 2) << 8) | (T(x0, 3) << 16) | (T(x1, 3) << 24);
+        s_out[(size_t)(zz * 4 + threadIdx.y) * stride + x] = o;
+      }
+    }
+  } else if (live) {
+    for (int m = (int)threadIdx.x; 4 * m < rp; m += blockDim.x) {
+      // per source plane a (z = zr0 - 1 + a, clamped) and source row (y0 | y1): bytes [0] = texel 4m-1 (clamped),
+      // [1..4] = texels 4m..4m+3 (clamped to r-1)
+      unsigned long long v[ZB + 1][2];
+#pragma unroll
+      for (int a = 0; a <= ZB; ++a) {
+        const int z = min(max(zr0 - 1 + a, 0), r - 1);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const uint8_t* row = lvl + (size_t)r * ((size_t)ys[k] + (size_t)r * z);
+          const uint32_t prev = row[max(4 * m - 1, 0)];
+          const uint32_t word = 4 * m < r ? *reinterpret_cast<const uint32_t*>(row + 4 * m) : (uint32_t)row[r - 1] * 0x01010101u;
+          v[a][k] = ((unsigned long long)word << 8) | prev;
+        }
+      }
+#pragma unroll
+      for (int zz = 0; zz < ZB; ++zz) {
+        uint2* row_out = s_out + (size_t)(zz * 4 + threadIdx.y) * stride;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { // (up to three slots past the row end are written: the rows are padded)
+          uint2 o;
+          o.x = (uint32_t)((v[zz][0] >> (8 * i)) & 0xffffu) | ((uint32_t)((v[zz][1] >> (8 * i)) & 0xffffu) << 16);
+          o.y = (uint32_t)((v[zz + 1][0] >> (8 * i)) & 0xffffu) | ((uint32_t)((v[zz + 1][1] >> (8 * i)) & 0xffffu) << 16);
+          row_out[4 * m + i] = o;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (live) {
+    for (int zz = 0; zz < ZB && zr0 + zz < rp; ++zz) {
+      const uint2* row_out = s_out + (size_t)(zz * 4 + threadIdx.y) * stride;
+      uint2* out = records + L.offset[l] + ((size_t)(zr0 + zz) * rp + yr) * rp;
+      for (int x = (int)threadIdx.x; x < rp; x += blockDim.x) out[x] = row_out[x];
+    }
+  }
 }
 
 } // namespace
@@ -308,8 +369,21 @@ static drv_status drv_impl_voxel_mips_and_records(drv_ctx* ctx) {
       L.offset[l] = ctx->voxel_record_offset[l];
       L.chain_offset[l] = (uint32_t)voxel_level_offset_bytes((uint32_t)res, l);
     }
-    const uint32_t total = (uint32_t)ctx->voxel_record_count;
-    voxel_records_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(L, ctx->voxel_chain, ctx->voxel_records, total);
+    RecordRows R;
+    memset(&R, 0, sizeof(R));
+    // four slabs per block while 16 rows of records fit the default 48 KB of dynamic shared memory (res <= 256)
+    const uint32_t zb = (size_t)16 * ((size_t)res + 4) * sizeof(uint2) <= 48 * 1024 ? 4u : 1u;
+    uint32_t groups = 0;
+    for (uint32_t l = 0; l < ctx->voxel_levels; ++l) {
+      R.z_offset[l] = groups;
+      groups += (((uint32_t)res >> l) + 1u + zb - 1u) / zb;
+    }
+    R.z_offset[ctx->voxel_levels] = groups;
+    // 64 x 4 threads: 64 groups of four records cover a row of up to 256 records (longer rows loop), 4 rows per block
+    const dim3 grid(((uint32_t)res + 1u + 3u) / 4u, groups), block(64, 4);
+    const size_t smem = (size_t)zb * 4 * ((size_t)res + 4) * sizeof(uint2);
+    if (zb == 4) voxel_records_kernel<4><<<grid, block, smem, ctx->stream>>>(L, R, ctx->voxel_chain, ctx->voxel_records);
+    else voxel_records_kernel<1><<<grid, block, smem, ctx->stream>>>(L, R, ctx->voxel_chain, ctx->voxel_records);
     DRV_LAUNCH_CHECK();
 
   }
