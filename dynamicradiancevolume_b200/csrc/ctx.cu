@@ -804,6 +804,8 @@ extern "C" drv_status drv_debug_host_frame_timeline(drv_ctx* ctx, float* out, ui
   NEED_CTX();
   const uint32_t nb = ctx->host_frame_bands;
   if (!out || !bands || !nb) return ctx->fail(DRV_ERR_NOT_BOUND, "drv_debug_host_frame_timeline: no host frame drawn yet");
+  if (!ctx->host_timeline)
+    return ctx->fail(DRV_ERR_NOT_BOUND, "drv_debug_host_frame_timeline: enable the stage timers before the first drv_draw_host_frame");
   if (capacity < 3 + 3 * nb) return ctx->fail(DRV_ERR_INVALID, "drv_debug_host_frame_timeline: capacity < 3 + 3 * bands");
   DRV_CUDA(cudaStreamSynchronize(ctx->copy_out));
   DRV_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -830,14 +832,17 @@ extern "C" drv_status drv_draw_host_frame(drv_ctx* ctx, const drv_host_frame* f)
   if (!ctx->copy_in) {
     DRV_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
     DRV_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
-    // timing events: the same events order the streams and give the frame's timeline (drv_debug_host_frame_timeline)
-    for (auto& e : ctx->ev_rsm) DRV_CUDA(cudaEventCreate(&e));
-    for (auto& e : ctx->ev_band_in) DRV_CUDA(cudaEventCreate(&e));
-    for (auto& e : ctx->ev_band_done) DRV_CUDA(cudaEventCreate(&e));
-    for (auto& e : ctx->ev_band_out) DRV_CUDA(cudaEventCreate(&e));
-    DRV_CUDA(cudaEventCreate(&ctx->ev_depth));
-    DRV_CUDA(cudaEventCreate(&ctx->ev_lit));
-    DRV_CUDA(cudaEventCreate(&ctx->ev_frame_start));
+    // the events that order the streams also give the frame's timeline (drv_debug_host_frame_timeline) when the
+    // stage timers are on at this point; otherwise they are created without time stamps (cheaper to record)
+    ctx->host_timeline = ctx->timers;
+    const unsigned ef = ctx->host_timeline ? cudaEventDefault : cudaEventDisableTiming;
+    for (auto& e : ctx->ev_rsm) DRV_CUDA(cudaEventCreateWithFlags(&e, ef));
+    for (auto& e : ctx->ev_band_in) DRV_CUDA(cudaEventCreateWithFlags(&e, ef));
+    for (auto& e : ctx->ev_band_done) DRV_CUDA(cudaEventCreateWithFlags(&e, ef));
+    for (auto& e : ctx->ev_band_out) DRV_CUDA(cudaEventCreateWithFlags(&e, ef));
+    DRV_CUDA(cudaEventCreateWithFlags(&ctx->ev_depth, ef));
+    DRV_CUDA(cudaEventCreateWithFlags(&ctx->ev_lit, ef));
+    DRV_CUDA(cudaEventCreateWithFlags(&ctx->ev_frame_start, ef));
   }
   if (!ctx->st_depth) {
     DRV_CUDA(dmalloc(&ctx->st_depth, px * 4));
@@ -908,7 +913,7 @@ extern "C" drv_status drv_draw_host_frame(drv_ctx* ctx, const drv_host_frame* f)
   if (st == DRV_OK) st = drv_impl_allocate(ctx);
   if (st == DRV_OK) st = drv_light_caches(ctx);
   if (st != DRV_OK) return st;
-  DRV_CUDA(cudaEventRecord(ctx->ev_lit, ctx->stream));
+  if (ctx->host_timeline) DRV_CUDA(cudaEventRecord(ctx->ev_lit, ctx->stream));
   ctx->host_frame_bands = bands;
   ctx->stage_begin(DRV_STAGE_APPLY_CACHES);
   for (uint32_t b = 0; b < bands; ++b) {
@@ -921,7 +926,7 @@ extern "C" drv_status drv_draw_host_frame(drv_ctx* ctx, const drv_host_frame* f)
     const size_t off = (size_t)y0 * W * 8, bytes = (size_t)(y1 - y0) * W * 8;
     DRV_CUDA(cudaMemcpyAsync((uint8_t*)f->hdr_out + off, (const uint8_t*)ctx->hdr16 + off, bytes, cudaMemcpyDeviceToHost,
                              ctx->copy_out));
-    DRV_CUDA(cudaEventRecord(ctx->ev_band_out[b], ctx->copy_out));
+    if (ctx->host_timeline) DRV_CUDA(cudaEventRecord(ctx->ev_band_out[b], ctx->copy_out));
   }
   ctx->stage_end(DRV_STAGE_APPLY_CACHES);
   DRV_CUDA(cudaStreamSynchronize(ctx->copy_out));

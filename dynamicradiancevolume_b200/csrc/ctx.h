@@ -139,6 +139,7 @@ struct drv_ctx {
   cudaEvent_t ev_rsm[DRV_MAX_LIGHTS]{}, ev_depth = nullptr, ev_band_in[32]{}, ev_band_done[32]{}, ev_frame_start = nullptr;
   cudaEvent_t ev_band_out[32]{}, ev_lit = nullptr; // timeline of the last host frame (drv_debug_host_frame_timeline)
   uint32_t host_frame_bands = 0;
+  bool host_timeline = false; // the events above carry time stamps (stage timers were on when they were created)
 
   // drv_draw_frame: light-side stream, fork / join events, recorded frame graph
   cudaStream_t side = nullptr, side2 = nullptr;

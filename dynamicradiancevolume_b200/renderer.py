@@ -506,6 +506,12 @@ class Renderer:
         self._rsms = {}
         self._hdr = None
         self._voxel_pending = 0.0
+        # indirect specular (renderer.cpp:43-45, 49): off by default, 16^2 texels per cache, no hole filling
+        self.m_indirectSpecular = False
+        self.m_specularEnvmapPerCacheSize = 16
+        self.m_specularEnvmapMaxFillHolesLevel = 0
+        self.m_specularEnvmapDirectWrite = True
+        self._rough_metal = None
         self.SetCAVCascades(3, 32)
 
     # ---- setters (renderer.hpp:63-141): each invalidates the context like a shader reload ----
@@ -530,6 +536,32 @@ class Renderer:
     def SetReadLightCacheCount(self, track): self.m_readLightCacheCount = bool(track); self.m_lastNumLightCaches = 0
     def GetReadLightCacheCount(self): return self.m_readLightCacheCount
     def GetLightCacheActiveCount(self): return self.m_lastNumLightCaches
+    # indirect specular, renderer.hpp:80-106
+    def SetIndirectSpecular(self, active): self.m_indirectSpecular = bool(active); self._invalidate()
+    def GetIndirectSpecular(self): return self.m_indirectSpecular
+
+    def SetPerCacheSpecularEnvMapSize(self, specularEnvmapPerCacheSize):
+        """renderer.cpp:453-464: a power of two; the hole-fill level is clamped to log2(size)."""
+        size = int(specularEnvmapPerCacheSize)
+        assert size > 0 and size & (size - 1) == 0
+        self.m_specularEnvmapPerCacheSize = size
+        self.m_specularEnvmapMaxFillHolesLevel = min(self.m_specularEnvmapMaxFillHolesLevel, int(math.log2(size)))
+        self._invalidate()
+
+    def GetPerCacheSpecularEnvMapSize(self): return self.m_specularEnvmapPerCacheSize
+
+    def SetSpecularEnvMapHoleFillLevel(self, holeFillLevel):
+        self.m_specularEnvmapMaxFillHolesLevel = min(int(holeFillLevel), int(math.log2(self.m_specularEnvmapPerCacheSize)))
+        self._invalidate()
+
+    def GetSpecularEnvMapHoleFillLevel(self): return self.m_specularEnvmapMaxFillHolesLevel
+
+    def SetSpecularEnvMapDirectWrite(self, directWrite):
+        if not directWrite:  # the shared-exponent register path (#ifndef DIRECT_SPECULAR_MAP_WRITE) is out of scope, DESIGN 7
+            raise NotImplementedError("only the reference's default, direct specular map write, is implemented")
+        self.m_specularEnvmapDirectWrite = True
+
+    def GetSpecularEnvMapDirectWrite(self): return self.m_specularEnvmapDirectWrite
     def GetCAVCascadeCount(self): return len(self.m_CAVCascadeWorldSize)
     def GetCAVResolution(self): return self.m_cavResolution
     def GetCAVCascadeTransitionSize(self): return self.m_CAVCascadeTransitionSize
@@ -561,11 +593,15 @@ class Renderer:
             self._invalidate()
 
     # ---- inputs the reference rasterises itself (DrawSceneToGBuffer / DrawShadowMaps) ----
-    def BindGBuffer(self, depth, normal, diffuse):
-        """Device tensors: depth f32 [H,W]; normal int16 [H,W,2]; diffuse uint8 [H,W,4] (renderer.cpp:727-738)."""
+    def BindGBuffer(self, depth, normal, diffuse, roughnessMetallic=None):
+        """Device tensors: depth f32 [H,W]; normal int16 [H,W,2]; diffuse uint8 [H,W,4]; roughnessMetallic uint8 [H,W,2]
+        (the RG8 attachment, read only with indirect specular) (renderer.cpp:727-738)."""
         self._gbuffer = (depth, normal, diffuse)
+        self._rough_metal = roughnessMetallic
         if self._ctx is not None:
             self._ctx.bind_gbuffer(depth, normal, diffuse)
+            if roughnessMetallic is not None and self.m_indirectSpecular:
+                self._ctx.bind_gbuffer_material(roughnessMetallic)
 
     def BindShadowMap(self, lightIndex, flux, normal, depthLinSq):
         """Level 0 of a light's RSM at rsmResolution (renderer.cpp:1288-1291)."""
@@ -584,9 +620,14 @@ class Renderer:
                                 sh_order=self.m_indirectDiffuseMode, indirect_shadow=self.m_indirectShadow,
                                 cascade_transitions=self.m_CAVCascadeTransitionSize > 0.0, width=self.m_resolution[0],
                                 height=self.m_resolution[1], max_lights=max(1, len(lights)), max_rsm_resolution=max_rsm,
-                                device=self._device, stream=self._stream, gather_variant=self._variant)
+                                device=self._device, stream=self._stream, gather_variant=self._variant,
+                                indirect_specular=self.m_indirectSpecular,
+                                specular_per_cache_size=self.m_specularEnvmapPerCacheSize,
+                                specular_fill_holes_level=self.m_specularEnvmapMaxFillHolesLevel)
             if self._gbuffer is not None:
                 self._ctx.bind_gbuffer(*self._gbuffer)
+                if self._rough_metal is not None and self.m_indirectSpecular:
+                    self._ctx.bind_gbuffer_material(self._rough_metal)
             for i, t in self._rsms.items():
                 self._ctx.bind_rsm(i, *t)
                 self._ctx.prepare_rsm(i)
@@ -597,6 +638,8 @@ class Renderer:
     def UpdateConstantUBO(self):
         c = pack_constant(self.m_resolution[0], self.m_resolution[1], self.m_voxelResolution, self.m_cavResolution,
                           len(self.m_CAVCascadeWorldSize), self.m_maxNumLightCaches)
+        if self.m_indirectSpecular:  # SpecularEnvmap* members, renderer.cpp:317-319
+            pack_specular(c, self.m_maxNumLightCaches, self.m_specularEnvmapPerCacheSize)
         self.m_constant = c
         if self._ctx is not None:
             self._ctx.set_constant(c)
@@ -646,6 +689,10 @@ class Renderer:
 
     def LightCachesRSM(self):
         self.context().light_caches()
+
+    def PrepareSpecularEnvmaps(self):
+        """Renderer::PrepareSpecularEnvmaps (renderer.cpp:994-1045): mip chain of the atlas, then hole filling."""
+        self.context().prepare_specular_envmaps()
 
     def ApplyCaches(self, hdr=None, fmt=abi.DRV_HDR_RGBA16F_ADD):
         import torch
@@ -698,6 +745,8 @@ class Renderer:
         if not detachViewFromCameraUpdate:
             self.AllocateCaches()
             self.LightCachesRSM()
+            if self.m_indirectSpecular:  # renderer.cpp:557-558
+                self.PrepareSpecularEnvmaps()
         if hdr is None and self._hdr is not None:  # glClear(GL_COLOR_BUFFER_BIT), renderer.cpp:562
             if self._tstream is not None:
                 import torch

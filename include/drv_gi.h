@@ -570,7 +570,8 @@ drv_status drv_debug_cone_steps(drv_ctx* ctx, uint64_t* steps);
 /* Diagnostics: timeline of the last drv_draw_host_frame, in ms after its first copy was queued (waits for the
  * frame): out[0] = RSMs on the device, out[1] = depth on the device, out[2] = caches lit, then for every band b
  * out[3+3b] = its normals / albedo on the device, out[4+3b] = band applied, out[5+3b] = band back on the host.
- * capacity >= 3 + 3 * bands (bands <= 32). */
+ * capacity >= 3 + 3 * bands (bands <= 32). The time stamps are taken only if drv_enable_stage_timers(ctx, 1) was
+ * called before the context's first drv_draw_host_frame. */
 drv_status drv_debug_host_frame_timeline(drv_ctx* ctx, float* out, uint32_t capacity, uint32_t* bands);
 
 #ifdef __cplusplus

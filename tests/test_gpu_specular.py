@@ -122,3 +122,50 @@ def test_indirect_specular_needs_its_inputs(cuda_device):
         g.frame()
     assert e.value.status == abi.DRV_ERR_NOT_BOUND
     g.close()
+
+
+def test_renderer_mirror_with_indirect_specular(cuda_device):
+    """The reference-shaped setters (renderer.hpp:80-106) drive the same frame as the context-level calls: Draw with
+    SetIndirectSpecular(true) runs PrepareSpecularEnvmaps between the light and the apply pass (renderer.cpp:557-558)."""
+    import torch
+    wl = workloads.atrium(width=320, height=180, rsm_res=256, read_lod=1, cav_resolution=32, sh_order=1,
+                          max_caches=16384).build()
+    rm = torch.from_numpy(_rough_metal(wl)).cuda()
+    # context-level frame
+    drv.pack_specular(wl.constant, wl.max_caches, 8)
+    g = workloads.DeviceFrame(wl, indirect_specular=True, specular_per_cache_size=8, specular_fill_holes_level=1)
+    g.ctx.set_constant(wl.constant)
+    g.ctx.bind_gbuffer_material(rm)
+    g.prepare_inputs()
+    hdr_ref = torch.zeros(wl.height, wl.width, 4, dtype=torch.float16, device="cuda")
+    g.ctx.draw(hdr_ref, abi.DRV_HDR_RGBA16F_ADD)
+    torch.cuda.synchronize()
+    # the mirror
+    scene = drv.Scene(lights=wl.lights, bbox_min=wl.bbox[0], bbox_max=wl.bbox[1])
+    r = drv.Renderer(scene, (wl.width, wl.height))
+    r.SetCAVCascades(wl.cav_cascades, wl.cav_resolution)
+    for i, s in enumerate(wl.cascade_sizes):
+        r.SetCAVCascadeWorldSize(i, s)
+    r.SetCAVCascadeTransitionSize(wl.transition)
+    r.SetIndirectShadow(False)
+    r.SetMaxCacheCount(wl.max_caches)
+    assert r.GetIndirectSpecular() is False and r.GetPerCacheSpecularEnvMapSize() == 16  # renderer.cpp:43-49
+    r.SetIndirectSpecular(True)
+    r.SetSpecularEnvMapHoleFillLevel(9)
+    assert r.GetSpecularEnvMapHoleFillLevel() == 4  # clamped to log2(16), renderer.hpp:101
+    r.SetPerCacheSpecularEnvMapSize(8)
+    assert r.GetSpecularEnvMapHoleFillLevel() == 3  # re-clamped, renderer.cpp:459
+    r.SetSpecularEnvMapHoleFillLevel(1)
+    with pytest.raises(NotImplementedError):
+        r.SetSpecularEnvMapDirectWrite(False)
+    dev = [torch.from_numpy(a).cuda() for a in (wl.depth, wl.normal, wl.diffuse)]
+    rsm = [torch.from_numpy(a).cuda() for a in wl.rsms[0]]
+    torch.cuda.synchronize()
+    r.BindGBuffer(*dev, roughnessMetallic=rm)
+    r.BindShadowMap(0, *rsm)
+    hdr = r.Draw(wl.camera, False, 0.0)
+    torch.cuda.synchronize()
+    assert r.m_constant.SpecularEnvmapPerCacheSize_Texel == 8
+    assert torch.equal(hdr, hdr_ref)
+    assert float(hdr.float().abs().max()) > 0
+    g.close()

@@ -336,6 +336,36 @@ def test_gather_cone_traced_shadows(cuda_device, sh_order, variant):
     g.close()
 
 
+@pytest.mark.parametrize("shrink", [0.35, 0.6])
+def test_cones_that_leave_the_voxel_volume(cuda_device, shrink):
+    """The voxel volume covers only the middle of the scene, so caches and VAL blocks lie outside it and their cones
+    start, end or run outside: the march's clamp-to-edge path (and the warps that mix it with the clamp-free one)
+    against the oracle's sampler (clamp to edge)."""
+    import dynamicradiancevolume_b200 as drv
+    wl = workloads.cornell(sh_order=1, indirect_shadow=True, voxel_resolution=32).build()
+    lo, hi = np.asarray(wl.bbox[0], np.float64), np.asarray(wl.bbox[1], np.float64)
+    mid, half = (lo + hi) / 2, (hi - lo) / 2 * shrink
+    wl.volume = drv.pack_volume_info(wl.camera, tuple(mid - half), tuple(mid + half), wl.voxel_resolution,
+                                     wl.cav_resolution, wl.cascade_sizes, wl.transition)
+    g, o = workloads.DeviceFrame(wl), OracleFrame(wl)
+    g.prepare_inputs()
+    o.prepare_inputs()
+    assert np.array_equal(g.ctx.read_voxel_chain(), o.chain) and o.chain.any()
+    g.ctx.allocate_caches()
+    g.ctx.light_caches()
+    o.allocate()
+    o.light()
+    n = o.count
+    pos = o.entries[:n, :3]
+    vmin, vmax = np.asarray(wl.volume.VolumeWorldMin[:3]), np.asarray(wl.volume.VolumeWorldMax[:3])
+    outside = ((pos < vmin) | (pos > vmax)).any(axis=1)
+    assert outside.any() and not outside.all()  # both kinds of cone in one frame
+    e = g.ctx.read_entries(n)
+    ok, ratio = close(e[:, 4:], o.entries[:n, 4:])
+    assert ok, "worst |err|/tol = %.3f" % ratio
+    g.close()
+
+
 def test_cone_trace_extremes(cuda_device):
     """Empty volume => shadowing 1 (equals the unshadowed gather); full volume => every SH coefficient 0."""
     torch = _torch()

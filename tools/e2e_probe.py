@@ -26,6 +26,7 @@ def main():
     stream = torch.cuda.Stream()
     g = workloads.DeviceFrame(wl, device=0, stream=stream)
     ctx = g.ctx
+    ctx.enable_stage_timers(True)  # before the first host frame: its events then carry time stamps (the timeline)
     pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
     h_gb = [pin(x) for x in (wl.depth, wl.normal, wl.diffuse)]
     h_rsm = [[pin(x) for x in r] for r in wl.rsms]
