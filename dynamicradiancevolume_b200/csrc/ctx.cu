@@ -113,7 +113,8 @@ extern "C" drv_status drv_create(const drv_config* cfg, drv_ctx** out) {
   if (ctx->voxel_levels > 15) { g_create_error = "drv_create: voxel_resolution too large"; drv_destroy(ctx); return DRV_ERR_INVALID; }
   for (uint32_t l = 0, r = vr; l < ctx->voxel_levels; ++l, r >>= 1) {
     ctx->voxel_record_offset[l] = (uint32_t)ctx->voxel_record_count;
-    ctx->voxel_record_count += (uint64_t)(r + 1) * (r + 1) * (r + 1);
+    const uint64_t d = (uint64_t)r + 1 + 2 * kVoxelRecordPad;
+    ctx->voxel_record_count += d * d * d;
   }
   if (ctx->voxel_record_count >= (1ull << 31)) { g_create_error = "drv_create: voxel_resolution too large"; drv_destroy(ctx); return DRV_ERR_INVALID; }
   if (c.indirect_shadow) {

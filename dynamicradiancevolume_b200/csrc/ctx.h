@@ -204,6 +204,11 @@ drv_status drv_impl_prepare_specular(drv_ctx* ctx);
 drv_status drv_impl_apply_specular(drv_ctx* ctx, void* out, uint32_t format, uint32_t y_begin, uint32_t y_end, bool timed,
                                    const float* srgb_lut_dev);
 constexpr size_t kSyncBytes = 256;
+// Gather-ready voxel records (voxel.cu / voxel_sample.cuh): a level of resolution r holds (r + 1 + 2 kVoxelRecordPad)^3
+// records, one per footprint lower corner in [-1 - pad, r - 1 + pad]^3 (clamp to edge baked in), so that a cone whose
+// samples stray a few voxels outside the volume — caches and lights ON its boundary walls — needs no index clamp.
+// A multiple of 4: the record build reads aligned words.
+constexpr uint32_t kVoxelRecordPad = 4;
 void drv_impl_upload_srgb_lut();
 drv_status drv_impl_build_ndc_tables(drv_ctx* ctx);
 

@@ -273,21 +273,21 @@ __device__ __forceinline__ float cone_trace(const VoxelVol& V, float wx, float w
 //    footprint directly, and level l sees w * 2^-l + (2^-l - 1) — one FFMA, exact for l = 0;
 //  * the "+1" of the record index (records are addressed by lower corner + 1) and the start of the level are one
 //    constant per level (ConeTables::rec_k);
-//  * INSIDE: a cone whose two ends lie inside the volume (by a margin that covers the last step's overshoot) never
-//    leaves it, every lower corner is in [-1, r - 1] at every level, and the clamp disappears: the index is formed
+//  * INSIDE: the record grid is padded by kVoxelRecordPad corners on every side (clamp to edge baked in), so a cone
+//    whose first and last possible sample lie within the padded range needs no clamp at any level: the index is formed
 //    from the raw float bits of the rounded coordinates (the 0x4B400000 bias of all three is folded into
 //    ConeTables::rec_kb). A warp takes this path when all its cones are inside — nearly always: caches and VAL
 //    blocks are surface points of the scene the volume encloses;
 //  * an empty footprint (most of a scene's volume) filters to exactly 0 and occ = fma(1 - occ, 0, occ) is occ, bit
 //    for bit, so unpack + trilinear + blend are skipped.
 struct ConeTables {
-  uint32_t rec_k[16];  // rec_offset[l] + 1 + S + S^2,                     S = (res >> l) + 1
+  uint32_t rec_k[16];  // rec_offset[l] + (1 + pad) (1 + S + S^2),        S = (res >> l) + 1 + 2 pad (kVoxelRecordPad)
   uint32_t rec_kb[16]; // rec_k[l] - 0x4B400000 * (1 + S + S^2)  (mod 2^32)
 };
 
 template <bool INSIDE>
 __device__ __forceinline__ uint32_t record_index(const ConeTables& T, int l, int r, float2 mxy, float mz) {
-  const int S = r + 1;
+  const int S = r + 1 + 2 * (int)kVoxelRecordPad;
   if (INSIDE) // raw bits: 0x4B400000 + corner each; the bias is in rec_kb (unsigned: the sum wraps by design)
     return __float_as_uint(mxy.x) + (uint32_t)S * (__float_as_uint(mxy.y) + (uint32_t)S * __float_as_uint(mz)) + T.rec_kb[l];
   const int x = min(max(__float_as_int(mxy.x) - 0x4B400000, -1), r - 1);
@@ -385,13 +385,15 @@ __device__ __forceinline__ float cone_trace_simple(const VoxelVol& V, const Cone
   const float distVox = ex_div(lightDist, V.voxel_size);
   const float goal = ex_sub(distVox, 2.0f);                                         // :206
   const float radToStep = ex_div(2.0f, ex_sub(1.0f, kk));                           // :209
-  // Inside test. The last sample lies less than one step beyond `goal`, and no step is longer than
-  // max(1, goal * kk * radToStep): both ends of [cache, light + overshoot] inside the texel range [0, res] (w in
-  // [-1, res - 1]) by that margin (+1 for rounding) => every sample is. NaN / inf fail the comparisons.
-  const float over = fmaxf(1.0f, distVox * kk * radToStep) + 1.0f;
-  const float hi = (float)V.res - 1.0f - over, lo = over - 1.0f;
-  const float ex = fmaf(dxy.x, distVox, sx), ey = fmaf(dxy.y, distVox, sy), ez = fmaf(dz, distVox, sz);
-  const bool inside = sx >= lo && sx <= hi && sy >= lo && sy <= hi && sz >= lo && sz <= hi &&
+  // Inside test. Every sample lies on the segment from the start position to less than one step beyond the light
+  // (the march starts two voxels in and ends at the first distance >= lightDist - 2), and no step is longer than
+  // max(1, lightDist * kk * radToStep). The record grid holds the lower corners [-1 - pad, res - 1 + pad] (ctx.h), a
+  // corner is round(w), and level l sees (w + 1) 2^-l - 1: both ends of the segment within that range, less half
+  // a voxel for the rounding => every corner of every level is. NaN / inf fail the comparisons.
+  const float over = fmaxf(1.0f, distVox * kk * radToStep);
+  const float lo = -0.5f - (float)kVoxelRecordPad, hi = (float)V.res - 1.5f + (float)kVoxelRecordPad;
+  const float ex = fmaf(dxy.x, distVox + over, sx), ey = fmaf(dxy.y, distVox + over, sy), ez = fmaf(dz, distVox + over, sz);
+  const bool inside = cxy.x >= lo && cxy.x <= hi && cxy.y >= lo && cxy.y <= hi && cz >= lo && cz <= hi &&
                       ex >= lo && ex <= hi && ey >= lo && ey <= hi && ez >= lo && ez <= hi;
   if (__all_sync(__activemask(), inside))
     return cone_march<true>(V, T, dxy, dz, cxy, cz, kk, goal, radToStep, steps);
@@ -1595,8 +1597,8 @@ drv_status drv_impl_gather(drv_ctx* ctx, bool overwrite) {
   c.rec = ctx->voxel_records;
   for (int l = 0; l < 16; ++l) {
     c.rec_offset[l] = ctx->voxel_record_offset[l];
-    const uint32_t S = ((uint32_t)ctx->cfg.voxel_resolution >> l) + 1u, K = 1u + S + S * S;
-    c.tables.rec_k[l] = c.rec_offset[l] + K;
+    const uint32_t S = ((uint32_t)ctx->cfg.voxel_resolution >> l) + 1u + 2u * kVoxelRecordPad, K = 1u + S + S * S;
+    c.tables.rec_k[l] = c.rec_offset[l] + (1u + kVoxelRecordPad) * K;
     c.tables.rec_kb[l] = c.tables.rec_k[l] - 0x4B400000u * K;
   }
   c.vres = (int)ctx->cfg.voxel_resolution;

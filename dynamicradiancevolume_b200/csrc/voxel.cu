@@ -258,36 +258,41 @@ struct RecordLevels {
   int levels, res;
 };
 
-// Block = 4 record rows (y) x ZB slabs (z) of one level, 64 threads per row. Record x (lower corner x - 1) reads
-// texels max(x-1, 0) and min(x, r-1) per axis: per source row one aligned 32-bit word (texels 4m..4m+3) and the byte
-// before it cover the four records 4m..4m+3, and the ZB slabs share their ZB + 1 source planes — 2 (ZB + 1) x 2 loads,
-// all in flight together, per 4 ZB records (the kernel is latency-bound: a record costs 8 dependent-free byte loads
-// and one store, and 8 000 small blocks ran in ~60 waves). The records pass through shared memory so that the
-// 8-byte stores of a warp are consecutive. blockIdx.y = slab group summed over the levels (RecordRows),
-// blockIdx.x * 4 + threadIdx.y = y; levels with r < 4 take the byte path.
+// Block = 4 record rows (y) x ZB slabs (z) of one level, 64 threads per row. The record grid of a level is padded:
+// D = r + 1 + 2 P records per axis (P = kVoxelRecordPad), record x <-> lower corner x - 1 - P, which reads texels
+// clamp(x - 1 - P) and clamp(x - P) per axis (clamp to [0, r - 1]). Per source row one aligned 32-bit word (texels
+// 4m-4..4m-1; P is a multiple of 4) and the byte before it cover the four records 4m..4m+3, and the ZB slabs share
+// their ZB + 1 source planes — 2 (ZB + 1) x 2 loads, all in flight together, per 4 ZB records (the kernel is
+// latency-bound: a record costs 8 dependent-free byte loads and one store, and 8 000 small blocks ran in ~60
+// waves). The records pass through shared memory so that the 8-byte stores of a warp are consecutive.
+// blockIdx.y = slab group summed over the levels (RecordRows), blockIdx.x * 4 + threadIdx.y = y; levels with r < 4
+// take the byte path.
 struct RecordRows {
-  uint32_t z_offset[17]; // first blockIdx.y of level l (level l has ceil((r + 1) / ZB) of them), [levels] = total
+  uint32_t z_offset[17]; // first blockIdx.y of level l (level l has ceil(D / ZB) of them), [levels] = total
 };
 
 template <int ZB>
 __global__ void __launch_bounds__(256) voxel_records_kernel(RecordLevels L, RecordRows R, const uint8_t* __restrict__ chain,
                                                             uint2* __restrict__ records) {
   extern __shared__ uint2 s_out[]; // ZB x 4 rows of (level-0 row length + 3) records
+  constexpr int P = (int)kVoxelRecordPad;
+  static_assert(P % 4 == 0, "the word loads of the record build need a pad that is a multiple of 4");
   int l = 0;
 #pragma unroll 1
   while (l + 1 < L.levels && blockIdx.y >= R.z_offset[l + 1]) ++l;
-  const int r = L.res >> l, rp = r + 1;
+  const int r = L.res >> l, D = r + 1 + 2 * P;
   const int yr = (int)(blockIdx.x * blockDim.y + threadIdx.y), zr0 = (int)(blockIdx.y - R.z_offset[l]) * ZB;
-  if ((int)(blockIdx.x * blockDim.y) >= rp) return; // block-uniform
-  const bool live = yr < rp;
+  if ((int)(blockIdx.x * blockDim.y) >= D) return; // block-uniform
+  const bool live = yr < D;
   const uint8_t* lvl = chain + L.chain_offset[l];
-  const int ys[2] = {max(yr - 1, 0), min(yr, r - 1)};
-  const int stride = L.res + 4;
+  auto clampt = [&](int t) { return min(max(t, 0), r - 1); };
+  const int ys[2] = {clampt(yr - 1 - P), clampt(yr - P)};
+  const int stride = L.res + 1 + 2 * P + 3;
   if (live && r < 4) {
-    for (int zz = 0; zz < ZB && zr0 + zz < rp; ++zz) {
-      const int zr = zr0 + zz, zs[2] = {max(zr - 1, 0), min(zr, r - 1)};
-      for (int x = (int)threadIdx.x; x < rp; x += blockDim.x) {
-        const int x0 = max(x - 1, 0), x1 = min(x, r - 1);
+    for (int zz = 0; zz < ZB && zr0 + zz < D; ++zz) {
+      const int zr = zr0 + zz, zs[2] = {clampt(zr - 1 - P), clampt(zr - P)};
+      for (int x = (int)threadIdx.x; x < D; x += blockDim.x) {
+        const int x0 = clampt(x - 1 - P), x1 = clampt(x - P);
         auto T = [&](int xx, int k) -> uint32_t { return lvl[(size_t)xx + (size_t)r * ((size_t)ys[k & 1] + (size_t)r * zs[k >> 1])]; };
         uint2 o;
         o.x = T(x0, 0) | (T(x1, 0) << 8) | (T(x0, 1) << 16) | (T(x1, 1) << 24);
@@ -296,18 +301,20 @@ __global__ void __launch_bounds__(256) voxel_records_kernel(RecordLevels L, Reco
       }
     }
   } else if (live) {
-    for (int m = (int)threadIdx.x; 4 * m < rp; m += blockDim.x) {
-      // per source plane a (z = zr0 - 1 + a, clamped) and source row (y0 | y1): bytes [0] = texel 4m-1 (clamped),
-      // [1..4] = texels 4m..4m+3 (clamped to r-1)
+    for (int m = (int)threadIdx.x; 4 * m < D; m += blockDim.x) {
+      // per source plane a (z = zr0 - 1 - P + a, clamped) and source row (y0 | y1): bytes [0] = texel t0 - 1,
+      // [1..4] = texels t0..t0+3 with t0 = 4m - P (all clamped to [0, r-1]; t0 is a multiple of 4)
+      const int t0 = 4 * m - P;
       unsigned long long v[ZB + 1][2];
 #pragma unroll
       for (int a = 0; a <= ZB; ++a) {
-        const int z = min(max(zr0 - 1 + a, 0), r - 1);
+        const int z = clampt(zr0 - 1 - P + a);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const uint8_t* row = lvl + (size_t)r * ((size_t)ys[k] + (size_t)r * z);
-          const uint32_t prev = row[max(4 * m - 1, 0)];
-          const uint32_t word = 4 * m < r ? *reinterpret_cast<const uint32_t*>(row + 4 * m) : (uint32_t)row[r - 1] * 0x01010101u;
+          const uint32_t prev = row[clampt(t0 - 1)];
+          const uint32_t word = (t0 >= 0 && t0 < r) ? *reinterpret_cast<const uint32_t*>(row + t0)
+                                                    : (uint32_t)row[t0 < 0 ? 0 : r - 1] * 0x01010101u;
           v[a][k] = ((unsigned long long)word << 8) | prev;
         }
       }
@@ -326,10 +333,10 @@ __global__ void __launch_bounds__(256) voxel_records_kernel(RecordLevels L, Reco
   }
   __syncthreads();
   if (live) {
-    for (int zz = 0; zz < ZB && zr0 + zz < rp; ++zz) {
+    for (int zz = 0; zz < ZB && zr0 + zz < D; ++zz) {
       const uint2* row_out = s_out + (size_t)(zz * 4 + threadIdx.y) * stride;
-      uint2* out = records + L.offset[l] + ((size_t)(zr0 + zz) * rp + yr) * rp;
-      for (int x = (int)threadIdx.x; x < rp; x += blockDim.x) out[x] = row_out[x];
+      uint2* out = records + L.offset[l] + ((size_t)(zr0 + zz) * D + yr) * D;
+      for (int x = (int)threadIdx.x; x < D; x += blockDim.x) out[x] = row_out[x];
     }
   }
 }
@@ -371,17 +378,18 @@ static drv_status drv_impl_voxel_mips_and_records(drv_ctx* ctx) {
     }
     RecordRows R;
     memset(&R, 0, sizeof(R));
+    const uint32_t d0 = (uint32_t)res + 1u + 2u * kVoxelRecordPad; // records per axis of level 0
     // four slabs per block while 16 rows of records fit the default 48 KB of dynamic shared memory (res <= 256)
-    const uint32_t zb = (size_t)16 * ((size_t)res + 4) * sizeof(uint2) <= 48 * 1024 ? 4u : 1u;
+    const uint32_t zb = (size_t)16 * ((size_t)d0 + 3) * sizeof(uint2) <= 48 * 1024 ? 4u : 1u;
     uint32_t groups = 0;
     for (uint32_t l = 0; l < ctx->voxel_levels; ++l) {
       R.z_offset[l] = groups;
-      groups += (((uint32_t)res >> l) + 1u + zb - 1u) / zb;
+      groups += (((uint32_t)res >> l) + 1u + 2u * kVoxelRecordPad + zb - 1u) / zb;
     }
     R.z_offset[ctx->voxel_levels] = groups;
     // 64 x 4 threads: 64 groups of four records cover a row of up to 256 records (longer rows loop), 4 rows per block
-    const dim3 grid(((uint32_t)res + 1u + 3u) / 4u, groups), block(64, 4);
-    const size_t smem = (size_t)zb * 4 * ((size_t)res + 4) * sizeof(uint2);
+    const dim3 grid((d0 + 3u) / 4u, groups), block(64, 4);
+    const size_t smem = (size_t)zb * 4 * ((size_t)d0 + 3) * sizeof(uint2);
     if (zb == 4) voxel_records_kernel<4><<<grid, block, smem, ctx->stream>>>(L, R, ctx->voxel_chain, ctx->voxel_records);
     else voxel_records_kernel<1><<<grid, block, smem, ctx->stream>>>(L, R, ctx->voxel_chain, ctx->voxel_records);
     DRV_LAUNCH_CHECK();

@@ -3,6 +3,7 @@
 // (gather.cu) and the cone-traced ambient occlusion (adjacent.cu).
 #pragma once
 
+#include "ctx.h"
 #include "device_math.cuh"
 
 namespace drvk {
@@ -10,8 +11,8 @@ namespace drvk {
 // ---------------------------------------------------------------- cone trace
 // The voxel chain is read through its gather-ready copy (voxel.cu: voxel_records_kernel): one 64-bit load
 // returns the eight clamp-to-edge texels of a trilinear footprint, instead of eight byte loads with per-corner
-// address clamping. Records of level l start at rec_offset[l]; a level holds (r+1)^3 of them, indexed by the
-// footprint's lower corner + 1.
+// address clamping. Records of level l start at rec_offset[l]; a level holds (r + 1 + 2 pad)^3 of them, indexed by the
+// footprint's lower corner + 1 + pad (kVoxelRecordPad, ctx.h).
 struct VoxelVol {
   const uint2* rec;
   const uint32_t* rec_offset; // GatherParams::rec_offset in the kernel's constant bank (LDC with a register index)
@@ -75,7 +76,9 @@ __device__ __forceinline__ Footprint footprint(const VoxelVol& V, int l, float2 
   x = min(max(x, -1), r - 1) + 1;
   y = min(max(y, -1), r - 1) + 1;
   z = min(max(z, -1), r - 1) + 1;
-  F.index = V.rec_offset[l] + (uint32_t)(x + (r + 1) * (y + (r + 1) * z));
+  constexpr int P = (int)kVoxelRecordPad; // the record grid is padded by P corners on every side (ctx.h)
+  const int D = r + 1 + 2 * P;
+  F.index = V.rec_offset[l] + (uint32_t)((x + P) + D * ((y + P) + D * (z + P)));
   return F;
 }
 
