@@ -37,10 +37,10 @@ struct AllocParams {
   float inv_voxel[DRV_MAX_CASCADES];
 };
 
-constexpr int kGroups = 2;                    // 8-cell groups per thread of the scan + compact kernel
-constexpr int kCellsPerThread = 8 * kGroups;
+// scan + compact kernel: 256 threads, GROUPS 8-cell groups per thread. 2 (4096 cells per tile) for frame-sized
+// grids; 4 / 8 when 4096-cell tiles would be more than the GPU holds at once (a second wave of tiles can only start
+// when first-wave blocks retire, and those wait for their own look-back: 4 x 128^3 cells = 2048 tiles took 47 us)
 constexpr int kScanThreads = 256;
-constexpr int kCellsPerBlock = kCellsPerThread * kScanThreads; // 4096
 
 // ndc tables: ((i + .5) / N) * 2 - 1, cacheGather.comp:113-116
 __global__ void ndc_table_kernel(float* __restrict__ out, int W, int H) {
@@ -173,13 +173,14 @@ struct ScanState {
 };
 constexpr uint32_t kFlagAggregate = 1u, kFlagPrefix = 2u;
 
-template <int STRIDE, bool ZERO_SH>
+template <int STRIDE, bool ZERO_SH, int kGroups>
 __global__ void __launch_bounds__(kScanThreads) scan_compact_kernel(AllocParams p, uint8_t* __restrict__ flags,
                                                                     uint32_t num_cells, ScanState st, uint32_t max_caches,
                                                                     uint32_t* __restrict__ atlas, uint8_t* __restrict__ entries,
                                                                     drv_cache_counter* __restrict__ counter,
                                                                     uint32_t* __restrict__ stats) {
   constexpr int NW = kScanThreads / 32;
+  constexpr int kCellsPerThread = 8 * kGroups;
   __shared__ uint32_t warp_tot[NW];
   __shared__ uint32_t s_prefix, s_tile;
   __shared__ uint32_t lb_sum[NW];   // look-back: per warp, the values up to (and including) its nearest inclusive prefix
@@ -468,10 +469,17 @@ drv_status drv_impl_allocate_compact(drv_ctx* ctx, bool zero_sh) {
   st.words = ctx->scan_words;
   st.epoch = ctx->scan_epoch;
   st.oob_accum = ctx->scan_epoch + 2;
-#define DRV_SCAN(ST, Z) scan_compact_kernel<ST, Z><<<ctx->num_scan_blocks, kScanThreads, 0, ctx->stream>>>( \
+#define DRV_SCAN_G(ST, Z, G) scan_compact_kernel<ST, Z, G><<<(ctx->num_cells + 2048u * G - 1u) / (2048u * G), kScanThreads, 0, ctx->stream>>>( \
     p, ctx->cell_flags, ctx->num_cells, st, ctx->cfg.max_cache_count, ctx->atlas, ctx->entries, ctx->counter, ctx->stats)
+  // tiles per launch <= what one wave of resident blocks covers (8 blocks of 256 threads per SM). Measured (stage
+  // AllocateCaches): 4 x 128^3 cells 154 -> 144 us with 8192-cell tiles (152 with 16384), 2 x 256^3 cells 169 -> 115 us
+  // with 16384-cell tiles (119 with 32768)
+  const uint32_t wave = (uint32_t)ctx->num_sms * 8u;
+  const int groups = ctx->num_scan_blocks <= wave ? 2 : (ctx->num_scan_blocks <= 2 * wave ? 4 : 8);
+#define DRV_SCAN(ST, Z) do { if (groups == 2) DRV_SCAN_G(ST, Z, 2); else if (groups == 4) DRV_SCAN_G(ST, Z, 4); else DRV_SCAN_G(ST, Z, 8); } while (0)
   if (ctx->entry_stride == 64) { if (zero_sh) DRV_SCAN(64, true); else DRV_SCAN(64, false); }
   else { if (zero_sh) DRV_SCAN(128, true); else DRV_SCAN(128, false); }
+#undef DRV_SCAN_G
 #undef DRV_SCAN
   DRV_LAUNCH_CHECK();
   ctx->stage_end(DRV_STAGE_ALLOCATE_CACHES);
