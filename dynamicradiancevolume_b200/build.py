@@ -66,8 +66,9 @@ def build_host():
 
 
 def build_aux():
-    """Build the test/bench helper libraries (oracle, scenes) with make."""
-    for d in ("oracle", "scenes"):
+    """Build the test/bench helper libraries (oracle, scenes) and the C++ test of the host-side mirror
+    (tests/cpp: drv::Renderer of include/drv_renderer.hpp against the oracle) with make."""
+    for d in ("oracle", "scenes", os.path.join("tests", "cpp")):
         r = subprocess.run(["make", "-C", os.path.join(ROOT, d)], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("make -C %s failed:\n%s\n%s" % (d, r.stdout, r.stderr))

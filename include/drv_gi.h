@@ -68,7 +68,7 @@ typedef struct drv_constant {
   int32_t AddressVolumeResolution;/* @52 */
   int32_t NumAddressVolumeCascades;/* @56 */
   uint32_t MaxNumLightCaches;     /* @60 (never read by the shaders) */
-  int32_t SpecularEnvmapTotalSize;            /* @64 unused: INDIRECT_SPECULAR is out of scope */
+  int32_t SpecularEnvmapTotalSize;            /* @64 read only with drv_config.indirect_specular (drv_pack_specular) */
   int32_t SpecularEnvmapPerCacheSize_Texel;   /* @68 */
   float SpecularEnvmapPerCacheSize_Texcoord;  /* @72 */
   int32_t SpecularEnvmapNumCachesPerDimension;/* @76 */
