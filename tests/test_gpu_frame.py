@@ -369,13 +369,15 @@ def test_frame_graph_survives_a_moving_camera(cuda_device):
     g.close()
 
 
-def test_config2_with_256_cubed_voxels(cuda_device):
-    """BASELINE configs[2] with the voxel volume at 256^3 (the reference's own sweep goes up to 512^3,
-    application.cpp:296-592): chain and gather-ready records (136 MB, past the 126 MB L2) bit-exact / within the
-    gate, SH on every 16th entry, the whole image through the oracle's apply pass."""
+@pytest.mark.parametrize("res", [256, 512])
+def test_config2_with_larger_voxel_volumes(cuda_device, res):
+    """BASELINE configs[2] with the voxel volume at 256^3 and 512^3 (the reference's own sweep and its UI go up to
+    512^3, application.cpp:345, tweakbarsetup.cpp:185): chain bit-exact, gather-ready records (175 MB / 1.3 GB, past
+    the 126 MB L2) exercised by the cone pass: SH on every 16th entry within the gate, the whole image through the
+    oracle's apply pass."""
     import torch
     from oracle.subsample import check_frame
-    wl = workloads.config(2, voxel_resolution=256).build()
+    wl = workloads.config(2, voxel_resolution=res).build()
     g = workloads.DeviceFrame(wl)
     g.prepare_inputs()
     g.frame()

@@ -137,7 +137,8 @@ def test_vpl_generation(cuda_device, shadow):
 
 
 # ---------------------------------------------------------------------------- stage 3: voxels
-@pytest.mark.parametrize("scene,res", [("cornell", 64), ("atrium", 128), ("atrium", 32), ("atrium", 256)])
+@pytest.mark.parametrize("scene,res", [("cornell", 64), ("atrium", 128), ("atrium", 32), ("atrium", 256),
+                                       ("atrium", 512)])  # 512^3: the top of the reference's range (tweakbarsetup.cpp:185)
 def test_voxelize_blend_mips_bit_exact(cuda_device, scene, res):
     wl = (workloads.cornell(indirect_shadow=True, voxel_resolution=res) if scene == "cornell" else
           workloads.atrium(width=64, height=64, rsm_res=64, read_lod=0, indirect_shadow=True, voxel_resolution=res))
