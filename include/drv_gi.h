@@ -288,7 +288,13 @@ drv_status drv_set_voxel_volume(drv_ctx* ctx, const uint8_t* level0);
 drv_status drv_allocate_caches(drv_ctx* ctx);
 
 /* ≙ Renderer::LightCachesRSM (renderer.cpp:899-933): for every light, VPL
- * generation + cacheLightingRSM.comp; results accumulate into the entries. */
+ * generation + cacheLightingRSM.comp; results accumulate into the entries.
+ * Scratch memory, grown on demand by the first call that needs it (that call synchronises the stream once and is
+ * therefore never part of a recorded frame graph — drv_draw_frame runs one eager frame first): the partial sums of
+ * the pair kernel (CTAs x 2 x coefficients x tile entries floats: 2.7 MB for SH1, 4.1 MB for SH2 on 148 SMs), and with indirect_shadow the visibility table, one float per
+ * (shadow block, cache): total_blocks x min(262144, max_cache_count rounded up to 512) x 4 B, capped at 6 GiB by
+ * halving the cache chunk (the frame then walks the entries in chunks). BASELINE configs[2]: 1024 x 65536 x 4 B =
+ * 256 MB; configs[3]: 4096 x 262144 x 4 B = 4 GiB. */
 drv_status drv_light_caches(drv_ctx* ctx);
 
 /* ≙ Renderer::ApplyCaches (renderer.cpp:1047-1079): cacheApply.frag. */
