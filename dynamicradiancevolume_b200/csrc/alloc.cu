@@ -61,13 +61,18 @@ __device__ __forceinline__ int compute_cascade(const AllocParams& p, F3 wp) {
   return c;
 }
 
-// lightcache.glsl:125-134
-__device__ __forceinline__ float cascade_transition(const AllocParams& p, F3 wp, int c) {
+// lightcache.glsl:125-134, as the allocation uses it (cacheGather.comp:133-134): only whether the transition is > 0.
+// saturate(1 - minDist / d) > 0  <=>  fl(minDist / d) < 1  <=>  minDist < d  for a correctly rounded division by a
+// positive finite d (the largest float below d divided by d rounds to at most 1 - 2^-24; 1 - q is then exact and
+// positive) — so the division is only evaluated when d is not a positive number (zone <= 0, NaN).
+__device__ __forceinline__ bool in_cascade_transition(const AllocParams& p, F3 wp, int c) {
   const drv_cav_cascade& k = p.casc[c];
   float ax = ex_sub(k.DecisionMax[0], wp.x), ay = ex_sub(k.DecisionMax[1], wp.y), az = ex_sub(k.DecisionMax[2], wp.z);
   float bx = ex_sub(wp.x, k.DecisionMin[0]), by = ex_sub(wp.y, k.DecisionMin[1]), bz = ex_sub(wp.z, k.DecisionMin[2]);
   float minDist = fminf(fminf(fminf(ax, ay), az), fminf(fminf(bx, by), bz));
-  return saturatef(ex_sub(1.0f, ex_div(minDist, ex_mul(k.WorldVoxelSize, p.zone))));
+  const float d = ex_mul(k.WorldVoxelSize, p.zone);
+  if (d > 0.0f && d <= 3.0e38f) return minDist < d;
+  return saturatef(ex_sub(1.0f, ex_div(minDist, d))) > 0.0f;
 }
 
 // cacheGather.comp:20-30; the cell is kept as (x,y,z) packed 10:10:10 next to its linear id
@@ -133,8 +138,7 @@ __global__ void __launch_bounds__(256) mark_kernel(AllocParams p, const float* _
       casc = compute_cascade(p, wp);
       own = cache_cell(p, wp, casc);
       if (p.transitions && casc < p.C - 1) {
-        float t = cascade_transition(p, wp, casc);
-        if (t > 0.0f) own2 = cache_cell(p, wp, casc + 1);
+        if (in_cascade_transition(p, wp, casc)) own2 = cache_cell(p, wp, casc + 1);
       }
     }
   }

@@ -45,7 +45,11 @@ __device__ __forceinline__ float cascade_transition(const ApplyParams& p, F3 wp,
   float ax = ex_sub(k.DecisionMax[0], wp.x), ay = ex_sub(k.DecisionMax[1], wp.y), az = ex_sub(k.DecisionMax[2], wp.z);
   float bx = ex_sub(wp.x, k.DecisionMin[0]), by = ex_sub(wp.y, k.DecisionMin[1]), bz = ex_sub(wp.z, k.DecisionMin[2]);
   float minDist = fminf(fminf(fminf(ax, ay), az), fminf(fminf(bx, by), bz));
-  return saturatef(ex_sub(1.0f, ex_div(minDist, ex_mul(k.WorldVoxelSize, p.zone))));
+  // Outside the transition zone — nearly every pixel — the division is not needed: for a positive finite d and
+  // minDist >= d the correctly rounded quotient is >= 1, so saturate(1 - q) is exactly +0 (NaN saturates to 0 too).
+  const float d = ex_mul(k.WorldVoxelSize, p.zone);
+  if (d > 0.0f && d <= 3.0e38f && !(minDist < d)) return 0.0f;
+  return saturatef(ex_sub(1.0f, ex_div(minDist, d)));
 }
 
 // SampleCacheIrradiance, lightcache.glsl:137-183. nb* = the per-pixel normal
@@ -56,10 +60,14 @@ struct NormalBasis {
   float b2xy, b2yz, b20, b2xz, b2dd;   // band 2
 };
 
-// One corner: entry `address` weighted by w. Branch-free: a corner without a cache (`valid` false) reads entry 0
-// — always inside the buffer — and selects zero irradiance, so the 24 (56) entry loads of a pixel are independent
-// of each other and of the atlas contents and can all be in flight together.
-template <int ORDER>
+// One corner: entry `address` weighted by w. Branch-free, so the 24 (56) entry loads of a pixel are independent of
+// each other and of the atlas contents and can all be in flight together. A corner without a cache (`valid` false):
+//  * SH2 (ZERO_SLOT false): reads entry 0 — always inside the buffer — and selects zero irradiance;
+//  * SH1 (ZERO_SLOT true): `address` is max_cache_count. The LightCacheBuffer is max_cache_count x 128 bytes whatever
+//    the mode (renderer.cpp:266-269), SH1 entries are 64 bytes, so slot max_cache_count lies in the half of the
+//    buffer no stage ever writes: zeros since drv_create. Its irradiance is max(+0, 0) = 0 and fma(0, w, r) == r bit
+//    for bit — no selects, and the address is one unsigned min instead of a compare + select.
+template <int ORDER, bool ZERO_SLOT>
 __device__ __forceinline__ void accumulate_corner(const ApplyParams& p, const uint8_t* __restrict__ entries,
                                                   uint32_t address, bool valid, const NormalBasis<ORDER>& nb, float w,
                                                   float& r, float& g, float& b) {
@@ -80,9 +88,15 @@ __device__ __forceinline__ void accumulate_corner(const ApplyParams& p, const ui
     ir = fmaf(q7.x, nb.b2dd, ir);  ig = fmaf(q7.y, nb.b2dd, ig);  ib = fmaf(q7.z, nb.b2dd, ib);
   }
   // max(irradiance, 0) then * weight, lightcache.glsl:178, cacheApply.frag:110; no cache -> exactly zero
-  r = fmaf(valid ? fmaxf(ir, 0.0f) : 0.0f, w, r);
-  g = fmaf(valid ? fmaxf(ig, 0.0f) : 0.0f, w, g);
-  b = fmaf(valid ? fmaxf(ib, 0.0f) : 0.0f, w, b);
+  if (ZERO_SLOT) {
+    r = fmaf(fmaxf(ir, 0.0f), w, r);
+    g = fmaf(fmaxf(ig, 0.0f), w, g);
+    b = fmaf(fmaxf(ib, 0.0f), w, b);
+  } else {
+    r = fmaf(valid ? fmaxf(ir, 0.0f) : 0.0f, w, r);
+    g = fmaf(valid ? fmaxf(ig, 0.0f) : 0.0f, w, g);
+    b = fmaf(valid ? fmaxf(ib, 0.0f) : 0.0f, w, b);
+  }
 }
 
 // ComputeLightingFromCaches, cacheApply.frag:28-118 (before the * diffuse / PI).
@@ -123,8 +137,12 @@ __device__ __forceinline__ void lighting_from_caches(const ApplyParams& p, const
   for (int i = 0; i < 8; ++i) { // offsets in cacheApply.frag:43-54 order: x fastest, then y, then z
     const float w = wxy[i & 3] * ((i >> 2) ? fz : gz);
     const uint32_t address = addr[i] - 1u; // atlas 0 -> 0xFFFFFFFF: no cache, contributes zero
-    const bool valid = address < p.max_caches;
-    accumulate_corner<ORDER>(p, entries, valid ? address : 0u, valid, nb, w, r, g, b);
+    if (ORDER == 1) { // the never-written slot max_caches of the SH1 layout stands in for "no cache"
+      accumulate_corner<ORDER, true>(p, entries, min(address, p.max_caches), true, nb, w, r, g, b);
+    } else {
+      const bool valid = address < p.max_caches;
+      accumulate_corner<ORDER, false>(p, entries, valid ? address : 0u, valid, nb, w, r, g, b);
+    }
   }
 }
 
