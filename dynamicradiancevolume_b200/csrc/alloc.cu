@@ -54,8 +54,9 @@ __device__ __forceinline__ int compute_cascade(const AllocParams& p, F3 wp) {
   int c = 0;
   for (; c < p.C - 1; ++c) {
     const drv_cav_cascade& k = p.casc[c];
-    if (wp.x <= k.DecisionMax[0] && wp.y <= k.DecisionMax[1] && wp.z <= k.DecisionMax[2] &&
-        wp.x >= k.DecisionMin[0] && wp.y >= k.DecisionMin[1] && wp.z >= k.DecisionMin[2])
+    // six compares and one branch (bitwise &: no short-circuit jumps; NaN fails every compare either way)
+    if ((wp.x <= k.DecisionMax[0]) & (wp.y <= k.DecisionMax[1]) & (wp.z <= k.DecisionMax[2]) &
+        (wp.x >= k.DecisionMin[0]) & (wp.y >= k.DecisionMin[1]) & (wp.z >= k.DecisionMin[2]))
       break;
   }
   return c;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(256) mark_kernel(AllocParams p, const float* _
   Cell own = {-1, 0, 0, 0}, own2 = {-1, 0, 0, 0};
   int casc = -1;
   if (x < p.W && y < p.H) {
-    float d = __ldg(depth + (size_t)y * p.W + x);
+    float d = __ldg(depth + (uint32_t)(y * p.W + x)); // < 2^31 pixels: checked at create
     if (d > 0.0001f) {
       F3 wp = ex_unproject(p.ivp, __ldg(ndc_xy + x), __ldg(ndc_xy + p.W + y), d);
       casc = compute_cascade(p, wp);
@@ -145,15 +146,15 @@ __global__ void __launch_bounds__(256) mark_kernel(AllocParams p, const float* _
   T1[lx][ly] = own.id;
   if (p.transitions) T2[lx][ly] = own2.id;
   __syncthreads();
-  {
-    int ax = max(0, lx - 1), ay = max(0, ly - 1);
-    if (((T1[lx][ay] != own.id && T1[ax][ly] != own.id && T1[ax][ay] != own.id) || (ax == lx && ay == ly)) && own.id != -1)
-      mark_corners(p, own, casc, flags, oob_accum);
+  { // cacheGather.comp:142-146; (ax == lx && ay == ly) is the tile's corner thread. Bitwise logic: no short-circuit jumps
+    const int ax = max(0, lx - 1), ay = max(0, ly - 1), id = own.id;
+    const bool fresh = ((T1[lx][ay] != id) & (T1[ax][ly] != id) & (T1[ax][ay] != id)) | ((lx | ly) == 0);
+    if (fresh & (id != -1)) mark_corners(p, own, casc, flags, oob_accum);
   }
-  if (p.transitions) {
-    int bx = min(15, lx + 1), by = min(15, ly + 1);
-    if (((T2[lx][by] != own2.id && T2[bx][ly] != own2.id && T2[bx][by] != own2.id) || (bx == 15 && by == 15)) && own2.id != -1)
-      mark_corners(p, own2, casc + 1, flags, oob_accum);
+  if (p.transitions) { // cacheGather.comp:147-150 (the mirrored neighbours)
+    const int bx = min(15, lx + 1), by = min(15, ly + 1), id = own2.id;
+    const bool fresh = ((T2[lx][by] != id) & (T2[bx][ly] != id) & (T2[bx][by] != id)) | ((lx & ly) == 15);
+    if (fresh & (id != -1)) mark_corners(p, own2, casc + 1, flags, oob_accum);
   }
 }
 

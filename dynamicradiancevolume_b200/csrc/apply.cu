@@ -33,8 +33,9 @@ __device__ __forceinline__ int compute_cascade(const ApplyParams& p, F3 wp) { //
   int c = 0;
   for (; c < p.C - 1; ++c) {
     const drv_cav_cascade& k = p.casc[c];
-    if (wp.x <= k.DecisionMax[0] && wp.y <= k.DecisionMax[1] && wp.z <= k.DecisionMax[2] &&
-        wp.x >= k.DecisionMin[0] && wp.y >= k.DecisionMin[1] && wp.z >= k.DecisionMin[2])
+    // six compares and one branch (bitwise &: no short-circuit jumps; NaN fails every compare either way)
+    if ((wp.x <= k.DecisionMax[0]) & (wp.y <= k.DecisionMax[1]) & (wp.z <= k.DecisionMax[2]) &
+        (wp.x >= k.DecisionMin[0]) & (wp.y >= k.DecisionMin[1]) & (wp.z >= k.DecisionMin[2]))
       break;
   }
   return c;

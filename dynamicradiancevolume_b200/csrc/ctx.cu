@@ -50,7 +50,8 @@ extern "C" drv_status drv_create(const drv_config* cfg, drv_ctx** out) {
   const drv_config& c = *cfg;
   if (c.max_cache_count == 0 || c.max_cache_count > (1u << 24) || c.cav_resolution > 256 || c.cav_cascades < 1 || c.cav_cascades > DRV_MAX_CASCADES || c.cav_resolution < 8 ||
       (c.cav_resolution % 8) != 0 || (c.sh_order != 1 && c.sh_order != 2) || c.backbuffer_width == 0 ||
-      c.backbuffer_height == 0 || c.max_lights > DRV_MAX_LIGHTS || !is_pow2(c.voxel_resolution) ||
+      c.backbuffer_height == 0 || (uint64_t)c.backbuffer_width * c.backbuffer_height > (1ull << 30) /* 32-bit pixel indices */ ||
+      c.max_lights > DRV_MAX_LIGHTS || !is_pow2(c.voxel_resolution) ||
       c.voxel_resolution < 16 || (c.max_lights > 0 && !is_pow2(c.max_rsm_resolution))) {
     g_create_error = "drv_create: invalid configuration";
     return DRV_ERR_INVALID;
