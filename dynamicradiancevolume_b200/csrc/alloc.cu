@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) mark_kernel(AllocParams p, const float* _
   if (x < p.W && y < p.H) {
     float d = __ldg(depth + (uint32_t)(y * p.W + x)); // < 2^31 pixels: checked at create
     if (d > 0.0001f) {
-      F3 wp = ex_unproject(p.ivp, __ldg(ndc_xy + x), __ldg(ndc_xy + p.W + y), d);
+      F3 wp = ex_unproject(p.ivp, __ldg(ndc_xy + (uint32_t)x), __ldg(ndc_xy + (uint32_t)(p.W + y)), d);
       casc = compute_cascade(p, wp);
       own = cache_cell(p, wp, casc);
       if (p.transitions && casc < p.C - 1) {

@@ -163,7 +163,7 @@ __device__ __forceinline__ void shade_pixel(const ApplyParams& p, const float* s
     return;
   }
   // gl_FragCoord.xy -> NDC (:134) through the per-context tables
-  F3 wp = ex_unproject(p.ivp, __ldg(ndc_xy + x), __ldg(ndc_xy + p.W + y), d);
+  F3 wp = ex_unproject(p.ivp, __ldg(ndc_xy + (uint32_t)x), __ldg(ndc_xy + (uint32_t)(p.W + y)), d);
   const int c = compute_cascade(p, wp); // :138
   F3 n = unpack_normal16i_fast((int)(short)(pn & 0xffff), (int)(short)((uint32_t)pn >> 16)); // :140
   const float albr = s_srgb[dc.x], albg = s_srgb[dc.y], albb = s_srgb[dc.z]; // :144

@@ -43,11 +43,15 @@ struct F3 { float x, y, z; };
 
 // `vec4(v,1) * M` on the raw row-major ei bytes, then the perspective divide
 // (cacheGather.comp:118-119, cacheApply.frag:134-135).
+// row . (v, 1): the last product is r[3] * 1.0f, which is r[3] bit for bit (NaN payloads aside) — no multiply issued
+__device__ __forceinline__ float ex_dot4_w1(const float* r, float v0, float v1, float v2) {
+  return ex_add(ex_add(ex_add(ex_mul(r[0], v0), ex_mul(r[1], v1)), ex_mul(r[2], v2)), r[3]);
+}
 __device__ __forceinline__ F3 ex_unproject(const float* m, float x, float y, float z) {
-  float w0 = ex_dot4(m + 0, x, y, z, 1.0f);
-  float w1 = ex_dot4(m + 4, x, y, z, 1.0f);
-  float w2 = ex_dot4(m + 8, x, y, z, 1.0f);
-  float w3 = ex_dot4(m + 12, x, y, z, 1.0f);
+  float w0 = ex_dot4_w1(m + 0, x, y, z);
+  float w1 = ex_dot4_w1(m + 4, x, y, z);
+  float w2 = ex_dot4_w1(m + 8, x, y, z);
+  float w3 = ex_dot4_w1(m + 12, x, y, z);
   F3 r = {ex_div(w0, w3), ex_div(w1, w3), ex_div(w2, w3)};
   return r;
 }
