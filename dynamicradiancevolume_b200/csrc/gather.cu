@@ -548,10 +548,14 @@ struct ScalarMath {
 // .x/.y halves of 64-bit registers. The shared-memory VPL record duplicates
 // every scalar into both halves so it feeds FFMA2 without register shuffles:
 //  q0 = (x,x,y,y) q1 = (z,z,area,area) q2 = (nx,nx,ny,ny) q3 = (nz,nz,fr,fr) q4 = (fg,fg,fb,fb)
-template <int ORDER, bool SHADOW, int PAIRS>
+// BCAST: the shared-memory record is the plain 48-byte VPL (three float4) and every per-VPL scalar enters the packed
+// instructions as a 32-bit BROADCAST operand — sm_100's FFMA2 / FADD2 / FMUL2 take `R.F32` next to `R.F32x2` (nvcc
+// emits it for make_float2(s, s)). Against the duplicated record: 3 instead of 5 LDS.128 per VPL, 10 instead of 20
+// registers per VPL in flight, and 19 of the 27 packed instructions of a pair read five registers instead of six.
+template <int ORDER, bool SHADOW, int PAIRS, bool BCAST = false>
 struct PackedMath {
   static constexpr int CPT = PAIRS * 2;
-  static constexpr int kSmemPerVpl = 5;
+  static constexpr int kSmemPerVpl = BCAST ? 3 : 5;
   float2 npx[PAIRS], npy[PAIRS], npz[PAIRS]; // NEGATED cache positions
   float2 shadow[PAIRS];
   bool live[CPT];
@@ -571,6 +575,7 @@ struct PackedMath {
     }
   }
   static __device__ __forceinline__ void stage(float4* d, float4 r0, float4 r1, float4 r2) {
+    if (BCAST) { d[0] = r0; d[1] = r1; d[2] = r2; return; }
     d[0] = make_float4(r0.x, r0.x, r0.y, r0.y);
     d[1] = make_float4(r0.z, r0.z, r0.w, r0.w);
     d[2] = make_float4(r1.x, r1.x, r1.y, r1.y);
@@ -582,11 +587,20 @@ struct PackedMath {
     for (int j = 0; j < PAIRS; ++j) { shadow[j].x = v[2 * j]; shadow[j].y = v[2 * j + 1]; }
   }
   __device__ __forceinline__ void eval(const float4* q) {
-    float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
-    const float2 vx = make_float2(q0.x, q0.y), vy = make_float2(q0.z, q0.w), vz = make_float2(q1.x, q1.y);
-    const float2 ar = make_float2(q1.z, q1.w);
-    const float2 nx = make_float2(q2.x, q2.y), ny = make_float2(q2.z, q2.w), nz = make_float2(q3.x, q3.y);
-    const float2 fl[3] = {make_float2(q3.z, q3.w), make_float2(q4.x, q4.y), make_float2(q4.z, q4.w)};
+    float2 vx, vy, vz, ar, nx, ny, nz, fl[3];
+    if (BCAST) {
+      const float4 r0 = q[0], r1 = q[1], r2 = q[2]; // (x, y, z, area) (nx, ny, nz, block) (fr, fg, fb, -)
+      vx = make_float2(r0.x, r0.x); vy = make_float2(r0.y, r0.y); vz = make_float2(r0.z, r0.z);
+      ar = make_float2(r0.w, r0.w);
+      nx = make_float2(r1.x, r1.x); ny = make_float2(r1.y, r1.y); nz = make_float2(r1.z, r1.z);
+      fl[0] = make_float2(r2.x, r2.x); fl[1] = make_float2(r2.y, r2.y); fl[2] = make_float2(r2.z, r2.z);
+    } else {
+      const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
+      vx = make_float2(q0.x, q0.y); vy = make_float2(q0.z, q0.w); vz = make_float2(q1.x, q1.y);
+      ar = make_float2(q1.z, q1.w);
+      nx = make_float2(q2.x, q2.y); ny = make_float2(q2.z, q2.w); nz = make_float2(q3.x, q3.y);
+      fl[0] = make_float2(q3.z, q3.w); fl[1] = make_float2(q4.x, q4.y); fl[2] = make_float2(q4.z, q4.w);
+    }
 #pragma unroll
     for (int j = 0; j < PAIRS; ++j) {
       float2 tx = __fadd2_rn(vx, npx[j]), ty = __fadd2_rn(vy, npy[j]), tz = __fadd2_rn(vz, npz[j]);
@@ -1378,7 +1392,7 @@ template <bool SH>
 GatherFn select_kernel(int order, uint32_t variant, int* tile, int* threads, bool* ws) {
   *threads = kThreads;
   *ws = false;
-  if (variant == 0) variant = 31; // the default: fastest at every measured size (profiles/r2_gather_variants.md)
+  if (variant == 0) variant = 35; // the default: fastest at every measured size (profiles/r2_gather_variants.md)
   if (variant == 31 || variant == 32) { // three (SH1) / two (SH2) packed pairs per thread, one 8-warp CTA per SM
     using P1 = PackedMath<1, SH, 3>; using P2 = PackedMath<2, SH, 2>;
     *ws = true;
@@ -1386,6 +1400,28 @@ GatherFn select_kernel(int order, uint32_t variant, int* tile, int* threads, boo
     *threads = 256;
     if (order == 1) return variant == 31 ? gather_ws_kernel<1, SH, P1, 8, 8, 2> : gather_ws_kernel<1, SH, P1, 8, 4, 2>;
     return variant == 31 ? gather_ws_kernel<2, SH, P2, 8, 4, 2> : gather_ws_kernel<2, SH, P2, 8, 2, 2>;
+  }
+  if (variant >= 35 && variant <= 38) { // as 31, the per-VPL scalars as 32-bit broadcast operands (PackedMath BCAST)
+    using P1 = PackedMath<1, SH, 3, true>; using P2 = PackedMath<2, SH, 2, true>;
+    using Q1 = PackedMath<1, SH, 4, true>; using Q2 = PackedMath<2, SH, 3, true>;
+    *ws = true;
+    *threads = 256;
+    if (variant == 37 || variant == 38) { // four (SH1) / three (SH2) packed pairs per thread
+      *tile = 32 * (order == 1 ? Q1::CPT : Q2::CPT);
+      if (order == 1) return variant == 37 ? gather_ws_kernel<1, SH, Q1, 8, 4, 2> : gather_ws_kernel<1, SH, Q1, 8, 8, 2>;
+      return variant == 37 ? gather_ws_kernel<2, SH, Q2, 8, 2, 2> : gather_ws_kernel<2, SH, Q2, 8, 4, 2>;
+    }
+    *tile = 32 * (order == 1 ? P1::CPT : P2::CPT);
+    if (order == 1) return variant == 35 ? gather_ws_kernel<1, SH, P1, 8, 8, 2> : gather_ws_kernel<1, SH, P1, 8, 4, 2>;
+    return variant == 35 ? gather_ws_kernel<2, SH, P2, 8, 8, 2> : gather_ws_kernel<2, SH, P2, 8, 4, 2>;
+  }
+  if (variant == 39 || variant == 40) { // as 35 with 768 VPLs per staged tile (39) / the VPL loop unrolled 16x / 8x, 256 per tile (40)
+    using P1 = PackedMath<1, SH, 3, true>; using P2 = PackedMath<2, SH, 2, true>;
+    *ws = true;
+    *threads = 256;
+    *tile = 32 * (order == 1 ? P1::CPT : P2::CPT);
+    if (order == 1) return variant == 39 ? gather_ws_kernel<1, SH, P1, 8, 8, 3> : gather_ws_kernel<1, SH, P1, 8, 16, 2>;
+    return variant == 39 ? gather_ws_kernel<2, SH, P2, 8, 8, 3> : gather_ws_kernel<2, SH, P2, 8, 8, 1>;
   }
   if (variant == 33 || variant == 34) { // four packed pairs per thread (SH1), 256-entry tiles
     using P1 = PackedMath<1, SH, 4>; using P2 = PackedMath<2, SH, 2>;

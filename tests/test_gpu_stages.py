@@ -223,7 +223,8 @@ def _sweep_oracle(cb, pos, vpls_list, sh_order, fp64=False):
     return e
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3, 4, 7, 8, 9, 11, 12, 20, 21, 22, 23, 24, 25, 26, 27, 28, 30, 31, 32, 33, 34])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4, 7, 8, 9, 11, 12, 20, 21, 22, 23, 24, 25, 26, 27, 28, 30, 31, 32, 33, 34,
+                                     35, 36, 37, 38, 39, 40])
 @pytest.mark.parametrize("sh_order", [1, 2])
 @pytest.mark.parametrize("n_cache,n_vpl", [(1000, 4096), (70000, 1024), (37, 2500), (5000, 16384), (129, 9), (300000, 100)])
 def test_gather_unshadowed_variants(cuda_device, variant, sh_order, n_cache, n_vpl):
@@ -267,7 +268,7 @@ def test_gather_drops_zero_flux_vpls(cuda_device, pattern):
         ctx.close()
 
 
-@pytest.mark.parametrize("variant", [0, 20, 26, 28, 30])
+@pytest.mark.parametrize("variant", [0, 20, 26, 28, 30, 35, 37])
 def test_gather_accumulates_over_lights_and_calls(cuda_device, variant):
     """`entry.SH += acc` per light (cacheLightingRSM.comp:358-373): two lights, then a second call."""
     ctx, cb, pos, vpls = _sweep_ctx(3000, 4096, 2, variant)
@@ -395,7 +396,7 @@ def test_cone_trace_extremes(cuda_device):
     g.close()
 
 
-@pytest.mark.parametrize("variant", [0, 7, 8, 12, 20, 21, 25, 26, 27, 28, 30, 31])
+@pytest.mark.parametrize("variant", [0, 7, 8, 12, 20, 21, 25, 26, 27, 28, 30, 31, 35, 37])
 def test_shadowed_gather_variants_agree(cuda_device, variant):
     """Packed (default) and scalar pair kernels reading the same visibility table."""
     wl = workloads.atrium(width=320, height=180, rsm_res=64, read_lod=0, sh_order=2, indirect_shadow=True,
