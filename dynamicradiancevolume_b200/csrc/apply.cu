@@ -100,8 +100,27 @@ __device__ __forceinline__ void accumulate_corner(const ApplyParams& p, const ui
   }
 }
 
+// The SH1 corner with red and green riding in one packed register pair: the .xy of every coefficient's float4 IS an
+// aligned pair, the per-pixel basis factor enters as a 32-bit broadcast operand (FFMA2 R.F32 form). The same fused
+// operations in the same order as the scalar form — bit-identical — in 13 instead of 18 FP32-pipe instructions.
+__device__ __forceinline__ void accumulate_corner_sh1_packed(const ApplyParams& p, const uint8_t* __restrict__ entries,
+                                                             uint32_t address, const NormalBasis<1>& nb, float w,
+                                                             float2& rg, float& b) {
+  const float4* e = reinterpret_cast<const float4*>(entries + address * 64u);
+  const float4 q1 = __ldg(e + 1), q2 = __ldg(e + 2), q3 = __ldg(e + 3);
+  float2 irg = make_float2(q1.w * p.g0, q2.w * p.g0);
+  float ib = q3.w * p.g0;
+  // fma(-a, b, c) == fma(a, -b, c) exactly: the sign moves to the broadcast factor
+  irg = __ffma2_rn(make_float2(q1.x, q1.y), make_float2(-nb.b1y, -nb.b1y), irg); ib = fmaf(-q1.z, nb.b1y, ib);
+  irg = __ffma2_rn(make_float2(q2.x, q2.y), make_float2(nb.b1z, nb.b1z), irg);   ib = fmaf(q2.z, nb.b1z, ib);
+  irg = __ffma2_rn(make_float2(q3.x, q3.y), make_float2(-nb.b1x, -nb.b1x), irg); ib = fmaf(-q3.z, nb.b1x, ib);
+  irg.x = fmaxf(irg.x, 0.0f); irg.y = fmaxf(irg.y, 0.0f);
+  rg = __ffma2_rn(irg, make_float2(w, w), rg);
+  b = fmaf(fmaxf(ib, 0.0f), w, b);
+}
+
 // ComputeLightingFromCaches, cacheApply.frag:28-118 (before the * diffuse / PI).
-template <int ORDER>
+template <int ORDER, bool PACK>
 __device__ __forceinline__ void lighting_from_caches(const ApplyParams& p, const uint32_t* __restrict__ atlas,
                                                      const uint8_t* __restrict__ entries, F3 wp,
                                                      const NormalBasis<ORDER>& nb, int c, float& r, float& g, float& b) {
@@ -134,17 +153,21 @@ __device__ __forceinline__ void lighting_from_caches(const ApplyParams& p, const
     }
   }
   const float wxy[4] = {gx * gy, fx * gy, gx * fy, fx * fy};
+  float2 rg = make_float2(0.0f, 0.0f);
 #pragma unroll
   for (int i = 0; i < 8; ++i) { // offsets in cacheApply.frag:43-54 order: x fastest, then y, then z
     const float w = wxy[i & 3] * ((i >> 2) ? fz : gz);
     const uint32_t address = addr[i] - 1u; // atlas 0 -> 0xFFFFFFFF: no cache, contributes zero
-    if (ORDER == 1) { // the never-written slot max_caches of the SH1 layout stands in for "no cache"
+    if constexpr (ORDER == 1 && PACK) {
+      accumulate_corner_sh1_packed(p, entries, min(address, p.max_caches), nb, w, rg, b);
+    } else if (ORDER == 1) { // the never-written slot max_caches of the SH1 layout stands in for "no cache"
       accumulate_corner<ORDER, true>(p, entries, min(address, p.max_caches), true, nb, w, r, g, b);
     } else {
       const bool valid = address < p.max_caches;
       accumulate_corner<ORDER, false>(p, entries, valid ? address : 0u, valid, nb, w, r, g, b);
     }
   }
+  if constexpr (ORDER == 1 && PACK) { r = rg.x; g = rg.y; }
 }
 
 // Pixels per thread: a thread walks kApplyIter rows (8 apart... see the kernel) and fetches the G-buffer texels of
@@ -152,7 +175,7 @@ __device__ __forceinline__ void lighting_from_caches(const ApplyParams& p, const
 // overlaps the atlas + entry gathers of the previous pixel.
 constexpr int kApplyIter = 4;
 
-template <int ORDER>
+template <int ORDER, bool PACK>
 __device__ __forceinline__ void shade_pixel(const ApplyParams& p, const float* s_srgb, const uint32_t* __restrict__ atlas,
                                             const uint8_t* __restrict__ entries, const float* __restrict__ ndc_xy,
                                             void* __restrict__ out, int format, int x, int y, float d, int pn, uchar4 dc) {
@@ -177,12 +200,12 @@ __device__ __forceinline__ void shade_pixel(const ApplyParams& p, const float* s
     nb.b2dd = p.g22 * (n.x * n.x - n.y * n.y);
   }
   float r, g, b;
-  lighting_from_caches<ORDER>(p, atlas, entries, wp, nb, c, r, g, b);
+  lighting_from_caches<ORDER, PACK>(p, atlas, entries, wp, nb, c, r, g, b);
   if (p.transitions && c < p.C - 1) { // :172-184
     float tr = cascade_transition(p, wp, c);
     if (tr > 0.0f) {
       float r2, g2, b2;
-      lighting_from_caches<ORDER>(p, atlas, entries, wp, nb, c + 1, r2, g2, b2);
+      lighting_from_caches<ORDER, PACK>(p, atlas, entries, wp, nb, c + 1, r2, g2, b2);
       r = fmaf(r2 - r, tr, r); g = fmaf(g2 - g, tr, g); b = fmaf(b2 - b, tr, b);
     }
   }
@@ -212,7 +235,7 @@ __device__ __forceinline__ void shade_pixel(const ApplyParams& p, const float* s
 }
 
 // Block = 32 x 8 threads = a 32-wide column strip; it walks ITER consecutive 8-row groups.
-template <int ORDER, int MINB, int ITER>
+template <int ORDER, int MINB, int ITER, bool PACK = false>
 __global__ void __launch_bounds__(256, MINB) apply_kernel(ApplyParams p, const float* __restrict__ depth,
                                                           const int* __restrict__ normal, const uchar4* __restrict__ diffuse,
                                                           const uint32_t* __restrict__ atlas, const uint8_t* __restrict__ entries,
@@ -237,7 +260,7 @@ __global__ void __launch_bounds__(256, MINB) apply_kernel(ApplyParams p, const f
       const uint32_t t = (uint32_t)(y + 8) * p.W + x;
       d = __ldg(depth + t); pn = __ldg(normal + t); dc = __ldg(diffuse + t);
     }
-    shade_pixel<ORDER>(p, s_srgb, atlas, entries, ndc_xy, out, format, x, y, d0, pn0, dc0);
+    shade_pixel<ORDER, PACK>(p, s_srgb, atlas, entries, ndc_xy, out, format, x, y, d0, pn0, dc0);
   }
 }
 
@@ -309,6 +332,11 @@ drv_status drv_impl_apply_rows(drv_ctx* ctx, void* out, uint32_t format, uint32_
   do {                                                                                                          \
     if (tune == 4) DRV_APPLY(ORD, 4, IT); else if (tune == 6) DRV_APPLY(ORD, 6, IT); else DRV_APPLY(ORD, 5, IT); \
   } while (0)
+  if (tune == 7 && ctx->cfg.sh_order == 1 && iter == (uint32_t)kApplyIter) { // SH1 with red / green packed (A/B switch)
+    apply_kernel<1, 5, kApplyIter, true><<<grid, block, 0, ctx->stream>>>(p, ctx->gb_depth, (const int*)ctx->gb_normal,
+                                                                          (const uchar4*)ctx->gb_diffuse, ctx->atlas, ctx->entries,
+                                                                          ctx->ndc_xy, out, (int)format, (int)y_begin, (int)y_end);
+  } else
   if (ctx->cfg.sh_order == 2) {
     if (iter == 1) DRV_APPLY_MB(2, 1); else if (iter == 2) DRV_APPLY_MB(2, 2); else if (iter == 8) DRV_APPLY_MB(2, 8);
     else DRV_APPLY_MB(2, kApplyIter);

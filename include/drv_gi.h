@@ -211,11 +211,14 @@ typedef struct drv_config {
   int32_t  device;            /* CUDA device ordinal */
   void*    stream;            /* cudaStream_t; NULL = context creates its own */
   uint32_t gather_variant;    /* 0 = default. Tuning switches measured in profiles/ (DESIGN.md 4.1, 4.5):
-                                 bits 0..7   pair-kernel variant (0 = 31 warp-split kernel, one 8-warp CTA per SM;
-                                             30 the cooperative stream-K kernel; 1 TMA staging, 3/4/12 scalar or
+                                 bits 0..7   pair-kernel variant (0 = 35: warp-split kernel, one 8-warp CTA per SM, per-VPL
+                                             scalars as 32-bit broadcast operands of the packed instructions; 31 the same
+                                             with the duplicated shared-memory record of round 2's first half; 36..40 other
+                                             shapes of 35; 30 the cooperative stream-K kernel; 1 TMA staging, 3/4/12 scalar or
                                              single-pair maths, 6 three CTAs/SM, 7/8 64-/32-thread CTAs, 9/10/11 VPL
                                              loop unrolled 2/8/4x, 20..28 / 32..34 other warp-split shapes)
-                                 bits 8..11  apply: resident blocks/SM the kernel is compiled for (4, 6; default 5)
+                                 bits 8..11  apply: resident blocks/SM the kernel is compiled for (4, 6; default 5);
+                                             7 = SH1 with red / green in packed FFMA2 (bit-identical, measured equal)
                                  bits 12..15 apply: rows per thread (1, 2, 8; default 4)
                                  bit 16      variant 30: two-kernel gather + finalize instead of the cooperative launch
                                  bit 17      software-pipelined cone march instead of the plain loop
