@@ -146,14 +146,15 @@ __global__ void __launch_bounds__(256) mark_kernel(AllocParams p, const float* _
   T1[lx][ly] = own.id;
   if (p.transitions) T2[lx][ly] = own2.id;
   __syncthreads();
-  { // cacheGather.comp:142-146; (ax == lx && ay == ly) is the tile's corner thread. Bitwise logic: no short-circuit jumps
+  { // cacheGather.comp:142-146, conditions kept literally. Bitwise logic: no short-circuit jumps
     const int ax = max(0, lx - 1), ay = max(0, ly - 1), id = own.id;
-    const bool fresh = ((T1[lx][ay] != id) & (T1[ax][ly] != id) & (T1[ax][ay] != id)) | ((lx | ly) == 0);
+    const bool fresh = ((T1[lx][ay] != id) & (T1[ax][ly] != id) & (T1[ax][ay] != id)) | ((ax == lx) & (ay == ly));
     if (fresh & (id != -1)) mark_corners(p, own, casc, flags, oob_accum);
   }
   if (p.transitions) { // cacheGather.comp:147-150 (the mirrored neighbours)
     const int bx = min(15, lx + 1), by = min(15, ly + 1), id = own2.id;
-    const bool fresh = ((T2[lx][by] != id) & (T2[bx][ly] != id) & (T2[bx][by] != id)) | ((lx & ly) == 15);
+    // (bx == 15 && by == 15) holds for lx >= 14 && ly >= 14 — four threads, not one: the shader's own condition, kept literally
+    const bool fresh = ((T2[lx][by] != id) & (T2[bx][ly] != id) & (T2[bx][by] != id)) | ((bx == 15) & (by == 15));
     if (fresh & (id != -1)) mark_corners(p, own2, casc + 1, flags, oob_accum);
   }
 }

@@ -38,6 +38,10 @@ def _frames(wl, **kw):
     ("atrium-3casc", lambda: workloads.atrium(width=640, height=360, rsm_res=64, read_lod=0, cascades=3,
                                               cav_resolution=32, first_cascade=4.0)),
     ("atrium-1080p", lambda: workloads.atrium(rsm_res=64, read_lod=0)),
+    # a frame whose second-cascade cells are partly registered only by the threads with local x, y >= 14 of a tile
+    # (the `lookUpThread == LOCAL_SIZE - 1` clause of cacheGather.comp:147-150)
+    ("atrium-r16-transitions", lambda: workloads.atrium(width=160, height=90, rsm_res=32, read_lod=0, cav_resolution=16,
+                                                        first_cascade=8.0, max_caches=8192)),
 ])
 def test_allocation_bit_exact(cuda_device, name, make):
     wl = make()
