@@ -32,62 +32,38 @@
 #include <vector>
 
 #include "drv_gi.h"
+#include "drv_math.h"
 
 namespace drv {
 
-// camera/camera.hpp:15-39; defaults of application.cpp:51-52
-struct Camera {
-  float position[3] = {0.0f, 2.5f, 5.0f};
-  float direction[3] = {0.0f, -2.5f, -5.0f};
-  float up[3] = {0.0f, 1.0f, 0.0f};
-  float hfovDegrees = 60.0f;
-  float aspectRatio = 16.0f / 9.0f;
-  float nearPlane = 0.1f;
-  float farPlane = 1000.0f;
-
-  drv_camera_desc Desc() const {
-    drv_camera_desc d;
-    std::memcpy(d.position, position, sizeof(position));
-    std::memcpy(d.direction, direction, sizeof(direction));
-    std::memcpy(d.up, up, sizeof(up));
-    d.hfov_degrees = hfovDegrees;
-    d.aspect_ratio = aspectRatio;
-    d.near_plane = nearPlane;
-    d.far_plane = farPlane;
-    return d;
-  }
-};
-
-// scene/light.hpp:8-55 with its constructor defaults; near / far plane: scene/scene.cpp:6-7
-struct Light {
-  float intensity[3] = {10.0f, 10.0f, 10.0f};
-  float position[3] = {0.0f, 0.0f, 0.0f};
-  float direction[3] = {0.0f, 0.0f, 1.0f};
-  float halfAngle = 0.5f;
-  unsigned int rsmResolution = 1024;
-  unsigned int rsmReadLod = 4;
-  float normalOffsetShadowBias = 0.01f;
-  float shadowBias = 0.0001f;
-  unsigned int indirectShadowComputationLod = 2;
-  float nearPlane = 0.1f;
-  float farPlane = 10000.0f;
-
-  drv_light_desc Desc() const {
-    drv_light_desc d;
-    std::memcpy(d.intensity, intensity, sizeof(intensity));
-    std::memcpy(d.position, position, sizeof(position));
-    std::memcpy(d.direction, direction, sizeof(direction));
-    d.half_angle = halfAngle;
-    d.rsm_resolution = rsmResolution;
-    d.rsm_read_lod = rsmReadLod;
-    d.normal_offset_shadow_bias = normalOffsetShadowBias;
-    d.shadow_bias = shadowBias;
-    d.indirect_shadow_lod = indirectShadowComputationLod;
-    d.near_plane = nearPlane;
-    d.far_plane = farPlane;
-    return d;
-  }
-};
+// Camera (camera/camera.hpp:15-39) and Light (scene/light.hpp:8-55) are the structs of include/drv_math.h, which also
+// holds the packers as header code; the mirror goes through their C entry points (drv_pack_*) like any other host.
+inline drv_camera_desc ToDesc(const Camera& c) {
+  drv_camera_desc d;
+  store3(d.position, c.position);
+  store3(d.direction, c.direction);
+  store3(d.up, c.up);
+  d.hfov_degrees = c.hfovDegrees;
+  d.aspect_ratio = c.aspectRatio;
+  d.near_plane = c.nearPlane;
+  d.far_plane = c.farPlane;
+  return d;
+}
+inline drv_light_desc ToDesc(const Light& l) {
+  drv_light_desc d;
+  store3(d.intensity, l.intensity);
+  store3(d.position, l.position);
+  store3(d.direction, l.direction);
+  d.half_angle = l.halfAngle;
+  d.rsm_resolution = l.rsmResolution;
+  d.rsm_read_lod = l.rsmReadLod;
+  d.normal_offset_shadow_bias = l.normalOffsetShadowBias;
+  d.shadow_bias = l.shadowBias;
+  d.indirect_shadow_lod = l.indirectShadowComputationLod;
+  d.near_plane = l.nearPlane;
+  d.far_plane = l.farPlane;
+  return d;
+}
 
 // The slice of SceneEntity / Model (scene/sceneentity.hpp, scene/model.hpp) the voxeliser consumes.
 struct SceneEntity {
@@ -316,12 +292,12 @@ class Renderer {
     if (m_ctx) Check(drv_set_constant(m_ctx, &m_constant));
   }
   void UpdatePerFrameUBO(const Camera& camera) {  // renderer.cpp:324-344
-    const drv_camera_desc d = camera.Desc();
+    const drv_camera_desc d = ToDesc(camera);
     drv_pack_per_frame(&m_perFrame, &d, m_passedTime);
     if (Context()) Check(drv_set_per_frame(m_ctx, &m_perFrame));
   }
   void UpdateVolumeUBO(const Camera& camera) {  // renderer.cpp:346-431
-    const drv_camera_desc d = camera.Desc();
+    const drv_camera_desc d = ToDesc(camera);
     drv_pack_volume_info(&m_volumeInfo, &d, m_scene->GetBoundingBoxMin(), m_scene->GetBoundingBoxMax(), (int32_t)m_voxelResolution,
                          (int32_t)m_cavResolution, (int32_t)m_CAVCascadeWorldSize.size(), m_CAVCascadeWorldSize.data(),
                          m_CAVCascadeTransitionSize);
@@ -341,7 +317,7 @@ class Renderer {
     m_spotLights.resize(lights.size());
     m_uploadedSpotLights.resize(lights.size());
     for (size_t i = 0; i < lights.size(); ++i) {
-      const drv_light_desc d = lights[i].Desc();
+      const drv_light_desc d = ToDesc(lights[i]);
       drv_pack_spot_light(&m_spotLights[i], &d);
       if (!m_uploadedSpotLights[i].valid || std::memcmp(&m_uploadedSpotLights[i].block, &m_spotLights[i], sizeof(drv_spot_light)) != 0) {
         Check(drv_set_spot_light(m_ctx, (uint32_t)i, &m_spotLights[i]));

@@ -87,9 +87,9 @@ struct Cornell {
     scn_triangles(geo, triangles.data(), nt);
     camera.aspectRatio = (float)width / (float)height;
     drv::Light l;
-    l.intensity[0] = l.intensity[1] = l.intensity[2] = 100.0f;
-    l.position[0] = 0.0f; l.position[1] = 1.7f; l.position[2] = 3.3f;
-    l.direction[0] = 0.0f; l.direction[1] = 0.0f; l.direction[2] = -1.0f;
+    l.intensity = drv::Vec3(100.0f, 100.0f, 100.0f);
+    l.position = drv::Vec3(0.0f, 1.7f, 3.3f);
+    l.direction = drv::Vec3(0.0f, 0.0f, -1.0f);
     l.halfAngle = 30.0f * 3.14159265358979f / 180.0f;
     l.rsmResolution = rsmResolution;
     l.rsmReadLod = rsmReadLod;
@@ -162,6 +162,25 @@ int host_selftest() {
   EXPECT(c.BackbufferResolution[0] == 1920 && c.BackbufferResolution[1] == 1080, "resolution");
   EXPECT(c.AddressVolumeResolution == 64 && c.NumAddressVolumeCascades == 3 && c.VoxelResolution == 128, "volume fields");
   EXPECT(c.MaxNumLightCaches == 16384u, "max caches");
+  // the header packers of include/drv_math.h (what a C++ host may call directly) and their C entry points agree byte for byte
+  {
+    drv::Camera cam;
+    cam.aspectRatio = 1920.0f / 1080.0f;
+    drv_per_frame a, b;
+    std::memset(&a, 0, sizeof(a)); std::memset(&b, 0, sizeof(b));
+    drv::packPerFrame(&a, cam, 1.5f);
+    const drv_camera_desc cd = drv::ToDesc(cam);
+    drv_pack_per_frame(&b, &cd, 1.5f);
+    EXPECT(std::memcmp(&a, &b, sizeof(a)) == 0, "packPerFrame != drv_pack_per_frame");
+    drv_spot_light la, lb;
+    std::memset(&la, 0, sizeof(la)); std::memset(&lb, 0, sizeof(lb));
+    const drv::Light& light = wl.scene->GetLights()[0];
+    drv::packSpotLight(&la, light);
+    const drv_light_desc ld = drv::ToDesc(light);
+    drv_pack_spot_light(&lb, &ld);
+    EXPECT(std::memcmp(&la, &lb, sizeof(la)) == 0, "packSpotLight != drv_pack_spot_light");
+    EXPECT(la.RSMReadResolution == 64 && la.IndirectShadowComputationSampleInterval == 16, "light block fields");
+  }
   static_assert(sizeof(drv_constant) == 80 && sizeof(drv_per_frame) == 288 && sizeof(drv_volume_info) == 288 &&
                     sizeof(drv_spot_light) == 224, "std140 block sizes (SURVEY A.1)");
   std::printf(g_failures ? "HOST FAILED (%d)\n" : "HOST OK\n", g_failures);
@@ -327,7 +346,7 @@ void frame_parity(bool sh2, bool shadow) {
 
   // ---- detachViewFromCameraUpdate: caches stay where they are, only the view changes (renderer.hpp:43-45)
   drv::Camera moved = wl.camera;
-  moved.position[0] += 0.25f;
+  moved.position.x += 0.25f;
   const uint64_t launches = drv_kernel_launches(r.Context());
   r.Draw(moved, true, 0.0f);
   r.Finish();

@@ -48,3 +48,18 @@ def test_cpp_mirror_frames_match_the_oracle(cuda_device):
     C++ against the oracle: allocation bit-exact, SH and radiance inside the 1e-3 / 1e-5 gate."""
     r = subprocess.run([_exe()], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "PARITY OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_public_headers_compile_standalone(tmp_path):
+    """include/drv_gi.h is plain C99 (a cgo / JNI / ctypes binding generator can read it); include/drv_renderer.hpp is
+    self-contained C++17, warning-free under -Wall -Wextra -Wpedantic."""
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Wpedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(inc, "drv_gi.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = tmp_path / "tu.cpp"
+    src.write_text('#include "drv_renderer.hpp"\n#include "drv_math.h"\nint main() { return 0; }\n')
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Wpedantic", "-I" + inc, "-isystem", cuda_inc,
+                        "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0 and "warning" not in r.stderr, r.stderr
